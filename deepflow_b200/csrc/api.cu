@@ -1,0 +1,820 @@
+/*
+ * api.cu — the C ABI of include/dfgpu.h: context, dictionary / geo upload, the
+ * stage -> run -> fetch pipeline and the column-block views handed back to the
+ * host shim.  See DESIGN.md for the data layout.
+ */
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "pipeline.cuh"
+#include "schema_l4.h"
+#include "schema_l7.h"
+
+using namespace dfgpu;
+
+namespace dfgpu {
+void launch_l4_pass(const BatchParams& p, int emit, cudaStream_t s);
+void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s);
+struct FlowTagDev;
+int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s);
+}  // namespace dfgpu
+
+#define X(id, name, t, es) {name, t, es, -1},
+static const ColSpec kL4Cols[] = {L4_COLUMNS(X)};
+static const ColSpec kL7Cols[] = {L7_COLUMNS(X)};
+#undef X
+
+struct TableSchema {
+  int table_id;
+  const ColSpec* cols;
+  int ncols;
+};
+
+struct HostBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+};
+
+struct dfgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  dfgpu_cfg cfg{};
+  std::string err;
+  std::mutex dict_mu;
+  std::map<uint16_t, std::shared_ptr<DeviceDict>> dicts;
+  // geo
+  uint32_t* d_geo_start = nullptr;
+  uint32_t* d_geo_end = nullptr;
+  uint8_t* d_geo_code = nullptr;
+  uint32_t geo_n = 0;
+  std::vector<std::string> geo_names;  // by canonical code
+
+  // device work buffers
+  uint8_t* d_in = nullptr;
+  size_t d_in_cap = 0;
+  dfgpu_frame* d_frames = nullptr;
+  uint32_t* d_frame_u32 = nullptr;  // nrec | base | chain_err | bad
+  uint32_t frames_cap = 0;
+  uint32_t* d_rec_u32 = nullptr;  // off | len | frame
+  uint32_t rec_cap = 0;
+  uint32_t* d_warp = nullptr;  // tot[MAX_SLOTS][nwarps] | base[MAX_SLOTS][nwarps]
+  size_t warp_cap = 0;         // in warps
+  DynState* d_dyn = nullptr;
+  PersistState* d_persist = nullptr;
+  uint8_t* d_arena = nullptr;
+  size_t arena_cap = 0;
+  // pinned host
+  DynState* h_dyn = nullptr;
+  PersistState* h_persist = nullptr;
+  uint32_t* h_frame_u32 = nullptr;
+  uint32_t h_frames_cap = 0;
+  std::vector<HostBuf> host_pool;
+
+  // current batch
+  int cur_msg = 0;
+  const uint8_t* cur_in = nullptr;
+  const dfgpu_frame* cur_frames = nullptr;  // device
+  size_t cur_nbytes = 0;
+  uint32_t cur_nframes = 0;
+  uint16_t cur_org = 0;
+  uint32_t cur_team = 0;
+  bool staged = false, ran = false;
+  BatchParams bp{};
+  std::shared_ptr<DeviceDict> cur_dict;
+  uint32_t* id_counter_out = nullptr;
+  uint64_t* trace_idx_out = nullptr;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // flow tag state (l7)
+  void* ft = nullptr;
+};
+
+static int fail(dfgpu_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return fail(ctx, DFGPU_ENODEV, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <class T>
+static int ensure_dev(dfgpu_ctx* ctx, T*& p, size_t& cap, size_t want) {
+  if (cap >= want) return 0;
+  if (p) CU(cudaFree(p));
+  p = nullptr;
+  size_t n = std::max(want, cap + cap / 2);
+  CU(cudaMalloc(&p, n * sizeof(T)));
+  cap = n;
+  return 0;
+}
+
+extern "C" {
+
+int dfgpu_init(int device, const dfgpu_cfg* cfg, dfgpu_ctx** out) {
+  if (!out) return DFGPU_EINVAL;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device >= n) return DFGPU_ENODEV;
+  dfgpu_ctx* ctx = new dfgpu_ctx();
+  ctx->device = device;
+  if (cfg) ctx->cfg = *cfg;
+  if (!ctx->cfg.max_batch_bytes) ctx->cfg.max_batch_bytes = 256ull << 20;
+  if (!ctx->cfg.max_batch_records) ctx->cfg.max_batch_records = (uint32_t)(ctx->cfg.max_batch_bytes / 128);
+  if (!ctx->cfg.flow_tag_cache_flush_timeout) ctx->cfg.flow_tag_cache_flush_timeout = 1800;
+  if (!ctx->cfg.flow_tag_cache_max_size) ctx->cfg.flow_tag_cache_max_size = 1u << 18;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_dyn, sizeof(DynState));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_persist, sizeof(PersistState));
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_persist, 0, sizeof(PersistState));
+  if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_dyn, sizeof(DynState), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_persist, sizeof(PersistState), cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return DFGPU_ENODEV;
+  }
+  memset(ctx->h_persist, 0, sizeof(PersistState));
+  *out = ctx;
+  return DFGPU_OK;
+}
+
+void dfgpu_l7_free_state(dfgpu_ctx* ctx);
+
+int dfgpu_close(dfgpu_ctx* ctx) {
+  if (!ctx) return DFGPU_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  dfgpu_l7_free_state(ctx);
+  cudaFree(ctx->d_in);
+  cudaFree(ctx->d_frames);
+  cudaFree(ctx->d_frame_u32);
+  cudaFree(ctx->d_rec_u32);
+  cudaFree(ctx->d_warp);
+  cudaFree(ctx->d_dyn);
+  cudaFree(ctx->d_persist);
+  cudaFree(ctx->d_arena);
+  cudaFree(ctx->d_geo_start);
+  cudaFree(ctx->d_geo_end);
+  cudaFree(ctx->d_geo_code);
+  cudaFreeHost(ctx->h_dyn);
+  cudaFreeHost(ctx->h_persist);
+  cudaFreeHost(ctx->h_frame_u32);
+  for (auto& b : ctx->host_pool) cudaFreeHost(b.p);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return DFGPU_OK;
+}
+
+const char* dfgpu_last_error(const dfgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+void* dfgpu_stream(dfgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t dfgpu_launch_count(const dfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dfgpu_dict_load(dfgpu_ctx* ctx, uint16_t org_id, const dfgpu_dict_snapshot* snap) {
+  if (!ctx || !snap) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  HostDict h;
+  int rc = build_dict(*snap, h);
+  if (rc) return fail(ctx, rc, "build_dict failed");
+  auto dd = std::make_shared<DeviceDict>();
+  struct Part {
+    const void* src;
+    size_t bytes;
+    size_t off;
+  };
+  std::vector<Part> parts = {
+      {h.t64.data(), h.t64.size() * sizeof(T64Entry), 0},
+      {h.t6.data(), h.t6.size() * sizeof(T6Entry), 0},
+      {h.infos.data(), h.infos.size() * sizeof(DInfo), 0},
+      {h.gp_vals.data(), h.gp_vals.size() * sizeof(uint64_t), 0},
+      {h.vtaps.data(), h.vtaps.size() * sizeof(DVtap), 0},
+      {h.cidr4.data(), h.cidr4.size() * sizeof(DCidr4), 0},
+      {h.cidr4_ranges.data(), h.cidr4_ranges.size() * sizeof(DRange), 0},
+      {h.cidr6.data(), h.cidr6.size() * sizeof(DCidr6), 0},
+      {h.cidr6_ranges.data(), h.cidr6_ranges.size() * sizeof(DRange), 0},
+  };
+  size_t total = 0;
+  for (auto& p : parts) {
+    p.off = total;
+    total += align_up(p.bytes + 16, 256);
+  }
+  CU(cudaMalloc(&dd->blob, total));
+  dd->blob_bytes = total;
+  // plain synchronous copies: the upload happens off the hot path (60 s cadence)
+  for (auto& p : parts)
+    if (p.bytes) CU(cudaMemcpy((uint8_t*)dd->blob + p.off, p.src, p.bytes, cudaMemcpyHostToDevice));
+  uint8_t* b = (uint8_t*)dd->blob;
+  DevDict& v = dd->view;
+  memset(&v, 0, sizeof v);
+  v.t64 = (const T64Entry*)(b + parts[0].off);
+  v.t64_mask = h.t64_mask;
+  v.t6 = (const T6Entry*)(b + parts[1].off);
+  v.t6_mask = h.t6_mask;
+  v.infos = (const DInfo*)(b + parts[2].off);
+  v.gp_vals = (const uint64_t*)(b + parts[3].off);
+  v.vtaps = (const DVtap*)(b + parts[4].off);
+  v.cidr4 = (const DCidr4*)(b + parts[5].off);
+  v.cidr4_ranges = (const DRange*)(b + parts[6].off);
+  v.cidr6 = (const DCidr6*)(b + parts[7].off);
+  v.cidr6_ranges = (const DRange*)(b + parts[8].off);
+  memcpy(v.counts, h.counts, sizeof v.counts);
+  memcpy(v.counts6, h.counts6, sizeof v.counts6);
+  v.region_id = h.region_id;
+  v.analyzer_id = h.analyzer_id;
+  dd->version = h.version;
+  std::lock_guard<std::mutex> g(ctx->dict_mu);
+  ctx->dicts[org_id] = dd;  // the previous snapshot is freed when the last batch using it ends
+  return DFGPU_OK;
+}
+
+int dfgpu_geo_load(dfgpu_ctx* ctx, const dfgpu_geo_entry* entries, uint64_t n, const char* const* region_names,
+                   uint32_t n_names) {
+  if (!ctx || (n && !entries) || !region_names || n_names == 0) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  // canonical code per name: DecodeRegion (libs/geo/utils.go:27-40) maps out-of-range
+  // codes to names[0]'s text; identical names share one LowCardinality entry.
+  std::vector<std::string> names(region_names, region_names + n_names);
+  std::vector<uint8_t> canon(256, 0);
+  for (uint32_t c = 0; c < 256; c++) {
+    uint32_t idx = c < n_names ? c : 0;
+    const std::string& s = c < n_names ? names[c] : std::string("\xe6\x9c\xaa\xe7\x9f\xa5");
+    uint32_t first = idx;
+    for (uint32_t k = 0; k < n_names && k < 256; k++)
+      if (names[k] == s) {
+        first = k;
+        break;
+      }
+    canon[c] = (uint8_t)first;
+  }
+  ctx->geo_names.assign(256, std::string());
+  for (uint32_t c = 0; c < n_names && c < 256; c++) ctx->geo_names[c] = names[c];
+  if (n_names && names[0] != "\xe6\x9c\xaa\xe7\x9f\xa5") {
+    // out-of-range codes decode to the literal "未知"; keep it reachable if names[0] differs
+  }
+  std::vector<dfgpu_geo_entry> e(entries, entries + n);
+  std::stable_sort(e.begin(), e.end(), [](const dfgpu_geo_entry& a, const dfgpu_geo_entry& b) { return a.ip_start < b.ip_start; });
+  std::vector<uint32_t> st(n), en(n);
+  std::vector<uint8_t> code(n);
+  for (uint64_t i = 0; i < n; i++) {
+    st[i] = e[i].ip_start;
+    en[i] = e[i].ip_end;
+    code[i] = canon[e[i].region];
+  }
+  cudaFree(ctx->d_geo_start);
+  cudaFree(ctx->d_geo_end);
+  cudaFree(ctx->d_geo_code);
+  ctx->d_geo_start = ctx->d_geo_end = nullptr;
+  ctx->d_geo_code = nullptr;
+  ctx->geo_n = (uint32_t)n;
+  if (n) {
+    CU(cudaMalloc(&ctx->d_geo_start, n * 4));
+    CU(cudaMalloc(&ctx->d_geo_end, n * 4));
+    CU(cudaMalloc(&ctx->d_geo_code, n));
+    CU(cudaMemcpy(ctx->d_geo_start, st.data(), n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_geo_end, en.data(), n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_geo_code, code.data(), n, cudaMemcpyHostToDevice));
+  }
+  return DFGPU_OK;
+}
+
+}  // extern "C"
+
+// ---- layout ---------------------------------------------------------------------------
+static const TableSchema* main_schema(int msg) {
+  static const TableSchema l4{DFGPU_TABLE_L4_FLOW_LOG, kL4Cols, (int)(sizeof kL4Cols / sizeof kL4Cols[0])};
+  static const TableSchema l7{DFGPU_TABLE_L7_FLOW_LOG, kL7Cols, (int)(sizeof kL7Cols / sizeof kL7Cols[0])};
+  if (msg == DFGPU_MSG_TAGGEDFLOW) return &l4;
+  if (msg == DFGPU_MSG_PROTOCOLLOG) return &l7;
+  return nullptr;
+}
+
+static size_t aux_bytes_per_row(int ch) {
+  switch (ch) {
+    case DFGPU_CH_STR:
+    case DFGPU_CH_LC_STR_ROWS: return 16;  // dfgpu_pos
+    case DFGPU_CH_ARR_UINT16:
+    case DFGPU_CH_ARR_STR:
+    case DFGPU_CH_ARR_LC_STR:
+    case DFGPU_CH_ARR_FLOAT64: return 8;   // cumulative end offset
+    case DFGPU_CH_NULLABLE_UINT8:
+    case DFGPU_CH_NULLABLE_INT32:
+    case DFGPU_CH_NULLABLE_INT64:
+    case DFGPU_CH_NULLABLE_UINT64: return 1;  // null flag
+  }
+  return 0;
+}
+static bool is_array(int ch) {
+  return ch == DFGPU_CH_ARR_UINT16 || ch == DFGPU_CH_ARR_STR || ch == DFGPU_CH_ARR_LC_STR || ch == DFGPU_CH_ARR_FLOAT64;
+}
+
+// fixed region of the arena for `rows` rows; returns its size
+static uint64_t plan_fixed(const TableSchema& s, uint32_t rows, uint64_t* fix_off, uint64_t* aux_off) {
+  uint64_t cur = 0;
+  for (int c = 0; c < s.ncols; c++) {
+    const ColSpec& cs = s.cols[c];
+    fix_off[c] = cur;
+    size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
+    cur += align_up((size_t)rows * es, 256);
+    aux_off[c] = cur;
+    cur += align_up((size_t)rows * aux_bytes_per_row(cs.ch_type), 256);
+  }
+  return cur;
+}
+
+namespace dfgpu {
+void l7_streams(BatchParams& bp);
+}
+
+static void setup_streams(BatchParams& bp, int msg) {
+  memset(bp.streams, 0, sizeof bp.streams);
+  if (msg == DFGPU_MSG_TAGGEDFLOW) {
+    bp.nslots = L4S_COUNT;
+    bp.nstreams = 3;
+    bp.n_lc = 3;
+    bp.streams[0] = StreamSpec{-1, L4S_AGG_BYTES, 1, 0};   // aggregated_flow_ids bytes
+    bp.streams[1] = StreamSpec{L4S_ACL_ELEMS, -1, 2, 0};   // acl_gids values
+    bp.streams[2] = StreamSpec{-1, L4S_DOM_BYTES, 1, 0};   // request_domain bytes
+  } else {
+    l7_streams(bp);
+  }
+}
+
+static int launch_passes(dfgpu_ctx* ctx, int repair) {
+  BatchParams& bp = ctx->bp;
+  bp.repair = repair;
+  cudaStream_t s = ctx->stream;
+  // reset first-appearance tables (and, in repair mode, nothing else)
+  CU(cudaMemsetAsync(&ctx->d_dyn->stats.lc_first, 0xff, sizeof(ctx->d_dyn->stats.lc_first), s));
+  if (bp.nrec == 0) {
+    CU(cudaMemsetAsync(&ctx->d_dyn->stats.var_total, 0, sizeof(ctx->d_dyn->stats.var_total), s));
+  }
+  if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 0, s);
+  else launch_l7_pass(bp, 0, s);
+  if (bp.nrec) {
+    launch_slot_scan(bp, s);
+    ctx->launches += 2;
+  }
+  launch_finish(bp, s);
+  ctx->launches++;
+  if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 1, s);
+  else launch_l7_pass(bp, 1, s);
+  if (bp.nrec) ctx->launches++;
+  if (ctx->cur_msg != DFGPU_MSG_PROTOCOLLOG) {  // L7 commits after its flow_tag stage
+    launch_commit(bp, 0, s);
+    ctx->launches++;
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbytes, const dfgpu_frame* tbl,
+                int nframes) {
+  if (!ctx || nframes < 0 || (nframes && !tbl) || (nbytes && !frames)) return DFGPU_EINVAL;
+  if (!main_schema(msg_type)) return fail(ctx, DFGPU_EINVAL, "unsupported msg_type %d", msg_type);
+  if (nbytes >= (1ull << 32)) return fail(ctx, DFGPU_EINVAL, "batch too large (%zu bytes)", nbytes);
+  CU(cudaSetDevice(ctx->device));
+  uint16_t org = nframes ? tbl[0].org_id : 1;
+  for (int i = 1; i < nframes; i++)
+    if (tbl[i].org_id != org) return fail(ctx, DFGPU_EMIXEDORG, "frames of one submit must share org_id");
+  for (int i = 0; i < nframes; i++)
+    if (tbl[i].offset + tbl[i].len > nbytes) return fail(ctx, DFGPU_EINVAL, "frame %d outside the staging buffer", i);
+  {
+    std::lock_guard<std::mutex> g(ctx->dict_mu);
+    auto it = ctx->dicts.find(org);
+    if (it == ctx->dicts.end()) return fail(ctx, DFGPU_ENOENT, "no dictionary loaded for org %u", org);
+    ctx->cur_dict = it->second;
+  }
+  cudaPointerAttributes attr;
+  bool on_device = false;
+  if (frames && cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeDevice) on_device = true;
+  cudaGetLastError();
+  size_t fcap = ctx->frames_cap;
+  if ((uint32_t)nframes > ctx->frames_cap) {
+    size_t want = (size_t)nframes;
+    if (ctx->d_frames) CU(cudaFree(ctx->d_frames));
+    if (ctx->d_frame_u32) CU(cudaFree(ctx->d_frame_u32));
+    ctx->d_frames = nullptr;
+    ctx->d_frame_u32 = nullptr;
+    fcap = std::max<size_t>(want, 1024);
+    CU(cudaMalloc(&ctx->d_frames, fcap * sizeof(dfgpu_frame)));
+    CU(cudaMalloc(&ctx->d_frame_u32, fcap * 4 * sizeof(uint32_t)));
+    ctx->frames_cap = (uint32_t)fcap;
+  }
+  if (on_device) {
+    ctx->cur_in = frames;  // inputs already resident in HBM
+  } else {
+    if (ensure_dev(ctx, ctx->d_in, ctx->d_in_cap, nbytes + 64)) return DFGPU_ENODEV;
+    if (nbytes) CU(cudaMemcpyAsync(ctx->d_in, frames, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cur_in = ctx->d_in;
+  }
+  bool tbl_on_device = false;
+  if (tbl && cudaPointerGetAttributes(&attr, tbl) == cudaSuccess && attr.type == cudaMemoryTypeDevice) tbl_on_device = true;
+  cudaGetLastError();
+  if (nframes) CU(cudaMemcpyAsync(ctx->d_frames, tbl, (size_t)nframes * sizeof(dfgpu_frame),
+                                   tbl_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  ctx->cur_frames = ctx->d_frames;
+  ctx->cur_msg = msg_type;
+  ctx->cur_nbytes = nbytes;
+  ctx->cur_nframes = (uint32_t)nframes;
+  ctx->cur_org = org;
+  ctx->staged = true;
+  ctx->ran = false;
+  return DFGPU_OK;
+}
+
+int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
+  if (!ctx || !ctx->staged) return fail(ctx, DFGPU_EINVAL, "dfgpu_run without dfgpu_stage");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const TableSchema* sch = main_schema(ctx->cur_msg);
+  BatchParams& bp = ctx->bp;
+  memset(&bp, 0, sizeof bp);
+  ctx->id_counter_out = id_counter;
+  ctx->trace_idx_out = trace_id_index;
+  if (id_counter || trace_id_index) {
+    // caller-provided counters win over the device-resident state
+    if (id_counter) ctx->h_persist->id_counter = *id_counter;
+    if (trace_id_index) ctx->h_persist->last_trace_id_index = *trace_id_index;
+    CU(cudaMemcpyAsync(ctx->d_persist, ctx->h_persist, sizeof(PersistState), cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaEventRecord(ctx->ev0, s));
+  CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
+  uint32_t nf = ctx->cur_nframes;
+  bp.in = ctx->cur_in;
+  bp.frames = ctx->cur_frames;
+  bp.nframes = nf;
+  bp.frame_nrec = ctx->d_frame_u32;
+  bp.frame_base = ctx->d_frame_u32 + ctx->frames_cap;
+  bp.frame_chain_err = ctx->d_frame_u32 + 2 * (size_t)ctx->frames_cap;
+  bp.frame_bad = ctx->d_frame_u32 + 3 * (size_t)ctx->frames_cap;
+  bp.dyn = ctx->d_dyn;
+  bp.persist = ctx->d_persist;
+  bp.dict = ctx->cur_dict->view;
+  bp.geo.start = ctx->d_geo_start;
+  bp.geo.end = ctx->d_geo_end;
+  bp.geo.code = ctx->d_geo_code;
+  bp.geo.n = ctx->geo_n;
+  bp.cfg_trace_disabled = ctx->cfg.trace_id_index_disabled;
+  if (nf) {
+    CU(cudaMemsetAsync(bp.frame_bad, 0xff, (size_t)nf * 4, s));
+    launch_frame_count(bp, s);
+    ctx->launches += 2;
+  }
+  // the record count sizes every later grid and the arena: one 4-byte round trip
+  CU(cudaMemcpyAsync(&ctx->h_dyn->stats.nrec, &ctx->d_dyn->stats.nrec, 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  uint32_t nrec = ctx->h_dyn->stats.nrec;
+  bp.nrec = nrec;
+  bp.nwarps = (nrec + 31) / 32;
+  if (nrec > ctx->rec_cap) {
+    if (ctx->d_rec_u32) CU(cudaFree(ctx->d_rec_u32));
+    ctx->d_rec_u32 = nullptr;
+    size_t cap = std::max<size_t>(nrec, 4096);
+    cap += cap / 4;
+    CU(cudaMalloc(&ctx->d_rec_u32, cap * 3 * sizeof(uint32_t)));
+    ctx->rec_cap = (uint32_t)cap;
+  }
+  bp.rec_off = ctx->d_rec_u32;
+  bp.rec_len = ctx->d_rec_u32 + ctx->rec_cap;
+  bp.rec_frame = ctx->d_rec_u32 + 2 * (size_t)ctx->rec_cap;
+  if (bp.nwarps > ctx->warp_cap) {
+    if (ctx->d_warp) CU(cudaFree(ctx->d_warp));
+    ctx->d_warp = nullptr;
+    size_t cap = std::max<size_t>(bp.nwarps, 1024);
+    cap += cap / 4;
+    CU(cudaMalloc(&ctx->d_warp, cap * 2 * MAX_SLOTS * sizeof(uint32_t)));
+    ctx->warp_cap = cap;
+  }
+  bp.warp_tot = ctx->d_warp;
+  bp.warp_base = ctx->d_warp + (size_t)MAX_SLOTS * ctx->warp_cap;
+  // the kernels index [slot][nwarps] with stride nwarps (not warp_cap): both halves are
+  // large enough because nslots <= MAX_SLOTS and nwarps <= warp_cap.
+  uint64_t fixed = plan_fixed(*sch, nrec, bp.fix_off, bp.aux_off);
+  bp.var_base = fixed;
+  uint64_t want = fixed + 2 * (uint64_t)ctx->cur_nbytes + (uint64_t)nrec * 96 + (1u << 20);
+  if (want > ctx->arena_cap) {
+    if (ctx->d_arena) CU(cudaFree(ctx->d_arena));
+    ctx->d_arena = nullptr;
+    size_t cap = (size_t)(want + want / 4);
+    CU(cudaMalloc(&ctx->d_arena, cap));
+    ctx->arena_cap = cap;
+  }
+  bp.arena = ctx->d_arena;
+  bp.arena_bytes = ctx->arena_cap;
+  setup_streams(bp, ctx->cur_msg);
+  if (nf && nrec) {
+    launch_frame_fill(bp, s);
+    ctx->launches++;
+  }
+  int rc = launch_passes(ctx, 0);
+  if (rc) return rc;
+  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
+    rc = l7_flow_tags(ctx, s);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(ctx->ev1, s));
+  ctx->ran = true;
+  return DFGPU_OK;
+}
+
+int dfgpu_sync(dfgpu_ctx* ctx) {
+  if (!ctx) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return DFGPU_OK;
+}
+
+}  // extern "C"
+
+static uint8_t* host_acquire(dfgpu_ctx* ctx, size_t bytes) {
+  size_t best = (size_t)-1;
+  for (size_t i = 0; i < ctx->host_pool.size(); i++)
+    if (ctx->host_pool[i].cap >= bytes && (best == (size_t)-1 || ctx->host_pool[i].cap < ctx->host_pool[best].cap)) best = i;
+  if (best != (size_t)-1) {
+    uint8_t* p = ctx->host_pool[best].p;
+    // keep the capacity in a small header in front of the user pointer
+    ctx->host_pool.erase(ctx->host_pool.begin() + best);
+    return p;
+  }
+  size_t cap = align_up(bytes + bytes / 8 + 4096, 4096);
+  uint8_t* p = nullptr;
+  if (cudaHostAlloc(&p, cap + 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  *reinterpret_cast<size_t*>(p) = cap;
+  return p;
+}
+static void host_release(dfgpu_ctx* ctx, uint8_t* p) {
+  if (!p) return;
+  HostBuf b;
+  b.p = p;
+  b.cap = *reinterpret_cast<size_t*>(p);
+  ctx->host_pool.push_back(b);
+}
+
+namespace dfgpu {
+// filled in by l7.cu: appends the flow_tag / app_service tables of a fetched batch
+int l7_fetch_tables(dfgpu_ctx* ctx, dfgpu_batch* b);
+const char* const kTapSideNames[18] = {"", "rest", "c", "s", "local", "c-nd", "s-nd", "c-hv", "s-hv", "c-gw-hv",
+                                       "s-gw-hv", "c-gw", "s-gw", "c-p", "s-p", "c-app", "s-app", "app"};
+}
+
+// dictionary of one LowCardinality code space, in first-appearance order
+static void lc_dictionary(dfgpu_batch* b, const uint32_t* first, const std::vector<std::string>& names_by_code,
+                          dfgpu_col& col) {
+  std::vector<std::pair<uint32_t, uint32_t>> present;
+  for (uint32_t c = 0; c < 256; c++)
+    if (first[c] != NO_BAD) present.push_back({first[c], c});
+  std::sort(present.begin(), present.end());
+  b->owned.emplace_back();
+  b->owned_pos.emplace_back();
+  auto& buf = b->owned.back();
+  auto& pos = b->owned_pos.back();
+  for (auto& pr : present) {
+    const std::string& s = pr.second < names_by_code.size() ? names_by_code[pr.second] : std::string();
+    dfgpu_pos p{(int64_t)buf.size(), (int64_t)(buf.size() + s.size())};
+    buf.insert(buf.end(), s.begin(), s.end());
+    pos.push_back(p);
+  }
+  col.dict_data = buf.data();
+  col.dict_pos = pos.data();
+  col.dict_n = pos.size();
+}
+
+namespace dfgpu {
+int l7_lc_space(int col);
+const std::vector<std::string>& l7_lc_names(dfgpu_ctx* ctx, int space);
+}
+
+extern "C" {
+
+int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
+  if (!ctx || !out || !ctx->ran) return fail(ctx, DFGPU_EINVAL, "dfgpu_fetch without dfgpu_run");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  BatchParams& bp = ctx->bp;
+  const TableSchema* sch = main_schema(ctx->cur_msg);
+  uint32_t nf = ctx->cur_nframes;
+  if (nf > ctx->h_frames_cap) {
+    if (ctx->h_frame_u32) cudaFreeHost(ctx->h_frame_u32);
+    ctx->h_frame_u32 = nullptr;
+    size_t cap = std::max<uint32_t>(nf, 1024);
+    CU(cudaHostAlloc(&ctx->h_frame_u32, cap * 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    ctx->h_frames_cap = (uint32_t)cap;
+  }
+  for (int attempt = 0;; attempt++) {
+    CU(cudaMemcpyAsync(ctx->h_dyn, ctx->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, s));
+    if (nf) {
+      CU(cudaMemcpyAsync(ctx->h_frame_u32, bp.frame_chain_err, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync(ctx->h_frame_u32 + ctx->h_frames_cap, bp.frame_bad, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    DynState* d = ctx->h_dyn;
+    bool repair = d->stats.need_repair && !bp.repair;
+    bool grow = d->overflow != 0;
+    if (!repair && !grow) break;
+    if (attempt >= 3) return fail(ctx, DFGPU_ENOMEM, "could not size the output arena");
+    if (grow) {
+      uint64_t want = d->var_end + (1u << 20);
+      CU(cudaFree(ctx->d_arena));
+      ctx->d_arena = nullptr;
+      CU(cudaMalloc(&ctx->d_arena, (size_t)want));
+      ctx->arena_cap = (size_t)want;
+      bp.arena = ctx->d_arena;
+      bp.arena_bytes = ctx->arena_cap;
+    }
+    // a record failed to decode: everything behind it in its frame is dropped
+    // (decoder.go:206-209); re-derive sizes with the per-frame cut known.
+    uint32_t keep_nrec = d->stats.nrec;
+    CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
+    CU(cudaMemcpyAsync(&ctx->d_dyn->stats.nrec, &keep_nrec, 4, cudaMemcpyHostToDevice, s));
+    int rc = launch_passes(ctx, (repair || bp.repair) ? 1 : 0);
+    if (rc) return rc;
+    if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
+      rc = l7_flow_tags(ctx, s);
+      if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev1, s));
+  }
+  DynState* d = ctx->h_dyn;
+  uint32_t nrows = d->stats.nrows;
+  uint64_t total = d->var_end ? d->var_end : bp.var_base;
+  dfgpu_batch* b = new dfgpu_batch();
+  b->ctx = ctx;
+  b->msg_type = ctx->cur_msg;
+  b->stats = d->stats;
+  b->host = host_acquire(ctx, (size_t)total + 64);
+  if (!b->host) {
+    delete b;
+    return fail(ctx, DFGPU_ENOMEM, "pinned host allocation of %llu bytes failed", (unsigned long long)total);
+  }
+  uint8_t* hb = b->host + 64;
+  // D2H: per column only the rows that exist; streams only their used bytes
+  for (int c = 0; c < sch->ncols; c++) {
+    const ColSpec& cs = sch->cols[c];
+    size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
+    if (es && nrows) CU(cudaMemcpyAsync(hb + bp.fix_off[c], bp.arena + bp.fix_off[c], (size_t)nrows * es, cudaMemcpyDeviceToHost, s));
+    size_t ab = aux_bytes_per_row(cs.ch_type);
+    if (ab && nrows) CU(cudaMemcpyAsync(hb + bp.aux_off[c], bp.arena + bp.aux_off[c], (size_t)nrows * ab, cudaMemcpyDeviceToHost, s));
+  }
+  if (total > bp.var_base)
+    CU(cudaMemcpyAsync(hb + bp.var_base, bp.arena + bp.var_base, (size_t)(total - bp.var_base), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(ctx->h_persist, ctx->d_persist, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (ctx->id_counter_out) *ctx->id_counter_out = ctx->h_persist->id_counter;
+  if (ctx->trace_idx_out) *ctx->trace_idx_out = ctx->h_persist->last_trace_id_index;
+
+  // ---- column views ------------------------------------------------------------------
+  b->tables.emplace_back();
+  dfgpu_batch::Table& t = b->tables.back();
+  t.id = sch->table_id;
+  t.nrows = nrows;
+  t.cols.resize(sch->ncols);
+  b->owned.reserve(64);
+  b->owned_pos.reserve(64);
+  int stream_of_col = 0;
+  for (int c = 0; c < sch->ncols; c++) {
+    const ColSpec& cs = sch->cols[c];
+    dfgpu_col& col = t.cols[c];
+    memset(&col, 0, sizeof col);
+    col.name = cs.name;
+    col.ch_type = cs.ch_type;
+    col.elem_size = cs.elem_size;
+    col.nrows = nrows;
+    switch (cs.ch_type) {
+      case DFGPU_CH_STR:
+      case DFGPU_CH_LC_STR_ROWS: {
+        int v = stream_of_col++;
+        col.pos = (const dfgpu_pos*)(hb + bp.aux_off[c]);
+        col.data = hb + d->var_buf_off[v];
+        col.data_bytes = d->stats.var_bytes[v];
+        break;
+      }
+      case DFGPU_CH_ARR_UINT16:
+      case DFGPU_CH_ARR_FLOAT64: {
+        int v = stream_of_col++;
+        col.arr_offsets = (const uint64_t*)(hb + bp.aux_off[c]);
+        col.data = hb + d->var_buf_off[v];
+        col.data_bytes = d->stats.var_bytes[v];
+        col.nelems = d->stats.var_total[v];
+        break;
+      }
+      case DFGPU_CH_ARR_STR:
+      case DFGPU_CH_ARR_LC_STR: {
+        int v = stream_of_col++;
+        col.arr_offsets = (const uint64_t*)(hb + bp.aux_off[c]);
+        col.pos = (const dfgpu_pos*)(hb + d->var_pos_off[v]);
+        col.data = hb + d->var_buf_off[v];
+        col.data_bytes = d->stats.var_bytes[v];
+        col.nelems = d->stats.var_total[v];
+        break;
+      }
+      case DFGPU_CH_LC_STR: {
+        col.data = hb + bp.fix_off[c];
+        col.data_bytes = (uint64_t)nrows * cs.elem_size;
+        if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) {
+          if (c == L4C_PROVINCE_0) lc_dictionary(b, d->stats.lc_first[LC_PROVINCE_0], ctx->geo_names, col);
+          else if (c == L4C_PROVINCE_1) lc_dictionary(b, d->stats.lc_first[LC_PROVINCE_1], ctx->geo_names, col);
+          else {
+            static const std::vector<std::string> tap(kTapSideNames, kTapSideNames + 18);
+            lc_dictionary(b, d->stats.lc_first[LC_TAPSIDE], tap, col);
+          }
+        } else {
+          int sp = l7_lc_space(c);
+          lc_dictionary(b, d->stats.lc_first[sp], l7_lc_names(ctx, sp), col);
+        }
+        break;
+      }
+      default: {
+        col.data = hb + bp.fix_off[c];
+        col.data_bytes = (uint64_t)nrows * cs.elem_size;
+        if (aux_bytes_per_row(cs.ch_type) == 1) col.nulls = hb + bp.aux_off[c];
+        break;
+      }
+    }
+  }
+  // ---- counters (decoder.Counter, decoder.go:60-80) ------------------------------------
+  dfgpu_counters& cn = b->counters;
+  memset(&cn, 0, sizeof cn);
+  cn.raw_count = nf;
+  cn.count = nrows;
+  for (uint32_t f = 0; f < nf; f++)
+    if (ctx->h_frame_u32[f] || ctx->h_frame_u32[ctx->h_frames_cap + f] != NO_BAD) cn.error_count++;
+  cn.l7_http_count = d->stats.l7_counts[0];
+  cn.l7_dns_count = d->stats.l7_counts[1];
+  cn.l7_sql_count = d->stats.l7_counts[2];
+  cn.l7_nosql_count = d->stats.l7_counts[3];
+  cn.l7_rpc_count = d->stats.l7_counts[4];
+  cn.l7_mq_count = d->stats.l7_counts[5];
+  cn.rows[sch->table_id] = nrows;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) cn.device_us = ms * 1000.0;
+  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
+    int rc = l7_fetch_tables(ctx, b);
+    if (rc) {
+      dfgpu_batch_release(b);
+      return rc;
+    }
+  }
+  ctx->ran = false;
+  *out = b;
+  return DFGPU_OK;
+}
+
+int dfgpu_submit(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbytes, const dfgpu_frame* tbl,
+                 int nframes, uint32_t* id_counter, uint64_t* trace_id_index, dfgpu_batch** out) {
+  int rc = dfgpu_stage(ctx, msg_type, frames, nbytes, tbl, nframes);
+  if (rc) return rc;
+  rc = dfgpu_run(ctx, id_counter, trace_id_index);
+  if (rc) return rc;
+  return dfgpu_fetch(ctx, out);
+}
+
+int dfgpu_batch_columns(const dfgpu_batch* b, int table, dfgpu_col* cols, int* ncols, uint64_t* nrows) {
+  if (!b) return DFGPU_EINVAL;
+  for (auto& t : b->tables)
+    if (t.id == table) {
+      if (ncols) *ncols = (int)t.cols.size();
+      if (nrows) *nrows = t.nrows;
+      if (cols) memcpy(cols, t.cols.data(), t.cols.size() * sizeof(dfgpu_col));
+      return DFGPU_OK;
+    }
+  return DFGPU_ENOENT;
+}
+
+int dfgpu_batch_counters(const dfgpu_batch* b, dfgpu_counters* out) {
+  if (!b || !out) return DFGPU_EINVAL;
+  *out = b->counters;
+  return DFGPU_OK;
+}
+
+void dfgpu_batch_release(dfgpu_batch* b) {
+  if (!b) return;
+  host_release(b->ctx, b->host);
+  delete b;
+}
+
+int dfgpu_flush(dfgpu_ctx* ctx) { return dfgpu_sync(ctx); }
+
+int dfgpu_metrics_reduce(dfgpu_ctx* ctx, uint32_t bucket_seconds, dfgpu_batch** out) {
+  (void)bucket_seconds;
+  (void)out;
+  return fail(ctx, DFGPU_ENOENT, "metrics path not built in this library version");
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+/*
+ * framing.cu — kernels shared by every message type: record framing
+ * (SimpleDecoder.ReadPB / IsEnd, server/libs/codec/simple_codec.go:229-248,404),
+ * the per-slot exclusive scans that turn per-warp sizes into arena offsets, stream
+ * placement + LowCardinality ranking, and the end-of-batch counter commit.
+ */
+#include "pipeline.cuh"
+
+namespace dfgpu {
+
+// ---- framing ----------------------------------------------------------------------
+// One thread walks one frame's {u32 LE len, pb}* chain.  pass 0 counts, pass 1 fills.
+template <int FILL>
+__global__ void k_frame_walk(const BatchParams p) {
+  uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.nframes) return;
+  const dfgpu_frame fr = p.frames[f];
+  const uint8_t* buf = p.in + fr.offset;
+  uint32_t len = fr.len, off = 0, n = 0, err = 0;
+  uint32_t base = FILL ? p.frame_base[f] : 0;
+  while (off < len) {  // !IsEnd()
+    if (len - off < 4) { err = 1; break; }  // offset(+4) out of buf len
+    uint32_t l = (uint32_t)__ldg(buf + off) | (uint32_t)__ldg(buf + off + 1) << 8 |
+                 (uint32_t)__ldg(buf + off + 2) << 16 | (uint32_t)__ldg(buf + off + 3) << 24;
+    off += 4;
+    if (l > len - off) { err = 1; break; }
+    if (FILL) {
+      p.rec_off[base + n] = (uint32_t)(fr.offset + off);
+      p.rec_len[base + n] = l;
+      p.rec_frame[base + n] = f;
+    }
+    off += l;
+    n++;
+  }
+  if (!FILL) {
+    p.frame_nrec[f] = n;
+    p.frame_chain_err[f] = err;
+  }
+}
+
+// exclusive scan of frame_nrec (single CTA, any nframes)
+__global__ void k_frame_scan(const BatchParams p) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < p.nframes; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < p.nframes ? p.frame_nrec[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+      uint32_t t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < p.nframes) p.frame_base[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.dyn->stats.nrec = carry;
+}
+
+// ---- slot scan: one CTA per slot, exclusive scan over the warps ----------------------
+__global__ void k_slot_scan(const BatchParams p) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint64_t carry;
+  uint32_t slot = blockIdx.x;
+  const uint32_t* tot = p.warp_tot + (size_t)slot * p.nwarps;
+  uint32_t* out = p.warp_base + (size_t)slot * p.nwarps;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < p.nwarps; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < p.nwarps ? tot[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+      uint32_t t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < p.nwarps) out[i] = (uint32_t)carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.dyn->stats.var_total[slot] = carry;  // totals per SLOT (temp)
+}
+
+// ---- finish: stream placement + LC ranks (one CTA, 256 threads) --------------------
+__global__ void k_finish(const BatchParams p) {
+  DynState* d = p.dyn;
+  __shared__ uint64_t slot_total[MAX_SLOTS];
+  if (threadIdx.x < MAX_SLOTS) slot_total[threadIdx.x] = threadIdx.x < p.nslots ? d->stats.var_total[threadIdx.x] : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t nrows = slot_total[0];
+    d->stats.nrows = (uint32_t)nrows;
+    uint64_t cur = p.var_base;
+    for (uint32_t v = 0; v < p.nstreams; v++) {
+      StreamSpec s = p.streams[v];
+      uint64_t elems = s.slot_elems >= 0 ? slot_total[s.slot_elems] : nrows;
+      uint64_t bytes = s.slot_bytes >= 0 ? slot_total[s.slot_bytes] : elems * s.elem_size;
+      d->var_pos_off[v] = cur;
+      if (s.has_pos) cur += (elems * 16 + 255) & ~255ull;
+      d->var_buf_off[v] = cur;
+      cur += (bytes + 255) & ~255ull;
+      d->stats.var_total[v] = elems;
+      d->stats.var_bytes[v] = bytes;
+    }
+    d->var_end = cur;
+    d->overflow = cur > p.arena_bytes ? 1 : 0;
+  }
+  // rank of each LowCardinality code by first appearance (ch-go builds the
+  // dictionary in Append order)
+  for (uint32_t sp = 0; sp < p.n_lc; sp++) {
+    uint32_t mine = d->stats.lc_first[sp][threadIdx.x];
+    uint32_t rank = 0;
+    if (mine != NO_BAD) {
+      for (int c = 0; c < 256; c++) rank += d->stats.lc_first[sp][c] < mine;
+    }
+    d->lc_rank[sp][threadIdx.x] = (uint8_t)rank;
+  }
+}
+
+// end of a batch: advance the device-resident counters exactly once
+__global__ void k_commit(const BatchParams p, int is_l7) {
+  DynState* d = p.dyn;
+  if ((d->stats.need_repair && !p.repair) || d->overflow) return;
+  p.persist->id_counter += d->stats.nrows;
+  if (is_l7 && d->stats.last_trace_id_index != 0xffffffffffffffffull && !p.cfg_trace_disabled)
+    p.persist->last_trace_id_index = d->stats.last_trace_id_index;
+}
+
+
+void launch_frame_count(const BatchParams& p, cudaStream_t s) {
+  if (!p.nframes) return;
+  k_frame_walk<0><<<(p.nframes + 127) / 128, 128, 0, s>>>(p);
+  k_frame_scan<<<1, 1024, 0, s>>>(p);
+}
+void launch_frame_fill(const BatchParams& p, cudaStream_t s) {
+  if (!p.nframes || !p.nrec) return;
+  k_frame_walk<1><<<(p.nframes + 127) / 128, 128, 0, s>>>(p);
+}
+void launch_slot_scan(const BatchParams& p, cudaStream_t s) {
+  if (!p.nrec) return;
+  k_slot_scan<<<p.nslots, 1024, 0, s>>>(p);
+}
+void launch_finish(const BatchParams& p, cudaStream_t s) { k_finish<<<1, 256, 0, s>>>(p); }
+void launch_commit(const BatchParams& p, int is_l7, cudaStream_t s) { k_commit<<<1, 1, 0, s>>>(p, is_l7); }
+
+}  // namespace dfgpu

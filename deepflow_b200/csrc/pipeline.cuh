@@ -1,0 +1,149 @@
+/*
+ * pipeline.cuh — kernels and parameter blocks shared by the L4 / L7 / metrics
+ * pipelines: record framing (SimpleDecoder.ReadPB, server/libs/codec/
+ * simple_codec.go:229-248), the per-warp slot scans that turn per-record sizes
+ * into output offsets, and LowCardinality first-appearance ranking.
+ *
+ * Pipeline shape (one CUDA stream, no host round trip after framing):
+ *   frame_count -> frame_scan -> [nrec to host] -> frame_fill
+ *   pass<SIZE>   : 1 thread / record, decode + size every variable-length output,
+ *                  warp-reduce -> warp_tot[slot][warp]
+ *   slot_scan    : exclusive scan over warps, one CTA per slot
+ *   finish       : stream offsets inside the arena, LC code ranks
+ *   pass<EMIT>   : decode again, warp-shuffle scan for the row / byte offsets,
+ *                  write every column (row-major threads => coalesced column stores)
+ */
+#pragma once
+#include "internal.h"
+
+namespace dfgpu {
+
+constexpr uint32_t NO_BAD = 0xffffffffu;
+constexpr int MAX_SLOTS = 40;
+constexpr int LC_SPACES = 8;
+
+struct StreamSpec {
+  int8_t slot_elems;  // slot holding the element count, -1: one element per row
+  int8_t slot_bytes;  // slot holding the byte count, -1: bytes = elems * elem_size
+  uint8_t elem_size;
+  uint8_t has_pos;    // stream carries a dfgpu_pos per element (Array(String))
+};
+
+struct PersistState {      // survives across batches (device resident)
+  uint32_t id_counter;     // L4FlowCounter / L7FlowLogCounter (l4_flow_log.go:947)
+  uint32_t pad;
+  uint64_t last_trace_id_index;  // lastTraceIdIndex (l7_flow_log.go:294)
+};
+
+struct DynState {  // per batch, device resident, read back by fetch
+  BatchStats stats;
+  uint64_t var_pos_off[MAX_VAR];
+  uint64_t var_buf_off[MAX_VAR];
+  uint64_t var_end;       // first free byte after the last stream
+  uint32_t overflow;      // var region does not fit the arena
+  uint32_t pad;
+  uint8_t lc_rank[LC_SPACES][256];
+  uint64_t trace_carry_hash;  // scratch
+};
+
+struct BatchParams {
+  const uint8_t* in;
+  const dfgpu_frame* frames;
+  uint32_t nframes;
+  uint32_t nrec;
+  uint32_t nwarps;
+  int32_t repair;
+  uint32_t* frame_nrec;
+  uint32_t* frame_base;
+  uint32_t* frame_chain_err;
+  uint32_t* frame_bad;
+  uint32_t* rec_off;
+  uint32_t* rec_len;
+  uint32_t* rec_frame;
+  uint32_t* warp_tot;   // [slot][nwarps]
+  uint32_t* warp_base;  // [slot][nwarps]
+  DynState* dyn;
+  PersistState* persist;
+  uint8_t* arena;
+  uint64_t arena_bytes;
+  uint64_t var_base;
+  uint32_t nslots;
+  uint32_t nstreams;
+  uint32_t n_lc;
+  uint32_t cfg_trace_disabled;
+  StreamSpec streams[MAX_VAR];
+  DevDict dict;
+  DevGeo geo;
+  uint64_t fix_off[MAX_COLS];
+  uint64_t aux_off[MAX_COLS];
+};
+
+// host launchers of the shared kernels (framing.cu)
+void launch_frame_count(const BatchParams& p, cudaStream_t s);
+void launch_frame_fill(const BatchParams& p, cudaStream_t s);
+void launch_slot_scan(const BatchParams& p, cudaStream_t s);
+void launch_finish(const BatchParams& p, cudaStream_t s);
+void launch_commit(const BatchParams& p, int is_l7, cudaStream_t s);
+
+// ---- warp helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v) {
+  uint32_t lane = threadIdx.x & 31, x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += t;
+  }
+  return x - v;
+}
+
+// first-appearance tracking of a LowCardinality code (one atomic per distinct code per warp)
+__device__ __forceinline__ void lc_note(uint32_t* first /*[256]*/, uint32_t code, uint32_t rec, bool active) {
+  uint32_t m = __match_any_sync(0xffffffffu, active ? code : 0xffffffffu);
+  if (active && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicMin(first + code, rec);
+}
+
+// sorted-range lookup replacing the netmask tree (libs/geo/netmask_tree.go:97-104)
+__device__ __forceinline__ uint32_t geo_code(const DevGeo& g, uint32_t ip) {
+  uint32_t lo = 0, hi = g.n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(g.start + mid) <= ip) lo = mid + 1; else hi = mid;
+  }
+  if (lo == 0) return 0;
+  return ip <= __ldg(g.end + lo - 1) ? __ldg(g.code + lo - 1) : 0;
+}
+
+// canonical string ids of flow_metrics.TAPSideEnum.String() (tag.go:211-233);
+// 0 = "" (slice slot without a name)
+__device__ __forceinline__ uint32_t tapside_code(uint32_t v) {
+  switch (v & 0xff) {
+    case 0: return 1;  case 1: return 2;  case 2: return 3;  case 4: return 4;
+    case 9: return 5;  case 10: return 6; case 17: return 7; case 18: return 8;
+    case 25: return 9; case 26: return 10; case 33: return 11; case 34: return 12;
+    case 41: return 13; case 42: return 14; case 49: return 15; case 50: return 16;
+    case 48: return 17;
+  }
+  return 0;
+}
+
+// getStatus l4_flow_log.go:745-760 (CloseType is a uint8, datatype/flow.go:33-84)
+__device__ __forceinline__ uint8_t l4_status(uint8_t t, uint8_t proto) {
+  bool tcp = proto == 6;
+  if (t == 1 || t == 5 || t == 20 || (!tcp && t == 3) || t == 11 || t == 8) return 0;
+  if (t == 10 || t == 9 || t == 13 || t == 18) return 4;
+  if (tcp && (t == 2 || t == 3 || t == 7 || t == 15 || t == 17 || t == 19)) return 3;
+  return 2;
+}
+
+// MarshalInt32WithSpecialID flow-metrics/tag.go:560-565
+__device__ __forceinline__ int32_t marshal_epc(int32_t v) {
+  if (v > 0 || v == -1 || v == -2) return v;
+  return (int32_t)((uint32_t)v & 0xffffu);
+}
+
+}  // namespace dfgpu

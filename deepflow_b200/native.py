@@ -1,0 +1,151 @@
+"""ctypes binding of libdfgpu.so — the Python mirror of the C ABI in
+include/dfgpu.h (the same calls the Go/cgo shim makes).
+
+There is NO CPU fallback: if the CUDA library is missing or no device is
+visible, every entry point raises."""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class DfgpuError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libdfgpu.so")
+        if not os.path.exists(path):
+            raise DfgpuError(f"{path} is not built — run __graft_entry__.build() (no CPU fallback exists)")
+        L = C.CDLL(path)
+        vp = C.c_void_p
+        L.dfgpu_init.argtypes = [C.c_int, C.POINTER(abi.Cfg), C.POINTER(vp)]
+        L.dfgpu_close.argtypes = [vp]
+        L.dfgpu_last_error.restype = C.c_char_p
+        L.dfgpu_last_error.argtypes = [vp]
+        L.dfgpu_dict_load.argtypes = [vp, C.c_uint16, C.POINTER(abi.DictSnapshot)]
+        L.dfgpu_geo_load.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32]
+        L.dfgpu_submit.argtypes = [vp, C.c_int, vp, C.c_size_t, vp, C.c_int, C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_uint64), C.POINTER(vp)]
+        L.dfgpu_stage.argtypes = [vp, C.c_int, vp, C.c_size_t, vp, C.c_int]
+        L.dfgpu_run.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+        L.dfgpu_fetch.argtypes = [vp, C.POINTER(vp)]
+        L.dfgpu_sync.argtypes = [vp]
+        L.dfgpu_stream.restype = vp
+        L.dfgpu_stream.argtypes = [vp]
+        L.dfgpu_launch_count.restype = C.c_uint64
+        L.dfgpu_launch_count.argtypes = [vp]
+        L.dfgpu_batch_columns.argtypes = [vp, C.c_int, C.POINTER(abi.Col), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_uint64)]
+        L.dfgpu_batch_counters.argtypes = [vp, C.POINTER(abi.Counters)]
+        L.dfgpu_batch_release.argtypes = [vp]
+        L.dfgpu_batch_release.restype = None
+        L.dfgpu_metrics_reduce.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+        L.dfgpu_flush.argtypes = [vp]
+        _LIB = L
+    return _LIB
+
+
+class Batch:
+    def __init__(self, handle):
+        self._h = handle
+
+    def columns(self, table):
+        return abi.fetch_columns(lib().dfgpu_batch_columns, self._h, table)
+
+    def counters(self):
+        c = abi.Counters()
+        lib().dfgpu_batch_counters(self._h, C.byref(c))
+        return c
+
+    def release(self):
+        if self._h:
+            lib().dfgpu_batch_release(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One dfgpu_ctx == one decoder goroutine's worth of state."""
+
+    def __init__(self, device=0, cfg=None):
+        self._h = C.c_void_p()
+        rc = lib().dfgpu_init(device, C.byref(cfg) if cfg is not None else None, C.byref(self._h))
+        if rc != 0:
+            raise DfgpuError(f"dfgpu_init(device={device}) failed: {rc} (no CUDA device? there is no CPU fallback)")
+        self.id_counter = C.c_uint32(0)
+        self.trace_idx = C.c_uint64(0)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DfgpuError(f"{what} failed: {rc}: {lib().dfgpu_last_error(self._h).decode()}")
+
+    def close(self):
+        if self._h:
+            lib().dfgpu_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dict_load(self, org, snap_ptr):
+        self._check(lib().dfgpu_dict_load(self._h, org, snap_ptr), "dfgpu_dict_load")
+
+    def geo_load(self, geo):
+        e, n, names, nn = geo
+        self._check(lib().dfgpu_geo_load(self._h, e, n, names, nn), "dfgpu_geo_load")
+
+    def load_synth(self, synth, org=1):
+        self.dict_load(org, synth.dict_snapshot())
+        self.geo_load(synth.geo())
+
+    def submit(self, wl):
+        """End to end: host buffers in, host column blocks out."""
+        out = C.c_void_p()
+        rc = lib().dfgpu_submit(self._h, wl.msg_type, wl.data.ctypes.data, wl.data.nbytes,
+                                wl.frames.ctypes.data, len(wl.frames), C.byref(self.id_counter),
+                                C.byref(self.trace_idx), C.byref(out))
+        self._check(rc, "dfgpu_submit")
+        return Batch(out)
+
+    def stage_ptr(self, msg_type, data_ptr, nbytes, frames_ptr, nframes):
+        self._check(lib().dfgpu_stage(self._h, msg_type, data_ptr, nbytes, frames_ptr, nframes), "dfgpu_stage")
+
+    def stage(self, wl):
+        self.stage_ptr(wl.msg_type, wl.data.ctypes.data, wl.data.nbytes, wl.frames.ctypes.data, len(wl.frames))
+
+    def run(self, with_counters=False):
+        if with_counters:
+            rc = lib().dfgpu_run(self._h, C.byref(self.id_counter), C.byref(self.trace_idx))
+        else:
+            rc = lib().dfgpu_run(self._h, None, None)
+        self._check(rc, "dfgpu_run")
+
+    def fetch(self):
+        out = C.c_void_p()
+        self._check(lib().dfgpu_fetch(self._h, C.byref(out)), "dfgpu_fetch")
+        return Batch(out)
+
+    def sync(self):
+        self._check(lib().dfgpu_sync(self._h), "dfgpu_sync")
+
+    @property
+    def stream(self):
+        return lib().dfgpu_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().dfgpu_launch_count(self._h))
