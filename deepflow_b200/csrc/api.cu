@@ -8,7 +8,7 @@
 #include <cstring>
 #include <mutex>
 
-#include "pipeline.cuh"
+#include "ctx.h"
 #include "schema_l4.h"
 #include "schema_l7.h"
 
@@ -19,6 +19,7 @@ void launch_l4_pass(const BatchParams& p, int emit, cudaStream_t s);
 void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s);
 struct FlowTagDev;
 int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s);
+int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s);
 }  // namespace dfgpu
 
 #define X(id, name, t, es) {name, t, es, -1},
@@ -31,84 +32,6 @@ struct TableSchema {
   const ColSpec* cols;
   int ncols;
 };
-
-struct HostBuf {
-  uint8_t* p = nullptr;
-  size_t cap = 0;
-};
-
-struct dfgpu_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  dfgpu_cfg cfg{};
-  std::string err;
-  std::mutex dict_mu;
-  std::map<uint16_t, std::shared_ptr<DeviceDict>> dicts;
-  // geo
-  uint32_t* d_geo_start = nullptr;
-  uint32_t* d_geo_end = nullptr;
-  uint8_t* d_geo_code = nullptr;
-  uint32_t geo_n = 0;
-  std::vector<std::string> geo_names;  // by canonical code
-
-  // device work buffers
-  uint8_t* d_in = nullptr;
-  size_t d_in_cap = 0;
-  dfgpu_frame* d_frames = nullptr;
-  uint32_t* d_frame_u32 = nullptr;  // nrec | base | chain_err | bad
-  uint32_t frames_cap = 0;
-  uint32_t* d_rec_u32 = nullptr;  // off | len | frame
-  uint32_t rec_cap = 0;
-  uint32_t* d_warp = nullptr;  // tot[MAX_SLOTS][nwarps] | base[MAX_SLOTS][nwarps]
-  size_t warp_cap = 0;         // in warps
-  DynState* d_dyn = nullptr;
-  PersistState* d_persist = nullptr;
-  uint8_t* d_arena = nullptr;
-  size_t arena_cap = 0;
-  // pinned host
-  DynState* h_dyn = nullptr;
-  PersistState* h_persist = nullptr;
-  uint32_t* h_frame_u32 = nullptr;
-  uint32_t h_frames_cap = 0;
-  std::vector<HostBuf> host_pool;
-
-  // current batch
-  int cur_msg = 0;
-  const uint8_t* cur_in = nullptr;
-  const dfgpu_frame* cur_frames = nullptr;  // device
-  size_t cur_nbytes = 0;
-  uint32_t cur_nframes = 0;
-  uint16_t cur_org = 0;
-  uint32_t cur_team = 0;
-  bool staged = false, ran = false;
-  BatchParams bp{};
-  std::shared_ptr<DeviceDict> cur_dict;
-  uint32_t* id_counter_out = nullptr;
-  uint64_t* trace_idx_out = nullptr;
-  uint64_t launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-
-  // flow tag state (l7)
-  void* ft = nullptr;
-};
-
-static int fail(dfgpu_ctx* c, int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  if (c) c->err = buf;
-  return code;
-}
-#define CU(call)                                                                       \
-  do {                                                                                 \
-    cudaError_t _e = (call);                                                           \
-    if (_e != cudaSuccess)                                                             \
-      return fail(ctx, DFGPU_ENODEV, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
-  } while (0)
-
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <class T>
 static int ensure_dev(dfgpu_ctx* ctx, T*& p, size_t& cap, size_t want) {
@@ -523,7 +446,12 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
     launch_frame_fill(bp, s);
     ctx->launches++;
   }
-  int rc = launch_passes(ctx, 0);
+  int rc = 0;
+  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
+    rc = l7_prepare(ctx, s);
+    if (rc) return rc;
+  }
+  rc = launch_passes(ctx, 0);
   if (rc) return rc;
   if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
     rc = l7_flow_tags(ctx, s);
@@ -570,8 +498,6 @@ static void host_release(dfgpu_ctx* ctx, uint8_t* p) {
 namespace dfgpu {
 // filled in by l7.cu: appends the flow_tag / app_service tables of a fetched batch
 int l7_fetch_tables(dfgpu_ctx* ctx, dfgpu_batch* b);
-const char* const kTapSideNames[18] = {"", "rest", "c", "s", "local", "c-nd", "s-nd", "c-hv", "s-hv", "c-gw-hv",
-                                       "s-gw-hv", "c-gw", "s-gw", "c-p", "s-p", "c-app", "s-app", "app"};
 }
 
 // dictionary of one LowCardinality code space, in first-appearance order

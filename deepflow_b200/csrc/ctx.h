@@ -1,0 +1,89 @@
+/*
+ * ctx.h — the context object behind dfgpu_ctx* (one per decoder goroutine).
+ */
+#pragma once
+#include <cstdarg>
+#include <mutex>
+
+#include "pipeline.cuh"
+
+using namespace dfgpu;
+
+struct HostBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+};
+
+struct dfgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  dfgpu_cfg cfg{};
+  std::string err;
+  std::mutex dict_mu;
+  std::map<uint16_t, std::shared_ptr<DeviceDict>> dicts;
+  // geo
+  uint32_t* d_geo_start = nullptr;
+  uint32_t* d_geo_end = nullptr;
+  uint8_t* d_geo_code = nullptr;
+  uint32_t geo_n = 0;
+  std::vector<std::string> geo_names;  // by canonical code
+
+  // device work buffers
+  uint8_t* d_in = nullptr;
+  size_t d_in_cap = 0;
+  dfgpu_frame* d_frames = nullptr;
+  uint32_t* d_frame_u32 = nullptr;  // nrec | base | chain_err | bad
+  uint32_t frames_cap = 0;
+  uint32_t* d_rec_u32 = nullptr;  // off | len | frame
+  uint32_t rec_cap = 0;
+  uint32_t* d_warp = nullptr;  // tot[MAX_SLOTS][nwarps] | base[MAX_SLOTS][nwarps]
+  size_t warp_cap = 0;         // in warps
+  DynState* d_dyn = nullptr;
+  PersistState* d_persist = nullptr;
+  uint8_t* d_arena = nullptr;
+  size_t arena_cap = 0;
+  // pinned host
+  DynState* h_dyn = nullptr;
+  PersistState* h_persist = nullptr;
+  uint32_t* h_frame_u32 = nullptr;
+  uint32_t h_frames_cap = 0;
+  std::vector<HostBuf> host_pool;
+
+  // current batch
+  int cur_msg = 0;
+  const uint8_t* cur_in = nullptr;
+  const dfgpu_frame* cur_frames = nullptr;  // device
+  size_t cur_nbytes = 0;
+  uint32_t cur_nframes = 0;
+  uint16_t cur_org = 0;
+  uint32_t cur_team = 0;
+  bool staged = false, ran = false;
+  BatchParams bp{};
+  std::shared_ptr<DeviceDict> cur_dict;
+  uint32_t* id_counter_out = nullptr;
+  uint64_t* trace_idx_out = nullptr;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // flow tag state (l7)
+  void* ft = nullptr;
+};
+
+inline int fail(dfgpu_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return fail(ctx, DFGPU_ENODEV, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+

@@ -8,6 +8,10 @@
 
 namespace dfgpu {
 
+// flow-metrics/tag.go:211-233; index = canonical code of tapside_code(), 0 = unnamed slot ""
+extern const char* const kTapSideNames[18] = {"", "rest", "c", "s", "local", "c-nd", "s-nd", "c-hv", "s-hv", "c-gw-hv",
+                                              "s-gw-hv", "c-gw", "s-gw", "c-p", "s-p", "c-app", "s-app", "app"};
+
 // ---- framing ----------------------------------------------------------------------
 // One thread walks one frame's {u32 LE len, pb}* chain.  pass 0 counts, pass 1 fills.
 template <int FILL>
@@ -64,7 +68,7 @@ __global__ void k_frame_scan(const BatchParams p) {
 }
 
 // ---- slot scan: one CTA per slot, exclusive scan over the warps ----------------------
-__global__ void k_slot_scan(const BatchParams p) {
+__global__ void k_slot_scan(const BatchParams p, uint64_t* totals_out) {
   __shared__ uint32_t sh[1024];
   __shared__ uint64_t carry;
   uint32_t slot = blockIdx.x;
@@ -88,7 +92,7 @@ __global__ void k_slot_scan(const BatchParams p) {
     if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
     __syncthreads();
   }
-  if (threadIdx.x == 0) p.dyn->stats.var_total[slot] = carry;  // totals per SLOT (temp)
+  if (threadIdx.x == 0) totals_out[slot] = carry;
 }
 
 // ---- finish: stream placement + LC ranks (one CTA, 256 threads) --------------------
@@ -148,7 +152,11 @@ void launch_frame_fill(const BatchParams& p, cudaStream_t s) {
 }
 void launch_slot_scan(const BatchParams& p, cudaStream_t s) {
   if (!p.nrec) return;
-  k_slot_scan<<<p.nslots, 1024, 0, s>>>(p);
+  // totals per SLOT land in stats.var_total (scratch until k_finish rewrites it per stream)
+  k_slot_scan<<<p.nslots, 1024, 0, s>>>(p, p.dyn->stats.var_total);
+}
+void launch_slot_scan_to(const BatchParams& p, uint32_t nslots, uint64_t* totals_out, cudaStream_t s) {
+  k_slot_scan<<<nslots, 1024, 0, s>>>(p, totals_out);
 }
 void launch_finish(const BatchParams& p, cudaStream_t s) { k_finish<<<1, 256, 0, s>>>(p); }
 void launch_commit(const BatchParams& p, int is_l7, cudaStream_t s) { k_commit<<<1, 1, 0, s>>>(p, is_l7); }

@@ -86,8 +86,11 @@ struct BatchStats {
   uint32_t pad;
   uint64_t var_total[MAX_VAR];  // elements of stream v
   uint64_t var_bytes[MAX_VAR];  // bytes of stream v
-  uint64_t ft_rows[4];          // flow_tag field rows, field_value rows, app_service rows, spare
-  uint64_t ft_bytes[8];
+  uint64_t ft_tot[8];           // flow_tag stage totals (see l7.cu FT_* slots)
+  uint64_t ft_off[32];          // flow_tag table column offsets inside the ft arena
+  uint64_t ft_end;              // bytes used in the ft arena
+  uint32_t ft_overflow;         // ft arena too small: host grows it and re-runs the writer
+  uint32_t ft_full;             // the device tag set is full (capacity)
   uint64_t last_trace_id_index;
   uint32_t lc_first[8][256];    // first record index each LowCardinality code appears at
 };

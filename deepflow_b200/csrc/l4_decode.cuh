@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
   return n;
 }
 
-__device__ bool dec_flow_key(Rd r, const uint8_t* base, L4Rec& o) {
+__device__ inline bool dec_flow_key(Rd r, const uint8_t* base, L4Rec& o) {
   uint32_t f, wt;
   while (r.i < r.l) {
     if (!rd_tag(r, f, wt)) return false;
@@ -80,7 +80,7 @@ __device__ bool dec_flow_key(Rd r, const uint8_t* base, L4Rec& o) {
   return true;
 }
 
-__device__ bool dec_peer(Rd r, L4Peer& o) {
+__device__ inline bool dec_peer(Rd r, L4Peer& o) {
   uint32_t f, wt, dummy32;
   uint64_t dummy64;
   while (r.i < r.l) {
@@ -113,7 +113,7 @@ __device__ bool dec_peer(Rd r, L4Peer& o) {
   return true;
 }
 
-__device__ bool dec_tunnel(Rd r, L4Rec& o) {
+__device__ inline bool dec_tunnel(Rd r, L4Rec& o) {
   uint32_t f, wt, dummy32;
   while (r.i < r.l) {
     if (!rd_tag(r, f, wt)) return false;
@@ -138,7 +138,7 @@ __device__ bool dec_tunnel(Rd r, L4Rec& o) {
   return true;
 }
 
-__device__ bool dec_counts(Rd r, uint32_t& retrans, uint32_t& zero_win, uint32_t& ooo) {
+__device__ inline bool dec_counts(Rd r, uint32_t& retrans, uint32_t& zero_win, uint32_t& ooo) {
   uint32_t f, wt;
   while (r.i < r.l) {
     if (!rd_tag(r, f, wt)) return false;
@@ -152,7 +152,7 @@ __device__ bool dec_counts(Rd r, uint32_t& retrans, uint32_t& zero_win, uint32_t
   return true;
 }
 
-__device__ bool dec_tcp(Rd r, L4Rec& o) {
+__device__ inline bool dec_tcp(Rd r, L4Rec& o) {
   uint32_t f, wt, dummy32;
   while (r.i < r.l) {
     if (!rd_tag(r, f, wt)) return false;
@@ -191,7 +191,7 @@ __device__ bool dec_tcp(Rd r, L4Rec& o) {
   return true;
 }
 
-__device__ bool dec_l7perf(Rd r, L4Rec& o) {
+__device__ inline bool dec_l7perf(Rd r, L4Rec& o) {
   uint32_t f, wt;
   while (r.i < r.l) {
     if (!rd_tag(r, f, wt)) return false;
@@ -211,7 +211,7 @@ __device__ bool dec_l7perf(Rd r, L4Rec& o) {
   return true;
 }
 
-__device__ bool dec_perf(Rd r, L4Rec& o) {
+__device__ inline bool dec_perf(Rd r, L4Rec& o) {
   uint32_t f, wt, dummy32;
   while (r.i < r.l) {
     if (!rd_tag(r, f, wt)) return false;
@@ -242,7 +242,7 @@ struct NoSink {
 };
 
 template <class Sink>
-__device__ bool dec_flow(Rd r, const uint8_t* base, L4Rec& o, Sink& sink) {
+__device__ inline bool dec_flow(Rd r, const uint8_t* base, L4Rec& o, Sink& sink) {
   uint32_t f, wt, dummy32;
   while (r.i < r.l) {
     if (!rd_tag(r, f, wt)) return false;
@@ -315,7 +315,7 @@ __device__ bool dec_flow(Rd r, const uint8_t* base, L4Rec& o, Sink& sink) {
 }
 
 template <class Sink>
-__device__ bool dec_tagged_flow(const uint8_t* rec, uint32_t len, L4Rec& o, Sink& sink) {
+__device__ inline bool dec_tagged_flow(const uint8_t* rec, uint32_t len, L4Rec& o, Sink& sink) {
   Rd r{rec, 0, len};
   const uint8_t* base = rec;
   uint32_t f, wt;

@@ -56,7 +56,7 @@ __device__ __forceinline__ bool rd_len(Rd& r, uint32_t& len) {
 }
 
 // skipFlowLog(): skip one unknown field whose tag (wire type wt) was just read
-__device__ bool rd_skip(Rd& r, uint32_t wt) {
+__device__ inline bool rd_skip(Rd& r, uint32_t wt) {
   int depth = 0;
 #pragma unroll 1
   for (;;) {

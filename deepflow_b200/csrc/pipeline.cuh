@@ -71,6 +71,7 @@ struct BatchParams {
   uint32_t nstreams;
   uint32_t n_lc;
   uint32_t cfg_trace_disabled;
+  const void* ext;  // message-type specific device state (L7Dev)
   StreamSpec streams[MAX_VAR];
   DevDict dict;
   DevGeo geo;
@@ -78,10 +79,13 @@ struct BatchParams {
   uint64_t aux_off[MAX_COLS];
 };
 
+extern const char* const kTapSideNames[18];  // TAPSideEnum.String() texts by canonical code (framing.cu)
 // host launchers of the shared kernels (framing.cu)
 void launch_frame_count(const BatchParams& p, cudaStream_t s);
 void launch_frame_fill(const BatchParams& p, cudaStream_t s);
 void launch_slot_scan(const BatchParams& p, cudaStream_t s);
+// generic: scan `nslots` slot rows of p.warp_tot into p.warp_base, totals to totals_out (device)
+void launch_slot_scan_to(const BatchParams& p, uint32_t nslots, uint64_t* totals_out, cudaStream_t s);
 void launch_finish(const BatchParams& p, cudaStream_t s);
 void launch_commit(const BatchParams& p, int is_l7, cudaStream_t s);
 
