@@ -18,22 +18,24 @@ namespace oracle {
 // ---- geo: netmask tree (libs/geo/netmask_tree.go) ------------------------------
 static uint32_t maskLenToNetmask(int i) { return i == 0 ? 0 : 0xFFFFFFFFu << (32 - i); }
 
+int getFirstMask(uint32_t start, uint32_t end) {  // netmask_tree.go:37-50
+  const int MIN_MASKLEN = 16, MAX_MASKLEN = 32;
+  int maxLen = MAX_MASKLEN;
+  for (; maxLen > MIN_MASKLEN; maxLen--) {
+    if (start & (1u << (uint32_t)(MAX_MASKLEN - maxLen))) break;
+    if ((uint32_t)(start + ~maskLenToNetmask(maxLen)) >= end ||
+        (uint32_t)(start + ~maskLenToNetmask(maxLen - 1)) > end)
+      break;
+  }
+  return maxLen;
+}
+
 void GeoTree::build(const dfgpu_geo_entry* e, uint64_t n, const char* const* names, uint32_t n_names) {
   region_names.clear();
   for (uint32_t i = 0; i < n_names; i++) region_names.emplace_back(names[i]);
   maxMask.assign(1 << 16, 0);
   cache.clear();
   const int MIN_MASKLEN = 16, MAX_MASKLEN = 32;
-  auto getFirstMask = [&](uint32_t start, uint32_t end) -> int {  // :37-50
-    int maxLen = MAX_MASKLEN;
-    for (; maxLen > MIN_MASKLEN; maxLen--) {
-      if (start & (1u << (uint32_t)(MAX_MASKLEN - maxLen))) break;
-      if ((uint32_t)(start + ~maskLenToNetmask(maxLen)) >= end ||
-          (uint32_t)(start + ~maskLenToNetmask(maxLen - 1)) > end)
-        break;
-    }
-    return maxLen;
-  };
   for (uint64_t i = 0; i < n; i++) {  // updateMask :52-62
     uint32_t start = e[i].ip_start, end = e[i].ip_end;
     while (end >= start) {

@@ -22,6 +22,7 @@ struct GeoTree {
 };
 
 uint64_t genID(uint32_t time, uint32_t* counter, uint32_t analyzerID);
+int getFirstMask(uint32_t start, uint32_t end);  // libs/geo/netmask_tree.go:37-50
 
 struct L4Block {
   Block b;

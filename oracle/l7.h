@@ -41,6 +41,11 @@ class LruCache {
     if ((int)lru.size() > capacity) removeOldest();
   }
   size_t Len() const { return lru.size(); }
+  int Keys(Key* out) const {  // oldest -> newest (lru.go:105-113)
+    int i = 0;
+    for (auto it = lru.rbegin(); it != lru.rend(); ++it) out[i++] = it->first;
+    return i;
+  }
 
  private:
   void removeOldest() {

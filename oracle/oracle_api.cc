@@ -188,4 +188,39 @@ int oracle_metrics_reduce(oracle_ctx* c, int table, uint32_t bucket_seconds) {
   return c->metrics->reduce(table - DFGPU_TABLE_METRICS_BASE, bucket_seconds);
 }
 
+// ---- known-answer hooks for the reference's own unit tests (tests/test_reference_kats.py)
+// libs/geo/netmask_tree_test.go:24-52 TestGetFirstMask
+void oracle_kat_first_mask_sequence(uint32_t start, uint32_t end, uint32_t* prefixes, uint8_t* masklens, int n) {
+  for (int k = 0; k < n; k++) {
+    int maxLen = getFirstMask(start, end);
+    prefixes[k] = start;
+    masklens[k] = (uint8_t)maxLen;
+    start += 1u << (uint32_t)(32 - maxLen);
+  }
+}
+const char* oracle_kat_province(oracle_ctx* c, uint32_t ip) {
+  static thread_local std::string s;
+  s = std::string(c->geo.province(ip));
+  return s.c_str();
+}
+int32_t oracle_kat_marshal_int32(int32_t v) { return MarshalInt32WithSpecialID(v); }
+const char* oracle_kat_tapside(uint32_t v) {
+  bool ok;
+  return TAPSideString(v, ok);
+}
+int oracle_kat_is_local_ip(int v6, uint32_t ip4, const uint8_t* ip6, uint32_t len) { return IsLocalIP(v6, ip4, ip6, len); }
+int oracle_kat_is_loopback(int v6, uint32_t ip4, const uint8_t* ip6, uint32_t len) { return IsLoopback(v6, ip4, ip6, len); }
+uint64_t oracle_kat_djb(uint64_t base, const char* s, uint32_t n) { return DJBHash(base, std::string_view(s, n)); }
+// libs/lru/lru_test.go TestKeys + eviction order: add keys[0..n) to a cache of `cap`,
+// touch `touch` (AddOrGet) when >= 0, then list the keys oldest -> newest.
+struct IntHash {
+  size_t operator()(int v) const { return (size_t)v * 0x9E3779B97F4A7C15ull; }
+};
+int oracle_kat_lru(int cap, int n, int touch, int* out_keys) {
+  LruCache<int, IntHash> c(cap);
+  for (int i = 0; i < n; i++) c.Add(i, (uint32_t)i);
+  if (touch >= 0) c.AddOrGet(touch, 0);
+  return c.Keys(out_keys);
+}
+
 }  // extern "C"

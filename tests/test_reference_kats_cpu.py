@@ -1,0 +1,131 @@
+"""CPU: known-answer tests lifted from the reference's own unit tests, run against
+the oracle's restatements (SURVEY §8c list)."""
+import ctypes as C
+
+import numpy as np
+
+
+def lib():
+    from oracle_binding import lib as L
+    l = L()
+    l.oracle_kat_marshal_int32.restype = C.c_int32
+    l.oracle_kat_marshal_int32.argtypes = [C.c_int32]
+    l.oracle_kat_tapside.restype = C.c_char_p
+    l.oracle_kat_tapside.argtypes = [C.c_uint32]
+    l.oracle_kat_djb.restype = C.c_uint64
+    l.oracle_kat_djb.argtypes = [C.c_uint64, C.c_char_p, C.c_uint32]
+    l.oracle_kat_first_mask_sequence.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+    l.oracle_kat_lru.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.oracle_kat_is_local_ip.argtypes = [C.c_int, C.c_uint32, C.c_char_p, C.c_uint32]
+    l.oracle_kat_is_loopback.argtypes = [C.c_int, C.c_uint32, C.c_char_p, C.c_uint32]
+    l.oracle_kat_province.restype = C.c_char_p
+    l.oracle_kat_province.argtypes = [C.c_void_p, C.c_uint32]
+    return l
+
+
+def test_int32_special_id_roundtrip(built):
+    """libs/flow-metrics/tag_test.go:45-56 TestInt16Unmarshal: int16(marshal(v)) == v."""
+    l = lib()
+    for i in range(-32768, 32768, 7):
+        m = l.oracle_kat_marshal_int32(i)
+        lo = m & 0xffff
+        assert (lo - 65536 if lo >= 32768 else lo) == i  # int16(v) of the marshalled value
+    assert l.oracle_kat_marshal_int32(-1) == -1 and l.oracle_kat_marshal_int32(-2) == -2
+    assert l.oracle_kat_marshal_int32(-3) == 65533 and l.oracle_kat_marshal_int32(0) == 0
+
+
+def test_tap_side_strings(built):
+    """tag_test.go:371-392 TestDirectionToTAPSide enum values + tag.go:211-233 names."""
+    l = lib()
+    node, hv, gwhv, gw, proc, app = 8, 16, 24, 32, 40, 48
+    exp = {0: b"rest", 1: b"c", 2: b"s", 4: b"local", 1 | node: b"c-nd", 2 | node: b"s-nd", 1 | hv: b"c-hv",
+           2 | hv: b"s-hv", 1 | gwhv: b"c-gw-hv", 2 | gwhv: b"s-gw-hv", 1 | gw: b"c-gw", 2 | gw: b"s-gw",
+           1 | proc: b"c-p", 2 | proc: b"s-p", 1 | app: b"c-app", 2 | app: b"s-app", app: b"app"}
+    for v in range(51):
+        assert l.oracle_kat_tapside(v) == exp.get(v, b"")
+
+
+def test_get_first_mask(built):
+    """libs/geo/netmask_tree_test.go:24-52 TestGetFirstMask."""
+    l = lib()
+    pre = (C.c_uint32 * 8)()
+    ml = (C.c_uint8 * 8)()
+    l.oracle_kat_first_mask_sequence(0x01000000, 0x010000fe, pre, ml, 8)
+    assert list(pre) == [0x01000000, 0x01000080, 0x010000c0, 0x010000e0, 0x010000f0, 0x010000f8, 0x010000fc, 0x010000fe]
+    assert list(ml) == [25, 26, 27, 28, 29, 30, 31, 32]
+    l.oracle_kat_first_mask_sequence(0x01000000, 0x010000ff, pre, ml, 1)
+    assert (pre[0], ml[0]) == (0x01000000, 24)
+
+
+def test_lru_order_and_eviction(built):
+    """libs/lru/lru_test.go:23-36 TestKeys (oldest -> newest) + capacity eviction and
+    MoveToFront on AddOrGet (lru.go:44-60)."""
+    l = lib()
+    out = (C.c_int * 200)()
+    n = l.oracle_kat_lru(100, 100, -1, out)
+    assert n == 100 and list(out[:100]) == list(range(100))
+    n = l.oracle_kat_lru(100, 130, -1, out)  # 30 oldest evicted
+    assert n == 100 and list(out[:100]) == list(range(30, 130))
+    n = l.oracle_kat_lru(100, 100, 5, out)  # touching 5 makes it the newest
+    assert list(out[:100]) == [i for i in range(100) if i != 5] + [5]
+
+
+def test_djb_hash(built):
+    """libs/utils/hash.go:37-43: hash = hash*33 + c, base 17 for trace ids."""
+    l = lib()
+
+    def ref(base, s):
+        h = base
+        for c in s:
+            h = ((h << 5) + h + c) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    for s in (b"", b"a", b"0123456789abcdef0123456789abcdef", bytes(range(256))):
+        assert l.oracle_kat_djb(17, s, len(s)) == ref(17, s)
+
+
+def test_go_ip_predicates(built):
+    """Go net.IP semantics behind utils.IsLocalIP / IsLoopback (utils.go:116-130)."""
+    l = lib()
+    ip4 = lambda a, b, c, d: (a << 24) | (b << 16) | (c << 8) | d
+    local4 = {ip4(0, 0, 0, 0), ip4(255, 255, 255, 255), ip4(127, 1, 2, 3), ip4(224, 0, 0, 1), ip4(239, 9, 9, 9),
+              ip4(169, 254, 0, 7)}
+    for v in local4:
+        assert l.oracle_kat_is_local_ip(0, v, None, 0) == 1
+    for v in (ip4(10, 0, 0, 1), ip4(8, 8, 8, 8), ip4(169, 253, 0, 1), ip4(223, 255, 255, 255), ip4(192, 168, 1, 1)):
+        assert l.oracle_kat_is_local_ip(0, v, None, 0) == 0
+    assert l.oracle_kat_is_loopback(0, ip4(127, 0, 0, 1), None, 0) == 1
+    assert l.oracle_kat_is_loopback(0, ip4(128, 0, 0, 1), None, 0) == 0
+    v6 = lambda s: bytes.fromhex(s)
+    assert l.oracle_kat_is_loopback(1, 0, v6("00" * 15 + "01"), 16) == 1
+    assert l.oracle_kat_is_local_ip(1, 0, v6("00" * 16), 16) == 1           # ::
+    assert l.oracle_kat_is_local_ip(1, 0, v6("fe80" + "00" * 14), 16) == 1   # link local
+    assert l.oracle_kat_is_local_ip(1, 0, v6("ff02" + "00" * 14), 16) == 1   # multicast
+    assert l.oracle_kat_is_local_ip(1, 0, v6("fd00" + "11" * 14), 16) == 0   # ULA is global unicast in Go
+    assert l.oracle_kat_is_local_ip(1, 0, v6("00" * 10 + "ffff" + "7f000001"), 16) == 1  # v4-mapped loopback
+    assert l.oracle_kat_is_local_ip(1, 0, v6("00" * 10 + "ffff" + "0a000001"), 16) == 0
+    assert l.oracle_kat_is_local_ip(1, 0, b"", 0) == 1                        # nil ip is not global unicast
+    assert l.oracle_kat_is_loopback(1, 0, b"", 0) == 0
+
+
+def test_geo_tianjin_golden(built):
+    """libs/geo/netmask_tree_test.go:54-64 TestNetmaskGeoTree: 223.104.x -> "天津", on the
+    slice of the reference's ip_info_mini.json committed under tests/golden/."""
+    import json
+    import os
+    from deepflow_b200 import abi
+    from oracle_binding import Oracle
+    path = os.path.join(os.path.dirname(__file__), "golden", "geo_slice.json")
+    g = json.load(open(path, encoding="utf-8"))
+    names = [n.encode("utf-8") for n in g["region_names"]]
+    ent = (abi.GeoEntry * len(g["entries"]))()
+    for i, (s, e, r) in enumerate(g["entries"]):
+        ent[i].ip_start, ent[i].ip_end, ent[i].region = s, e, r
+    arr = (C.c_char_p * len(names))(*names)
+    ora = Oracle()
+    ora.geo_load((C.cast(ent, C.c_void_p), len(g["entries"]), C.cast(arr, C.c_void_p), len(names)))
+    l = lib()
+    assert l.oracle_kat_province(ora._h, 3748071168).decode("utf-8") == "天津"
+    assert l.oracle_kat_province(ora._h, 1).decode("utf-8") == "未知"
+    for ip, region in g["probes"]:
+        assert l.oracle_kat_province(ora._h, ip).decode("utf-8") == region
