@@ -1,0 +1,386 @@
+#!/usr/bin/env python3
+"""bench.py — flow records/sec of the ingest hot path (decode -> SmartEncoding ->
+flow_tag -> ClickHouse column pack) on B200, per BASELINE.json.
+
+Workload at N=1 (BASELINE.json configs[1]): 10 M synthetic L7 HTTP
+AppProtoLogsData records, submitted the way the ingester's decoder sees them:
+sub-batches of <= 1024 agent frames (decoder.go:56 BUFFER_SIZE x 256 KiB frames).
+One "step" = one pass over all sub-batches.  Under torchrun every rank owns the
+vtap_id % N == rank shard of the firehose (weak scaling: 10 M records per GPU);
+the data path has no collective.
+
+  value     device-resident: inputs already in HBM, kernels only (CUDA events on the
+            library's stream)
+  e2e       through the C ABI with HOST buffers: pinned H2D of every sub-batch, all
+            kernels, D2H of every column block, inside the timed region
+  roofline  the dominant kernel (EMIT/pack pass): algorithmic bytes / its CUDA-event
+            time vs the measured HBM peak
+  cpu_baseline   the CPU oracle (a C++ restatement of the Go path) on a bounded sample
+
+--impl reference times that CPU restatement with all host threads instead (the Go
+reference cannot be built in this image: no Go toolchain).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from deepflow_b200 import abi  # noqa: E402
+
+MSG = abi.DFGPU_MSG_PROTOCOLLOG
+METRIC = "flow records/sec ingest+SmartEncode (L7 decode + tag-inject + flow_tag + column pack)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dfgpu", choices=["dfgpu", "reference"])
+    ap.add_argument("--records", type=int, default=10_000_000, help="records per GPU per step")
+    ap.add_argument("--sub-batch", type=int, default=625_000, help="records per dfgpu_submit")
+    ap.add_argument("--pods", type=int, default=100_000, help="dictionary size P (SURVEY §8d)")
+    ap.add_argument("--decoders", type=int, default=2, help="contexts per GPU in the e2e leg (DecoderQueueCount)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def gen_sub_batches(synth, n_total, sub, seed0, world, rank, threads=16):
+    """Generate ceil(n_total/sub) sub-batches in parallel threads (ctypes drops the GIL)."""
+    sizes = [min(sub, n_total - i) for i in range(0, n_total, sub)]
+    out = [None] * len(sizes)
+
+    def work(i):
+        out[i] = synth.gen(MSG, sizes[i], seed=seed0 + i, vtap_mod=world if world > 1 else 0, vtap_rem=rank)
+
+    it = iter(range(len(sizes)))
+    lock = threading.Lock()
+
+    def loop():
+        while True:
+            with lock:
+                i = next(it, None)
+            if i is None:
+                return
+            work(i)
+
+    ts = [threading.Thread(target=loop) for _ in range(min(threads, len(sizes)))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.p, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def output_bytes(batch):
+    """Exact size of the packed l7_flow_log column block (what the EMIT kernel writes)."""
+    cols, nrows = batch.columns(abi.TABLE_L7_FLOW_LOG)
+    total = 0
+    for c in cols:
+        t = c.ch_type
+        if t in (abi.CH_STR, abi.CH_LC_STR_ROWS):
+            total += nrows * 16 + c.buf.nbytes
+        elif t in (abi.CH_ARR_STR, abi.CH_ARR_LC_STR):
+            total += nrows * 8 + c.pos.nbytes + c.buf.nbytes
+        elif t in (abi.CH_ARR_UINT16, abi.CH_ARR_FLOAT64):
+            total += nrows * 8 + c.values.nbytes
+        else:
+            total += nrows * c.elem_size + (nrows if c.nulls is not None else 0)
+    return total, nrows
+
+
+def cpu_port_run(synth, sample_records, threads, seed):
+    """The CPU oracle (C++ restatement of decoder.Run ... AppendToColumnBlock) on `threads`
+    independent decoder instances, each with its own dictionary view and caches."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import Oracle
+    oras, wls = [], []
+    for t in range(threads):
+        o = Oracle()
+        o.load_synth(synth)
+        oras.append(o)
+        wls.append(synth.gen(MSG, sample_records, seed=seed + t))
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=o.submit, args=(w,)) for o, w in zip(oras, wls)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    dt = time.perf_counter() - t0
+    n = sum(w.nrecords for w in wls)
+    for o in oras:
+        o.close()
+    return n / dt, n, dt
+
+
+def main():
+    a = parse_args()
+    rank, world, local = dist_env()
+    if world != a.gpus and world > 1:
+        a.gpus = world
+    from deepflow_b200 import build
+    from deepflow_b200.synth import Synth
+    if rank == 0:
+        build.build_synth()
+    synth = None
+    cfg_common = {"workload": "C2: L7 HTTP AppProtoLogsData, SmartEncoding on, flow_tag on (BASELINE.json configs[1])",
+                  "records_per_gpu_per_step": a.records, "sub_batch_records": a.sub_batch,
+                  "dictionary_pods": a.pods, "sharding": "vtap_id % n_gpus" if a.gpus > 1 else "none",
+                  "l2": "inputs 4+ GB per step >> 126 MB L2 (no flush needed)"}
+
+    # ------------------------------------------------------------------ reference arm --
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        build.build_oracle()
+        synth = Synth(n_pods=a.pods)
+        cores = os.cpu_count() or 1
+        threads = min(cores, 64)
+        sample = 20000
+        for _ in range(a.warmup):
+            cpu_port_run(synth, 2000, threads, 900)
+        t_all, n_all = 0.0, 0
+        for s in range(a.steps):
+            v, n, dt = cpu_port_run(synth, sample, threads, 1000 + s * 100)
+            t_all += dt
+            n_all += n
+        value = n_all / t_all
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "records/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * t_all / max(1, a.steps),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer",
+                "data": "synthetic", "config": cfg_common,
+                "cpu_baseline": {"value": value, "unit": "records/s", "cores": threads, "kind": "port",
+                                 "sample": f"{threads} decoder instances x {sample} L7 records per step "
+                                           "(C++ restatement of the Go path; the Go ingester cannot be built here)"},
+                "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------ GPU arm --
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: libdfgpu has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from deepflow_b200.native import Engine
+    synth = Synth(n_pods=a.pods)
+    t0 = time.time()
+    subs = gen_sub_batches(synth, a.records, a.sub_batch, 1000 + 7919 * rank, world, rank)
+    nrec_step = sum(w.nrecords for w in subs)
+    in_bytes = sum(w.nbytes for w in subs)
+    gen_s = time.time() - t0
+
+    # pinned host copies of every sub-batch (the Go shim's staging buffers)
+    pinned = []
+    for w in subs:
+        t = torch.empty(max(1, w.nbytes), dtype=torch.uint8, pin_memory=True)
+        t[:w.nbytes].copy_(torch.from_numpy(w.data))
+        pinned.append(t)
+    # device-resident copies for the `value` leg
+    dev_data = [p.to(f"cuda:{local}", non_blocking=True) for p in pinned]
+    dev_frames = [torch.from_numpy(w.frames.view(np.uint8).reshape(-1).copy()).to(f"cuda:{local}") for w in subs]
+    torch.cuda.synchronize()
+
+    cfg = abi.Cfg()
+    cfg.max_batch_bytes = max(w.nbytes for w in subs) + (1 << 20)
+    engines = [Engine(local, cfg) for _ in range(max(1, a.decoders))]
+    for e in engines:
+        e.load_synth(synth)
+    main_eng = engines[0]
+    stream = torch.cuda.ExternalStream(main_eng.stream, device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, kernels only --------------------------------------
+    def resident_step(eng):
+        for i, w in enumerate(subs):
+            eng.stage_ptr(MSG, dev_data[i].data_ptr(), w.nbytes, dev_frames[i].data_ptr(), len(w.frames))
+            eng.run()
+
+    for _ in range(a.warmup):
+        resident_step(main_eng)
+    main_eng.sync()
+    main_eng.profile_enable(True)
+    sampler = ClockSampler(local)
+    launches0 = sum(e.launch_count for e in engines)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        resident_step(main_eng)
+    ev1.record(stream)
+    main_eng.sync()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    emit_ms, emit_n, emit_in = main_eng.profile_read()
+    main_eng.profile_enable(False)
+    launches_value = sum(e.launch_count for e in engines) - launches0
+    # validate the last resident run + get exact output sizes for the roofline
+    b = main_eng.fetch()
+    cnt = b.counters()
+    assert cnt.error_count == 0 and cnt.count == subs[-1].nrecords, (cnt.error_count, cnt.count)
+    out_b_last, rows_last = output_bytes(b)
+    b.release()
+
+    # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H per sub-batch -------------
+    d2h_total = [0]
+
+    def e2e_step():
+        err = []
+
+        def worker(k):
+            eng = engines[k]
+            try:
+                for i in range(k, len(subs), len(engines)):
+                    w = subs[i]
+                    out = C.c_void_p()
+                    from deepflow_b200.native import lib
+                    rc = lib().dfgpu_submit(eng._h, MSG, pinned[i].data_ptr(), w.nbytes, w.frames.ctypes.data,
+                                            len(w.frames), None, None, C.byref(out))
+                    if rc != 0:
+                        raise RuntimeError(f"dfgpu_submit rc={rc}")
+                    lib().dfgpu_batch_release(out)
+            except Exception as ex:  # noqa: BLE001
+                err.append(ex)
+
+        ts = [threading.Thread(target=worker, args=(k,)) for k in range(len(engines))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        if err:
+            raise err[0]
+
+    for _ in range(a.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    for e in engines:
+        e.sync()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # per-step byte accounting for e2e (H2D = staging buffers + frame tables; D2H = column blocks)
+    bytes_per_row = out_b_last / max(1, rows_last)
+    d2h_per_step = int(bytes_per_row * nrec_step)
+    h2d_per_step = int(in_bytes + sum(w.frames.nbytes for w in subs))
+
+    # ---- max over ranks ----------------------------------------------------------------------
+    times = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=f"cuda:{local}")
+    recs = torch.tensor([float(nrec_step)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(recs, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = times.tolist()
+    total_recs_step = recs.item()
+
+    if rank == 0:
+        value = total_recs_step * a.steps / (dev_ms_max / 1000.0)
+        e2e_value = total_recs_step * a.steps / (e2e_ms_max / 1000.0)
+        peak, peak_src = measured_peak_hbm()
+        # algorithmic bytes of one EMIT launch (SURVEY §8d B_L7): wire + 4 B length prefix per
+        # record + every byte of the packed block + 32 B per dictionary probe (12 / record)
+        alg_per_rec = in_bytes / nrec_step + bytes_per_row + 32 * 12
+        emit_launch_s = emit_ms / 1000.0 / max(1, emit_n)
+        recs_per_launch = nrec_step * a.steps / max(1, emit_n)
+        achieved = alg_per_rec * recs_per_launch / emit_launch_s / 1e9 if emit_launch_s > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "k_l7_pass<EMIT>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_record": alg_per_rec, "launches_timed": emit_n,
+                "avg_launch_ms": emit_ms / max(1, emit_n),
+                "share_of_device_time": emit_ms / dev_ms if dev_ms else None}
+        line = {"metric": METRIC, "value": value, "unit": "records/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer (f64 casts only at pack)",
+                "data": "synthetic", "config": dict(cfg_common, mean_wire_bytes=in_bytes / nrec_step,
+                                                    packed_bytes_per_row=bytes_per_row, gen_seconds=gen_s,
+                                                    decoders_per_gpu=len(engines)),
+                "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": h2d_per_step,
+                        "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms_max / a.steps},
+                "gpu_launches": int(launches_value), "clocks": clocks, "roofline": roof}
+        if not a.no_cpu_baseline:
+            build.build_oracle()
+            v, n, dt = cpu_port_run(synth, 400_000, 1, 4242)
+            line["cpu_baseline"] = {"value": v, "unit": "records/s", "cores": 1, "kind": "port",
+                                    "sample": f"{n} L7 records of the same generator, one decoder instance, {dt:.1f} s"}
+        print(json.dumps(line))
+    for e in engines:
+        e.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

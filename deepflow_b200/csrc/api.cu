@@ -294,8 +294,17 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
   }
   launch_finish(bp, s);
   ctx->launches++;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (ctx->prof_on && bp.nrec && ctx->prof_used < dfgpu_ctx::PROF_SLOTS) {
+    pe0 = ctx->prof_ev[2 * ctx->prof_used];
+    pe1 = ctx->prof_ev[2 * ctx->prof_used + 1];
+    ctx->prof_bytes[ctx->prof_used] = ctx->cur_nbytes;
+    ctx->prof_used++;
+    CU(cudaEventRecord(pe0, s));
+  }
   if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 1, s);
   else launch_l7_pass(bp, 1, s);
+  if (pe1) CU(cudaEventRecord(pe1, s));
   if (bp.nrec) ctx->launches++;
   if (ctx->cur_msg != DFGPU_MSG_PROTOCOLLOG) {  // L7 commits after its flow_tag stage
     launch_commit(bp, 0, s);
@@ -736,6 +745,37 @@ void dfgpu_batch_release(dfgpu_batch* b) {
 }
 
 int dfgpu_flush(dfgpu_ctx* ctx) { return dfgpu_sync(ctx); }
+
+// Measurement hook (bench.py roofline leg): CUDA events recorded on the ctx stream
+// right around the dominant kernel (the EMIT pass) of every dfgpu_run.
+int dfgpu_profile_enable(dfgpu_ctx* ctx, int on) {
+  if (!ctx) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  if (on && !ctx->prof_ev[0])
+    for (int i = 0; i < 2 * dfgpu_ctx::PROF_SLOTS; i++) CU(cudaEventCreate(&ctx->prof_ev[i]));
+  ctx->prof_on = on != 0;
+  ctx->prof_used = 0;
+  return DFGPU_OK;
+}
+// Sums and resets: emit-kernel milliseconds, launches, input bytes of those launches.
+int dfgpu_profile_read(dfgpu_ctx* ctx, double* emit_ms, uint64_t* launches, uint64_t* in_bytes) {
+  if (!ctx) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  double ms = 0;
+  uint64_t bytes = 0;
+  for (int i = 0; i < ctx->prof_used; i++) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+    ms += t;
+    bytes += ctx->prof_bytes[i];
+  }
+  if (emit_ms) *emit_ms = ms;
+  if (launches) *launches = (uint64_t)ctx->prof_used;
+  if (in_bytes) *in_bytes = bytes;
+  ctx->prof_used = 0;
+  return DFGPU_OK;
+}
 
 int dfgpu_metrics_reduce(dfgpu_ctx* ctx, uint32_t bucket_seconds, dfgpu_batch** out) {
   (void)bucket_seconds;

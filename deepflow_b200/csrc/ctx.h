@@ -64,6 +64,12 @@ struct dfgpu_ctx {
   uint64_t* trace_idx_out = nullptr;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // optional per-kernel timing (dfgpu_profile_enable)
+  static constexpr int PROF_SLOTS = 256;
+  bool prof_on = false;
+  int prof_used = 0;
+  cudaEvent_t prof_ev[2 * PROF_SLOTS] = {nullptr};
+  uint64_t prof_bytes[PROF_SLOTS] = {0};
 
   // flow tag state (l7)
   void* ft = nullptr;

@@ -47,6 +47,8 @@ def lib():
         L.dfgpu_batch_release.restype = None
         L.dfgpu_metrics_reduce.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
         L.dfgpu_flush.argtypes = [vp]
+        L.dfgpu_profile_enable.argtypes = [vp, C.c_int]
+        L.dfgpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _LIB = L
     return _LIB
 
@@ -141,6 +143,14 @@ class Engine:
 
     def sync(self):
         self._check(lib().dfgpu_sync(self._h), "dfgpu_sync")
+
+    def profile_enable(self, on=True):
+        self._check(lib().dfgpu_profile_enable(self._h, 1 if on else 0), "dfgpu_profile_enable")
+
+    def profile_read(self):
+        ms, n, b = C.c_double(), C.c_uint64(), C.c_uint64()
+        self._check(lib().dfgpu_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(b)), "dfgpu_profile_read")
+        return ms.value, int(n.value), int(b.value)
 
     @property
     def stream(self):

@@ -35,7 +35,8 @@ def lib():
         L.synth_geo.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
                                 C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
         L.synth_gen.restype = C.c_void_p
-        L.synth_gen.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint16]
+        L.synth_gen.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint16,
+                                C.c_uint32, C.c_uint32]
         L.synth_batch_view.argtypes = [C.c_void_p, C.POINTER(_Frames)]
         L.synth_batch_free.argtypes = [C.c_void_p]
         _LIB = L
@@ -96,8 +97,8 @@ class Synth:
         lib().synth_geo(self._h, C.byref(e), C.byref(n), C.byref(names), C.byref(nn))
         return e, n.value, names, nn.value
 
-    def gen(self, msg_type, nrecords, seed=1, flags=0, max_frame_bytes=0, org_id=1):
-        b = lib().synth_gen(self._h, msg_type, seed, nrecords, flags, max_frame_bytes, org_id)
+    def gen(self, msg_type, nrecords, seed=1, flags=0, max_frame_bytes=0, org_id=1, vtap_mod=0, vtap_rem=0):
+        b = lib().synth_gen(self._h, msg_type, seed, nrecords, flags, max_frame_bytes, org_id, vtap_mod, vtap_rem)
         if not b:
             raise ValueError("unsupported msg_type for the generator")
         v = _Frames()

@@ -958,8 +958,10 @@ int synth_geo(synth_ctx* c, const dfgpu_geo_entry** e, uint64_t* n, const char* 
   return 0;
 }
 
+// vtap_mod/vtap_rem: only agents with vtap_id % vtap_mod == vtap_rem send frames (the
+// per-GPU shard of a vtap-sharded firehose); vtap_mod <= 1 = every agent.
 synth_batch* synth_gen(synth_ctx* c, int msg_type, uint64_t seed, uint64_t nrecords, uint32_t flags,
-                       uint32_t max_frame_bytes, uint16_t org_id) {
+                       uint32_t max_frame_bytes, uint16_t org_id, uint32_t vtap_mod, uint32_t vtap_rem) {
   auto* b = new synth_batch();
   Rng r(seed * 1000003ull + (uint64_t)msg_type);
   if (!max_frame_bytes) max_frame_bytes = 256 * 1024;
@@ -972,6 +974,11 @@ synth_batch* synth_gen(synth_ctx* c, int msg_type, uint64_t seed, uint64_t nreco
     memset(&fr, 0, sizeof fr);
     fr.offset = b->data.size();
     fr.vtap_id = (uint16_t)(1 + r.below(c->n_vtap));
+    if (vtap_mod > 1) {
+      uint32_t first = vtap_rem % vtap_mod ? vtap_rem % vtap_mod : vtap_mod;
+      uint32_t count = first <= c->n_vtap ? (c->n_vtap - first) / vtap_mod + 1 : 1;
+      fr.vtap_id = (uint16_t)(first + vtap_mod * r.below(count));
+    }
     fr.org_id = org_id;
     fr.team_id = 1 + (fr.vtap_id % 3);
     // agents flush by size or time: vary the frame fill

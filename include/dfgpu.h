@@ -285,6 +285,12 @@ int dfgpu_sync(dfgpu_ctx* ctx);
 void* dfgpu_stream(dfgpu_ctx* ctx);
 /* number of kernels this ctx has launched since init                           */
 uint64_t dfgpu_launch_count(const dfgpu_ctx* ctx);
+/* Measurement hooks: CUDA events recorded on the ctx stream right around the
+ * dominant kernel (the pack/EMIT pass) of every dfgpu_run (<= 256 runs between reads).
+ * dfgpu_profile_read synchronises, sums and resets.                               */
+int dfgpu_profile_enable(dfgpu_ctx* ctx, int on);
+int dfgpu_profile_read(dfgpu_ctx* ctx, double* emit_ms, uint64_t* launches, uint64_t* in_bytes);
+int dfgpu_flush(dfgpu_ctx* ctx);
 
 /* Column block of one table of a batch, in ToInput order.  cols may be NULL to
  * query *ncols / *nrows only.                                                  */
