@@ -899,12 +899,15 @@ void gen_l7(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flag
   if (r.chance(0.2)) ext.str(10, hexid(r, 24));
   uint32_t nval = nattr;
   if ((flags & F_DUP_FIELDS) && r.chance(0.05)) nval = nattr ? nattr - 1 : 1;  // mismatched lengths
+  // 300 names x ~167 values each = 50 k distinct (name, value) pairs
+  uint32_t name_idx[8];
   for (uint32_t i = 0; i < nattr; i++) {
-    snprintf(t, sizeof t, "attr_%u", r.skew(300));
+    name_idx[i] = r.skew(300);
+    snprintf(t, sizeof t, "attr_%u", name_idx[i]);
     ext.str_always(16, t);
   }
   for (uint32_t i = 0; i < nval; i++) {
-    snprintf(t, sizeof t, "val-%u", r.skew(50000));
+    snprintf(t, sizeof t, "val-%u", (i < nattr ? name_idx[i] : 0) * 167 + r.skew(167));
     ext.str_always(17, r.chance(0.03) ? std::string() : std::string(t));
   }
   if (r.chance(0.1)) {

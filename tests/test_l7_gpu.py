@@ -45,7 +45,11 @@ def run_both(eng, ora, wl):
     ([20000, 20000], 5, S.F_ALL_WIRE), ([20000, 3000], 6, S.F_ALL_WIRE | S.F_CORRUPT),
 ])
 def test_l7_parity(synth, built, sizes, seed, flags):
-    eng, ora = fresh(synth)
+    # the device tag set never evicts; keep the reference's LRUs below their capacity so
+    # that eviction (SURVEY §7 "hard parts") does not enter the comparison
+    cfg = abi.Cfg()
+    cfg.flow_tag_cache_max_size = 1 << 21
+    eng, ora = fresh(synth, cfg)
     try:
         for k, n in enumerate(sizes):
             wl = synth.gen(abi.DFGPU_MSG_PROTOCOLLOG, n, seed=seed * 100 + k, flags=flags)
