@@ -322,6 +322,10 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
   if (!main_schema(msg_type)) return fail(ctx, DFGPU_EINVAL, "unsupported msg_type %d", msg_type);
   if (nbytes >= (1ull << 32)) return fail(ctx, DFGPU_EINVAL, "batch too large (%zu bytes)", nbytes);
   CU(cudaSetDevice(ctx->device));
+  cudaPointerAttributes attr;
+  if (tbl && cudaPointerGetAttributes(&attr, tbl) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
+    return fail(ctx, DFGPU_EINVAL, "the frame table must be host memory (only `frames` may be device resident)");
+  cudaGetLastError();
   uint16_t org = nframes ? tbl[0].org_id : 1;
   for (int i = 1; i < nframes; i++)
     if (tbl[i].org_id != org) return fail(ctx, DFGPU_EMIXEDORG, "frames of one submit must share org_id");
@@ -333,7 +337,6 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
     if (it == ctx->dicts.end()) return fail(ctx, DFGPU_ENOENT, "no dictionary loaded for org %u", org);
     ctx->cur_dict = it->second;
   }
-  cudaPointerAttributes attr;
   bool on_device = false;
   if (frames && cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeDevice) on_device = true;
   cudaGetLastError();
@@ -356,11 +359,7 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
     if (nbytes) CU(cudaMemcpyAsync(ctx->d_in, frames, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->cur_in = ctx->d_in;
   }
-  bool tbl_on_device = false;
-  if (tbl && cudaPointerGetAttributes(&attr, tbl) == cudaSuccess && attr.type == cudaMemoryTypeDevice) tbl_on_device = true;
-  cudaGetLastError();
-  if (nframes) CU(cudaMemcpyAsync(ctx->d_frames, tbl, (size_t)nframes * sizeof(dfgpu_frame),
-                                   tbl_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  if (nframes) CU(cudaMemcpyAsync(ctx->d_frames, tbl, (size_t)nframes * sizeof(dfgpu_frame), cudaMemcpyHostToDevice, ctx->stream));
   ctx->cur_frames = ctx->d_frames;
   ctx->cur_msg = msg_type;
   ctx->cur_nbytes = nbytes;

