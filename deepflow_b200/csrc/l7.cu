@@ -16,44 +16,9 @@
  *                   app_service_tag_writer.go:92-113
  *   counters        updateCounter decoder.go:498-525
  */
-#include "ctx.h"
-#include "l7_decode.cuh"
-#include "schema_l7.h"
-
-#include "../../include/dfgpu_exception_tables.h"
+#include "l7_dev.h"
 
 namespace dfgpu {
-
-// ---- constant strings the path can emit (protocol names, pseudo attribute names,
-// exception descriptions): one device blob, addressed by id -------------------------
-enum : uint32_t {
-  CS_EMPTY = 0, CS_ATTR_UA, CS_ATTR_REFERER, CS_ATTR_RPC, CS_FT_APP_SERVICE, CS_FT_ENDPOINT,
-  CS_FT_APP_INSTANCE, CS_PROTO_NA, CS_PROTO_TLS, CS_DNS_AVAILABLE, CS_DNS_PRIVATE, CS_KAFKA_UNKNOWN,
-  CS_FIXED_COUNT
-};
-
-struct FtEntry {  // one slot of the device tag set (32 B = one HBM sector)
-  unsigned long long fp_lo, fp_hi;  // 128-bit fingerprint of the lru key; 0/0 = empty
-  unsigned long long first_pos;     // (epoch << 48) | (2^48-1 - position): atomicMax keeps the FIRST
-                                    // candidate of the NEWEST batch; 0 = none
-  uint32_t time;                    // value stored by lru Add(): time of the last emission
-  uint32_t state;                   // 0 = inserted but never emitted, 1 = emitted
-};
-static_assert(sizeof(FtEntry) == 32, "FtEntry");
-
-struct L7Dev {
-  const uint8_t* cs_blob;
-  const uint32_t* cs_off;  // [n+1]
-  uint32_t cs_http, cs_dns, cs_dubbo, cs_kafka, cs_mqtt3, cs_mqtt5;  // base ids of the tables
-  uint16_t proto_cs[256][2];  // L7Protocol.String(isTLS) -> cs id
-  FtEntry* ft;
-  uint32_t ft_mask;
-  uint32_t ft_timeout;
-  uint32_t epoch;
-  uint16_t org_id;
-  uint8_t* ft_arena;
-  uint64_t ft_arena_bytes;
-};
 
 struct L7Host {  // host mirror kept in ctx->ft
   L7Dev dev{};
@@ -68,557 +33,7 @@ struct L7Host {  // host mirror kept in ctx->ft
 
 namespace {
 
-__device__ __forceinline__ SRef cs_ref(const L7Dev* d, uint32_t id) {
-  uint32_t a = d->cs_off[id], b = d->cs_off[id + 1];
-  return SRef{d->cs_blob + a, b - a};
-}
-__device__ __forceinline__ SRef cs_tbl(const L7Dev* d, uint32_t base, int32_t idx, int32_t n) {
-  if (idx >= 0 && idx < n) return cs_ref(d, base + (uint32_t)idx);
-  return SRef{nullptr, 0};
-}
-
-__device__ __forceinline__ uint64_t djb_hash(uint64_t h, const uint8_t* p, uint32_t n) {
-  for (uint32_t i = 0; i < n; i++) h = ((h << 5) + h) + (uint64_t)ldb(p + i);
-  return h;
-}
-
-__device__ bool str_eq(SRef s, const char* lit) {
-  uint32_t i = 0;
-  for (; lit[i]; i++)
-    if (i >= s.n || ldb(s.p + i) != (uint8_t)lit[i]) return false;
-  return i == s.n;
-}
-
-template <class T>
-__device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, T v) {
-  reinterpret_cast<T*>(p.arena + p.fix_off[col])[row] = v;
-}
-__device__ __forceinline__ void st_ip6(const BatchParams& p, int col, uint32_t row, SRef s) {
-  uint32_t w[4] = {0, 0, 0, 0};
-  uint8_t* b = reinterpret_cast<uint8_t*>(w);
-  uint32_t n = s.n > 16 ? 16 : s.n;
-  for (uint32_t i = 0; i < n; i++) b[i] = ldb(s.p + i);
-  reinterpret_cast<uint4*>(p.arena + p.fix_off[col])[row] = make_uint4(w[0], w[1], w[2], w[3]);
-}
-template <class T>
-__device__ __forceinline__ void st_nullable(const BatchParams& p, int col, uint32_t row, bool has, T v) {
-  reinterpret_cast<T*>(p.arena + p.fix_off[col])[row] = has ? v : T(0);
-  (p.arena + p.aux_off[col])[row] = has ? 0 : 1;
-}
-__device__ __forceinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, uint32_t n) {
-  for (uint32_t i = 0; i < n; i++) dst[i] = ldb(src + i);
-}
-
-struct L7EmitSink {
-  dfgpu_pos* an_pos; uint8_t* an_buf; uint64_t an_off;  // attribute_names
-  dfgpu_pos* av_pos; uint8_t* av_buf; uint64_t av_off;  // attribute_values
-  dfgpu_pos* mn_pos; uint8_t* mn_buf; uint64_t mn_off;  // metrics_names
-  uint64_t* mv;                                          // metrics_values (f64 bit patterns)
-  __device__ __forceinline__ void put(dfgpu_pos*& pos, uint8_t* buf, uint64_t& off, const uint8_t* s, uint32_t n) {
-    *pos++ = dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
-    copy_bytes(buf + off, s, n);
-    off += n;
-  }
-  __device__ __forceinline__ void attr_name(const uint8_t* s, uint32_t n) { put(an_pos, an_buf, an_off, s, n); }
-  __device__ __forceinline__ void attr_value(const uint8_t* s, uint32_t n) { put(av_pos, av_buf, av_off, s, n); }
-  __device__ __forceinline__ void metric_name(const uint8_t* s, uint32_t n) { put(mn_pos, mn_buf, mn_off, s, n); }
-  __device__ __forceinline__ void metric_value(uint64_t v) { *mv++ = v; }
-};
-
-// The derived (post-Fill) view of one record: every output string and nullable.
-struct L7Row {
-  SRef str[22];  // streams 0..21
-  uint8_t type, is_tls, is_async, is_reversed, l7_protocol, response_status;
-  bool has_request_id, has_response_code, has_request_length, has_response_length, has_sql_rows;
-  uint64_t request_id, sql_rows;
-  int32_t response_code;
-  int64_t request_length, response_length;
-  uint32_t n_pseudo, pseudo_name_bytes, pseudo_value_bytes;
-  bool trace_nonempty;
-  uint64_t trace_hash;
-};
-
-// L7FlowLog.Fill + fillL7FlowLog, strings only referenced (never copied here)
-__device__ void l7_derive(const L7Dev* dv, const L7Rec& r, L7Row& o) {
-  const SRef none{nullptr, 0};
-#pragma unroll
-  for (int i = 0; i < 22; i++) o.str[i] = none;
-  o.type = (uint8_t)r.head_msg_type;
-  o.is_tls = (r.flags & 1) ? 1 : 0;
-  o.is_async = (r.flags & 2) ? 1 : 0;
-  o.is_reversed = (r.flags & 4) ? 1 : 0;
-  o.l7_protocol = (uint8_t)r.head_proto;
-  o.str[L7V_BIZ_CODE] = r.biz_code;
-  o.str[L7V_BIZ_SCENARIO] = r.biz_scenario;
-  o.str[L7V_BIZ_RESPONSE_CODE] = r.biz_response_code;
-  o.str[L7V_KNAME_0] = r.process_kname_0;
-  o.str[L7V_KNAME_1] = r.process_kname_1;
-  if (r.has_ext && r.protocol_str.n) o.str[L7V_BIZ_PROTOCOL] = r.protocol_str;
-  else o.str[L7V_BIZ_PROTOCOL] = cs_ref(dv, dv->proto_cs[o.l7_protocol][o.is_tls]);
-  o.str[L7V_VERSION] = r.version;
-  o.response_status = 5;  // STATUS_UNKNOWN
-  o.request_length = (int64_t)r.req_len;
-  o.response_length = (int64_t)r.resp_len;
-  o.sql_rows = (uint64_t)r.row_effect;
-  o.has_sql_rows = o.sql_rows != 0;
-  o.has_request_length = o.has_response_length = o.has_response_code = o.has_request_id = false;
-  o.response_code = 0;
-  o.request_id = 0;
-  if (r.has_req) {  // :379-387
-    o.str[L7V_REQUEST_DOMAIN] = r.domain;
-    o.str[L7V_REQUEST_RESOURCE] = r.resource;
-    o.str[L7V_REQUEST_TYPE] = r.req_type;
-    if (o.request_length != -1 && o.type != 1) o.has_request_length = true;
-    o.str[L7V_ENDPOINT] = r.endpoint;
-  }
-  if (r.has_resp) {  // :389-409
-    o.response_status = (uint8_t)r.resp_status;
-    if (o.type != 0) {
-      o.str[L7V_RESPONSE_RESULT] = r.result;
-      o.response_code = r.resp_code;
-      SRef exc = r.exception;
-      if (exc.n == 0 && (o.response_status == 3 || o.response_status == 4)) {  // fillExceptionDesc
-        int32_t code = r.resp_code;
-        switch (o.l7_protocol) {
-          case 20:
-          case 21: exc = cs_tbl(dv, dv->cs_http, (int32_t)(uint16_t)code, DFGPU_EXC_HTTP_LEN); break;
-          case 120: {
-            uint16_t c = (uint16_t)code;
-            if (c < DFGPU_EXC_DNS_LEN) exc = cs_ref(dv, dv->cs_dns + c);
-            else if (c >= 22 && c <= 3840) exc = cs_ref(dv, CS_DNS_AVAILABLE);
-            else if (c >= 3841 && c <= 4095) exc = cs_ref(dv, CS_DNS_PRIVATE);
-            else exc = cs_ref(dv, CS_DNS_AVAILABLE);
-            break;
-          }
-          case 40: exc = cs_tbl(dv, dv->cs_dubbo, (int32_t)(uint16_t)code, DFGPU_EXC_DUBBO_LEN); break;
-          case 100: {
-            int16_t c = (int16_t)code;
-            if (c == -1) exc = cs_ref(dv, CS_KAFKA_UNKNOWN);
-            else if (c > 0 && c < DFGPU_EXC_KAFKA_LEN) exc = cs_ref(dv, dv->cs_kafka + c);
-            break;
-          }
-          case 101: {
-            uint16_t c = (uint16_t)code;
-            bool v5 = str_eq(r.version, "5");
-            if (!v5) { if (c > 0 && c < DFGPU_EXC_MQTT_V3_LEN) exc = cs_ref(dv, dv->cs_mqtt3 + c); }
-            else { if (c > 0 && c < DFGPU_EXC_MQTT_V5_LEN) exc = cs_ref(dv, dv->cs_mqtt5 + c); }
-            break;
-          }
-          default: break;  // h.ResponseException = l.Resp.Exception (empty)
-        }
-      }
-      o.str[L7V_RESPONSE_EXCEPTION] = exc;
-      if (o.response_code != -32768) o.has_response_code = true;
-      if (o.response_length != -1) o.has_response_length = true;
-    }
-  }
-  o.n_pseudo = o.pseudo_name_bytes = o.pseudo_value_bytes = 0;
-  if (r.has_ext) {  // :411-433
-    o.request_id = (uint64_t)r.request_id;
-    if (o.request_id != 0) o.has_request_id = true;
-    o.str[L7V_APP_SERVICE] = r.service_name;
-    o.str[L7V_X_REQUEST_ID_0] = r.x_request_id_0;
-    o.str[L7V_X_REQUEST_ID_1] = r.x_request_id_1;
-    o.str[L7V_HTTP_PROXY_CLIENT] = r.client_ip;
-    if (r.http_user_agent.n) { o.n_pseudo++; o.pseudo_name_bytes += 15; o.pseudo_value_bytes += r.http_user_agent.n; }
-    if (r.http_referer.n) { o.n_pseudo++; o.pseudo_name_bytes += 12; o.pseudo_value_bytes += r.http_referer.n; }
-    if (r.rpc_service.n) { o.n_pseudo++; o.pseudo_name_bytes += 11; o.pseudo_value_bytes += r.rpc_service.n; }
-  }
-  SRef trace_id = none;
-  if (r.has_trace) {  // :434-438 + fillTraceIds :344-360
-    o.str[L7V_SPAN_ID] = r.span_id;
-    if (r.n_trace_ids > 0) trace_id = r.trace_ids0;
-    if (r.n_trace_ids > 1) o.str[L7V_TRACE_ID_2] = r.trace_ids1;
-    if (trace_id.n == 0) trace_id = r.trace_id;
-    o.str[L7V_PARENT_SPAN_ID] = r.parent_span_id;
-  }
-  o.str[L7V_TRACE_ID] = trace_id;
-  o.trace_nonempty = trace_id.n != 0;
-  o.trace_hash = o.trace_nonempty ? djb_hash(17, trace_id.p, trace_id.n) : 0;
-  switch (o.l7_protocol) {  // :438-451
-    case 100:
-      if (r.has_req) {
-        bool supported = str_eq(r.req_type, "Fetch") || str_eq(r.req_type, "Produce") || str_eq(r.req_type, "JoinGroup") ||
-                         str_eq(r.req_type, "LeaveGroup") || str_eq(r.req_type, "SyncGroup");
-        if (o.response_code == 0 && !supported) {
-          o.response_status = 2;
-          o.has_response_code = false;
-        }
-        o.has_request_id = true;
-      }
-      break;
-    case 43: o.has_request_id = true; break;
-  }
-}
-
 }  // namespace
-
-template <int EMIT>
-__global__ void __launch_bounds__(256) k_l7_pass(const __grid_constant__ BatchParams p) {
-  const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
-  const bool in_range = rec < p.nrec;
-  DynState* dyn = p.dyn;
-  const L7Dev* dv = reinterpret_cast<const L7Dev*>(p.ext);
-  if (EMIT && (dyn->stats.need_repair && !p.repair)) return;
-  if (EMIT && dyn->overflow) return;
-
-  L7Rec r;
-  memset(&r, 0, sizeof r);
-  bool ok = false;
-  uint32_t frame = 0;
-  const uint8_t* base = nullptr;
-  uint32_t len = 0;
-  if (in_range) {
-    frame = p.rec_frame[rec];
-    base = p.in + p.rec_off[rec];
-    len = p.rec_len[rec];
-    if (p.repair && rec >= p.frame_bad[frame]) {
-      ok = false;
-    } else {
-      L7NoSink ns;
-      ok = dec_app_proto_log(base, len, r, ns);
-      if (!ok && !p.repair) {
-        atomicMin(&p.frame_bad[frame], rec);
-        dyn->stats.need_repair = 1;
-      }
-    }
-  }
-  // AppProtoLogsData.IsValid() (datatype/pb/flow_log.go:82-89) cannot fail: Base and
-  // Base.Head are pre-allocated.
-  L7Row w;
-  l7_derive(dv, r, w);
-
-  uint32_t sz[L7S_COUNT];
-  sz[L7S_ROWS] = ok ? 1u : 0u;
-#pragma unroll
-  for (int i = 0; i < 22; i++) sz[L7S_STR0 + i] = ok ? w.str[i].n : 0u;
-  sz[L7S_AN_ELEMS] = ok ? w.n_pseudo + r.n_attr_names : 0u;
-  sz[L7S_AN_BYTES] = ok ? w.pseudo_name_bytes + r.b_attr_names : 0u;
-  sz[L7S_AV_ELEMS] = ok ? w.n_pseudo + r.n_attr_values : 0u;
-  sz[L7S_AV_BYTES] = ok ? w.pseudo_value_bytes + r.b_attr_values : 0u;
-  sz[L7S_MN_ELEMS] = ok ? r.n_metrics_names : 0u;
-  sz[L7S_MN_BYTES] = ok ? r.b_metrics_names : 0u;
-  sz[L7S_MV_ELEMS] = ok ? r.n_metrics_values : 0u;
-  const uint32_t tside = ok ? tapside_code(r.tap_side) : 0;
-  const bool has_trace = ok && w.trace_nonempty;
-  const uint32_t trace_mask = __ballot_sync(0xffffffffu, has_trace);
-
-  if (!EMIT) {
-#pragma unroll
-    for (int s = 0; s < L7S_COUNT; s++) {
-      uint32_t t = warp_sum(sz[s]);
-      if (lane == 0 && warp < p.nwarps) p.warp_tot[(size_t)s * p.nwarps + warp] = t;
-    }
-    // last record of the warp carrying a trace id: feeds the lastTraceIdIndex carry
-    int last = trace_mask ? 31 - __clz(trace_mask) : 0;
-    uint64_t h = __shfl_sync(0xffffffffu, w.trace_hash, last);
-    if (lane == 0 && warp < p.nwarps) {
-      p.warp_tot[(size_t)L7S_TRACE_HAS * p.nwarps + warp] = trace_mask ? 1 : 0;
-      p.warp_tot[(size_t)L7S_TRACE_LO * p.nwarps + warp] = (uint32_t)h;
-      p.warp_tot[(size_t)L7S_TRACE_HI * p.nwarps + warp] = (uint32_t)(h >> 32);
-    }
-    lc_note(dyn->stats.lc_first[LC7_TAPSIDE], tside, rec, ok);
-    return;
-  }
-
-  // ---- EMIT ---------------------------------------------------------------------------
-  uint32_t ex[L7S_COUNT];
-#pragma unroll
-  for (int s = 0; s < L7S_COUNT; s++) ex[s] = warp_excl_scan(sz[s]);
-  // trace_id_index (ParseTraceIdIndex :296-310): hash, or previous valid hash + 1
-  uint64_t trace_index = 0;
-  {
-    const uint32_t wb0 = warp < p.nwarps ? warp : 0;
-    uint64_t carry = (uint64_t)p.warp_base[(size_t)L7S_TRACE_HI * p.nwarps + wb0] << 32 |
-                     p.warp_base[(size_t)L7S_TRACE_LO * p.nwarps + wb0];
-    uint32_t before = trace_mask & ((1u << lane) - 1);
-    int src = before ? 31 - __clz(before) : 0;
-    uint64_t prev = __shfl_sync(0xffffffffu, w.trace_hash, src);
-    if (!before) prev = carry;
-    trace_index = p.cfg_trace_disabled ? 0 : (w.trace_nonempty ? w.trace_hash : prev + 1);
-  }
-  // updateCounter decoder.go:498-525 (one atomic per class per warp)
-  {
-    int cls = -1;
-    if (ok) {
-      switch (w.l7_protocol) {
-        case 20: case 21: cls = 0; break;
-        case 120: cls = 1; break;
-        case 60: case 61: cls = 2; break;
-        case 80: cls = 3; break;
-        case 40: cls = 4; break;
-        case 101: cls = 5; break;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      uint32_t m = __ballot_sync(0xffffffffu, cls == c);
-      if (lane == 0 && m) atomicAdd(&dyn->stats.l7_counts[c], __popc(m));
-    }
-  }
-  if (!ok) return;
-  const uint32_t wb = warp < p.nwarps ? warp : 0;
-#define WBASE(s) ((uint64_t)p.warp_base[(size_t)(s) * p.nwarps + wb] + ex[s])
-  const uint32_t row = (uint32_t)WBASE(L7S_ROWS);
-  const dfgpu_frame fr = p.frames[frame];
-  const bool v6 = r.is_ipv6 == 1;
-  const uint32_t time_s = (uint32_t)(r.end_time / 1000000000ull);
-
-  // ---- KnowledgeGraph.FillL7 :599-613 ---------------------------------------------------
-  KG k;
-  {
-    KGInput in;
-    in.v6 = v6;
-    in.vip[0] = r.is_vip_interface_src == 1;
-    in.vip[1] = r.is_vip_interface_dst == 1;
-    in.l3_epc[0] = r.l3_epc_id_src;
-    in.l3_epc[1] = r.l3_epc_id_dst;
-    in.ip[0].ip4 = r.ip_src;
-    in.ip[1].ip4 = r.ip_dst;
-    in.ip[0].ip6len = r.ip6_src.n;
-    in.ip[1].ip6len = r.ip6_dst.n;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      in.ip[0].ip6[i] = (uint32_t)i < r.ip6_src.n ? ldb(r.ip6_src.p + i) : 0;
-      in.ip[1].ip6[i] = (uint32_t)i < r.ip6_dst.n ? ldb(r.ip6_dst.p + i) : 0;
-    }
-    in.mac[0] = r.mac_src;
-    in.mac[1] = r.mac_dst;
-    in.gpid[0] = r.gpid_0;
-    in.gpid[1] = r.gpid_1;
-    in.pod_id[0] = r.pod_id_0;
-    in.pod_id[1] = r.pod_id_1;
-    in.vtap_id = (uint16_t)r.vtap_id;
-    in.port = (uint16_t)r.port_dst;
-    in.tap_side = r.tap_side;
-    in.protocol = (uint8_t)r.protocol;
-    kg_fill(p.dict, in, k);
-  }
-  uint32_t gpid0 = r.gpid_0, gpid1 = r.gpid_1;
-  if (r.process_id_0 != 0 && r.gpid_0 == 0) {  // :589-592
-    gpid0 = t64_getz(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)r.vtap_id << 32 | (uint64_t)r.process_id_0);
-    k.tag_source[0] |= TS_PROCESSID;
-  }
-  if (r.process_id_1 != 0 && r.gpid_1 == 0) {
-    gpid1 = t64_getz(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)r.vtap_id << 32 | (uint64_t)r.process_id_1);
-    k.tag_source[1] |= TS_PROCESSID;
-  }
-  st<uint16_t>(p, L7C_REGION_ID_0, row, k.region_id[0]);
-  st<uint16_t>(p, L7C_REGION_ID_1, row, k.region_id[1]);
-  st<uint16_t>(p, L7C_AZ_ID_0, row, k.az_id[0]);
-  st<uint16_t>(p, L7C_AZ_ID_1, row, k.az_id[1]);
-  st<uint16_t>(p, L7C_HOST_ID_0, row, k.host_id[0]);
-  st<uint16_t>(p, L7C_HOST_ID_1, row, k.host_id[1]);
-  st<uint8_t>(p, L7C_L3_DEVICE_TYPE_0, row, k.l3_device_type[0]);
-  st<uint8_t>(p, L7C_L3_DEVICE_TYPE_1, row, k.l3_device_type[1]);
-  st<uint32_t>(p, L7C_L3_DEVICE_ID_0, row, k.l3_device_id[0]);
-  st<uint32_t>(p, L7C_L3_DEVICE_ID_1, row, k.l3_device_id[1]);
-  st<uint32_t>(p, L7C_POD_NODE_ID_0, row, k.pod_node_id[0]);
-  st<uint32_t>(p, L7C_POD_NODE_ID_1, row, k.pod_node_id[1]);
-  st<uint16_t>(p, L7C_POD_NS_ID_0, row, k.pod_ns_id[0]);
-  st<uint16_t>(p, L7C_POD_NS_ID_1, row, k.pod_ns_id[1]);
-  st<uint32_t>(p, L7C_POD_GROUP_ID_0, row, k.pod_group_id[0]);
-  st<uint32_t>(p, L7C_POD_GROUP_ID_1, row, k.pod_group_id[1]);
-  st<uint32_t>(p, L7C_POD_ID_0, row, k.pod_id[0]);
-  st<uint32_t>(p, L7C_POD_ID_1, row, k.pod_id[1]);
-  st<uint16_t>(p, L7C_POD_CLUSTER_ID_0, row, k.pod_cluster_id[0]);
-  st<uint16_t>(p, L7C_POD_CLUSTER_ID_1, row, k.pod_cluster_id[1]);
-  st<int32_t>(p, L7C_L3_EPC_ID_0, row, k.l3_epc_id[0]);
-  st<int32_t>(p, L7C_L3_EPC_ID_1, row, k.l3_epc_id[1]);
-  st<int32_t>(p, L7C_EPC_ID_0, row, k.epc_id[0]);
-  st<int32_t>(p, L7C_EPC_ID_1, row, k.epc_id[1]);
-  st<uint16_t>(p, L7C_SUBNET_ID_0, row, k.subnet_id[0]);
-  st<uint16_t>(p, L7C_SUBNET_ID_1, row, k.subnet_id[1]);
-  st<uint32_t>(p, L7C_SERVICE_ID_0, row, k.service_id[0]);
-  st<uint32_t>(p, L7C_SERVICE_ID_1, row, k.service_id[1]);
-  st<uint32_t>(p, L7C_AUTO_INSTANCE_ID_0, row, k.auto_instance_id[0]);
-  st<uint8_t>(p, L7C_AUTO_INSTANCE_TYPE_0, row, k.auto_instance_type[0]);
-  st<uint32_t>(p, L7C_AUTO_SERVICE_ID_0, row, k.auto_service_id[0]);
-  st<uint8_t>(p, L7C_AUTO_SERVICE_TYPE_0, row, k.auto_service_type[0]);
-  st<uint32_t>(p, L7C_AUTO_INSTANCE_ID_1, row, k.auto_instance_id[1]);
-  st<uint8_t>(p, L7C_AUTO_INSTANCE_TYPE_1, row, k.auto_instance_type[1]);
-  st<uint32_t>(p, L7C_AUTO_SERVICE_ID_1, row, k.auto_service_id[1]);
-  st<uint8_t>(p, L7C_AUTO_SERVICE_TYPE_1, row, k.auto_service_type[1]);
-  st<uint8_t>(p, L7C_TAG_SOURCE_0, row, k.tag_source[0]);
-  st<uint8_t>(p, L7C_TAG_SOURCE_1, row, k.tag_source[1]);
-  st<uint16_t>(p, L7C_TEAM_ID, row, (uint16_t)fr.team_id);
-
-  // ---- L7Base.Fill :514-582 ---------------------------------------------------------------
-  st<uint32_t>(p, L7C_TIME, row, time_s);
-  st<uint32_t>(p, L7C_IP4_0, row, v6 ? 0u : r.ip_src);
-  st<uint32_t>(p, L7C_IP4_1, row, v6 ? 0u : r.ip_dst);
-  st_ip6(p, L7C_IP6_0, row, v6 ? r.ip6_src : SRef{nullptr, 0});
-  st_ip6(p, L7C_IP6_1, row, v6 ? r.ip6_dst : SRef{nullptr, 0});
-  st<uint8_t>(p, L7C_IS_IPV4, row, v6 ? 0 : 1);
-  st<uint8_t>(p, L7C_PROTOCOL, row, (uint8_t)r.protocol);
-  st<uint16_t>(p, L7C_CLIENT_PORT, row, (uint16_t)r.port_src);
-  st<uint16_t>(p, L7C_SERVER_PORT, row, (uint16_t)r.port_dst);
-  st<uint64_t>(p, L7C_FLOW_ID, row, r.flow_id);
-  st<uint8_t>(p, L7C_CAPTURE_NETWORK_TYPE_ID, row, (uint8_t)r.tap_type);
-  const uint8_t tap_port_type = (uint8_t)(r.tap_port >> 60);
-  st<uint8_t>(p, L7C_NAT_SOURCE, row, (uint8_t)((r.tap_port >> 36) & 0xf));
-  st<uint8_t>(p, L7C_CAPTURE_NIC_TYPE, row, tap_port_type);
-  st<uint16_t>(p, L7C_SIGNAL_SOURCE, row, tap_port_type == 8 ? 4 : tap_port_type == 7 ? 3 : 0);
-  st<uint8_t>(p, L7C_TUNNEL_TYPE, row, (uint8_t)((r.tap_port >> 32) & 0xf));
-  st<uint32_t>(p, L7C_CAPTURE_NIC, row, (uint32_t)r.tap_port);
-  st<uint8_t>(p, L7C_OBSERVATION_POINT, row, dyn->lc_rank[LC7_TAPSIDE][tside]);
-  st<uint16_t>(p, L7C_AGENT_ID, row, (uint16_t)r.vtap_id);
-  st<uint32_t>(p, L7C_REQ_TCP_SEQ, row, r.req_tcp_seq);
-  st<uint32_t>(p, L7C_RESP_TCP_SEQ, row, r.resp_tcp_seq);
-  st<int64_t>(p, L7C_START_TIME, row, (int64_t)r.start_time / 1000);
-  st<int64_t>(p, L7C_END_TIME, row, (int64_t)r.end_time / 1000);
-  st<uint32_t>(p, L7C_GPROCESS_ID_0, row, gpid0);
-  st<uint32_t>(p, L7C_GPROCESS_ID_1, row, gpid1);
-  st<uint8_t>(p, L7C_BIZ_TYPE, row, (uint8_t)r.biz_type);
-  st<int32_t>(p, L7C_PROCESS_ID_0, row, (int32_t)r.process_id_0);
-  st<int32_t>(p, L7C_PROCESS_ID_1, row, (int32_t)r.process_id_1);
-  st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_REQUEST, row, r.syscall_trace_id_request);
-  st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_RESPONSE, row, r.syscall_trace_id_response);
-  st<uint32_t>(p, L7C_SYSCALL_THREAD_0, row, r.syscall_trace_id_thread_0);
-  st<uint32_t>(p, L7C_SYSCALL_THREAD_1, row, r.syscall_trace_id_thread_1);
-  st<uint64_t>(p, L7C_SYSCALL_COROUTINE_0, row, r.syscall_coroutine_0);
-  st<uint64_t>(p, L7C_SYSCALL_COROUTINE_1, row, r.syscall_coroutine_1);
-  st<uint32_t>(p, L7C_SYSCALL_CAP_SEQ_0, row, r.syscall_cap_seq_0);
-  st<uint32_t>(p, L7C_SYSCALL_CAP_SEQ_1, row, r.syscall_cap_seq_1);
-  // ---- L7FlowLog block ----------------------------------------------------------------------
-  {
-    uint32_t count = p.persist->id_counter + row + 1;  // genID l4_flow_log.go:949-953
-    st<uint64_t>(p, L7C__ID, row,
-                 (uint64_t)time_s << 32 | (uint64_t)(p.dict.analyzer_id & 0x3ff) << 22 | ((uint64_t)count & 0x3fffff));
-  }
-  st<uint8_t>(p, L7C_L7_PROTOCOL, row, w.l7_protocol);
-  st<uint8_t>(p, L7C_TYPE, row, w.type);
-  st<uint8_t>(p, L7C_IS_TLS, row, w.is_tls);
-  st<uint8_t>(p, L7C_IS_ASYNC, row, w.is_async);
-  st<uint8_t>(p, L7C_IS_REVERSED, row, w.is_reversed);
-  st_nullable<uint64_t>(p, L7C_REQUEST_ID, row, w.has_request_id, w.request_id);
-  st<uint8_t>(p, L7C_RESPONSE_STATUS, row, w.response_status);
-  st_nullable<int32_t>(p, L7C_RESPONSE_CODE, row, w.has_response_code, w.response_code);
-  st<uint64_t>(p, L7C_TRACE_ID_INDEX, row, trace_index);
-  st_nullable<uint8_t>(p, L7C_SPAN_KIND, row, false, 0);
-  st<uint64_t>(p, L7C_RESPONSE_DURATION, row, r.head_rrt / 1000);
-  st_nullable<int64_t>(p, L7C_REQUEST_LENGTH, row, w.has_request_length, w.request_length);
-  st_nullable<int64_t>(p, L7C_RESPONSE_LENGTH, row, w.has_response_length, w.response_length);
-  st_nullable<uint64_t>(p, L7C_SQL_AFFECTED_ROWS, row, w.has_sql_rows, w.sql_rows);
-  st<uint8_t>(p, L7C_DIRECTION_SCORE, row, (uint8_t)r.direction_score);
-  st<uint32_t>(p, L7C_CAPTURED_REQUEST_BYTE, row, r.captured_request_byte);
-  st<uint32_t>(p, L7C_CAPTURED_RESPONSE_BYTE, row, r.captured_response_byte);
-
-  // ---- the 22 per-row string columns: Pos + bytes -------------------------------------------
-  {
-    const int cols[22] = {L7C_BIZ_CODE, L7C_BIZ_SCENARIO, L7C_BIZ_RESPONSE_CODE, L7C_PROCESS_KNAME_0,
-                          L7C_PROCESS_KNAME_1, L7C_BIZ_PROTOCOL, L7C_VERSION, L7C_REQUEST_TYPE,
-                          L7C_REQUEST_DOMAIN, L7C_REQUEST_RESOURCE, L7C_ENDPOINT, L7C_RESPONSE_EXCEPTION,
-                          L7C_RESPONSE_RESULT, L7C_HTTP_PROXY_CLIENT, L7C_X_REQUEST_ID_0, L7C_X_REQUEST_ID_1,
-                          L7C_TRACE_ID, L7C_TRACE_ID_2, L7C_SPAN_ID, L7C_PARENT_SPAN_ID, L7C_APP_SERVICE,
-                          L7C_APP_INSTANCE};
-#pragma unroll
-    for (int i = 0; i < 22; i++) {
-      uint64_t off = WBASE(L7S_STR0 + i);
-      uint32_t n = w.str[i].n;
-      reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[cols[i]])[row] = dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
-      if (n) copy_bytes(p.arena + dyn->var_buf_off[i] + off, w.str[i].p, n);
-    }
-    // events: always empty on this path (only the OTel import fills it)
-    reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[L7C_EVENTS])[row] = dfgpu_pos{0, 0};
-  }
-  // ---- arrays: cumulative END offsets per row, then the elements ---------------------------
-  const uint64_t an_e = WBASE(L7S_AN_ELEMS), an_b = WBASE(L7S_AN_BYTES);
-  const uint64_t av_e = WBASE(L7S_AV_ELEMS), av_b = WBASE(L7S_AV_BYTES);
-  const uint64_t mn_e = WBASE(L7S_MN_ELEMS), mn_b = WBASE(L7S_MN_BYTES);
-  const uint64_t mv_e = WBASE(L7S_MV_ELEMS);
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_NAMES])[row] = an_e + sz[L7S_AN_ELEMS];
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_VALUES])[row] = av_e + sz[L7S_AV_ELEMS];
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_NAMES])[row] = mn_e + sz[L7S_MN_ELEMS];
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_VALUES])[row] = mv_e + sz[L7S_MV_ELEMS];
-  if (sz[L7S_AN_ELEMS] | sz[L7S_AV_ELEMS] | sz[L7S_MN_ELEMS] | sz[L7S_MV_ELEMS]) {
-    L7EmitSink sink;
-    sink.an_pos = reinterpret_cast<dfgpu_pos*>(p.arena + dyn->var_pos_off[L7V_ATTR_NAMES]) + an_e;
-    sink.an_buf = p.arena + dyn->var_buf_off[L7V_ATTR_NAMES];
-    sink.an_off = an_b;
-    sink.av_pos = reinterpret_cast<dfgpu_pos*>(p.arena + dyn->var_pos_off[L7V_ATTR_VALUES]) + av_e;
-    sink.av_buf = p.arena + dyn->var_buf_off[L7V_ATTR_VALUES];
-    sink.av_off = av_b;
-    sink.mn_pos = reinterpret_cast<dfgpu_pos*>(p.arena + dyn->var_pos_off[L7V_METRICS_NAMES]) + mn_e;
-    sink.mn_buf = p.arena + dyn->var_buf_off[L7V_METRICS_NAMES];
-    sink.mn_off = mn_b;
-    sink.mv = reinterpret_cast<uint64_t*>(p.arena + dyn->var_buf_off[L7V_METRICS_VALUES]) + mv_e;
-    // pseudo attributes first, in the reference's order (:418-429)
-    if (r.has_ext) {
-      if (r.http_user_agent.n) {
-        SRef nm = cs_ref(dv, CS_ATTR_UA);
-        sink.attr_name(nm.p, nm.n);
-        sink.attr_value(r.http_user_agent.p, r.http_user_agent.n);
-      }
-      if (r.http_referer.n) {
-        SRef nm = cs_ref(dv, CS_ATTR_REFERER);
-        sink.attr_name(nm.p, nm.n);
-        sink.attr_value(r.http_referer.p, r.http_referer.n);
-      }
-      if (r.rpc_service.n) {
-        SRef nm = cs_ref(dv, CS_ATTR_RPC);
-        sink.attr_name(nm.p, nm.n);
-        sink.attr_value(r.rpc_service.p, r.rpc_service.n);
-      }
-    }
-    if (r.n_attr_names | r.n_attr_values | r.n_metrics_names | r.n_metrics_values) {
-      L7Rec scratch;
-      memset(&scratch, 0, sizeof scratch);
-      dec_app_proto_log(base, len, scratch, sink);  // second walk streams the repeated fields
-    }
-  }
-#undef WBASE
-}
-
-// "last valid" carry of lastTraceIdIndex across warps (single CTA)
-__global__ void k_l7_trace_scan(const BatchParams p) {
-  __shared__ int sh[1024];
-  __shared__ unsigned long long carry;
-  const uint32_t* has = p.warp_tot + (size_t)L7S_TRACE_HAS * p.nwarps;
-  const uint32_t* lo = p.warp_tot + (size_t)L7S_TRACE_LO * p.nwarps;
-  const uint32_t* hi = p.warp_tot + (size_t)L7S_TRACE_HI * p.nwarps;
-  uint32_t* olo = p.warp_base + (size_t)L7S_TRACE_LO * p.nwarps;
-  uint32_t* ohi = p.warp_base + (size_t)L7S_TRACE_HI * p.nwarps;
-  if (threadIdx.x == 0) carry = p.persist->last_trace_id_index;
-  __syncthreads();
-  for (uint32_t base = 0; base < p.nwarps; base += blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    int v = (i < p.nwarps && has[i]) ? (int)threadIdx.x : -1;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
-      int t = threadIdx.x >= d ? sh[threadIdx.x - d] : -1;
-      __syncthreads();
-      if (t > sh[threadIdx.x]) sh[threadIdx.x] = t;
-      __syncthreads();
-    }
-    // exclusive: the carry INTO warp i is the last valid among warps < i
-    int prev = threadIdx.x > 0 ? sh[threadIdx.x - 1] : -1;
-    unsigned long long c = carry;
-    if (prev >= 0) c = (unsigned long long)hi[base + prev] << 32 | lo[base + prev];
-    if (i < p.nwarps) {
-      olo[i] = (uint32_t)c;
-      ohi[i] = (uint32_t)(c >> 32);
-    }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) {
-      int last = sh[threadIdx.x];
-      if (last >= 0) carry = (unsigned long long)hi[base + last] << 32 | lo[base + last];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) p.dyn->stats.last_trace_id_index = carry;
-}
-
-void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s) {
-  if (!emit) {
-    if (p.nrec) k_l7_pass<0><<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
-    k_l7_trace_scan<<<1, 1024, 0, s>>>(p);
-  } else if (p.nrec) {
-    k_l7_pass<1><<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
-  }
-}
 
 void l7_streams(BatchParams& bp) {
   bp.nslots = L7S_COUNT;
@@ -1085,6 +500,10 @@ static int l7_ensure_state(dfgpu_ctx* ctx) {
   cs[CS_KAFKA_UNKNOWN] = DFGPU_EXC_KAFKA_UNKNOWN_SERVER_ERROR;
   L7Dev& d = h->dev;
   memset(&d, 0, sizeof d);
+  {
+    std::vector<uint32_t> t = l7_pb_table();
+    memcpy(d.pb_tbl, t.data(), sizeof d.pb_tbl);
+  }
   for (int i = 0; i < 256; i++) d.proto_cs[i][0] = d.proto_cs[i][1] = CS_PROTO_NA;
   struct PN { int id; const char* name; };
   static const PN protos[] = {  // L7Protocol.String, datatype/flow.go:623-803

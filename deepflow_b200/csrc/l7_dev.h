@@ -1,0 +1,53 @@
+/*
+ * l7_dev.h — device-side state shared by the L7 pass kernels (l7_pass.cu) and the
+ * flow_tag stage (l7.cu).
+ */
+#pragma once
+#include "ctx.h"
+#include "l7_decode.cuh"
+#include "l7_slots.h"
+#include "schema_l7.h"
+
+#include "../../include/dfgpu_exception_tables.h"
+
+namespace dfgpu {
+
+// ---- constant strings the path can emit (protocol names, pseudo attribute names,
+// exception descriptions): one device blob, addressed by id -------------------------
+enum : uint32_t {
+  CS_EMPTY = 0, CS_ATTR_UA, CS_ATTR_REFERER, CS_ATTR_RPC, CS_FT_APP_SERVICE, CS_FT_ENDPOINT,
+  CS_FT_APP_INSTANCE, CS_PROTO_NA, CS_PROTO_TLS, CS_DNS_AVAILABLE, CS_DNS_PRIVATE, CS_KAFKA_UNKNOWN,
+  CS_FIXED_COUNT
+};
+
+struct FtEntry {  // one slot of the device tag set (32 B = one HBM sector)
+  unsigned long long fp_lo, fp_hi;  // 128-bit fingerprint of the lru key; 0/0 = empty
+  unsigned long long first_pos;     // (epoch << 48) | (2^48-1 - position): atomicMax keeps the FIRST
+                                    // candidate of the NEWEST batch; 0 = none
+  uint32_t time;                    // value stored by lru Add(): time of the last emission
+  uint32_t state;                   // 0 = inserted but never emitted, 1 = emitted
+};
+static_assert(sizeof(FtEntry) == 32, "FtEntry");
+
+struct L7Dev {
+  const uint8_t* cs_blob;
+  const uint32_t* cs_off;  // [n+1]
+  uint32_t cs_http, cs_dns, cs_dubbo, cs_kafka, cs_mqtt3, cs_mqtt5;  // base ids of the tables
+  uint16_t proto_cs[256][2];  // L7Protocol.String(isTLS) -> cs id
+  uint32_t pb_tbl[M7_COUNT * L7_MAXF];  // pb_interp table (l7_slots.h)
+  FtEntry* ft;
+  uint32_t ft_mask;
+  uint32_t ft_timeout;
+  uint32_t epoch;
+  uint16_t org_id;
+  uint8_t* ft_arena;
+  uint64_t ft_arena_bytes;
+};
+
+
+__device__ __forceinline__ SRef cs_ref(const L7Dev* d, uint32_t id) {
+  uint32_t a = d->cs_off[id], b = d->cs_off[id + 1];
+  return SRef{d->cs_blob + a, b - a};
+}
+
+}  // namespace dfgpu
