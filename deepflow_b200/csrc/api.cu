@@ -86,6 +86,7 @@ int dfgpu_close(dfgpu_ctx* ctx) {
   cudaFree(ctx->d_frames);
   cudaFree(ctx->d_frame_u32);
   cudaFree(ctx->d_rec_u32);
+  cudaFree(ctx->d_rec_scratch);
   cudaFree(ctx->d_warp);
   cudaFree(ctx->d_dyn);
   cudaFree(ctx->d_persist);
@@ -403,6 +404,8 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
   bp.geo.code = ctx->d_geo_code;
   bp.geo.n = ctx->geo_n;
   bp.cfg_trace_disabled = ctx->cfg.trace_id_index_disabled;
+  if (ensure_dev(ctx, ctx->d_rec_scratch, ctx->rec_scratch_cap, ctx->cur_nbytes / 4 + 2)) return DFGPU_ENODEV;
+  bp.rec_scratch = ctx->d_rec_scratch;
   if (nf) {
     CU(cudaMemsetAsync(bp.frame_bad, 0xff, (size_t)nf * 4, s));
     launch_frame_count(bp, s);

@@ -34,6 +34,8 @@ struct dfgpu_ctx {
   dfgpu_frame* d_frames = nullptr;
   uint32_t* d_frame_u32 = nullptr;  // nrec | base | chain_err | bad
   uint32_t frames_cap = 0;
+  uint32_t* d_rec_scratch = nullptr;  // framing scratch, cur_nbytes/4 + 2 entries
+  size_t rec_scratch_cap = 0;
   uint32_t* d_rec_u32 = nullptr;  // off | len | frame
   uint32_t rec_cap = 0;
   uint32_t* d_warp = nullptr;  // tot[MAX_SLOTS][nwarps] | base[MAX_SLOTS][nwarps]

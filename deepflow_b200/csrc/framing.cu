@@ -13,33 +13,53 @@ extern const char* const kTapSideNames[18] = {"", "rest", "c", "s", "local", "c-
                                               "s-gw-hv", "c-gw", "s-gw", "c-p", "s-p", "c-app", "s-app", "app"};
 
 // ---- framing ----------------------------------------------------------------------
-// One thread walks one frame's {u32 LE len, pb}* chain.  pass 0 counts, pass 1 fills.
-template <int FILL>
+// One thread walks one frame's {u32 LE len, pb}* chain (the chain is inherently serial:
+// each length says where the next one is).  The walk counts the records and drops each
+// record's payload offset into a scratch slot derived from the frame's own byte range
+// (a frame of `len` bytes holds at most len/4 records), so the per-record arrays can
+// be filled afterwards by a fully parallel kernel instead of a second serial walk.
+// The dependent loads are ~DRAM-latency bound; an L2 prefetch a few records ahead
+// (records are a few hundred bytes) turns most of them into L2 hits.
 __global__ void k_frame_walk(const BatchParams p) {
   uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= p.nframes) return;
   const dfgpu_frame fr = p.frames[f];
   const uint8_t* buf = p.in + fr.offset;
+  uint32_t* scratch = p.rec_scratch + (fr.offset >> 2);
   uint32_t len = fr.len, off = 0, n = 0, err = 0;
-  uint32_t base = FILL ? p.frame_base[f] : 0;
   while (off < len) {  // !IsEnd()
     if (len - off < 4) { err = 1; break; }  // offset(+4) out of buf len
+    if (len - off > 2048) asm volatile("prefetch.global.L2 [%0];" ::"l"(buf + off + 1536));
     uint32_t l = (uint32_t)__ldg(buf + off) | (uint32_t)__ldg(buf + off + 1) << 8 |
                  (uint32_t)__ldg(buf + off + 2) << 16 | (uint32_t)__ldg(buf + off + 3) << 24;
     off += 4;
     if (l > len - off) { err = 1; break; }
-    if (FILL) {
-      p.rec_off[base + n] = (uint32_t)(fr.offset + off);
-      p.rec_len[base + n] = l;
-      p.rec_frame[base + n] = f;
-    }
+    scratch[n] = (uint32_t)(fr.offset + off);
     off += l;
     n++;
   }
-  if (!FILL) {
-    p.frame_nrec[f] = n;
-    p.frame_chain_err[f] = err;
+  p.frame_nrec[f] = n;
+  p.frame_chain_err[f] = err;
+}
+
+// thread per record: locate its frame (binary search over the exclusive scan) and
+// publish (offset, length, frame)
+__global__ void k_frame_fill(const BatchParams p) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.nrec) return;
+  uint32_t lo = 0, hi = p.nframes;  // last frame with frame_base <= r
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(p.frame_base + mid) <= r) lo = mid; else hi = mid;
   }
+  // frames without records share a base with their successor: step to the owner
+  while (lo + 1 < p.nframes && __ldg(p.frame_base + lo + 1) <= r) lo++;
+  const uint32_t j = r - __ldg(p.frame_base + lo);
+  const uint32_t off = p.rec_scratch[(p.frames[lo].offset >> 2) + j];
+  const uint8_t* q = p.in + off - 4;
+  p.rec_off[r] = off;
+  p.rec_len[r] = (uint32_t)__ldg(q) | (uint32_t)__ldg(q + 1) << 8 | (uint32_t)__ldg(q + 2) << 16 | (uint32_t)__ldg(q + 3) << 24;
+  p.rec_frame[r] = lo;
 }
 
 // exclusive scan of frame_nrec (single CTA, any nframes)
@@ -143,12 +163,12 @@ __global__ void k_commit(const BatchParams p, int is_l7) {
 
 void launch_frame_count(const BatchParams& p, cudaStream_t s) {
   if (!p.nframes) return;
-  k_frame_walk<0><<<(p.nframes + 127) / 128, 128, 0, s>>>(p);
+  k_frame_walk<<<(p.nframes + 31) / 32, 32, 0, s>>>(p);
   k_frame_scan<<<1, 1024, 0, s>>>(p);
 }
 void launch_frame_fill(const BatchParams& p, cudaStream_t s) {
   if (!p.nframes || !p.nrec) return;
-  k_frame_walk<1><<<(p.nframes + 127) / 128, 128, 0, s>>>(p);
+  k_frame_fill<<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
 }
 void launch_slot_scan(const BatchParams& p, cudaStream_t s) {
   if (!p.nrec) return;

@@ -28,6 +28,8 @@ struct L7Host {  // host mirror kept in ctx->ft
   FtEntry* d_ft = nullptr;
   uint8_t* d_ft_arena = nullptr;
   size_t ft_arena_cap = 0;
+  uint8_t* d_row_flag = nullptr;
+  size_t row_flag_cap = 0;
   uint32_t epoch = 0;
 };
 
@@ -255,7 +257,11 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
   if (PHASE == 3 && dyn->stats.ft_overflow) return;
   const uint32_t nrows = dyn->stats.nrows;
   const uint32_t nwarps = p.nwarps;
-  const bool active = row < nrows;
+  // PHASE 0 notes per row whether ANY of its keys is new/expired; in steady state (a
+  // saturated tag set) almost no row is, and phases 1-3 skip the row without hashing
+  bool active = row < nrows;
+  if (PHASE != 0 && active) active = d->row_flag[row] != 0;
+  bool any_candidate = false;
   uint32_t c_fv = 0, b_fvn = 0, b_fvv = 0, c_f = 0, b_fn = 0, c_as = 0, b_as = 0;
 
   // PHASE 3 output cursors
@@ -298,7 +304,10 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
         unsigned long long pk = pos_key(d, row, side, 0, i);
         if (PHASE == 0) {
           FtEntry* e = ft_upsert(d, fpv, &dyn->stats.ft_full);
-          if (e && ft_candidate(e, v.time, timeout)) atomicMax(&e->first_pos, pk);
+          if (e && ft_candidate(e, v.time, timeout)) {
+            atomicMax(&e->first_pos, pk);
+            any_candidate = true;
+          }
           continue;
         }
         FtEntry* e = ft_find(d, fpv);
@@ -368,12 +377,15 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
         SRef name{v.mn_buf + q.start, (uint32_t)(q.end - q.start)};
         U128 fpf = key_fp(d, KIND_FIELD, name, SRef{nullptr, 0}, v.vpc[side], v.pod_ns[side], 1, v.team);
         unsigned long long pk = pos_key(d, row, side, 1, i);
-        if (PHASE == 0) continue;
-        if (PHASE == 1) {
+        if (PHASE == 0) {  // independent of the value keys: probe right away
           FtEntry* ef = ft_upsert(d, fpf, &dyn->stats.ft_full);
-          if (ef && ft_candidate(ef, v.time, timeout)) atomicMax(&ef->first_pos, pk);
+          if (ef && ft_candidate(ef, v.time, timeout)) {
+            atomicMax(&ef->first_pos, pk);
+            any_candidate = true;
+          }
           continue;
         }
+        if (PHASE == 1) continue;
         FtEntry* ef = ft_find(d, fpf);
         if (!ef || ef->first_pos != pk) continue;
         if (PHASE == 2) {
@@ -409,7 +421,10 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
       unsigned long long pk = pos_key(d, row, 0, 0, 0);
       if (PHASE == 0) {
         FtEntry* e = ft_upsert(d, fpa, &dyn->stats.ft_full);
-        if (e && ft_candidate(e, v.time_as, timeout)) atomicMax(&e->first_pos, pk);
+        if (e && ft_candidate(e, v.time_as, timeout)) {
+          atomicMax(&e->first_pos, pk);
+          any_candidate = true;
+        }
       } else {
         FtEntry* e = ft_find(d, fpa);
         if (e && e->first_pos == pk) {
@@ -436,6 +451,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
       }
     }
   }
+  if (PHASE == 0 && row < nrows) d->row_flag[row] = any_candidate ? 1 : 0;
   if (PHASE == 1 || PHASE == 2) {
     // per-warp totals of the rows/bytes decided in this phase
     uint32_t vals[FT_SLOTS] = {c_fv, b_fvn, b_fvv, c_f, b_fn, c_as, b_as};
@@ -572,6 +588,14 @@ int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s) {
     k_l7_ft_clear_pos<<<1024, 256, 0, s>>>(h->d_ft, h->dev.ft_mask);
     h->epoch = 1;
   }
+  if (ctx->bp.nrec > h->row_flag_cap) {
+    if (h->d_row_flag) CU(cudaFree(h->d_row_flag));
+    h->d_row_flag = nullptr;
+    size_t cap = (size_t)ctx->bp.nrec + ctx->bp.nrec / 4 + 4096;
+    CU(cudaMalloc(&h->d_row_flag, cap));
+    h->row_flag_cap = cap;
+  }
+  h->dev.row_flag = h->d_row_flag;
   h->dev.epoch = h->epoch;
   h->dev.org_id = ctx->cur_org;
   h->dev.ft_arena = h->d_ft_arena;
@@ -754,6 +778,7 @@ extern "C" void dfgpu_l7_free_state(dfgpu_ctx* ctx) {
   cudaFree(h->d_off);
   cudaFree(h->d_ft);
   cudaFree(h->d_ft_arena);
+  cudaFree(h->d_row_flag);
   cudaFree(h->d_dev);
   delete h;
   ctx->ft = nullptr;

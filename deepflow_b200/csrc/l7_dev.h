@@ -42,6 +42,7 @@ struct L7Dev {
   uint16_t org_id;
   uint8_t* ft_arena;
   uint64_t ft_arena_bytes;
+  uint8_t* row_flag;  // [nrows] set by flow_tag phase 0: the row has a new/expired key
 };
 
 

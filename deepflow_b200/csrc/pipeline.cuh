@@ -60,6 +60,7 @@ struct BatchParams {
   uint32_t* rec_off;
   uint32_t* rec_len;
   uint32_t* rec_frame;
+  uint32_t* rec_scratch;  // [nbytes/4 + 1] payload offsets, indexed by frame byte range
   uint32_t* warp_tot;   // [slot][nwarps]
   uint32_t* warp_base;  // [slot][nwarps]
   DynState* dyn;
