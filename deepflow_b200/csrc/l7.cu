@@ -87,35 +87,37 @@ __device__ __forceinline__ U128 cas128(FtEntry* e, U128 cmp, U128 val) {
   return old;
 }
 
-// 128-bit fingerprint of a lru key: two independent 64-bit mixes over the bytes
-struct Fp {
+// 128-bit fingerprint of a lru key.  Strings are hashed once (two independent 64-bit
+// streams, 8 bytes per step); a key combines its string hashes with the integer members.
+struct StrHash {
   uint64_t a, b;
-  __device__ __forceinline__ void init(uint64_t kind) {
-    a = 0x9E3779B97F4A7C15ull ^ kind;
-    b = 0xC2B2AE3D27D4EB4Full + kind * 0x165667B19E3779F9ull;
-  }
-  __device__ __forceinline__ void byte(uint8_t c) {
-    a = (a ^ c) * 0x100000001B3ull;
-    b = (b + c) * 0xFF51AFD7ED558CCDull;
+};
+__device__ __forceinline__ StrHash str_hash(const uint8_t* p, uint32_t n) {
+  uint64_t a = 0x9E3779B97F4A7C15ull ^ n, b = 0xC2B2AE3D27D4EB4Full + (uint64_t)n * 0x165667B19E3779F9ull;
+  uint32_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) w |= (uint64_t)p[i + k] << (8 * k);
+    a = (a ^ w) * 0x100000001B3ull;
+    a ^= a >> 32;
+    b = (b + w) * 0xFF51AFD7ED558CCDull;
     b ^= b >> 29;
   }
-  __device__ __forceinline__ void bytes(const uint8_t* p, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) byte(p[i]);
-    // length terminator keeps ("ab","c") and ("a","bc") apart
-    byte(0xff);
-    byte((uint8_t)n);
-    byte((uint8_t)(n >> 8));
-  }
-  __device__ __forceinline__ void u64(uint64_t v) {
-    for (int i = 0; i < 8; i++) byte((uint8_t)(v >> (8 * i)));
-  }
-  __device__ __forceinline__ U128 done() {
-    U128 r{mix64(a ^ (b >> 32)), mix64(b ^ (a << 1))};
-    if (r.lo == 0) r.lo = 1;  // both halves non-zero: 0 marks an empty / half-published slot
-    if (r.hi == 0) r.hi = 1;
-    return r;
-  }
-};
+  uint64_t w = 0;
+  for (uint32_t k = 0; i + k < n; k++) w |= (uint64_t)p[i + k] << (8 * k);
+  a = (a ^ w) * 0x100000001B3ull;
+  a ^= a >> 32;
+  b = (b + w) * 0xFF51AFD7ED558CCDull;
+  b ^= b >> 29;
+  return StrHash{a, b};
+}
+__device__ __forceinline__ U128 fp_finish(uint64_t lo, uint64_t hi) {
+  U128 r{mix64(lo), mix64(hi)};
+  if (r.lo == 0) r.lo = 1;  // both halves non-zero: 0 marks an empty / half-published slot
+  if (r.hi == 0) r.hi = 1;
+  return r;
+}
 
 // find-or-insert; returns the slot or nullptr when the table is full
 __device__ FtEntry* ft_upsert(const L7Dev* d, U128 fp, uint32_t* full_flag) {
@@ -224,15 +226,13 @@ __device__ __forceinline__ SRef attr_value_at(const RowView& v, uint32_t i) {
   return SRef{nullptr, 0};  // app_instance: always "" on this path
 }
 
-__device__ __forceinline__ U128 key_fp(const L7Dev* d, uint32_t kind, SRef name, SRef value, int32_t vpc,
+__device__ __forceinline__ U128 key_fp(const L7Dev* d, uint32_t kind, StrHash name, StrHash value, int32_t vpc,
                                        uint16_t pod_ns, uint8_t field_type, uint16_t team) {
-  Fp f;
-  f.init(kind);
-  f.bytes(name.p, name.n);
-  f.bytes(value.p, value.n);
-  f.u64((uint64_t)(uint32_t)vpc << 32 | (uint64_t)pod_ns << 16 | (uint64_t)field_type << 8);
-  f.u64((uint64_t)d->org_id << 16 | team);
-  return f.done();
+  const uint64_t x = (uint64_t)(uint32_t)vpc << 32 | (uint64_t)pod_ns << 16 | (uint64_t)field_type << 8 | kind;
+  const uint64_t y = (uint64_t)d->org_id << 16 | team;
+  uint64_t lo = name.a ^ mix64(value.a + x * 0x9E3779B97F4A7C15ull) ^ (y * 0xD6E8FEB86659FD93ull);
+  uint64_t hi = name.b + mix64(value.b ^ (x * 0xC2B2AE3D27D4EB4Full)) + (y * 0xA0761D6478BD642Full);
+  return fp_finish(lo, hi);
 }
 
 __device__ __forceinline__ unsigned long long pos_key(const L7Dev* d, uint32_t row, uint32_t side, uint32_t metric,
@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
   }
 
   RowView v;
+  constexpr uint32_t FT_HASH_CACHE = 8;
+  StrHash hcache[2 * FT_HASH_CACHE];
   const uint32_t timeout = d->ft_timeout;
   uint8_t* fa = d->ft_arena;
   const uint64_t* fo = dyn->stats.ft_off;
@@ -300,7 +302,20 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
     for (uint32_t side = 0; side < v.n_sides; side++) {
       for (uint32_t i = 0; i < min_len; i++) {
         SRef name = attr_name_at(d, v, i), value = attr_value_at(v, i);
-        U128 fpv = key_fp(d, KIND_FIELD_VALUE, name, value, v.vpc[side], v.pod_ns[side], 0, v.team);
+        // string hashes are side independent: computed at side 0, reused at side 1
+        StrHash hn, hv;
+        if (side == 0 || i >= FT_HASH_CACHE) {
+          hn = str_hash(name.p, name.n);
+          hv = str_hash(value.p, value.n);
+          if (i < FT_HASH_CACHE) {
+            hcache[2 * i] = hn;
+            hcache[2 * i + 1] = hv;
+          }
+        } else {
+          hn = hcache[2 * i];
+          hv = hcache[2 * i + 1];
+        }
+        U128 fpv = key_fp(d, KIND_FIELD_VALUE, hn, hv, v.vpc[side], v.pod_ns[side], 0, v.team);
         unsigned long long pk = pos_key(d, row, side, 0, i);
         if (PHASE == 0) {
           FtEntry* e = ft_upsert(d, fpv, &dyn->stats.ft_full);
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
         }
         // the tag-only key is only consulted when the value row was emitted (:703-722)
         if (i >= n_names) continue;
-        U128 fpf = key_fp(d, KIND_FIELD, name, SRef{nullptr, 0}, v.vpc[side], v.pod_ns[side], 0, v.team);
+        U128 fpf = key_fp(d, KIND_FIELD, hn, StrHash{0, 0}, v.vpc[side], v.pod_ns[side], 0, v.team);
         if (PHASE == 1) {
           FtEntry* ef = ft_upsert(d, fpf, &dyn->stats.ft_full);
           if (ef && ft_candidate(ef, v.time, timeout)) atomicMax(&ef->first_pos, pk);
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
       for (uint32_t i = 0; i < n_metrics; i++) {
         dfgpu_pos q = v.mn_pos[v.mn_lo + i];
         SRef name{v.mn_buf + q.start, (uint32_t)(q.end - q.start)};
-        U128 fpf = key_fp(d, KIND_FIELD, name, SRef{nullptr, 0}, v.vpc[side], v.pod_ns[side], 1, v.team);
+        U128 fpf = key_fp(d, KIND_FIELD, str_hash(name.p, name.n), StrHash{0, 0}, v.vpc[side], v.pod_ns[side], 1, v.team);
         unsigned long long pk = pos_key(d, row, side, 1, i);
         if (PHASE == 0) {  // independent of the value keys: probe right away
           FtEntry* ef = ft_upsert(d, fpf, &dyn->stats.ft_full);
@@ -413,11 +428,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
     }
     // app_service tag (decoder.go:464-472): AppInstance is always "" here
     if (v.app_service.n) {
-      Fp f;
-      f.init(KIND_APP_SERVICE);
-      f.bytes(v.app_service.p, v.app_service.n);
-      f.u64((uint64_t)d->org_id << 16 | v.team);
-      U128 fpa = f.done();
+      U128 fpa = key_fp(d, KIND_APP_SERVICE, str_hash(v.app_service.p, v.app_service.n), StrHash{0, 0}, 0, 0, 0, v.team);
       unsigned long long pk = pos_key(d, row, 0, 0, 0);
       if (PHASE == 0) {
         FtEntry* e = ft_upsert(d, fpa, &dyn->stats.ft_full);
@@ -559,8 +570,8 @@ static int l7_ensure_state(dfgpu_ctx* ctx) {
   CU(cudaMemcpy(h->d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
   d.cs_blob = h->d_blob;
   d.cs_off = h->d_off;
-  // ---- device tag set: never evicts, sized >= 8x the reference's three LRU capacities ----
-  uint64_t want = (uint64_t)ctx->cfg.flow_tag_cache_max_size * 3 * 8;
+  // ---- device tag set: never evicts, sized for 2x the reference's three LRU capacities ----
+  uint64_t want = (uint64_t)ctx->cfg.flow_tag_cache_max_size * 3 * 2;  // three LRUs, load <= 1/2
   uint32_t n = 1u << 16;
   while (n < want && n < (1u << 28)) n <<= 1;
   CU(cudaMalloc(&h->d_ft, (size_t)n * sizeof(FtEntry)));

@@ -243,7 +243,7 @@ __device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const uint64_t* 
 }  // namespace
 
 template <int EMIT>
-__global__ void __launch_bounds__(256) k_l7_pass(const __grid_constant__ BatchParams p) {
+__global__ void __launch_bounds__(256, EMIT ? 4 : 4) k_l7_pass(const __grid_constant__ BatchParams p) {
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
   const bool in_range = rec < p.nrec;
@@ -398,7 +398,11 @@ __global__ void __launch_bounds__(256) k_l7_pass(const __grid_constant__ BatchPa
     in.port = (uint16_t)sl_u32(sl, S7_PORT_DST);
     in.tap_side = tap_side;
     in.protocol = (uint8_t)sl_u32(sl, S7_PROTOCOL);
+#ifdef ABL_NO_KG
+    memset(&k, 0, sizeof k);
+#else
     kg_fill(p.dict, in, k);
+#endif
   }
   uint32_t gpid0 = sl_u32(sl, S7_GPID_0), gpid1 = sl_u32(sl, S7_GPID_1);
   const uint32_t pid0 = sl_u32(sl, S7_PID_0), pid1 = sl_u32(sl, S7_PID_1);
@@ -520,12 +524,14 @@ __global__ void __launch_bounds__(256) k_l7_pass(const __grid_constant__ BatchPa
                           L7C_RESPONSE_RESULT, L7C_HTTP_PROXY_CLIENT, L7C_X_REQUEST_ID_0, L7C_X_REQUEST_ID_1,
                           L7C_TRACE_ID, L7C_TRACE_ID_2, L7C_SPAN_ID, L7C_PARENT_SPAN_ID, L7C_APP_SERVICE,
                           L7C_APP_INSTANCE};
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 22; i++) {
       uint64_t off = WBASE(L7S_STR0 + i);
       uint32_t n = w.str[i].n;
       reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[cols[i]])[row] = dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
+#ifndef ABL_NO_STRCOPY
       if (n) copy_bytes(p.arena + dyn->var_buf_off[i] + off, w.str[i].p, n);
+#endif
     }
     // events: always empty on this path (only the OTel import fills it)
     reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[L7C_EVENTS])[row] = dfgpu_pos{0, 0};
@@ -539,7 +545,11 @@ __global__ void __launch_bounds__(256) k_l7_pass(const __grid_constant__ BatchPa
   reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_VALUES])[row] = av_e + sz[L7S_AV_ELEMS];
   reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_NAMES])[row] = mn_e + sz[L7S_MN_ELEMS];
   reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_VALUES])[row] = mv_e + sz[L7S_MV_ELEMS];
+#ifdef ABL_NO_ARRAYS
+  if (false) {
+#else
   if (sz[L7S_AN_ELEMS] | sz[L7S_AV_ELEMS] | sz[L7S_MN_ELEMS] | sz[L7S_MV_ELEMS]) {
+#endif
     L7EmitSink sink;
     sink.an_pos = reinterpret_cast<dfgpu_pos*>(p.arena + dyn->var_pos_off[L7V_ATTR_NAMES]) + an_e;
     sink.an_buf = p.arena + dyn->var_buf_off[L7V_ATTR_NAMES];

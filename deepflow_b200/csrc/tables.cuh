@@ -21,8 +21,10 @@
 
 #ifdef __CUDACC__
 #define DF_HD __host__ __device__ __forceinline__
+#define DF_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define DF_HD inline
+#define DF_HD_NOINLINE inline
 #endif
 
 namespace dfgpu {
@@ -242,7 +244,7 @@ DF_HD bool query_epc_base(const DevDict& d, int32_t epc, uint32_t& region) {
 
 // QueryIPV4Infos :292-308 = exact (epc,ip) -> first containing CIDR of the epc
 // (longest prefix first, :821-840) -> epc base region.
-DF_HD bool query_ip4(const DevDict& d, int32_t epc, uint32_t ip, InfoVal& out) {
+static DF_HD_NOINLINE bool query_ip4(const DevDict& d, int32_t epc, uint32_t ip, InfoVal& out) {
   if (epc == EPC_FROM_INTERNET) return false;
   uint32_t idx;
   if (t64_find(d.t64, d.t64_mask, TID_IP4, (uint64_t)(int64_t)epc << 32 | (uint64_t)ip, idx)) {
@@ -278,7 +280,7 @@ DF_HD bool ip6_is_v4mapped(const uint8_t* ip) {
 
 // QueryIPV6Infos :310-326.  `ip` points at 16 bytes (zero padded when the wire
 // carried fewer, like copy(key[4:], ipv6)); iplen is the wire length.
-DF_HD bool query_ip6(const DevDict& d, int32_t epc, const uint8_t* ip, uint32_t iplen, InfoVal& out) {
+static DF_HD_NOINLINE bool query_ip6(const DevDict& d, int32_t epc, const uint8_t* ip, uint32_t iplen, InfoVal& out) {
   if (epc == EPC_FROM_INTERNET) return false;
   uint32_t idx;
   if (t6_find(d.t6, d.t6_mask, T6_IP6, ip, epc, 0, 0, idx)) {

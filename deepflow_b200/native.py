@@ -19,7 +19,7 @@ class DfgpuError(RuntimeError):
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "libdfgpu.so")
+        path = os.environ.get("DFGPU_LIB") or os.path.join(_HERE, "libdfgpu.so")  # DFGPU_LIB: ablation builds
         if not os.path.exists(path):
             raise DfgpuError(f"{path} is not built — run __graft_entry__.build() (no CPU fallback exists)")
         L = C.CDLL(path)
