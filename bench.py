@@ -154,7 +154,7 @@ def output_bytes(batch):
     return total, nrows
 
 
-def cpu_port_run(synth, sample_records, threads, seed):
+def cpu_port_run(synth, sample_records, threads, seed, warm=True):
     """The CPU oracle (C++ restatement of decoder.Run ... AppendToColumnBlock) on `threads`
     independent decoder instances, each with its own dictionary view and caches."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -167,6 +167,11 @@ def cpu_port_run(synth, sample_records, threads, seed):
         o.load_synth(synth)
         oras.append(o)
         wls.append(synth.gen(MSG, sample_records, seed=seed + t))
+    if warm:
+        # steady state, like a long-running ingester: column blocks and caches already sized
+        ts = [threading.Thread(target=o.submit, args=(w,)) for o, w in zip(oras, wls)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
     t0 = time.perf_counter()
     ts = [threading.Thread(target=o.submit, args=(w,)) for o, w in zip(oras, wls)]
     [t.start() for t in ts]
@@ -201,7 +206,7 @@ def main():
         synth = Synth(n_pods=a.pods)
         cores = os.cpu_count() or 1
         threads = min(cores, 64)
-        sample = 20000
+        sample = 50000
         for _ in range(a.warmup):
             cpu_port_run(synth, 2000, threads, 900)
         t_all, n_all = 0.0, 0

@@ -105,6 +105,18 @@ struct Column {
     nrows++;
   }
 
+  void clear() {  // Reset(): keep the capacity, like the reference's pooled column blocks
+    nrows = 0;
+    nelems = 0;
+    data.clear();
+    pos.clear();
+    arr_off.clear();
+    nulls.clear();
+    dict_buf.clear();
+    dict_pos.clear();
+    dict_idx.clear();
+  }
+
   dfgpu_col view() const {
     dfgpu_col c;
     memset(&c, 0, sizeof(c));
@@ -133,6 +145,10 @@ struct Block {
     return cols.back();
   }
   Column& operator[](size_t i) { return cols[i]; }
+  void clear() {
+    nrows = 0;
+    for (auto& c : cols) c.clear();
+  }
 };
 
 }  // namespace oracle

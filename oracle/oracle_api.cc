@@ -79,11 +79,22 @@ int oracle_submit(oracle_ctx* c, int msg_type, const uint8_t* frames, size_t nby
   if (!trace_idx) trace_idx = &dummy_trace;
   L7Counters l7c;
   if (msg_type == DFGPU_MSG_TAGGEDFLOW) {
-    c->l4.reset(new L4Block());
-    c->l4->init();
+    if (!c->l4) {
+      c->l4.reset(new L4Block());
+      c->l4->init();
+    } else {
+      c->l4->b.clear();
+    }
   } else if (msg_type == DFGPU_MSG_PROTOCOLLOG) {
-    c->l7.reset(new L7Blocks());
-    c->l7->init();
+    if (!c->l7) {
+      c->l7.reset(new L7Blocks());
+      c->l7->init();
+    } else {
+      c->l7->l7.clear();
+      c->l7->field.clear();
+      c->l7->field_value.clear();
+      c->l7->app_service.clear();
+    }
   } else if (msg_type == DFGPU_MSG_METRICS) {
     c->metrics.reset(new MetricsBlocks());
     c->metrics->init();
