@@ -15,6 +15,8 @@ TABLE_L7_CUSTOM_FIELD = 2
 TABLE_L7_CUSTOM_FIELD_VALUE = 3
 TABLE_L7_APP_SERVICE = 4
 TABLE_METRICS_BASE = 16
+TABLE_METRICS_APP_SERVICE = 25
+TABLE_METRICS_REDUCED = 31
 TABLE_MAX = 32
 
 CH_UINT8, CH_UINT16, CH_UINT32, CH_UINT64 = 1, 2, 3, 4

@@ -70,86 +70,11 @@ enum {
   FO_AS_TIME, FO_AS_TABLE, FO_AS_SVC_POS, FO_AS_INST_POS, FO_AS_TEAM, FO_AS_BUF, FO_COUNT
 };
 
-struct U128 {
-  unsigned long long lo, hi;
-};
-__device__ __forceinline__ U128 cas128(FtEntry* e, U128 cmp, U128 val) {
-  U128 old;
-  asm volatile(
-      "{\n\t.reg .b128 c, v, o;\n\t"
-      "mov.b128 c, {%2, %3};\n\t"
-      "mov.b128 v, {%4, %5};\n\t"
-      "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
-      "mov.b128 {%0, %1}, o;\n\t}"
-      : "=l"(old.lo), "=l"(old.hi)
-      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(e)
-      : "memory");
-  return old;
+// find-or-insert in this context's tag set (tagset.cuh)
+__device__ __forceinline__ FtEntry* ft_upsert(const L7Dev* d, U128 fp, uint32_t* full_flag) {
+  return ts_upsert(d->ft, d->ft_mask, fp, full_flag);
 }
-
-// 128-bit fingerprint of a lru key.  Strings are hashed once (two independent 64-bit
-// streams, 8 bytes per step); a key combines its string hashes with the integer members.
-struct StrHash {
-  uint64_t a, b;
-};
-__device__ __forceinline__ StrHash str_hash(const uint8_t* p, uint32_t n) {
-  uint64_t a = 0x9E3779B97F4A7C15ull ^ n, b = 0xC2B2AE3D27D4EB4Full + (uint64_t)n * 0x165667B19E3779F9ull;
-  uint32_t i = 0;
-  for (; i + 8 <= n; i += 8) {
-    uint64_t w = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) w |= (uint64_t)p[i + k] << (8 * k);
-    a = (a ^ w) * 0x100000001B3ull;
-    a ^= a >> 32;
-    b = (b + w) * 0xFF51AFD7ED558CCDull;
-    b ^= b >> 29;
-  }
-  uint64_t w = 0;
-  for (uint32_t k = 0; i + k < n; k++) w |= (uint64_t)p[i + k] << (8 * k);
-  a = (a ^ w) * 0x100000001B3ull;
-  a ^= a >> 32;
-  b = (b + w) * 0xFF51AFD7ED558CCDull;
-  b ^= b >> 29;
-  return StrHash{a, b};
-}
-__device__ __forceinline__ U128 fp_finish(uint64_t lo, uint64_t hi) {
-  U128 r{mix64(lo), mix64(hi)};
-  if (r.lo == 0) r.lo = 1;  // both halves non-zero: 0 marks an empty / half-published slot
-  if (r.hi == 0) r.hi = 1;
-  return r;
-}
-
-// find-or-insert; returns the slot or nullptr when the table is full
-__device__ FtEntry* ft_upsert(const L7Dev* d, U128 fp, uint32_t* full_flag) {
-  uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & d->ft_mask;
-  // a healthy table (load <= 1/8) resolves in a few probes; a long run means it is
-  // saturated: give up, flag it, and let fetch report the capacity error
-  for (uint32_t probes = 0; probes < 512; probes++) {
-    FtEntry* e = d->ft + s;
-    unsigned long long lo, hi;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(e) : "memory");
-    if (lo == fp.lo && hi == fp.hi) return e;
-    if ((lo | hi) == 0) {
-      U128 old = cas128(e, U128{0, 0}, fp);
-      if ((old.lo | old.hi) == 0 || (old.lo == fp.lo && old.hi == fp.hi)) return e;
-    } else if (lo == 0 || hi == 0) {
-      continue;  // torn read of a concurrent 128-bit publish: re-read this slot
-    }
-    s = (s + 1) & d->ft_mask;
-  }
-  *full_flag = 1;
-  return nullptr;
-}
-__device__ FtEntry* ft_find(const L7Dev* d, U128 fp) {
-  uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & d->ft_mask;
-  for (uint32_t probes = 0; probes < 512; probes++) {
-    FtEntry* e = d->ft + s;
-    if (e->fp_lo == fp.lo && e->fp_hi == fp.hi) return e;
-    if ((e->fp_lo | e->fp_hi) == 0) return nullptr;
-    s = (s + 1) & d->ft_mask;
-  }
-  return nullptr;
-}
+__device__ __forceinline__ FtEntry* ft_find(const L7Dev* d, U128 fp) { return ts_find(d->ft, d->ft_mask, fp); }
 
 // lru semantics (l7_flow_log.go:693-701): emit when the key is new, or when
 // old + CacheFlushTimeout < time (uint32 arithmetic)

@@ -7,6 +7,7 @@
 #include "l7_decode.cuh"
 #include "l7_slots.h"
 #include "schema_l7.h"
+#include "tagset.cuh"
 
 #include "../../include/dfgpu_exception_tables.h"
 
@@ -20,14 +21,6 @@ enum : uint32_t {
   CS_FIXED_COUNT
 };
 
-struct FtEntry {  // one slot of the device tag set (32 B = one HBM sector)
-  unsigned long long fp_lo, fp_hi;  // 128-bit fingerprint of the lru key; 0/0 = empty
-  unsigned long long first_pos;     // (epoch << 48) | (2^48-1 - position): atomicMax keeps the FIRST
-                                    // candidate of the NEWEST batch; 0 = none
-  uint32_t time;                    // value stored by lru Add(): time of the last emission
-  uint32_t state;                   // 0 = inserted but never emitted, 1 = emitted
-};
-static_assert(sizeof(FtEntry) == 32, "FtEntry");
 
 struct L7Dev {
   const uint8_t* cs_blob;

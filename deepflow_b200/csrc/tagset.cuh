@@ -1,0 +1,121 @@
+/*
+ * tagset.cuh — the device-resident "seen" set that replaces the per-decoder lru.Cache
+ * of the flow_tag writers (server/libs/lru/lru.go:44-76, flow_tag_writer.go:65-77,
+ * app_service_tag_writer.go:52).  Used by the L7 flow_tag stage (l7.cu) and by the
+ * flow_metrics app_service tags (metrics.cu).
+ *
+ * A slot is 32 B (one HBM sector): a 128-bit fingerprint of the lru key published with
+ * one atom.cas.b128, the time stored by the last Add(), and an epoch-tagged "first
+ * candidate" word so that of all records of one batch that find the key new or expired,
+ * the FIRST in input order emits the row — the order the sequential Go loop produces.
+ */
+#pragma once
+#include <cstdint>
+
+#include "tables.cuh"
+
+namespace dfgpu {
+
+struct FtEntry {
+  unsigned long long fp_lo, fp_hi;  // 128-bit fingerprint of the lru key; 0/0 = empty
+  unsigned long long first_pos;     // (epoch << 48) | (2^48-1 - position): atomicMax keeps the FIRST
+                                    // candidate of the NEWEST batch; 0 = none
+  uint32_t time;                    // value stored by lru Add(): time of the last emission
+  uint32_t state;                   // 0 = inserted but never emitted, 1 = emitted
+};
+static_assert(sizeof(FtEntry) == 32, "FtEntry");
+
+struct U128 {
+  unsigned long long lo, hi;
+};
+__device__ __forceinline__ U128 cas128(FtEntry* e, U128 cmp, U128 val) {
+  U128 old;
+  asm volatile(
+      "{\n\t.reg .b128 c, v, o;\n\t"
+      "mov.b128 c, {%2, %3};\n\t"
+      "mov.b128 v, {%4, %5};\n\t"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(old.lo), "=l"(old.hi)
+      : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(e)
+      : "memory");
+  return old;
+}
+
+// Strings are hashed once (two independent 64-bit streams, 8 bytes per step); a key
+// combines its string hashes with its integer members.
+struct StrHash {
+  uint64_t a, b;
+};
+__device__ __forceinline__ StrHash str_hash(const uint8_t* p, uint32_t n) {
+  uint64_t a = 0x9E3779B97F4A7C15ull ^ n, b = 0xC2B2AE3D27D4EB4Full + (uint64_t)n * 0x165667B19E3779F9ull;
+  uint32_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) w |= (uint64_t)p[i + k] << (8 * k);
+    a = (a ^ w) * 0x100000001B3ull;
+    a ^= a >> 32;
+    b = (b + w) * 0xFF51AFD7ED558CCDull;
+    b ^= b >> 29;
+  }
+  uint64_t w = 0;
+  for (uint32_t k = 0; i + k < n; k++) w |= (uint64_t)p[i + k] << (8 * k);
+  a = (a ^ w) * 0x100000001B3ull;
+  a ^= a >> 32;
+  b = (b + w) * 0xFF51AFD7ED558CCDull;
+  b ^= b >> 29;
+  return StrHash{a, b};
+}
+__device__ __forceinline__ U128 fp_finish(uint64_t lo, uint64_t hi) {
+  U128 r{mix64(lo), mix64(hi)};
+  if (r.lo == 0) r.lo = 1;  // both halves non-zero: 0 marks an empty / half-published slot
+  if (r.hi == 0) r.hi = 1;
+  return r;
+}
+
+// find-or-insert; returns the slot or nullptr when the table is full
+__device__ __forceinline__ FtEntry* ts_upsert(FtEntry* tbl, uint32_t mask, U128 fp, uint32_t* full_flag) {
+  uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & mask;
+  // a healthy table resolves in a few probes; a long run means it is saturated: give
+  // up, flag it, and let fetch report the capacity error
+  for (uint32_t probes = 0; probes < 512; probes++) {
+    FtEntry* e = tbl + s;
+    unsigned long long lo, hi;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(e) : "memory");
+    if (lo == fp.lo && hi == fp.hi) return e;
+    if ((lo | hi) == 0) {
+      U128 old = cas128(e, U128{0, 0}, fp);
+      if ((old.lo | old.hi) == 0 || (old.lo == fp.lo && old.hi == fp.hi)) return e;
+    } else if (lo == 0 || hi == 0) {
+      continue;  // torn read of a concurrent 128-bit publish: re-read this slot
+    }
+    s = (s + 1) & mask;
+  }
+  *full_flag = 1;
+  return nullptr;
+}
+__device__ __forceinline__ FtEntry* ts_find(FtEntry* tbl, uint32_t mask, U128 fp) {
+  uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & mask;
+  for (uint32_t probes = 0; probes < 512; probes++) {
+    FtEntry* e = tbl + s;
+    if (e->fp_lo == fp.lo && e->fp_hi == fp.hi) return e;
+    if ((e->fp_lo | e->fp_hi) == 0) return nullptr;
+    s = (s + 1) & mask;
+  }
+  return nullptr;
+}
+
+// lru semantics (l7_flow_log.go:693-701, app_service_tag_writer.go:100-108): emit when
+// the key is new, or when old + CacheFlushTimeout < time (uint32 arithmetic)
+__device__ __forceinline__ bool ts_candidate(const FtEntry* e, uint32_t now, uint32_t timeout) {
+  if (e->state == 0) return true;
+  return (uint32_t)(e->time + timeout) < now;
+}
+
+// epoch-tagged position for atomicMax(first_pos): larger = newer batch, then earlier position
+__device__ __forceinline__ unsigned long long ts_pos_key(uint32_t epoch, unsigned long long pos) {
+  return (unsigned long long)(epoch & 0xffffu) << 48 | (0xffffffffffffull - pos);
+}
+
+}  // namespace dfgpu

@@ -946,6 +946,182 @@ void gen_l7(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flag
   if ((flags & F_UNKNOWN_FIELDS) && r.chance(0.1)) unknown_fields(out, r);
 }
 
+// ---- metric.proto Document (message/metric.proto:14-195), as the agent's collector emits
+// it: one MiniTag (single-side or edge code) + one meter.
+void sparse_u(PB& pb, Rng& r, uint32_t f, int bits, double p_zero = 0.6) {
+  if (!r.chance(p_zero)) pb.u(f, r.logu(bits));
+}
+
+void gen_metric(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flags, PB& out) {
+  // Code bits (flow-metrics/tag.go:38-94)
+  const uint64_t IP = 1, L3EPC = 2, MAC = 1ull << 11, GPID = 1ull << 15, PATH = 20;
+  const uint64_t DIRECTION = 1ull << 40, ACLGID = 1ull << 41, PROTOCOL = 1ull << 42, SERVERPORT = 1ull << 43,
+                 TAPTYPE = 1ull << 45, VTAPID = 1ull << 47, TAPSIDE = 1ull << 48, TAPPORT = 1ull << 49,
+                 L7PROTOCOL = 1ull << 51, TUNNELIPID = 1ull << 62;
+  uint32_t pick = r.below(100);
+  // 0 network, 1 network_map, 2 application, 3 application_map, 4 traffic_policy
+  int kind = pick < 25 ? 0 : pick < 55 ? 1 : pick < 72 ? 2 : pick < 94 ? 3 : 4;
+  const bool edge = kind == 1 || kind == 3, app = kind == 2 || kind == 3, policy = kind == 4;
+  const bool v6 = !policy && r.chance(0.10);
+  Side s0, s1;
+  auto mode = [&]() { uint32_t m = r.below(100); return m < 80 ? 0 : m < 92 ? 1 : 2; };
+  pick_side(c, r, s0, v6, mode());
+  pick_side(c, r, s1, v6, mode());
+
+  uint64_t code;
+  if (policy) code = ACLGID | TUNNELIPID | VTAPID;
+  else if (edge) code = (IP << PATH) | (L3EPC << PATH) | VTAPID | TAPTYPE | TAPSIDE | PROTOCOL | SERVERPORT | TAPPORT;
+  else code = IP | L3EPC | VTAPID | TAPTYPE | PROTOCOL | SERVERPORT | DIRECTION;
+  if (app) code |= L7PROTOCOL;
+  if (!policy && r.chance(0.2)) code |= edge ? (MAC << PATH) : MAC;   // ignored by TableID
+  if (!policy && r.chance(0.5)) code |= edge ? (GPID << PATH) : GPID;  // newer agents set it themselves
+  if (r.chance(0.04)) {  // codes that match no table -> DropDocCount
+    switch (r.below(4)) {
+      case 0: code &= ~SERVERPORT; break;
+      case 1: code |= edge ? DIRECTION : TAPSIDE; break;
+      case 2: code = 0; break;
+      case 3: code |= ACLGID; break;
+    }
+  }
+
+  PB f;  // MiniField
+  uint8_t ip4be[4];
+  auto put_ip = [&](uint32_t field, const Side& s) {
+    if (v6) f.bytes(field, s.ip6, 16);
+    else {
+      ip4be[0] = (uint8_t)(s.ip4 >> 24); ip4be[1] = (uint8_t)(s.ip4 >> 16);
+      ip4be[2] = (uint8_t)(s.ip4 >> 8);  ip4be[3] = (uint8_t)s.ip4;
+      f.tag(field, 2); f.varint(4); f.b.insert(f.b.end(), ip4be, ip4be + 4);  // always 4 bytes, even 0.0.0.0
+    }
+  };
+  put_ip(1, s0);
+  if (edge || r.chance(0.1)) put_ip(2, s1);
+  f.u(3, r.below(policy ? 4 : 40));
+  f.u(4, v6 ? 1 : 0);
+  int32_t epc0 = s0.epc, epc1 = s1.epc;
+  if (r.chance(0.01)) epc0 = -(int32_t)(3 + r.below(40000));
+  f.i32(5, epc0);
+  if (edge) f.i32(6, epc1);
+  if (r.chance(0.5)) f.u(7, s0.mac);
+  if (edge && r.chance(0.5)) f.u(8, s1.mac);
+  static const uint32_t kDirs[] = {1, 2, 4, 0, 1 | 8, 2 | 8, 1 | 16, 2 | 16, 1 | 40, 2 | 40, 1 | 48, 2 | 48, 3, 7};
+  uint32_t direction = kDirs[r.skew(14)];
+  f.u(9, direction);
+  uint32_t tap_side = kTapSides[r.below(17)];
+  if (r.chance(0.3)) tap_side = r.chance(0.5) ? 1 : 2;  // c / s: the region filter applies to these
+  f.u(10, tap_side);
+  f.u(11, r.chance(0.7) ? 6 : r.chance(0.7) ? 17 : r.below(256));
+  if (policy || r.chance(0.02)) f.u(12, 1 + r.below(3000));
+  uint32_t port = r.chance(0.85) ? c->svc_ports[r.below((uint32_t)c->svc_ports.size())] : r.below(65536);
+  if (r.chance(0.1)) port = 0;
+  f.u(13, (flags & F_WIDE_VARINT) && r.chance(0.05) ? (uint64_t)port | 0x70000ull : port);
+  f.u(14, vtap);
+  uint64_t tap_port = (uint64_t)(r.next() & 0xffffffffu) | (uint64_t)r.below(16) << 32 | (uint64_t)r.below(4) << 36 |
+                      (uint64_t)r.below(8) << 60;
+  if (edge || r.chance(0.2)) f.u(15, tap_port);
+  f.u(16, r.chance(0.9) ? 3 : 1 + r.below(255));
+  if (app) f.u(17, r.chance(0.6) ? 20 : r.chance(0.5) ? 120 : r.below(130));
+  if (r.chance(0.6)) f.u(20, s0.gpid);
+  if (edge && r.chance(0.6)) f.u(21, s1.gpid);
+  uint32_t sig = r.below(100);
+  f.u(22, sig < 55 ? 0 : sig < 85 ? 3 : sig < 95 ? 4 : r.below(8));
+  if (app) {
+    char tmp[48];
+    if (r.chance(0.7)) { snprintf(tmp, sizeof tmp, "svc-%u", r.skew(60)); f.str(23, tmp); }
+    if (r.chance(0.3)) { snprintf(tmp, sizeof tmp, "inst-%u", r.skew(25)); f.str(24, tmp); }
+    if (r.chance(0.8)) { snprintf(tmp, sizeof tmp, "/api/v%u/resource/%u", 1 + r.below(3), r.skew(300)); f.str(25, tmp); }
+    if (r.chance(0.1)) f.u(28, 1 + r.below(5));
+  }
+  if (r.chance(0.3)) {
+    const Side& ps = (edge && (direction & 7) == 2) ? s1 : s0;
+    f.u(27, ps.pod_id);
+  }
+  if ((flags & F_UNKNOWN_FIELDS) && r.chance(0.1)) unknown_fields(f, r);
+
+  PB tag;
+  tag.msg(1, f);
+  tag.u(2, code);
+  if ((flags & F_DUP_FIELDS) && r.chance(0.1)) {  // a second MiniField occurrence merges into the first
+    PB f2;
+    f2.u(14, vtap);
+    f2.u(11, 6);
+    tag.msg(1, f2);
+  }
+
+  PB meter;
+  const bool omit = (flags & F_OMIT_SUBMSG) != 0;
+  uint32_t meter_id = policy ? 4 : app ? 5 : 1;
+  if (r.chance(0.01)) meter_id = policy ? 1 : 4;  // meter / table mismatch -> dropped
+  if ((flags & F_CORRUPT) && r.chance(0.0005)) meter_id = r.chance(0.5) ? 2 : 7;  // unknown meter: frame abandoned
+  meter.u(1, (flags & F_WIDE_VARINT) && r.chance(0.05) ? (uint64_t)meter_id + 256 : meter_id);  // uint8(MeterId)
+  if (meter_id == 1 || r.chance(0.02)) {
+    PB fm, tr, la, pe, an, fl;
+    for (uint32_t i = 1; i <= 10; i++) sparse_u(tr, r, i, r.chance(0.02) ? 62 : 40);
+    for (uint32_t i = 11; i <= 14; i++) sparse_u(tr, r, i, 24);
+    if ((flags & F_WIDE_VARINT) && r.chance(0.1)) tr.u(11, 0x100000000ull + r.below(1000));  // uint32 keeps the low bits
+    sparse_u(tr, r, 15, 8);
+    for (uint32_t i = 1; i <= 6; i++) sparse_u(la, r, i, 30);
+    sparse_u(la, r, 19, 30);
+    for (uint32_t i = 7; i <= 12; i++) sparse_u(la, r, i, r.chance(0.05) ? 63 : 44);  // > 2^53: f64 rounding
+    sparse_u(la, r, 20, 44);
+    for (uint32_t i = 13; i <= 18; i++) sparse_u(la, r, i, 20);
+    sparse_u(la, r, 21, 20);
+    for (uint32_t i = 1; i <= 4; i++) sparse_u(pe, r, i, 30);
+    sparse_u(pe, r, 5, 16);
+    sparse_u(pe, r, 6, 16);
+    for (uint32_t i = 1; i <= 12; i++) sparse_u(an, r, i, r.chance(0.01) ? 64 : 24, 0.75);
+    for (uint32_t i = 13; i <= 15; i++) sparse_u(an, r, i, 32, 0.75);
+    sparse_u(an, r, 20, 20, 0.8);
+    sparse_u(an, r, 21, 20, 0.8);
+    sparse_u(fl, r, 1, 16, 0.5);
+    if (!(omit && r.chance(0.2))) fm.msg(1, tr);
+    if (!(omit && r.chance(0.2))) fm.msg(2, la);
+    if (!(omit && r.chance(0.2))) fm.msg(3, pe);
+    if (!(omit && r.chance(0.2))) fm.msg(4, an);
+    if (!(omit && r.chance(0.2))) fm.msg(5, fl);
+    if ((flags & F_DUP_FIELDS) && r.chance(0.1)) {  // split sub-message: merged, last scalar wins
+      PB tr2;
+      tr2.u(1, 77);
+      tr2.u(15, 200);
+      fm.msg(1, tr2);
+    }
+    meter.msg(2, fm);
+  }
+  if (meter_id == 4 || r.chance(0.02)) {
+    PB um;
+    for (uint32_t i = 1; i <= 8; i++) sparse_u(um, r, i, 40, 0.3);
+    meter.msg(3, um);
+  }
+  if (meter_id == 5 || r.chance(0.02)) {
+    PB am, t, l, a;
+    sparse_u(t, r, 1, 24, 0.2);
+    sparse_u(t, r, 2, 24, 0.2);
+    sparse_u(t, r, 3, 8, 0.3);
+    sparse_u(l, r, 1, 30, 0.3);
+    sparse_u(l, r, 2, r.chance(0.05) ? 63 : 44, 0.3);
+    sparse_u(l, r, 3, 20, 0.3);
+    sparse_u(a, r, 1, r.chance(0.02) ? 32 : 16, 0.7);
+    sparse_u(a, r, 2, r.chance(0.02) ? 32 : 16, 0.7);
+    sparse_u(a, r, 3, 16, 0.7);
+    if (!(omit && r.chance(0.2))) am.msg(1, t);
+    if (!(omit && r.chance(0.2))) am.msg(2, l);
+    if (!(omit && r.chance(0.2))) am.msg(3, a);
+    meter.msg(4, am);
+  }
+  if ((flags & F_UNKNOWN_FIELDS) && r.chance(0.05)) unknown_fields(meter, r);
+
+  // 60 consecutive seconds; a few documents an hour later (second time bucket / lru expiry)
+  uint32_t ts = (uint32_t)(base_ns / 1000000000ull) + r.below(60) + (r.chance(0.01) ? 3600 : 0);
+  out.u(1, ts);
+  out.msg(2, tag);
+  out.msg(3, meter);
+  // FLAG_PER_SECOND_METRICS | an unused bit; traffic_policy has no per-second table (a
+  // per-second policy document would index past metricsTableCodes in the reference)
+  out.u(4, (!policy && r.chance(0.5) ? 1 : 0) | (r.chance(0.02) ? 2 : 0));
+  if ((flags & F_DUP_FIELDS) && r.chance(0.05)) out.u_always(1, ts);
+  if ((flags & F_UNKNOWN_FIELDS) && r.chance(0.1)) unknown_fields(out, r);
+}
+
 }  // namespace
 
 extern "C" {
@@ -997,6 +1173,7 @@ synth_batch* synth_gen(synth_ctx* c, int msg_type, uint64_t seed, uint64_t nreco
       pb.b.clear();
       if (msg_type == DFGPU_MSG_TAGGEDFLOW) gen_l4(c, r, fr.vtap_id, base_ns, flags, pb);
       else if (msg_type == DFGPU_MSG_PROTOCOLLOG) gen_l7(c, r, fr.vtap_id, base_ns, flags, pb);
+      else if (msg_type == DFGPU_MSG_METRICS) gen_metric(c, r, fr.vtap_id, base_ns, flags, pb);
       else { delete b; return nullptr; }
       uint32_t n = (uint32_t)pb.b.size();
       if (used && used + 4 + n > budget) break;

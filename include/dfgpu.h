@@ -53,6 +53,11 @@ extern "C" {
  * (server/libs/flow-metrics/tag.go:471-485: NETWORK_1M=0 .. TRAFFIC_POLICY_1M=4,
  *  NETWORK_1S=5 .. APPLICATION_MAP_1S=8)                                         */
 #define DFGPU_TABLE_METRICS_BASE 16
+/* flow_tag.<application|application_map>_app_service rows of the unmarshaller's
+ * AppServiceTagWriter (unmarshaller.go:309-327)                                  */
+#define DFGPU_TABLE_METRICS_APP_SERVICE 25
+/* output of dfgpu_metrics_reduce: same columns as the table that was reduced    */
+#define DFGPU_TABLE_METRICS_REDUCED 31
 #define DFGPU_TABLE_MAX 32
 
 /* ---- ch-go container kinds (server/libs/ckdb/ckdb.go, *_column_block.go) -- */
@@ -302,8 +307,11 @@ void dfgpu_batch_release(dfgpu_batch* b);
 /* flow_metrics reduce-by-key: merges the decoded Document rows of the
  * last metrics run by (time bucket, all tag columns) with the per-field rules of
  * FlowMeter.ConcurrentMerge (flow-metrics/basic_meter.go:94-113,277-315,417-424,
- * 556-577).  bucket_seconds = 60 for the 1s -> 1m rollup.                      */
-int dfgpu_metrics_reduce(dfgpu_ctx* ctx, uint32_t bucket_seconds, dfgpu_batch** out);
+ * 556-577).  bucket_seconds = 60 for the 1s -> 1m rollup.  `table` is one of
+ * DFGPU_TABLE_METRICS_BASE+0..8; its rows stay resident in HBM after the metrics
+ * run, the reduced rows come back as table DFGPU_TABLE_METRICS_REDUCED in
+ * first-appearance order of the groups.                                        */
+int dfgpu_metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch** out);
 
 #ifdef __cplusplus
 }

@@ -36,7 +36,7 @@ const char* TAPSideString(uint32_t v, bool& ok) {  // tag.go:211-233 (sparse sli
 }
 
 // common.go:160-198
-static void GetAutoInstance(uint32_t podID, uint32_t gpID, uint32_t podNodeID, uint32_t l3DeviceID,
+void GetAutoInstance(uint32_t podID, uint32_t gpID, uint32_t podNodeID, uint32_t l3DeviceID,
                             uint32_t subnetID, uint8_t l3DeviceType, int32_t l3EpcID, uint32_t& id,
                             uint8_t& type) {
   if (podID > 0) { id = podID; type = 10; }
@@ -46,7 +46,7 @@ static void GetAutoInstance(uint32_t podID, uint32_t gpID, uint32_t podNodeID, u
   else if (l3EpcID == EPC_FROM_INTERNET) { id = 0; type = 0; }
   else { id = subnetID; type = 255; }
 }
-static void GetAutoService(uint32_t customServiceID, uint32_t podServiceID, uint32_t podGroupID,
+void GetAutoService(uint32_t customServiceID, uint32_t podServiceID, uint32_t podGroupID,
                            uint32_t gpID, uint32_t podClusterID, uint32_t l3DeviceID,
                            uint32_t subnetID, uint8_t l3DeviceType, uint8_t podGroupType,
                            int32_t l3EpcID, uint32_t& id, uint8_t& type) {
@@ -59,11 +59,11 @@ static void GetAutoService(uint32_t customServiceID, uint32_t podServiceID, uint
   else if (l3EpcID == EPC_FROM_INTERNET) { id = 0; type = 0; }
   else { id = subnetID; type = 255; }
 }
-static bool IsPodServiceIP(uint8_t deviceType, uint32_t podId, uint32_t podNodeId) {
+bool IsPodServiceIP(uint8_t deviceType, uint32_t podId, uint32_t podNodeId) {
   return deviceType == 11 /*trident DEVICE_TYPE_POD_SERVICE*/ || podId != 0 || podNodeId != 0;
 }
 // common.go:137-143
-static bool RegetInfoFromIP(const PlatformInfoTable* pd, bool isIPv6, const uint8_t* ip6, size_t ip6len,
+bool RegetInfoFromIP(const PlatformInfoTable* pd, bool isIPv6, const uint8_t* ip6, size_t ip6len,
                             uint32_t ip4, int32_t epcID, Info& out) {
   return isIPv6 ? pd->QueryIPV6Infos(epcID, ip6, ip6len, out) : pd->QueryIPV4Infos(epcID, ip4, out);
 }

@@ -56,4 +56,14 @@ struct KnowledgeGraph {
 
 int32_t MarshalInt32WithSpecialID(int32_t v);  // flow-metrics/tag.go:560-565
 
+// server/ingester/common/common.go:137-198 (shared with the metrics twin, metrics.cc)
+void GetAutoInstance(uint32_t podID, uint32_t gpID, uint32_t podNodeID, uint32_t l3DeviceID, uint32_t subnetID,
+                     uint8_t l3DeviceType, int32_t l3EpcID, uint32_t& id, uint8_t& type);
+void GetAutoService(uint32_t customServiceID, uint32_t podServiceID, uint32_t podGroupID, uint32_t gpID,
+                    uint32_t podClusterID, uint32_t l3DeviceID, uint32_t subnetID, uint8_t l3DeviceType,
+                    uint8_t podGroupType, int32_t l3EpcID, uint32_t& id, uint8_t& type);
+bool IsPodServiceIP(uint8_t deviceType, uint32_t podId, uint32_t podNodeId);
+bool RegetInfoFromIP(const PlatformInfoTable* pd, bool isIPv6, const uint8_t* ip6, size_t ip6len, uint32_t ip4,
+                     int32_t epcID, Info& out);
+
 }  // namespace oracle

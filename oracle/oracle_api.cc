@@ -21,6 +21,7 @@ struct oracle_ctx {
   std::map<uint16_t, std::unique_ptr<PlatformInfoTable>> tables;
   GeoTree geo;
   std::unique_ptr<L7State> l7state;
+  std::unique_ptr<L7State> metrics_state;  // the unmarshaller's own AppServiceTagWriter cache
   std::unique_ptr<L4Block> l4;
   std::unique_ptr<L7Blocks> l7;
   std::unique_ptr<MetricsBlocks> metrics;
@@ -39,6 +40,7 @@ oracle_ctx* oracle_new(const dfgpu_cfg* cfg) {
   if (c->cfg.flow_tag_cache_flush_timeout) lc.flow_tag_cache_flush_timeout = c->cfg.flow_tag_cache_flush_timeout;
   if (c->cfg.flow_tag_cache_max_size) lc.flow_tag_cache_max_size = c->cfg.flow_tag_cache_max_size;
   c->l7state.reset(new L7State(lc));
+  c->metrics_state.reset(new L7State(lc));
   c->pbTaggedFlow.reset(new Msg(&schema().tagged_flow));
   c->pbAppLog.reset(new Msg(&schema().app_log));
   c->pbDoc.reset(new Msg(&metric_schema().document));
@@ -96,8 +98,12 @@ int oracle_submit(oracle_ctx* c, int msg_type, const uint8_t* frames, size_t nby
       c->l7->app_service.clear();
     }
   } else if (msg_type == DFGPU_MSG_METRICS) {
-    c->metrics.reset(new MetricsBlocks());
-    c->metrics->init();
+    if (!c->metrics) {
+      c->metrics.reset(new MetricsBlocks());
+      c->metrics->init();
+    } else {
+      c->metrics->clear();
+    }
   } else {
     return DFGPU_EINVAL;
   }
@@ -138,8 +144,14 @@ int oracle_submit(oracle_ctx* c, int msg_type, const uint8_t* frames, size_t nby
           c->counters.error_count++;  // unmarshaller.go:236-240 (ErrDocCount)
           break;
         }
-        c->counters.count++;
-        c->metrics->append_record(m, fr.org_id, (uint16_t)fr.team_id, pd, c->counters);
+        // an unknown meter id is a decode error too: it abandons the frame (codec.go:60-63)
+        uint8_t meter = (uint8_t)m.sub(3).u32(1);
+        if (meter != MT_METER_FLOW && meter != MT_METER_USAGE && meter != MT_METER_APP) {
+          c->counters.error_count++;
+          break;
+        }
+        c->counters.count++;  // DocCount, unmarshaller.go:124
+        c->metrics->append_record(m, fr.org_id, (uint16_t)fr.team_id, pd, c->counters, *c->metrics_state);
       }
     }
   }
@@ -159,7 +171,10 @@ int oracle_submit(oracle_ctx* c, int msg_type, const uint8_t* frames, size_t nby
     c->counters.rows[DFGPU_TABLE_L7_APP_SERVICE] = c->l7->app_service.nrows;
   }
   if (c->metrics && msg_type == DFGPU_MSG_METRICS)
+  {
     for (int t = 0; t < 9; t++) c->counters.rows[DFGPU_TABLE_METRICS_BASE + t] = c->metrics->tables[t].nrows;
+    c->counters.rows[DFGPU_TABLE_METRICS_APP_SERVICE] = c->metrics->app_service.nrows;
+  }
   return 0;
 }
 
@@ -173,7 +188,8 @@ static Block* find_block(oracle_ctx* c, int table) {
   }
   if (table >= DFGPU_TABLE_METRICS_BASE && table < DFGPU_TABLE_METRICS_BASE + 9 && c->metrics)
     return &c->metrics->tables[table - DFGPU_TABLE_METRICS_BASE];
-  if (table == DFGPU_TABLE_METRICS_BASE + 15 && c->metrics) return &c->metrics->reduced;
+  if (table == DFGPU_TABLE_METRICS_APP_SERVICE && c->metrics) return &c->metrics->app_service;
+  if (table == DFGPU_TABLE_METRICS_REDUCED && c->metrics) return &c->metrics->reduced;
   return nullptr;
 }
 
@@ -232,6 +248,140 @@ int oracle_kat_lru(int cap, int n, int touch, int* out_keys) {
   for (int i = 0; i < n; i++) c.Add(i, (uint32_t)i);
   if (touch >= 0) c.AddOrGet(touch, 0);
   return c.Keys(out_keys);
+}
+
+// flow-metrics/basic_meter_test.go:112-135 TestMerge, usage_meter_test.go:57-79
+// TestVTAPMeterMerge: a = every uint64/uint32 field set to `na` (uint8 fields stay 0, like
+// the test's reflect-based initMeter), b likewise with `nb`; a.ConcurrentMerge(b); the
+// fields come back in struct order.  kind: 1 flow, 4 usage, 5 app.
+extern "C++" {
+template <class T, size_t N>
+static int dump_fields(T (&p)[N], uint64_t* out) {
+  for (size_t i = 0; i < N; i++) out[i] = p[i];
+  return (int)N;
+}
+}
+int oracle_kat_meter_merge(int kind, uint64_t na, uint64_t nb, uint64_t* out) {
+  int n = 0;
+  if (kind == MT_METER_FLOW) {
+    MFlowMeter a, b;
+    MFlowMeter* ms[2] = {&a, &b};
+    uint64_t vs[2] = {na, nb};
+    for (int k = 0; k < 2; k++) {
+      MFlowMeter& m = *ms[k];
+      uint64_t v = vs[k];
+#define SETALL(M)                                                                                                   \
+  M(packet_tx) M(packet_rx) M(byte_tx) M(byte_rx) M(l3_byte_tx) M(l3_byte_rx) M(l4_byte_tx) M(l4_byte_rx)            \
+  M(new_flow) M(closed_flow) M(l7_request) M(l7_response) M(syn_count) M(synack_count) M(rtt_max) M(rtt_client_max)  \
+  M(rtt_server_max) M(srt_max) M(art_max) M(rrt_max) M(cit_max) M(rtt_sum) M(rtt_client_sum) M(rtt_server_sum)       \
+  M(srt_sum) M(art_sum) M(rrt_sum) M(cit_sum) M(rtt_count) M(rtt_client_count) M(rtt_server_count) M(srt_count)      \
+  M(art_count) M(rrt_count) M(cit_count) M(retrans_tx) M(retrans_rx) M(zero_win_tx) M(zero_win_rx) M(retrans_syn)    \
+  M(retrans_synack) M(client_rst_flow) M(server_rst_flow) M(server_syn_miss) M(client_ack_miss)                      \
+  M(client_half_close_flow) M(server_half_close_flow) M(client_source_port_reuse) M(client_establish_reset)          \
+  M(server_reset) M(server_queue_lack) M(server_establish_reset) M(tcp_timeout) M(client_establish_fail)             \
+  M(server_establish_fail) M(tcp_establish_fail) M(tcp_transfer_fail) M(tcp_rst_fail) M(l7_client_error)             \
+  M(l7_server_error) M(l7_timeout) M(ooo_tx) M(ooo_rx) M(flow_load)
+#define M(f) m.f = (decltype(m.f))v;
+      SETALL(M)
+#undef M
+    }
+    a.ConcurrentMerge(b);
+#define M(f) out[n++] = a.f;
+    SETALL(M)
+#undef M
+    out[n++] = a.direction_score;
+  } else if (kind == MT_METER_USAGE) {
+    MUsageMeter a, b;
+    // fillMetrics(hint) usage_meter_test.go:25-34
+    auto fill = [](MUsageMeter& m, uint64_t h) {
+      m.packet_tx = h * 3; m.packet_rx = h * 2; m.byte_tx = h * 97; m.byte_rx = h * 89;
+      m.l3_byte_tx = h * 96; m.l3_byte_rx = h * 88; m.l4_byte_tx = h * 95; m.l4_byte_rx = h * 87;
+    };
+    fill(a, na);
+    fill(b, nb);
+    a.ConcurrentMerge(b);
+    uint64_t f[] = {a.packet_tx, a.packet_rx, a.byte_tx, a.byte_rx, a.l3_byte_tx, a.l3_byte_rx, a.l4_byte_tx, a.l4_byte_rx};
+    n = dump_fields(f, out);
+  } else if (kind == MT_METER_APP) {
+    MAppMeter a, b;
+    MAppMeter* ms[2] = {&a, &b};
+    uint64_t vs[2] = {na, nb};
+    for (int k = 0; k < 2; k++) {
+      MAppMeter& m = *ms[k];
+      m.request = m.response = m.rrt_max = m.rrt_count = m.client_error = m.server_error = m.timeout = (uint32_t)vs[k];
+      m.rrt_sum = vs[k];
+    }
+    a.ConcurrentMerge(b);
+    uint64_t f[] = {a.request, a.response, a.direction_score, a.rrt_max, a.rrt_sum, a.rrt_count, a.client_error, a.server_error, a.timeout};
+    n = dump_fields(f, out);
+  }
+  return n;
+}
+// flow-metrics/tag_test.go:259-352 TestEncodeMiniTag: decode a pb.MiniTag and run
+// Tag.ReadFromPB; returns {code, ip4_0, ip4_1, l3_epc_0, l3_epc_1, vtap, protocol, server_port,
+// role, tap_type, acl_gid, is_ipv4, ip6_0[15], ip6_1[15], pod_id_0, pod_id_1, tunnel_ip_id}
+int oracle_kat_tag_read(const uint8_t* minitag, uint32_t n, int64_t* out) {
+  Msg m(&metric_schema().mini_tag);
+  m.reset();
+  if (!decode_msg(m, minitag, n)) return -1;
+  MTag t;
+  TagReadFromPB(t, m);
+  int64_t v[] = {(int64_t)t.code, t.ip4[0], t.ip4[1], t.l3_epc[0], t.l3_epc[1], t.vtap_id, t.protocol, t.server_port,
+                 t.role, t.tap_type, t.acl_gid, t.is_ipv4, t.ip6[0][15], t.ip6[1][15], t.pod_id[0], t.pod_id[1],
+                 t.tunnel_ip_id};
+  for (size_t i = 0; i < sizeof v / sizeof v[0]; i++) out[i] = v[i];
+  return (int)(sizeof v / sizeof v[0]);
+}
+// app.DecodePB (codec.go:28-65) of ONE Document, before DocumentExpand: hdr = {timestamp,
+// flags, uint8(meter_id)}; tag as oracle_kat_tag_read plus {gpid_0, gpid_1, signal_source,
+// tap_side, l7_protocol, biz_type, tap_port, tap_port_type, nat_source, tunnel_type, mac_0, mac_1, gtid};
+// meter fields in struct order (flow: SETALL order + direction_score).  Returns the meter field count, -1 on a decode error.
+int oracle_kat_doc_read(const uint8_t* doc, uint32_t n, uint32_t* hdr, int64_t* tag, uint64_t* meter) {
+  Msg m(&metric_schema().document);
+  m.reset();
+  if (!decode_msg(m, doc, n)) return -1;
+  hdr[0] = m.u32(1);
+  hdr[1] = m.u32(4);
+  hdr[2] = (uint8_t)m.sub(3).u32(1);
+  MTag t;
+  TagReadFromPB(t, m.sub(2));
+  int64_t v[] = {(int64_t)t.code, t.ip4[0], t.ip4[1], t.l3_epc[0], t.l3_epc[1], t.vtap_id, t.protocol, t.server_port,
+                 t.role, t.tap_type, t.acl_gid, t.is_ipv4, t.ip6[0][15], t.ip6[1][15], t.pod_id[0], t.pod_id[1],
+                 t.tunnel_ip_id, t.gpid[0], t.gpid[1], t.signal_source, t.tap_side, t.l7_protocol, t.biz_type,
+                 t.tap_port, t.tap_port_type, t.nat_source, t.tunnel_type, (int64_t)t.mac[0], (int64_t)t.mac[1], t.gtid};
+  for (size_t i = 0; i < sizeof v / sizeof v[0]; i++) tag[i] = v[i];
+  int k = 0;
+  if (hdr[2] == MT_METER_FLOW) {
+    MFlowMeter a;
+    a.ReadFromPB(m.sub(3).sub(2));
+#define M(f) meter[k++] = a.f;
+    SETALL(M)
+#undef M
+    meter[k++] = a.direction_score;
+  } else if (hdr[2] == MT_METER_USAGE) {
+    MUsageMeter a;
+    a.ReadFromPB(m.sub(3).sub(3));
+    uint64_t f[] = {a.packet_tx, a.packet_rx, a.byte_tx, a.byte_rx, a.l3_byte_tx, a.l3_byte_rx, a.l4_byte_tx, a.l4_byte_rx};
+    k = dump_fields(f, meter);
+  } else if (hdr[2] == MT_METER_APP) {
+    MAppMeter a;
+    a.ReadFromPB(m.sub(3).sub(4));
+    uint64_t f[] = {a.request, a.response, a.direction_score, a.rrt_max, a.rrt_sum, a.rrt_count, a.client_error, a.server_error, a.timeout};
+    k = dump_fields(f, meter);
+  }
+  return k;
+}
+#undef SETALL
+// Tag.TableID over a raw code (tag.go:920-931)
+int oracle_kat_table_id(uint64_t code, int is_second) { return TagTableID(code, is_second != 0); }
+// column names / container kinds of one metrics table, '\n'-joined "name:ch_type"
+const char* oracle_kat_metrics_columns(int table) {
+  static thread_local std::string s;
+  Block b;
+  MetricsBlocks::add_columns(b, table);
+  s.clear();
+  for (auto& c : b.cols) s += c.name + ":" + std::to_string(c.ch_type) + ":" + std::to_string(c.elem_size) + "\n";
+  return s.c_str();
 }
 
 }  // extern "C"

@@ -74,6 +74,46 @@ SCHEMA = {
                          ("row_effect", 16, U32), ("direction_score", 17, U32), ("flags", 18, U32),
                          ("captured_request_byte", 19, U32), ("captured_response_byte", 20, U32),
                          ("biz_code", 21, STR), ("biz_scenario", 22, STR), ("biz_response_code", 23, STR)],
+    # ---- message/metric.proto:14-195 ----
+    "MiniField": [("ip", 1, BYT), ("ip1", 2, BYT), ("global_thread_id", 3, U32), ("is_ipv6", 4, U32),
+                  ("l3_epc_id", 5, I32), ("l3_epc_id1", 6, I32), ("mac", 7, U64), ("mac1", 8, U64),
+                  ("direction", 9, U32), ("tap_side", 10, U32), ("protocol", 11, U32), ("acl_gid", 12, U32),
+                  ("server_port", 13, U32), ("vtap_id", 14, U32), ("tap_port", 15, U64), ("tap_type", 16, U32),
+                  ("l7_protocol", 17, U32), ("gpid", 20, U32), ("gpid1", 21, U32), ("signal_source", 22, U32),
+                  ("app_service", 23, STR), ("app_instance", 24, STR), ("endpoint", 25, STR), ("pod_id", 27, U32),
+                  ("biz_type", 28, U32)],
+    "MiniTag": [("field", 1, MSG, "MiniField"), ("code", 2, U64)],
+    "Traffic": [("packet_tx", 1, U64), ("packet_rx", 2, U64), ("byte_tx", 3, U64), ("byte_rx", 4, U64),
+                ("l3_byte_tx", 5, U64), ("l3_byte_rx", 6, U64), ("l4_byte_tx", 7, U64), ("l4_byte_rx", 8, U64),
+                ("new_flow", 9, U64), ("closed_flow", 10, U64), ("l7_request", 11, U32), ("l7_response", 12, U32),
+                ("syn", 13, U32), ("synack", 14, U32), ("direction_score", 15, U32)],
+    "Latency": [("rtt_max", 1, U32), ("rtt_client_max", 2, U32), ("rtt_server_max", 3, U32), ("srt_max", 4, U32),
+                ("art_max", 5, U32), ("rrt_max", 6, U32), ("cit_max", 19, U32), ("rtt_sum", 7, U64),
+                ("rtt_client_sum", 8, U64), ("rtt_server_sum", 9, U64), ("srt_sum", 10, U64), ("art_sum", 11, U64),
+                ("rrt_sum", 12, U64), ("cit_sum", 20, U64), ("rtt_count", 13, U32), ("rtt_client_count", 14, U32),
+                ("rtt_server_count", 15, U32), ("srt_count", 16, U32), ("art_count", 17, U32),
+                ("rrt_count", 18, U32), ("cit_count", 21, U32)],
+    "Performance": [("retrans_tx", 1, U64), ("retrans_rx", 2, U64), ("zero_win_tx", 3, U64), ("zero_win_rx", 4, U64),
+                    ("retrans_syn", 5, U32), ("retrans_synack", 6, U32)],
+    "Anomaly": [("client_rst_flow", 1, U64), ("server_rst_flow", 2, U64), ("server_syn_miss", 3, U64),
+                ("client_ack_miss", 4, U64), ("client_half_close_flow", 5, U64), ("server_half_close_flow", 6, U64),
+                ("client_source_port_reuse", 7, U64), ("client_establish_reset", 8, U64), ("server_reset", 9, U64),
+                ("server_queue_lack", 10, U64), ("server_establish_reset", 11, U64), ("tcp_timeout", 12, U64),
+                ("l7_client_error", 13, U32), ("l7_server_error", 14, U32), ("l7_timeout", 15, U32),
+                ("client_ooo", 20, U64), ("server_ooo", 21, U64)],
+    "FlowLoad": [("load", 1, U64)],
+    "FlowMeter": [("traffic", 1, MSG, "Traffic"), ("latency", 2, MSG, "Latency"),
+                  ("performance", 3, MSG, "Performance"), ("anomaly", 4, MSG, "Anomaly"),
+                  ("flow_load", 5, MSG, "FlowLoad")],
+    "UsageMeter": [("packet_tx", 1, U64), ("packet_rx", 2, U64), ("byte_tx", 3, U64), ("byte_rx", 4, U64),
+                   ("l3_byte_tx", 5, U64), ("l3_byte_rx", 6, U64), ("l4_byte_tx", 7, U64), ("l4_byte_rx", 8, U64)],
+    "AppTraffic": [("request", 1, U32), ("response", 2, U32), ("direction_score", 3, U32)],
+    "AppLatency": [("rrt_max", 1, U32), ("rrt_sum", 2, U64), ("rrt_count", 3, U32)],
+    "AppAnomaly": [("client_error", 1, U32), ("server_error", 2, U32), ("timeout", 3, U32)],
+    "AppMeter": [("traffic", 1, MSG, "AppTraffic"), ("latency", 2, MSG, "AppLatency"), ("anomaly", 3, MSG, "AppAnomaly")],
+    "Meter": [("meter_id", 1, U32), ("flow", 2, MSG, "FlowMeter"), ("usage", 3, MSG, "UsageMeter"),
+              ("app", 4, MSG, "AppMeter")],
+    "Document": [("timestamp", 1, U32), ("tag", 2, MSG, "MiniTag"), ("meter", 3, MSG, "Meter"), ("flags", 4, U32)],
 }
 
 _CLASSES = None
