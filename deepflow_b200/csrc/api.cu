@@ -20,6 +20,13 @@ void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s);
 struct FlowTagDev;
 int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s);
 int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s);
+// metrics.cu
+int metrics_passes(dfgpu_ctx* ctx, int repair);
+int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t));
+int metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch* b,
+                   uint8_t* (*acquire)(dfgpu_ctx*, size_t));
+uint64_t metrics_arena_need(uint32_t nrec, uint64_t nbytes);
+void metrics_free_state(dfgpu_ctx* ctx);
 }  // namespace dfgpu
 
 #define X(id, name, t, es) {name, t, es, -1},
@@ -82,6 +89,7 @@ int dfgpu_close(dfgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   dfgpu_l7_free_state(ctx);
+  metrics_free_state(ctx);
   cudaFree(ctx->d_in);
   cudaFree(ctx->d_frames);
   cudaFree(ctx->d_frame_u32);
@@ -320,7 +328,8 @@ extern "C" {
 int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbytes, const dfgpu_frame* tbl,
                 int nframes) {
   if (!ctx || nframes < 0 || (nframes && !tbl) || (nbytes && !frames)) return DFGPU_EINVAL;
-  if (!main_schema(msg_type)) return fail(ctx, DFGPU_EINVAL, "unsupported msg_type %d", msg_type);
+  if (!main_schema(msg_type) && msg_type != DFGPU_MSG_METRICS)
+    return fail(ctx, DFGPU_EINVAL, "unsupported msg_type %d", msg_type);
   if (nbytes >= (1ull << 32)) return fail(ctx, DFGPU_EINVAL, "batch too large (%zu bytes)", nbytes);
   CU(cudaSetDevice(ctx->device));
   cudaPointerAttributes attr;
@@ -368,6 +377,7 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
   ctx->cur_org = org;
   ctx->staged = true;
   ctx->ran = false;
+  ctx->metrics_resident = false;
   return DFGPU_OK;
 }
 
@@ -440,9 +450,11 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
   bp.warp_base = ctx->d_warp + (size_t)MAX_SLOTS * ctx->warp_cap;
   // the kernels index [slot][nwarps] with stride nwarps (not warp_cap): both halves are
   // large enough because nslots <= MAX_SLOTS and nwarps <= warp_cap.
-  uint64_t fixed = plan_fixed(*sch, nrec, bp.fix_off, bp.aux_off);
+  const bool is_metrics = ctx->cur_msg == DFGPU_MSG_METRICS;
+  uint64_t fixed = is_metrics ? 0 : plan_fixed(*sch, nrec, bp.fix_off, bp.aux_off);
   bp.var_base = fixed;
   uint64_t want = fixed + 2 * (uint64_t)ctx->cur_nbytes + (uint64_t)nrec * 96 + (1u << 20);
+  if (is_metrics) want = metrics_arena_need(nrec, ctx->cur_nbytes);
   if (want > ctx->arena_cap) {
     if (ctx->d_arena) CU(cudaFree(ctx->d_arena));
     ctx->d_arena = nullptr;
@@ -452,12 +464,19 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
   }
   bp.arena = ctx->d_arena;
   bp.arena_bytes = ctx->arena_cap;
-  setup_streams(bp, ctx->cur_msg);
+  if (!is_metrics) setup_streams(bp, ctx->cur_msg);
   if (nf && nrec) {
     launch_frame_fill(bp, s);
     ctx->launches++;
   }
   int rc = 0;
+  if (is_metrics) {
+    rc = metrics_passes(ctx, 0);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev1, s));
+    ctx->ran = true;
+    return DFGPU_OK;
+  }
   if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
     rc = l7_prepare(ctx, s);
     if (rc) return rc;
@@ -553,6 +572,31 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
     size_t cap = std::max<uint32_t>(nf, 1024);
     CU(cudaHostAlloc(&ctx->h_frame_u32, cap * 2 * sizeof(uint32_t), cudaHostAllocDefault));
     ctx->h_frames_cap = (uint32_t)cap;
+  }
+  if (ctx->cur_msg == DFGPU_MSG_METRICS) {
+    dfgpu_batch* b = new dfgpu_batch();
+    b->ctx = ctx;
+    b->msg_type = ctx->cur_msg;
+    memset(&b->counters, 0, sizeof b->counters);
+    int rc = metrics_fetch(ctx, b, host_acquire);
+    if (rc) {
+      dfgpu_batch_release(b);
+      return rc;
+    }
+    if (nf) {
+      CU(cudaMemcpyAsync(ctx->h_frame_u32, bp.frame_chain_err, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync(ctx->h_frame_u32 + ctx->h_frames_cap, bp.frame_bad, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+    }
+    b->counters.raw_count = nf;
+    for (uint32_t f = 0; f < nf; f++)  // ErrDocCount: one per abandoned frame (unmarshaller.go:236-240)
+      if (ctx->h_frame_u32[f] || ctx->h_frame_u32[ctx->h_frames_cap + f] != NO_BAD) b->counters.error_count++;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) b->counters.device_us = ms * 1000.0;
+    ctx->ran = false;
+    ctx->metrics_resident = true;
+    *out = b;
+    return DFGPU_OK;
   }
   for (int attempt = 0;; attempt++) {
     CU(cudaMemcpyAsync(ctx->h_dyn, ctx->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, s));
@@ -779,10 +823,23 @@ int dfgpu_profile_read(dfgpu_ctx* ctx, double* emit_ms, uint64_t* launches, uint
   return DFGPU_OK;
 }
 
-int dfgpu_metrics_reduce(dfgpu_ctx* ctx, uint32_t bucket_seconds, dfgpu_batch** out) {
-  (void)bucket_seconds;
-  (void)out;
-  return fail(ctx, DFGPU_ENOENT, "metrics path not built in this library version");
+int dfgpu_metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch** out) {
+  if (!ctx || !out || bucket_seconds == 0) return DFGPU_EINVAL;
+  if (table < DFGPU_TABLE_METRICS_BASE || table >= DFGPU_TABLE_METRICS_BASE + 9)
+    return fail(ctx, DFGPU_EINVAL, "table %d is not a flow_metrics table", table);
+  if (!ctx->metrics_resident) return fail(ctx, DFGPU_ENOENT, "no metrics batch resident on the device");
+  CU(cudaSetDevice(ctx->device));
+  dfgpu_batch* b = new dfgpu_batch();
+  b->ctx = ctx;
+  b->msg_type = DFGPU_MSG_METRICS;
+  memset(&b->counters, 0, sizeof b->counters);
+  int rc = metrics_reduce(ctx, table - DFGPU_TABLE_METRICS_BASE, bucket_seconds, b, host_acquire);
+  if (rc) {
+    dfgpu_batch_release(b);
+    return rc;
+  }
+  *out = b;
+  return DFGPU_OK;
 }
 
 }  // extern "C"

@@ -75,6 +75,9 @@ struct dfgpu_ctx {
 
   // flow tag state (l7)
   void* ft = nullptr;
+  // flow_metrics state (metrics.cu)
+  void* mt = nullptr;
+  bool metrics_resident = false;  // the arena still holds the tables of the last metrics batch
 };
 
 inline int fail(dfgpu_ctx* c, int code, const char* fmt, ...) {

@@ -45,7 +45,7 @@ def lib():
         L.dfgpu_batch_counters.argtypes = [vp, C.POINTER(abi.Counters)]
         L.dfgpu_batch_release.argtypes = [vp]
         L.dfgpu_batch_release.restype = None
-        L.dfgpu_metrics_reduce.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+        L.dfgpu_metrics_reduce.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(vp)]
         L.dfgpu_flush.argtypes = [vp]
         L.dfgpu_profile_enable.argtypes = [vp, C.c_int]
         L.dfgpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -143,6 +143,12 @@ class Engine:
 
     def sync(self):
         self._check(lib().dfgpu_sync(self._h), "dfgpu_sync")
+
+    def metrics_reduce(self, table, bucket_seconds=60):
+        """Reduce-by-key over one table of the last metrics batch (still resident in HBM)."""
+        out = C.c_void_p()
+        self._check(lib().dfgpu_metrics_reduce(self._h, table, bucket_seconds, C.byref(out)), "dfgpu_metrics_reduce")
+        return Batch(out)
 
     def profile_enable(self, on=True):
         self._check(lib().dfgpu_profile_enable(self._h, 1 if on else 0), "dfgpu_profile_enable")
