@@ -20,6 +20,7 @@ void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s);
 struct FlowTagDev;
 int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s);
 int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s);
+int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n);
 // metrics.cu
 int metrics_passes(dfgpu_ctx* ctx, int repair);
 int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t));
@@ -821,6 +822,23 @@ int dfgpu_profile_read(dfgpu_ctx* ctx, double* emit_ms, uint64_t* launches, uint
   if (in_bytes) *in_bytes = bytes;
   ctx->prof_used = 0;
   return DFGPU_OK;
+}
+
+int dfgpu_batch_tag_fingerprints(const dfgpu_batch* b, int table, const uint64_t** fps, uint64_t* n) {
+  if (!b || !fps || !n) return DFGPU_EINVAL;
+  for (auto& t : b->tag_fps)
+    if (t.table == table) {
+      *fps = t.fps;
+      *n = t.n;
+      return DFGPU_OK;
+    }
+  return DFGPU_ENOENT;
+}
+
+int dfgpu_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n) {
+  if (!ctx || (n && (!fps || !times))) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  return l7_tags_import(ctx, fps, times, n);
 }
 
 int dfgpu_metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch** out) {

@@ -109,6 +109,12 @@ struct dfgpu_batch {
     std::vector<dfgpu_col> cols;
   };
   std::vector<Table> tables;
+  struct TagFp {  // 128-bit lru-key fingerprints of a flow_tag table's rows, row order
+    int table;
+    const uint64_t* fps;
+    uint64_t n;
+  };
+  std::vector<TagFp> tag_fps;
   std::vector<std::vector<uint8_t>> owned;   // small host-built buffers (LC dictionaries)
   std::vector<std::vector<dfgpu_pos>> owned_pos;
 };

@@ -67,7 +67,9 @@ enum {
   FO_FV_TIME = 0, FO_FV_VPC, FO_FV_PODNS, FO_FV_FTYPE, FO_FV_FVTYPE, FO_FV_TEAM, FO_FV_TABLE, FO_FV_NAME_POS,
   FO_FV_VAL_POS, FO_FV_COUNT, FO_FV_NAME_BUF, FO_FV_VAL_BUF,
   FO_F_TIME, FO_F_VPC, FO_F_PODNS, FO_F_FTYPE, FO_F_FVTYPE, FO_F_TEAM, FO_F_TABLE, FO_F_NAME_POS, FO_F_NAME_BUF,
-  FO_AS_TIME, FO_AS_TABLE, FO_AS_SVC_POS, FO_AS_INST_POS, FO_AS_TEAM, FO_AS_BUF, FO_COUNT
+  FO_AS_TIME, FO_AS_TABLE, FO_AS_SVC_POS, FO_AS_INST_POS, FO_AS_TEAM, FO_AS_BUF,
+  FO_FV_FP, FO_F_FP, FO_AS_FP,  // 128-bit key fingerprint of every emitted row (multi-GPU tag merge)
+  FO_COUNT
 };
 
 // find-or-insert in this context's tag set (tagset.cuh)
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
           reinterpret_cast<dfgpu_pos*>(fa + fo[FO_FV_NAME_POS])[o_fv] = dfgpu_pos{(int64_t)o_fvn, (int64_t)(o_fvn + name.n)};
           reinterpret_cast<dfgpu_pos*>(fa + fo[FO_FV_VAL_POS])[o_fv] = dfgpu_pos{(int64_t)o_fvv, (int64_t)(o_fvv + value.n)};
           reinterpret_cast<uint64_t*>(fa + fo[FO_FV_COUNT])[o_fv] = 1;
+          reinterpret_cast<U128*>(fa + fo[FO_FV_FP])[o_fv] = fpv;
           for (uint32_t c = 0; c < name.n; c++) (fa + fo[FO_FV_NAME_BUF])[o_fvn + c] = name.p[c];
           for (uint32_t c = 0; c < value.n; c++) (fa + fo[FO_FV_VAL_BUF])[o_fvv + c] = value.p[c];
           o_fv++;
@@ -304,6 +307,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
           (fa + fo[FO_F_FVTYPE])[o_f] = 0;
           reinterpret_cast<uint16_t*>(fa + fo[FO_F_TEAM])[o_f] = v.team;
           (fa + fo[FO_F_TABLE])[o_f] = 0;
+          reinterpret_cast<U128*>(fa + fo[FO_F_FP])[o_f] = fpf;
           reinterpret_cast<dfgpu_pos*>(fa + fo[FO_F_NAME_POS])[o_f] = dfgpu_pos{(int64_t)o_fn, (int64_t)(o_fn + name.n)};
           for (uint32_t c = 0; c < name.n; c++) (fa + fo[FO_F_NAME_BUF])[o_fn + c] = name.p[c];
           o_f++;
@@ -344,6 +348,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
           (fa + fo[FO_F_FVTYPE])[o_f] = 1;  // "float": empty value and FieldType != tag
           reinterpret_cast<uint16_t*>(fa + fo[FO_F_TEAM])[o_f] = v.team;
           (fa + fo[FO_F_TABLE])[o_f] = 0;
+          reinterpret_cast<U128*>(fa + fo[FO_F_FP])[o_f] = fpf;
           reinterpret_cast<dfgpu_pos*>(fa + fo[FO_F_NAME_POS])[o_f] = dfgpu_pos{(int64_t)o_fn, (int64_t)(o_fn + name.n)};
           for (uint32_t c = 0; c < name.n; c++) (fa + fo[FO_F_NAME_BUF])[o_fn + c] = name.p[c];
           o_f++;
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
           if (writing) {
             reinterpret_cast<uint32_t*>(fa + fo[FO_AS_TIME])[o_as] = v.time_as;
             (fa + fo[FO_AS_TABLE])[o_as] = 0;
+            reinterpret_cast<U128*>(fa + fo[FO_AS_FP])[o_as] = fpa;
             reinterpret_cast<dfgpu_pos*>(fa + fo[FO_AS_SVC_POS])[o_as] =
                 dfgpu_pos{(int64_t)o_asb, (int64_t)(o_asb + v.app_service.n)};
             reinterpret_cast<dfgpu_pos*>(fa + fo[FO_AS_INST_POS])[o_as] = dfgpu_pos{0, 0};
@@ -428,6 +434,7 @@ __global__ void k_l7_ft_layout(const BatchParams p) {
   take(FO_F_NAME_BUF, tot[FT_F_NAME_B]);
   take(FO_AS_TIME, nas * 4); take(FO_AS_TABLE, nas); take(FO_AS_SVC_POS, nas * 16); take(FO_AS_INST_POS, nas * 16);
   take(FO_AS_TEAM, nas * 2); take(FO_AS_BUF, tot[FT_AS_B]);
+  take(FO_FV_FP, nfv * 16); take(FO_F_FP, nf * 16); take(FO_AS_FP, nas * 16);
   dyn->stats.ft_end = cur;
   dyn->stats.ft_overflow = cur > d->ft_arena_bytes ? 1 : 0;
 }
@@ -696,11 +703,54 @@ int l7_fetch_tables(dfgpu_ctx* ctx, dfgpu_batch* b) {
     strcol(t, "app_instance", DFGPU_CH_LC_STR_ROWS, fo[FO_AS_INST_POS], fo[FO_AS_BUF], 0, nas);
     fixed(t, "team_id", DFGPU_CH_UINT16, 2, fo[FO_AS_TEAM], nas);
   }
+  b->tag_fps.push_back({DFGPU_TABLE_L7_CUSTOM_FIELD, (const uint64_t*)(hb + fo[FO_F_FP]), nf});
+  b->tag_fps.push_back({DFGPU_TABLE_L7_CUSTOM_FIELD_VALUE, (const uint64_t*)(hb + fo[FO_FV_FP]), nfv});
+  b->tag_fps.push_back({DFGPU_TABLE_L7_APP_SERVICE, (const uint64_t*)(hb + fo[FO_AS_FP]), nas});
   b->counters.new_field_count = (int64_t)nf;
   b->counters.new_field_value_count = (int64_t)nfv;
   b->counters.rows[DFGPU_TABLE_L7_CUSTOM_FIELD] = (int64_t)nf;
   b->counters.rows[DFGPU_TABLE_L7_CUSTOM_FIELD_VALUE] = (int64_t)nfv;
   b->counters.rows[DFGPU_TABLE_L7_APP_SERVICE] = (int64_t)nas;
+  return 0;
+}
+
+// ---- multi-GPU tag merge: keys another rank emitted become "seen" here too -----------------------
+__global__ void k_l7_ft_import(FtEntry* tbl, uint32_t mask, const U128* fps, const uint32_t* times, uint32_t n,
+                               uint32_t* full) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  FtEntry* e = ts_upsert(tbl, mask, fps[i], full);
+  if (!e) return;
+  // the same key may arrive from several ranks: keep the newest emission time
+  atomicMax(&e->time, times[i]);
+  e->state = 1;
+}
+
+int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n) {
+  if (!n) return 0;
+  int rc = l7_ensure_state(ctx);
+  if (rc) return rc;
+  L7Host* h = reinterpret_cast<L7Host*>(ctx->ft);
+  cudaStream_t s = ctx->stream;
+  U128* d_fps = nullptr;
+  uint32_t* d_times = nullptr;
+  uint32_t* d_full = nullptr;
+  CU(cudaMalloc(&d_fps, n * 16 + n * 4 + 16));
+  d_times = reinterpret_cast<uint32_t*>(d_fps + n);
+  d_full = d_times + n;
+  cudaError_t e = cudaMemcpyAsync(d_fps, fps, n * 16, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_times, times, n * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_full, 0, 4, s);
+  uint32_t full = 0;
+  if (e == cudaSuccess) {
+    k_l7_ft_import<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->d_ft, h->dev.ft_mask, d_fps, d_times, (uint32_t)n, d_full);
+    ctx->launches++;
+    e = cudaMemcpyAsync(&full, d_full, 4, cudaMemcpyDeviceToHost, s);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_fps);
+  if (e != cudaSuccess) return fail(ctx, DFGPU_ENODEV, "tag import failed: %s", cudaGetErrorString(e));
+  if (full) return fail(ctx, DFGPU_ENOMEM, "flow_tag device set is full (raise flow_tag_cache_max_size)");
   return 0;
 }
 

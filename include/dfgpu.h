@@ -304,6 +304,19 @@ int dfgpu_batch_columns(const dfgpu_batch* b, int table, dfgpu_col* cols, int* n
 int dfgpu_batch_counters(const dfgpu_batch* b, dfgpu_counters* out);
 void dfgpu_batch_release(dfgpu_batch* b);
 
+/* Multi-GPU tag merge.  Records shard across GPUs by vtap_id; every decoder
+ * keeps its own flow_tag "seen" set (like the reference's per-decoder caches,
+ * flow_tag_writer.go:65-77).  After a batch each rank publishes the 128-bit lru-key
+ * fingerprints of the flow_tag rows it emitted (row order, 2 x u64 per row; tables
+ * L7_CUSTOM_FIELD, L7_CUSTOM_FIELD_VALUE, L7_APP_SERVICE), the ranks all-gather them
+ * (NCCL), and every rank imports the others' keys so that later batches do not emit
+ * them again.  The lowest rank that emitted a key in a step owns the row; the others
+ * drop theirs (host side, deepflow_b200/sharded.py).
+ *   fps   : pointer into the batch's host memory, valid until dfgpu_batch_release
+ *   times : the `time` column value of the emitting row (lru Add(key, time))          */
+int dfgpu_batch_tag_fingerprints(const dfgpu_batch* b, int table, const uint64_t** fps, uint64_t* n);
+int dfgpu_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n);
+
 /* flow_metrics reduce-by-key: merges the decoded Document rows of the
  * last metrics run by (time bucket, all tag columns) with the per-field rules of
  * FlowMeter.ConcurrentMerge (flow-metrics/basic_meter.go:94-113,277-315,417-424,
