@@ -7,7 +7,8 @@ AppProtoLogsData records, submitted the way the ingester's decoder sees them:
 sub-batches of <= 1024 agent frames (decoder.go:56 BUFFER_SIZE x 256 KiB frames).
 One "step" = one pass over all sub-batches.  Under torchrun every rank owns the
 vtap_id % N == rank shard of the firehose (weak scaling: 10 M records per GPU);
-the data path has no collective.
+per-record work has no collective — the only exchange is the all-gather of newly
+emitted flow_tag keys after every e2e step (deepflow_b200/sharded.py).
 
   value     device-resident: inputs already in HBM, kernels only (CUDA events on the
             library's stream)
@@ -302,9 +303,13 @@ def main():
 
     # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H per sub-batch -------------
     d2h_total = [0]
+    from deepflow_b200.native import Batch, lib
+    from deepflow_b200.sharded import FLOW_TAG_TABLES, TagMerge
+    merge = TagMerge(device=torch.device("cuda", local)) if world > 1 else None
 
     def e2e_step():
         err = []
+        new_fps, new_times = [], []
 
         def worker(k):
             eng = engines[k]
@@ -312,12 +317,21 @@ def main():
                 for i in range(k, len(subs), len(engines)):
                     w = subs[i]
                     out = C.c_void_p()
-                    from deepflow_b200.native import lib
                     rc = lib().dfgpu_submit(eng._h, MSG, pinned[i].data_ptr(), w.nbytes, w.frames.ctypes.data,
                                             len(w.frames), None, None, C.byref(out))
                     if rc != 0:
                         raise RuntimeError(f"dfgpu_submit rc={rc}")
-                    lib().dfgpu_batch_release(out)
+                    if merge is not None:  # keys this decoder discovered: published after the step
+                        b = Batch(out)
+                        for t in FLOW_TAG_TABLES:
+                            f = b.tag_fingerprints(t)
+                            if len(f):
+                                cols, _ = b.columns(t)
+                                new_fps.append(f)
+                                new_times.append(cols[0].values.astype(np.uint32))
+                        b.release()
+                    else:
+                        lib().dfgpu_batch_release(out)
             except Exception as ex:  # noqa: BLE001
                 err.append(ex)
 
@@ -326,6 +340,15 @@ def main():
         [t.join() for t in ts]
         if err:
             raise err[0]
+        if merge is not None:
+            # the one collective of the path: all-gather of the newly emitted flow_tag keys (NCCL),
+            # then every decoder of this rank imports the union
+            fps = np.concatenate(new_fps) if new_fps else np.zeros((0, 2), np.uint64)
+            tms = np.concatenate(new_times) if new_times else np.zeros(0, np.uint32)
+            _keep, rf, rt = merge.exchange(fps, tms)
+            allf, allt = np.concatenate([rf, fps]), np.concatenate([rt, tms])
+            for e in engines:
+                e.tags_import(allf, allt)
 
     for _ in range(a.warmup):
         e2e_step()
@@ -372,7 +395,12 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer (f64 casts only at pack)",
                 "data": "synthetic", "config": dict(cfg_common, mean_wire_bytes=in_bytes / nrec_step,
                                                     packed_bytes_per_row=bytes_per_row, gen_seconds=gen_s,
-                                                    decoders_per_gpu=len(engines)),
+                                                    decoders_per_gpu=len(engines),
+                                                    tag_merge=(None if merge is None else {
+                                                        "collective": "all_gather of emitted flow_tag key fingerprints, "
+                                                                      "once per e2e step (NCCL)",
+                                                        "bytes_sent_rank0": merge.bytes_sent,
+                                                        "seconds_rank0": merge.seconds})),
                 "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": h2d_per_step,
                         "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms_max / a.steps},
                 "gpu_launches": int(launches_value), "clocks": clocks, "roofline": roof}

@@ -71,7 +71,21 @@ def build_dfgpu(force=False, verbose=False):
     return "\n".join(log) if verbose else out
 
 
+def build_host(force=False):
+    """libdfhost.so: the C++ mirror of the decoder goroutine (queue -> dfgpu_submit -> blocks)."""
+    d = os.path.join(_HERE, "host")
+    out = os.path.join(d, "libdfhost.so")
+    srcs = glob.glob(os.path.join(d, "*.cc"))
+    deps = srcs + glob.glob(os.path.join(d, "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.h")) + \
+        [os.path.join(_HERE, "libdfgpu.so")]
+    if force or _newer(out, deps):
+        _run([CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", out] + srcs +
+             ["-I", os.path.join(ROOT, "include"), "-L", _HERE, "-ldfgpu", "-Wl,-rpath,$ORIGIN/.."])
+    return out
+
+
 def build_all(force=False):
     build_synth(force)
     build_dfgpu(force)
+    build_host(force)
     return True

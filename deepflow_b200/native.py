@@ -46,6 +46,8 @@ def lib():
         L.dfgpu_batch_release.argtypes = [vp]
         L.dfgpu_batch_release.restype = None
         L.dfgpu_metrics_reduce.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(vp)]
+        L.dfgpu_batch_tag_fingerprints.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
+        L.dfgpu_tags_import.argtypes = [vp, vp, vp, C.c_uint64]
         L.dfgpu_flush.argtypes = [vp]
         L.dfgpu_profile_enable.argtypes = [vp, C.c_int]
         L.dfgpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -64,6 +66,18 @@ class Batch:
         c = abi.Counters()
         lib().dfgpu_batch_counters(self._h, C.byref(c))
         return c
+
+    def tag_fingerprints(self, table):
+        """(n, 2) uint64 copy of the lru-key fingerprints of a flow_tag table's rows."""
+        import numpy as np
+        p = C.POINTER(C.c_uint64)()
+        n = C.c_uint64(0)
+        rc = lib().dfgpu_batch_tag_fingerprints(self._h, table, C.byref(p), C.byref(n))
+        if rc != 0:
+            raise DfgpuError(f"dfgpu_batch_tag_fingerprints(table={table}) failed: {rc}")
+        if n.value == 0:
+            return np.zeros((0, 2), np.uint64)
+        return np.ctypeslib.as_array(p, shape=(int(n.value), 2)).copy()
 
     def release(self):
         if self._h:
@@ -143,6 +157,15 @@ class Engine:
 
     def sync(self):
         self._check(lib().dfgpu_sync(self._h), "dfgpu_sync")
+
+    def tags_import(self, fps, times):
+        """Insert keys other ranks emitted: fps (n, 2) uint64, times (n,) uint32 (numpy, host)."""
+        import numpy as np
+        fps = np.ascontiguousarray(fps, np.uint64)
+        times = np.ascontiguousarray(times, np.uint32)
+        n = len(times)
+        if n:
+            self._check(lib().dfgpu_tags_import(self._h, fps.ctypes.data, times.ctypes.data, n), "dfgpu_tags_import")
 
     def metrics_reduce(self, table, bucket_seconds=60):
         """Reduce-by-key over one table of the last metrics batch (still resident in HBM)."""

@@ -1,0 +1,121 @@
+"""Multi-GPU host logic: one process per GPU, records sharded by vtap_id, and the
+only collective of the path — the merge of newly discovered flow_tag keys.
+
+Per-record work needs no exchange: the dictionary is replicated, `vtap_id` is part of every
+flow_metrics table code (server/libs/flow-metrics/tag.go:497-506) so reduced groups are
+disjoint across shards, and the `_id` / trace-index counters are per decoder exactly like the
+reference's per-goroutine state (flow_log.go:226-247).  What the reference does NOT share —
+the flow_tag lru of each decoder (flow_tag_writer.go:65-77) — is merged here so that the
+shards together emit what one global cache would:
+
+  step k:  every rank decodes its shard and emits rows for keys new to ITS set
+           all ranks all-gather (fingerprint, time) of the rows they emitted      [NCCL]
+           ownership: the lowest rank that emitted a key in this step keeps the row,
+                      higher ranks drop theirs
+           every rank imports the other ranks' keys into its device set
+
+Pure torch.distributed code: runs over NCCL with CUDA tensors (bench.py, one rank per GPU)
+and over gloo with CPU tensors (tests/test_sharded_cpu.py, world_size 2).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_of(vtap_id, world_size):
+    """gpu = hash(vtap_id) % G with hash = identity."""
+    return int(vtap_id) % int(world_size)
+
+
+def _void16(a):
+    a = np.ascontiguousarray(a, np.uint64).reshape(-1, 2)
+    return a.view(np.dtype((np.void, 16))).ravel()
+
+
+class TagMerge:
+    """All-gather of (fingerprint, time) lists + the ownership rule."""
+
+    def __init__(self, group=None, device=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = device if device is not None else torch.device("cpu")
+        self.bytes_sent = 0       # payload this rank contributed to all-gathers
+        self.seconds = 0.0
+
+    def exchange(self, fps, times):
+        """fps (n, 2) uint64, times (n,) uint32 (numpy) of the rows this rank emitted in this step.
+        Returns keep (n,) bool, remote_fps (m, 2) uint64, remote_times (m,) uint32."""
+        import time as _t
+        t0 = _t.perf_counter()
+        fps = np.ascontiguousarray(fps, np.uint64).reshape(-1, 2)
+        times = np.ascontiguousarray(times, np.uint32).reshape(-1)
+        n = len(times)
+        assert len(fps) == n
+        if self.world == 1:
+            return np.ones(n, bool), np.zeros((0, 2), np.uint64), np.zeros(0, np.uint32)
+        # 1) lengths
+        cnt = torch.tensor([n], dtype=torch.int64, device=self.device)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(cnts, cnt, group=self.group)
+        counts = [int(c.item()) for c in cnts]
+        m = max(counts)
+        remote_fps = np.zeros((0, 2), np.uint64)
+        remote_times = np.zeros(0, np.uint32)
+        keep = np.ones(n, bool)
+        if m:
+            # 2) padded payload: (m, 3) int64 = lo, hi, time
+            pay = np.zeros((m, 3), np.int64)
+            pay[:n, 0:2] = fps.view(np.int64)
+            pay[:n, 2] = times
+            mine = torch.from_numpy(pay).to(self.device)
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
+            self.bytes_sent += n * 24
+            got = [p.cpu().numpy() for p in parts]
+            lower = [got[r][:counts[r], 0:2] for r in range(self.rank) if counts[r]]
+            if lower and n:
+                keep = ~np.isin(_void16(fps), _void16(np.concatenate(lower).view(np.uint64)))
+            others = [got[r][:counts[r]] for r in range(self.world) if r != self.rank and counts[r]]
+            if others:
+                o = np.concatenate(others)
+                remote_fps = np.ascontiguousarray(o[:, 0:2]).view(np.uint64)
+                remote_times = o[:, 2].astype(np.uint32)
+        self.seconds += _t.perf_counter() - t0
+        return keep, remote_fps, remote_times
+
+
+FLOW_TAG_TABLES = (2, 3, 4)  # DFGPU_TABLE_L7_CUSTOM_FIELD, _VALUE, L7_APP_SERVICE
+
+
+class ShardedDecoder:
+    """One rank's decoder: an Engine on this rank's GPU + the tag merge after every L7 batch."""
+
+    def __init__(self, engine, merge):
+        self.engine = engine
+        self.merge = merge
+
+    def submit(self, wl):
+        """Returns (batch, {table: keep mask}).  Rows with keep == False were emitted by a lower
+        rank in the same step; the host shim drops them before the ckwriter hand-off."""
+        b = self.engine.submit(wl)
+        keeps = {}
+        if wl.msg_type != 5:  # only the L7 path discovers flow tags
+            return b, keeps
+        fps, times, sizes = [], [], []
+        for t in FLOW_TAG_TABLES:
+            f = b.tag_fingerprints(t)
+            cols, n = b.columns(t)
+            tm = cols[0].values.astype(np.uint32) if n else np.zeros(0, np.uint32)  # the `time` column
+            fps.append(f)
+            times.append(tm)
+            sizes.append(n)
+        allf = np.concatenate(fps) if sum(sizes) else np.zeros((0, 2), np.uint64)
+        allt = np.concatenate(times) if sum(sizes) else np.zeros(0, np.uint32)
+        keep, rf, rt = self.merge.exchange(allf, allt)
+        off = 0
+        for t, n in zip(FLOW_TAG_TABLES, sizes):
+            keeps[t] = keep[off:off + n]
+            off += n
+        self.engine.tags_import(rf, rt)
+        return b, keeps
