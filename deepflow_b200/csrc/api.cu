@@ -298,12 +298,14 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
   }
   if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 0, s);
   else launch_l7_pass(bp, 0, s);
+  ctx->mark(3);
   if (bp.nrec) {
     launch_slot_scan(bp, s);
     ctx->launches += 2;
   }
   launch_finish(bp, s);
   ctx->launches++;
+  ctx->mark(4);
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (ctx->prof_on && bp.nrec && ctx->prof_used < dfgpu_ctx::PROF_SLOTS) {
     pe0 = ctx->prof_ev[2 * ctx->prof_used];
@@ -315,6 +317,7 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
   if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 1, s);
   else launch_l7_pass(bp, 1, s);
   if (pe1) CU(cudaEventRecord(pe1, s));
+  ctx->mark(5);
   if (bp.nrec) ctx->launches++;
   if (ctx->cur_msg != DFGPU_MSG_PROTOCOLLOG) {  // L7 commits after its flow_tag stage
     launch_commit(bp, 0, s);
@@ -398,6 +401,8 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
     CU(cudaMemcpyAsync(ctx->d_persist, ctx->h_persist, sizeof(PersistState), cudaMemcpyHostToDevice, s));
   }
   CU(cudaEventRecord(ctx->ev0, s));
+  ctx->stage_open = ctx->prof_on && ctx->stage_used < dfgpu_ctx::PROF_SLOTS && ctx->cur_msg != DFGPU_MSG_METRICS;
+  ctx->mark(0);
   CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
   uint32_t nf = ctx->cur_nframes;
   bp.in = ctx->cur_in;
@@ -422,6 +427,7 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
     launch_frame_count(bp, s);
     ctx->launches += 2;
   }
+  ctx->mark(1);
   // the record count sizes every later grid and the arena: one 4-byte round trip
   CU(cudaMemcpyAsync(&ctx->h_dyn->stats.nrec, &ctx->d_dyn->stats.nrec, 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -482,11 +488,17 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
     rc = l7_prepare(ctx, s);
     if (rc) return rc;
   }
+  ctx->mark(2);
   rc = launch_passes(ctx, 0);
   if (rc) return rc;
   if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
     rc = l7_flow_tags(ctx, s);
     if (rc) return rc;
+  }
+  ctx->mark(6);
+  if (ctx->stage_open) {
+    ctx->stage_used++;
+    ctx->stage_open = false;
   }
   CU(cudaEventRecord(ctx->ev1, s));
   ctx->ran = true;
@@ -800,8 +812,31 @@ int dfgpu_profile_enable(dfgpu_ctx* ctx, int on) {
   CU(cudaSetDevice(ctx->device));
   if (on && !ctx->prof_ev[0])
     for (int i = 0; i < 2 * dfgpu_ctx::PROF_SLOTS; i++) CU(cudaEventCreate(&ctx->prof_ev[i]));
+  if (on && ctx->stage_ev.empty()) {
+    ctx->stage_ev.resize((size_t)dfgpu_ctx::PROF_SLOTS * dfgpu_ctx::STAGE_MARKS);
+    for (auto& e : ctx->stage_ev) CU(cudaEventCreate(&e));
+  }
   ctx->prof_on = on != 0;
   ctx->prof_used = 0;
+  ctx->stage_used = 0;
+  return DFGPU_OK;
+}
+// Sums and resets the stage times of the profiled runs (milliseconds):
+// framing, prepare (+ the nrec round trip), SIZE pass, scans, EMIT pass, flow_tag stage.
+int dfgpu_profile_stages(dfgpu_ctx* ctx, double* ms6, uint64_t* runs) {
+  if (!ctx || !ms6) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 6; k++) ms6[k] = 0;
+  for (int r = 0; r < ctx->stage_used; r++)
+    for (int k = 0; k < 6; k++) {
+      float t = 0;
+      CU(cudaEventElapsedTime(&t, ctx->stage_ev[(size_t)r * dfgpu_ctx::STAGE_MARKS + k],
+                              ctx->stage_ev[(size_t)r * dfgpu_ctx::STAGE_MARKS + k + 1]));
+      ms6[k] += t;
+    }
+  if (runs) *runs = (uint64_t)ctx->stage_used;
+  ctx->stage_used = 0;
   return DFGPU_OK;
 }
 // Sums and resets: emit-kernel milliseconds, launches, input bytes of those launches.

@@ -72,6 +72,14 @@ struct dfgpu_ctx {
   int prof_used = 0;
   cudaEvent_t prof_ev[2 * PROF_SLOTS] = {nullptr};
   uint64_t prof_bytes[PROF_SLOTS] = {0};
+  // stage marks of every dfgpu_run while profiling: start, framing, prepare, SIZE pass, scans, EMIT, flow_tag
+  static constexpr int STAGE_MARKS = 7;
+  std::vector<cudaEvent_t> stage_ev;  // [PROF_SLOTS][STAGE_MARKS], created on enable
+  int stage_used = 0;
+  bool stage_open = false;
+  void mark(int k) {
+    if (prof_on && stage_open && !stage_ev.empty()) cudaEventRecord(stage_ev[(size_t)stage_used * STAGE_MARKS + k], stream);
+  }
 
   // flow tag state (l7)
   void* ft = nullptr;

@@ -15,9 +15,28 @@ struct Rd {
   const uint8_t* p;  // start of the current (sub)message
   uint32_t i;        // cursor
   uint32_t l;        // length of the current (sub)message
+  // 8-byte register window over the input.  ncu (profiles/r01_*): the decode passes were bound by
+  // the long-scoreboard wait behind every LDG.U8 of the varint loops (one dependent L1 round trip
+  // per wire byte).  Reading the aligned 8-byte block once and shifting bytes out of a register
+  // cuts the dependent loads by ~8x.  The block never crosses the 8-byte granule that holds a
+  // valid byte, so it stays inside the (>= 16-byte granular) device allocation.
+  uint64_t w;        // bytes of the aligned block at address wblk
+  uint64_t wblk;     // 0 = no block loaded (aggregate initialisation `Rd{p, 0, n}` leaves it 0)
 };
 
 __device__ __forceinline__ uint8_t ldb(const uint8_t* p) { return __ldg(p); }
+
+// the byte at the cursor (no bounds check), cursor advanced
+__device__ __forceinline__ uint8_t rd_byte(Rd& r) {
+  const uint64_t addr = (uint64_t)(r.p + r.i);
+  const uint64_t blk = addr & ~7ull;
+  if (blk != r.wblk) {
+    r.w = __ldg(reinterpret_cast<const unsigned long long*>(blk));
+    r.wblk = blk;
+  }
+  r.i++;
+  return (uint8_t)(r.w >> ((uint32_t)(addr & 7) * 8));
+}
 
 __device__ __forceinline__ bool rd_varint(Rd& r, uint64_t& out) {
   uint64_t v = 0;
@@ -25,7 +44,7 @@ __device__ __forceinline__ bool rd_varint(Rd& r, uint64_t& out) {
   for (uint32_t shift = 0;; shift += 7) {
     if (shift >= 64) return false;
     if (r.i >= r.l) return false;
-    uint8_t b = ldb(r.p + r.i++);
+    uint8_t b = rd_byte(r);
     v |= (uint64_t)(b & 0x7f) << shift;
     if (b < 0x80) break;
   }
@@ -66,7 +85,7 @@ __device__ inline bool rd_skip(Rd& r, uint32_t wt) {
         for (;; shift += 7) {
           if (shift >= 64) return false;
           if (r.i >= r.l) return false;
-          if (ldb(r.p + r.i++) < 0x80) break;
+          if (rd_byte(r) < 0x80) break;
         }
         break;
       }

@@ -51,6 +51,7 @@ def lib():
         L.dfgpu_flush.argtypes = [vp]
         L.dfgpu_profile_enable.argtypes = [vp, C.c_int]
         L.dfgpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.dfgpu_profile_stages.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         _LIB = L
     return _LIB
 
@@ -180,6 +181,14 @@ class Engine:
         ms, n, b = C.c_double(), C.c_uint64(), C.c_uint64()
         self._check(lib().dfgpu_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(b)), "dfgpu_profile_read")
         return ms.value, int(n.value), int(b.value)
+
+    def profile_stages(self):
+        """ms per stage summed over the profiled runs: framing, prepare, SIZE pass, scans, EMIT, flow_tag."""
+        ms = (C.c_double * 6)()
+        n = C.c_uint64()
+        self._check(lib().dfgpu_profile_stages(self._h, ms, C.byref(n)), "dfgpu_profile_stages")
+        names = ("framing", "prepare", "size_pass", "scans", "emit_pass", "flow_tag")
+        return {k: ms[i] for i, k in enumerate(names)}, int(n.value)
 
     @property
     def stream(self):

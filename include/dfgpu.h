@@ -295,6 +295,8 @@ uint64_t dfgpu_launch_count(const dfgpu_ctx* ctx);
  * dfgpu_profile_read synchronises, sums and resets.                               */
 int dfgpu_profile_enable(dfgpu_ctx* ctx, int on);
 int dfgpu_profile_read(dfgpu_ctx* ctx, double* emit_ms, uint64_t* launches, uint64_t* in_bytes);
+/* stage breakdown of the profiled runs, ms: framing, prepare, SIZE pass, scans, EMIT pass, flow_tag */
+int dfgpu_profile_stages(dfgpu_ctx* ctx, double* ms6, uint64_t* runs);
 int dfgpu_flush(dfgpu_ctx* ctx);
 
 /* Column block of one table of a batch, in ToInput order.  cols may be NULL to

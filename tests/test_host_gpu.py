@@ -53,9 +53,9 @@ def test_decoder_loop_matches_oracle(synth, H, msg, tables):
     from parity import compare_tables
     cfg = abi.Cfg()
     cfg.flow_tag_cache_max_size = 1 << 21
-    wl = synth.gen(msg, 30000, seed=41, flags=S.F_CORRUPT, max_frame_bytes=8192)  # a few thousand frames
+    wl = synth.gen(msg, 30000, seed=41, flags=S.F_CORRUPT, max_frame_bytes=2048)  # a few thousand frames
     nf = len(wl.frames)
-    assert nf > 2048
+    assert nf > 1024  # more than one Gets() batch
     d = H.dfhost_decoder_new(0, msg, 0, C.byref(cfg), 1 << 14)
     assert d, "dfgpu_init failed (no CPU fallback)"
     ora = Oracle(cfg)
