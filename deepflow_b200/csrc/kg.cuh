@@ -60,7 +60,7 @@ DF_HD bool v4_is_global_unicast(uint8_t a, uint8_t b, uint8_t c, uint8_t d) {
   return true;
 }
 // utils.IsLoopback
-DF_HD bool is_loopback(bool v6, const IpAddr& a) {
+static DF_HD_NOINLINE bool is_loopback(bool v6, const IpAddr& a) {
   if (!v6) return (a.ip4 & 0xFF000000u) == 0x7F000000u;
   uint8_t v4[4];
   if (go_to4(a, v4)) return v4[0] == 127;
@@ -70,7 +70,7 @@ DF_HD bool is_loopback(bool v6, const IpAddr& a) {
   return a.ip6[15] == 1;
 }
 // utils.IsLocalIP = !ip.IsGlobalUnicast()
-DF_HD bool is_local_ip(bool v6, const IpAddr& a) {
+static DF_HD_NOINLINE bool is_local_ip(bool v6, const IpAddr& a) {
   if (!v6)
     return !v4_is_global_unicast((uint8_t)(a.ip4 >> 24), (uint8_t)(a.ip4 >> 16), (uint8_t)(a.ip4 >> 8),
                                  (uint8_t)a.ip4);

@@ -30,6 +30,8 @@ struct L7Host {  // host mirror kept in ctx->ft
   size_t ft_arena_cap = 0;
   uint8_t* d_row_flag = nullptr;
   size_t row_flag_cap = 0;
+  uint64_t* d_slotbuf = nullptr;
+  size_t slot_cap = 0;
   uint32_t epoch = 0;
 };
 
@@ -539,6 +541,15 @@ int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s) {
     h->row_flag_cap = cap;
   }
   h->dev.row_flag = h->d_row_flag;
+  if (ctx->bp.nrec > h->slot_cap) {
+    if (h->d_slotbuf) CU(cudaFree(h->d_slotbuf));
+    h->d_slotbuf = nullptr;
+    size_t cap = (size_t)ctx->bp.nrec + ctx->bp.nrec / 8 + 4096;
+    CU(cudaMalloc(&h->d_slotbuf, cap * (S7_COUNT + 1) * sizeof(uint64_t)));
+    h->slot_cap = cap;
+  }
+  h->dev.slotbuf = h->d_slotbuf;
+  h->dev.slot_stride = (uint32_t)h->slot_cap;
   h->dev.epoch = h->epoch;
   h->dev.org_id = ctx->cur_org;
   h->dev.ft_arena = h->d_ft_arena;
@@ -765,6 +776,7 @@ extern "C" void dfgpu_l7_free_state(dfgpu_ctx* ctx) {
   cudaFree(h->d_ft);
   cudaFree(h->d_ft_arena);
   cudaFree(h->d_row_flag);
+  cudaFree(h->d_slotbuf);
   cudaFree(h->d_dev);
   delete h;
   ctx->ft = nullptr;

@@ -73,7 +73,7 @@ struct L7EmitSink {
 };
 
 // streams fields 16..19 of ONE ExtendedInfo occurrence (already validated by pb_interp)
-__device__ void walk_ext_range(const uint8_t* p, uint32_t n, L7EmitSink& sink) {
+__device__ __noinline__ void walk_ext_range(const uint8_t* p, uint32_t n, L7EmitSink& sink) {
   Rd r{p, 0, n};
   while (r.i < r.l) {
     uint32_t f, wt;
@@ -106,6 +106,15 @@ __device__ void walk_ext_range(const uint8_t* p, uint32_t n, L7EmitSink& sink) {
       if (!rd_skip(r, wt)) return;
     }
   }
+}
+
+// rare: ext_info split over several occurrences.  Kept out of line so that the whole switch-based
+// decoder does not sit in the hot kernel's instruction stream (ncu: 31 % of the EMIT pass's stall
+// samples were instruction-fetch misses on a 230 KB kernel).
+__device__ __noinline__ void l7_arrays_slow(const uint8_t* base, uint32_t len, L7EmitSink& sink) {
+  L7Rec scratch;
+  memset(&scratch, 0, sizeof scratch);
+  dec_app_proto_log(base, len, scratch, sink);
 }
 
 // The derived (post-Fill) view of one record: every output string and nullable.
@@ -267,18 +276,30 @@ __global__ void __launch_bounds__(256, EMIT ? 4 : 4) k_l7_pass(const __grid_cons
     frame = p.rec_frame[rec];
     base = p.in + p.rec_off[rec];
     len = p.rec_len[rec];
-    if (p.repair && rec >= p.frame_bad[frame]) {
-      ok = false;
+    uint64_t* sb = dv->slotbuf + rec;
+    const size_t stride = dv->slot_stride;
+    if (EMIT) {
+      // decoded once, by the SIZE pass: slot-major buffer, one coalesced load per slot
+      ok = sb[(size_t)S7_COUNT * stride] != 0;
+#pragma unroll 4
+      for (int i = 0; i < S7_COUNT; i++) sl[i] = sb[(size_t)i * stride];
     } else {
-      ok = pb_interp(base, len, s_tbl, L7_MAXF, sl);
-      if (!ok) {
-        if (!p.repair) {
-          atomicMin(&p.frame_bad[frame], rec);
-          dyn->stats.need_repair = 1;
-        }
+      if (p.repair && rec >= p.frame_bad[frame]) {
+        ok = false;
+      } else {
+        ok = pb_interp(base, len, s_tbl, L7_MAXF, sl);
+        if (!ok) {
+          if (!p.repair) {
+            atomicMin(&p.frame_bad[frame], rec);
+            dyn->stats.need_repair = 1;
+          }
 #pragma unroll
-        for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
+          for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
+        }
       }
+#pragma unroll 4
+      for (int i = 0; i < S7_COUNT; i++) sb[(size_t)i * stride] = sl[i];
+      sb[(size_t)S7_COUNT * stride] = ok ? 1 : 0;
     }
   }
   // AppProtoLogsData.IsValid() (datatype/pb/flow_log.go:82-89) cannot fail: Base and
@@ -586,9 +607,7 @@ __global__ void __launch_bounds__(256, EMIT ? 4 : 4) k_l7_pass(const __grid_cons
         walk_ext_range(base + sl_off(sl, S7_EXT_RANGE), sl_len(sl, S7_EXT_RANGE), sink);
       } else {
         // ext_info split over several occurrences (merge semantics): full re-walk
-        L7Rec scratch;
-        memset(&scratch, 0, sizeof scratch);
-        dec_app_proto_log(base, len, scratch, sink);
+        l7_arrays_slow(base, len, sink);
       }
     }
   }

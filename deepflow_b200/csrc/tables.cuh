@@ -153,7 +153,7 @@ DF_HD uint32_t t64_slot(uint32_t tid, uint64_t key, uint32_t mask) {
   return (uint32_t)mix64(key ^ ((uint64_t)tid * 0x9E3779B97F4A7C15ull)) & mask;
 }
 
-DF_HD bool t64_find(const T64Entry* t, uint32_t mask, uint32_t tid, uint64_t key, uint32_t& val) {
+static DF_HD_NOINLINE bool t64_find(const T64Entry* t, uint32_t mask, uint32_t tid, uint64_t key, uint32_t& val) {
   uint32_t s = t64_slot(tid, key, mask);
   for (;;) {
 #if defined(__CUDA_ARCH__)
@@ -182,7 +182,7 @@ DF_HD uint64_t t6_hash(const uint8_t* ip6, int32_t epc, uint16_t port, uint8_t p
   uint64_t c = (uint64_t)(uint32_t)epc << 32 | (uint64_t)port << 16 | (uint64_t)proto << 8 | tid;
   return mix64(a ^ mix64(b ^ mix64(c)));
 }
-DF_HD bool t6_find(const T6Entry* t, uint32_t mask, uint8_t tid, const uint8_t* ip6, int32_t epc,
+static DF_HD_NOINLINE bool t6_find(const T6Entry* t, uint32_t mask, uint8_t tid, const uint8_t* ip6, int32_t epc,
                    uint16_t port, uint8_t proto, uint32_t& val) {
   uint32_t s = (uint32_t)t6_hash(ip6, epc, port, proto, tid) & mask;
   for (;;) {
@@ -318,14 +318,14 @@ static DF_HD_NOINLINE bool query_ip6(const DevDict& d, int32_t epc, const uint8_
 }
 
 // queryMacInfo :613-623 (DupCount > 0 => nil)
-DF_HD bool query_mac(const DevDict& d, uint64_t l3_epc_mac, InfoVal& out) {
+static DF_HD_NOINLINE bool query_mac(const DevDict& d, uint64_t l3_epc_mac, InfoVal& out) {
   uint32_t idx;
   if (!t64_find(d.t64, d.t64_mask, TID_MAC, l3_epc_mac, idx)) return false;
   if (d.infos[idx].dup) return false;
   info_load(d, idx, out);
   return true;
 }
-DF_HD bool query_pod(const DevDict& d, uint32_t pod_id, InfoVal& out) {  // :376-382
+static DF_HD_NOINLINE bool query_pod(const DevDict& d, uint32_t pod_id, InfoVal& out) {  // :376-382
   uint32_t idx;
   if (!t64_find(d.t64, d.t64_mask, TID_POD, pod_id, idx)) return false;
   info_load(d, idx, out);
