@@ -52,8 +52,10 @@ __device__ __forceinline__ void st_nullable(const BatchParams& p, int col, uint3
 __device__ __forceinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) dst[i] = ldb(src + i);
 }
-__device__ __forceinline__ SRef sref(const uint8_t* base, const uint64_t* sl, int i) {
-  return SRef{base + sl_off(sl, i), sl_len(sl, i)};
+template <class S>
+__device__ __forceinline__ SRef sref(const uint8_t* base, const S& sl, int i) {
+  const uint64_t v = sl[i];
+  return SRef{base + (uint32_t)v, (uint32_t)(v >> 32)};
 }
 
 struct L7EmitSink {
@@ -131,7 +133,8 @@ struct L7Row {
 };
 
 // L7FlowLog.Fill + fillL7FlowLog over the decoded slots; strings only referenced
-__device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const uint64_t* sl, L7Row& o) {
+template <class S>
+__device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const S& sl, L7Row& o) {
   const SRef none{nullptr, 0};
 #pragma unroll
   for (int i = 0; i < 22; i++) o.str[i] = none;
@@ -251,57 +254,22 @@ __device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const uint64_t* 
 
 }  // namespace
 
-template <int EMIT>
-__global__ void __launch_bounds__(256, EMIT ? 4 : 4) k_l7_pass(const __grid_constant__ BatchParams p) {
-  const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
-  const bool in_range = rec < p.nrec;
-  DynState* dyn = p.dyn;
-  const L7Dev* dv = reinterpret_cast<const L7Dev*>(p.ext);
-  if (EMIT && (dyn->stats.need_repair && !p.repair)) return;
-  if (EMIT && dyn->overflow) return;
+// The slots of one record inside the slot-major buffer the SIZE pass wrote: the EMIT pass reads each
+// slot where it needs it (one coalesced load across the warp) instead of copying all of them into a
+// per-thread array (ncu: 7 GB of local-memory traffic per 625 k records with the private copy).
+struct SlotsG {
+  const uint64_t* p;
+  size_t stride;
+  bool valid;
+  __device__ __forceinline__ uint64_t operator[](int i) const { return valid ? __ldg(p + (size_t)i * stride) : 0ull; }
+};
 
-  __shared__ uint32_t s_tbl[M7_COUNT * L7_MAXF];
-  for (uint32_t i = threadIdx.x; i < M7_COUNT * L7_MAXF; i += blockDim.x) s_tbl[i] = dv->pb_tbl[i];
-  __syncthreads();
-
-  uint64_t sl[S7_COUNT];
-#pragma unroll
-  for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
-  bool ok = false;
-  uint32_t frame = 0;
-  const uint8_t* base = p.in;
-  uint32_t len = 0;
-  if (in_range) {
-    frame = p.rec_frame[rec];
-    base = p.in + p.rec_off[rec];
-    len = p.rec_len[rec];
-    uint64_t* sb = dv->slotbuf + rec;
-    const size_t stride = dv->slot_stride;
-    if (EMIT) {
-      // decoded once, by the SIZE pass: slot-major buffer, one coalesced load per slot
-      ok = sb[(size_t)S7_COUNT * stride] != 0;
-#pragma unroll 4
-      for (int i = 0; i < S7_COUNT; i++) sl[i] = sb[(size_t)i * stride];
-    } else {
-      if (p.repair && rec >= p.frame_bad[frame]) {
-        ok = false;
-      } else {
-        ok = pb_interp(base, len, s_tbl, L7_MAXF, sl);
-        if (!ok) {
-          if (!p.repair) {
-            atomicMin(&p.frame_bad[frame], rec);
-            dyn->stats.need_repair = 1;
-          }
-#pragma unroll
-          for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
-        }
-      }
-#pragma unroll 4
-      for (int i = 0; i < S7_COUNT; i++) sb[(size_t)i * stride] = sl[i];
-      sb[(size_t)S7_COUNT * stride] = ok ? 1 : 0;
-    }
-  }
+// Everything after the decode: row build, sizes (SIZE pass) or column stores (EMIT pass).
+// S is the private slot array (SIZE) or SlotsG (EMIT).
+template <int EMIT, class S>
+__device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, DynState* dyn, const uint32_t rec,
+                                        const uint32_t warp, const uint32_t lane, const bool ok, const uint32_t frame,
+                                        const uint8_t* base, const uint32_t len, const S& sl) {
   // AppProtoLogsData.IsValid() (datatype/pb/flow_log.go:82-89) cannot fail: Base and
   // Base.Head are pre-allocated.
   L7Row w;
@@ -612,6 +580,58 @@ __global__ void __launch_bounds__(256, EMIT ? 4 : 4) k_l7_pass(const __grid_cons
     }
   }
 #undef WBASE
+}
+
+template <int EMIT>
+__global__ void __launch_bounds__(256, 4) k_l7_pass(const __grid_constant__ BatchParams p) {
+  const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
+  const bool in_range = rec < p.nrec;
+  DynState* dyn = p.dyn;
+  const L7Dev* dv = reinterpret_cast<const L7Dev*>(p.ext);
+  if (EMIT && (dyn->stats.need_repair && !p.repair)) return;
+  if (EMIT && dyn->overflow) return;
+  bool ok = false;
+  uint32_t frame = 0;
+  const uint8_t* base = p.in;
+  uint32_t len = 0;
+  if (in_range) {
+    frame = p.rec_frame[rec];
+    base = p.in + p.rec_off[rec];
+    len = p.rec_len[rec];
+  }
+  if (EMIT) {
+    // decoded once, by the SIZE pass
+    SlotsG sl{dv->slotbuf + rec, dv->slot_stride, in_range};
+    ok = sl[S7_COUNT] != 0;
+    l7_tail<1>(p, dv, dyn, rec, warp, lane, ok, frame, base, len, sl);
+    return;
+  }
+  __shared__ uint32_t s_tbl[M7_COUNT * L7_MAXF];
+  for (uint32_t i = threadIdx.x; i < M7_COUNT * L7_MAXF; i += blockDim.x) s_tbl[i] = dv->pb_tbl[i];
+  __syncthreads();
+  uint64_t sl[S7_COUNT];
+#pragma unroll
+  for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
+  if (in_range) {
+    if (!(p.repair && rec >= p.frame_bad[frame])) {
+      ok = pb_interp(base, len, s_tbl, L7_MAXF, sl);
+      if (!ok) {
+        if (!p.repair) {
+          atomicMin(&p.frame_bad[frame], rec);
+          dyn->stats.need_repair = 1;
+        }
+#pragma unroll
+        for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
+      }
+    }
+    uint64_t* sb = dv->slotbuf + rec;
+    const size_t stride = dv->slot_stride;
+#pragma unroll 4
+    for (int i = 0; i < S7_COUNT; i++) sb[(size_t)i * stride] = sl[i];
+    sb[(size_t)S7_COUNT * stride] = ok ? 1 : 0;
+  }
+  l7_tail<0>(p, dv, dyn, rec, warp, lane, ok, frame, base, len, sl);
 }
 
 // "last valid" carry of lastTraceIdIndex across warps (single CTA)

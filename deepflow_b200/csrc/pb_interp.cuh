@@ -135,9 +135,14 @@ __device__ __forceinline__ bool pb_interp(const uint8_t* rec, uint32_t len, cons
   }
 }
 
-__device__ __forceinline__ uint32_t sl_u32(const uint64_t* s, int i) { return (uint32_t)s[i]; }
-__device__ __forceinline__ int32_t sl_i32(const uint64_t* s, int i) { return (int32_t)(uint32_t)s[i]; }
-__device__ __forceinline__ uint32_t sl_off(const uint64_t* s, int i) { return (uint32_t)s[i]; }
-__device__ __forceinline__ uint32_t sl_len(const uint64_t* s, int i) { return (uint32_t)(s[i] >> 32); }
+// S: anything indexable by slot (the private array, or a view of the slot-major buffer)
+template <class S>
+__device__ __forceinline__ uint32_t sl_u32(const S& s, int i) { return (uint32_t)s[i]; }
+template <class S>
+__device__ __forceinline__ int32_t sl_i32(const S& s, int i) { return (int32_t)(uint32_t)s[i]; }
+template <class S>
+__device__ __forceinline__ uint32_t sl_off(const S& s, int i) { return (uint32_t)s[i]; }
+template <class S>
+__device__ __forceinline__ uint32_t sl_len(const S& s, int i) { return (uint32_t)(s[i] >> 32); }
 
 }  // namespace dfgpu
