@@ -264,6 +264,13 @@ struct SlotsG {
   __device__ __forceinline__ uint64_t operator[](int i) const { return valid ? __ldg(p + (size_t)i * stride) : 0ull; }
 };
 
+// The same column, read-write, for the pass that fills it.
+struct SlotsW {
+  uint64_t* p;
+  size_t stride;
+  __device__ __forceinline__ uint64_t& operator[](int i) const { return p[(size_t)i * stride]; }
+};
+
 // Everything after the decode: row build, sizes (SIZE pass) or column stores (EMIT pass).
 // S is the private slot array (SIZE) or SlotsG (EMIT).
 template <int EMIT, class S>
@@ -610,9 +617,12 @@ __global__ void __launch_bounds__(256, 4) k_l7_pass(const __grid_constant__ Batc
   __shared__ uint32_t s_tbl[M7_COUNT * L7_MAXF];
   for (uint32_t i = threadIdx.x; i < M7_COUNT * L7_MAXF; i += blockDim.x) s_tbl[i] = dv->pb_tbl[i];
   __syncthreads();
-  uint64_t sl[S7_COUNT];
-#pragma unroll
-  for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
+  // The interpreter writes its slots straight into the slot-major buffer the EMIT pass reads
+  // (same interleaving as a per-thread local array, without the zero / fill / copy-out round trip).
+  // Threads past the last record own a spare column too (slot_stride >= nrec + 4096 > grid size).
+  SlotsW sl{dv->slotbuf + rec, dv->slot_stride};
+#pragma unroll 4
+  for (int i = 0; i <= S7_COUNT; i++) sl[i] = 0;
   if (in_range) {
     if (!(p.repair && rec >= p.frame_bad[frame])) {
       ok = pb_interp(base, len, s_tbl, L7_MAXF, sl);
@@ -621,15 +631,11 @@ __global__ void __launch_bounds__(256, 4) k_l7_pass(const __grid_constant__ Batc
           atomicMin(&p.frame_bad[frame], rec);
           dyn->stats.need_repair = 1;
         }
-#pragma unroll
+#pragma unroll 4
         for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
       }
     }
-    uint64_t* sb = dv->slotbuf + rec;
-    const size_t stride = dv->slot_stride;
-#pragma unroll 4
-    for (int i = 0; i < S7_COUNT; i++) sb[(size_t)i * stride] = sl[i];
-    sb[(size_t)S7_COUNT * stride] = ok ? 1 : 0;
+    sl[S7_COUNT] = ok ? 1 : 0;
   }
   l7_tail<0>(p, dv, dyn, rec, warp, lane, ok, frame, base, len, sl);
 }

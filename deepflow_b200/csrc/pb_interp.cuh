@@ -45,8 +45,11 @@ __device__ __forceinline__ uint32_t pb_digits(uint64_t v) {
 
 // Decodes rec[0..len) (top-level message id 0) into slots[].  tbl is [nmsg][maxf].
 // Returns false on any error the generated Unmarshal would return.
+// SW: the slot store — a private uint64_t array, or a view that writes straight into a slot-major
+// global buffer (anything whose operator[] yields a uint64_t lvalue).
+template <class SW>
 __device__ __forceinline__ bool pb_interp(const uint8_t* rec, uint32_t len, const uint32_t* __restrict__ tbl,
-                                          uint32_t maxf, uint64_t* __restrict__ slots) {
+                                          uint32_t maxf, SW& slots) {
   uint32_t stack_end[PB_MAX_DEPTH];
   uint32_t stack_msg[PB_MAX_DEPTH];
   uint32_t depth = 0, msg = 0, end = len;
