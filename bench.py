@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--records", type=int, default=10_000_000, help="records per GPU per step")
     ap.add_argument("--sub-batch", type=int, default=625_000, help="records per dfgpu_submit")
     ap.add_argument("--pods", type=int, default=100_000, help="dictionary size P (SURVEY §8d)")
-    ap.add_argument("--decoders", type=int, default=2, help="contexts per GPU in the e2e leg (DecoderQueueCount)")
+    ap.add_argument("--decoders", type=int, default=3, help="contexts per GPU in the e2e leg (DecoderQueueCount)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

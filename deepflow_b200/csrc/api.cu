@@ -658,15 +658,19 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
     return fail(ctx, DFGPU_ENOMEM, "pinned host allocation of %llu bytes failed", (unsigned long long)total);
   }
   uint8_t* hb = b->host + 64;
-  // D2H: per column only the rows that exist; streams only their used bytes
-  for (int c = 0; c < sch->ncols; c++) {
+  // D2H.  Common case (every record produced a row): the fixed region was planned for exactly these
+  // rows, so the whole used arena is dense -> ONE copy instead of ~150 small ones.  Otherwise: per
+  // column only the rows that exist; streams only their used bytes.
+  const bool dense = nrows == bp.nrec && nrows > 0;
+  if (dense) CU(cudaMemcpyAsync(hb, bp.arena, (size_t)total, cudaMemcpyDeviceToHost, s));
+  for (int c = 0; c < sch->ncols && !dense; c++) {
     const ColSpec& cs = sch->cols[c];
     size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
     if (es && nrows) CU(cudaMemcpyAsync(hb + bp.fix_off[c], bp.arena + bp.fix_off[c], (size_t)nrows * es, cudaMemcpyDeviceToHost, s));
     size_t ab = aux_bytes_per_row(cs.ch_type);
     if (ab && nrows) CU(cudaMemcpyAsync(hb + bp.aux_off[c], bp.arena + bp.aux_off[c], (size_t)nrows * ab, cudaMemcpyDeviceToHost, s));
   }
-  if (total > bp.var_base)
+  if (!dense && total > bp.var_base)
     CU(cudaMemcpyAsync(hb + bp.var_base, bp.arena + bp.var_base, (size_t)(total - bp.var_base), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(ctx->h_persist, ctx->d_persist, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
