@@ -60,7 +60,7 @@ DF_HD bool v4_is_global_unicast(uint8_t a, uint8_t b, uint8_t c, uint8_t d) {
   return true;
 }
 // utils.IsLoopback
-static DF_HD_NOINLINE bool is_loopback(bool v6, const IpAddr& a) {
+DF_KG_FN bool is_loopback(bool v6, const IpAddr& a) {
   if (!v6) return (a.ip4 & 0xFF000000u) == 0x7F000000u;
   uint8_t v4[4];
   if (go_to4(a, v4)) return v4[0] == 127;
@@ -70,7 +70,7 @@ static DF_HD_NOINLINE bool is_loopback(bool v6, const IpAddr& a) {
   return a.ip6[15] == 1;
 }
 // utils.IsLocalIP = !ip.IsGlobalUnicast()
-static DF_HD_NOINLINE bool is_local_ip(bool v6, const IpAddr& a) {
+DF_KG_FN bool is_local_ip(bool v6, const IpAddr& a) {
   if (!v6)
     return !v4_is_global_unicast((uint8_t)(a.ip4 >> 24), (uint8_t)(a.ip4 >> 16), (uint8_t)(a.ip4 >> 8),
                                  (uint8_t)a.ip4);
@@ -109,7 +109,7 @@ DF_HD uint32_t t6_getz(const DevDict& d, uint8_t tid, const uint8_t* ip6, int32_
 }
 
 // grpc_service.go:138-193
-static DF_HD_NOINLINE uint32_t query_pod_service(const DevDict& d, uint32_t pod_id, uint32_t pod_node_id,
+DF_KG_FN uint32_t query_pod_service(const DevDict& d, uint32_t pod_id, uint32_t pod_node_id,
                                  uint32_t pod_cluster_id, uint32_t pod_group_id, int32_t epc, bool v6,
                                  const IpAddr& a, uint8_t protocol, uint16_t server_port) {
   if (server_port == 0) protocol = 0;
@@ -131,7 +131,7 @@ static DF_HD_NOINLINE uint32_t query_pod_service(const DevDict& d, uint32_t pod_
 }
 
 // grpc_service.go:195-323
-static DF_HD_NOINLINE uint32_t query_custom_service(const DevDict& d, int32_t epc, bool v6, const IpAddr& a,
+DF_KG_FN uint32_t query_custom_service(const DevDict& d, int32_t epc, bool v6, const IpAddr& a,
                                     uint16_t server_port, uint32_t pod_service_id, uint32_t pod_group_id,
                                     uint32_t l3_device_id, uint32_t pod_id, uint32_t pod_cluster_id,
                                     uint8_t l3_device_type, uint8_t protocol) {
@@ -252,8 +252,8 @@ DF_HD void kg_copy_info(KG& k, int s, const InfoVal& i) {  // :677-704
   k.subnet_id[s] = (uint16_t)i.subnet_id;
 }
 
-static DF_HD_NOINLINE void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
-#pragma unroll 1
+DF_KG_FN void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
+DF_KG_SIDE_LOOP
   for (int s = 0; s < 2; s++) {
     k.region_id[s] = k.az_id[s] = k.host_id[s] = 0;
     k.l3_device_type[s] = 0;
@@ -281,13 +281,13 @@ static DF_HD_NOINLINE void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
     pod[1] = pod[0];
   }
   if (in.tap_side == 4) {  // Local :570-585
-#pragma unroll 1
+DF_KG_SIDE_LOOP
     for (int s = 0; s < 2; s++)
       if (is_local_ip(in.v6, in.ip[s])) {
         if (in.mac[s] != 0) by_mac[s] = true; else by_agent[s] = true;
       }
   } else if (in.tap_side == 41 || in.tap_side == 42) {  // ClientProcess / ServerProcess :586-598
-#pragma unroll 1
+DF_KG_SIDE_LOOP
     for (int s = 0; s < 2; s++) {
       if (in.mac[s] != 0) by_mac[s] = true;
       else if (is_local_ip(in.v6, in.ip[s])) by_agent[s] = true;
@@ -295,7 +295,7 @@ static DF_HD_NOINLINE void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
   }
   uint64_t l3mac[2] = {in.mac[0] | (uint64_t)(int64_t)in.l3_epc[0] << 48,
                        in.mac[1] | (uint64_t)(int64_t)in.l3_epc[1] << 48};
-#pragma unroll 1
+DF_KG_SIDE_LOOP
   for (int s = 0; s < 2; s++) {  // :601-614 gpid -> pod
     if (in.gpid[s] != 0 && pod[s] == 0) {
       uint32_t gi;
@@ -311,13 +311,13 @@ static DF_HD_NOINLINE void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
   }
   InfoVal info[2], agent;
   bool has[2] = {false, false}, has_agent = false;
-#pragma unroll 1
+DF_KG_SIDE_LOOP
   for (int s = 0; s < 2; s++)
     if (pod[s] != 0) {  // :617-624
       k.tag_source[s] |= TS_PODID;
       has[s] = query_pod(d, pod[s], info[s]);
     }
-#pragma unroll 1
+DF_KG_SIDE_LOOP
   for (int s = 0; s < 2; s++) {  // :626-666
     if (has[s]) continue;
     if (by_mac[s]) {
@@ -356,7 +356,7 @@ static DF_HD_NOINLINE void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
     }
   }
   // :668-675 L2 epc through the mac table (only sides with l3_epc > 0)
-#pragma unroll 1
+DF_KG_SIDE_LOOP
   for (int s = 0; s < 2; s++) {
     bool want = in.l3_epc[s] > 0;
     if (want) {
@@ -364,7 +364,7 @@ static DF_HD_NOINLINE void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
       if (query_mac(d, l3mac[s], l2)) k.epc_id[s] = l2.l2_epc;
     }
   }
-#pragma unroll 1
+DF_KG_SIDE_LOOP
   for (int s = 0; s < 2; s++) {
     if (has[s]) kg_copy_info(k, s, info[s]);
     k.l3_epc_id[s] = in.l3_epc[s];
@@ -376,7 +376,7 @@ static DF_HD_NOINLINE void kg_fill(const DevDict& d, const KGInput& in, KG& k) {
   if (k.l3_device_type[1] == 11 || k.pod_id[1] != 0 || k.pod_node_id[1] != 0)
     k.service_id[1] = query_pod_service(d, k.pod_id[1], k.pod_node_id[1], k.pod_cluster_id[1],
                                         k.pod_group_id[1], in.l3_epc[1], in.v6, in.ip[1], in.protocol, in.port);
-#pragma unroll 1
+DF_KG_SIDE_LOOP
   for (int s = 0; s < 2; s++) {  // :721-727
     uint16_t port = s == 0 ? 0 : in.port;
     get_auto_instance(k.pod_id[s], in.gpid[s], k.pod_node_id[s], k.l3_device_id[s], k.subnet_id[s],
