@@ -47,20 +47,37 @@ __device__ __forceinline__ U128 cas128(FtEntry* e, U128 cmp, U128 val) {
 struct StrHash {
   uint64_t a, b;
 };
+// Little-endian 8-byte words of the string, the last one zero padded.  The bytes come out of aligned
+// 8-byte blocks (one load per 8 bytes instead of 8 byte loads); a block is only touched when it holds
+// a byte of the string.
 __device__ __forceinline__ StrHash str_hash(const uint8_t* p, uint32_t n) {
   uint64_t a = 0x9E3779B97F4A7C15ull ^ n, b = 0xC2B2AE3D27D4EB4Full + (uint64_t)n * 0x165667B19E3779F9ull;
-  uint32_t i = 0;
-  for (; i + 8 <= n; i += 8) {
-    uint64_t w = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) w |= (uint64_t)p[i + k] << (8 * k);
-    a = (a ^ w) * 0x100000001B3ull;
-    a ^= a >> 32;
-    b = (b + w) * 0xFF51AFD7ED558CCDull;
-    b ^= b >> 29;
-  }
   uint64_t w = 0;
-  for (uint32_t k = 0; i + k < n; k++) w |= (uint64_t)p[i + k] << (8 * k);
+  if (n) {
+    const unsigned long long* sb = reinterpret_cast<const unsigned long long*>((uintptr_t)p & ~(uintptr_t)7);
+    const uint32_t sh = ((uint32_t)(uintptr_t)p & 7u) * 8u;
+    unsigned long long cur = *sb;
+    uint32_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      const bool need = sh != 0 || i + 8 < n;
+      const unsigned long long nxt = need ? sb[1] : 0ull;
+      w = sh ? (cur >> sh) | (nxt << (64 - sh)) : cur;
+      a = (a ^ w) * 0x100000001B3ull;
+      a ^= a >> 32;
+      b = (b + w) * 0xFF51AFD7ED558CCDull;
+      b ^= b >> 29;
+      cur = nxt;
+      sb++;
+    }
+    const uint32_t r = n - i;  // 0..7 tail bytes
+    w = 0;
+    if (r) {
+      const bool need = sh + r * 8 > 64;  // the tail runs into the next block
+      const unsigned long long nxt = need ? sb[1] : 0ull;
+      w = sh ? (cur >> sh) | (nxt << (64 - sh)) : cur;
+      w &= ~0ull >> (64 - r * 8);
+    }
+  }
   a = (a ^ w) * 0x100000001B3ull;
   a ^= a >> 32;
   b = (b + w) * 0xFF51AFD7ED558CCDull;
