@@ -545,7 +545,7 @@ int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s) {
     if (h->d_slotbuf) CU(cudaFree(h->d_slotbuf));
     h->d_slotbuf = nullptr;
     size_t cap = (size_t)ctx->bp.nrec + ctx->bp.nrec / 8 + 4096;
-    CU(cudaMalloc(&h->d_slotbuf, cap * (S7_COUNT + 1) * sizeof(uint64_t)));
+    CU(cudaMalloc(&h->d_slotbuf, cap * (S7_COUNT + 2) * sizeof(uint64_t)));  // + 2 presence words
     h->slot_cap = cap;
   }
   h->dev.slotbuf = h->d_slotbuf;

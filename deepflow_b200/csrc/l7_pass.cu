@@ -283,19 +283,53 @@ __device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const S& sl, L7R
 // The slots of one record inside the slot-major buffer the SIZE pass wrote: the EMIT pass reads each
 // slot where it needs it (one coalesced load across the warp) instead of copying all of them into a
 // per-thread array (ncu: 7 GB of local-memory traffic per 625 k records with the private copy).
+// Only slots the record actually carried are stored; a presence bitmap (rows S7_COUNT and S7_COUNT+1 of
+// the buffer, bit 63 of the second word = the record decoded) says which — absent slots read as 0
+// without touching memory, and the SIZE pass does not have to zero 760 bytes per record first.
 struct SlotsG {
   const uint64_t* p;
   size_t stride;
-  bool valid;
-  __device__ __forceinline__ uint64_t operator[](int i) const { return valid ? __ldg(p + (size_t)i * stride) : 0ull; }
+  uint64_t m0, m1;
+  __device__ __forceinline__ SlotsG(const uint64_t* col, size_t st, bool valid) : p(col), stride(st) {
+    m0 = valid ? __ldg(p + (size_t)S7_COUNT * stride) : 0ull;
+    m1 = valid ? __ldg(p + (size_t)(S7_COUNT + 1) * stride) : 0ull;
+  }
+  __device__ __forceinline__ bool ok() const { return (m1 >> 63) != 0; }
+  __device__ __forceinline__ uint64_t operator[](int i) const {
+    const uint64_t m = i < 64 ? m0 >> i : m1 >> (i - 64);
+    return (m & 1) ? __ldg(p + (size_t)i * stride) : 0ull;
+  }
 };
 
 // The same column, read-write, for the pass that fills it.
 struct SlotsW {
   uint64_t* p;
   size_t stride;
-  __device__ __forceinline__ uint64_t& operator[](int i) const { return p[(size_t)i * stride]; }
+  uint64_t m0 = 0, m1 = 0;
+  struct Ref {
+    SlotsW* s;
+    int i;
+    __device__ __forceinline__ operator uint64_t() const { return s->get(i); }
+    __device__ __forceinline__ Ref& operator=(uint64_t v) {
+      s->p[(size_t)i * s->stride] = v;
+      if (i < 64) s->m0 |= 1ull << i; else s->m1 |= 1ull << (i - 64);
+      return *this;
+    }
+    __device__ __forceinline__ Ref& operator+=(uint64_t v) { return *this = s->get(i) + v; }
+  };
+  __device__ __forceinline__ uint64_t get(int i) const {
+    const uint64_t m = i < 64 ? m0 >> i : m1 >> (i - 64);
+    return (m & 1) ? p[(size_t)i * stride] : 0ull;
+  }
+  __device__ __forceinline__ Ref operator[](int i) { return Ref{this, i}; }
+  __device__ __forceinline__ uint64_t operator[](int i) const { return get(i); }
+  __device__ __forceinline__ void clear() { m0 = m1 = 0; }
+  __device__ __forceinline__ void finish(bool ok) {
+    p[(size_t)S7_COUNT * stride] = m0;
+    p[(size_t)(S7_COUNT + 1) * stride] = m1 | (uint64_t)(ok ? 1 : 0) << 63;
+  }
 };
+static_assert(S7_COUNT <= 64 + 63, "presence bitmap: two words, bit 63 of the second is the ok flag");
 
 // Everything after the decode: row build, sizes (SIZE pass) or column stores (EMIT pass).
 // S is the private slot array (SIZE) or SlotsG (EMIT).
@@ -637,8 +671,8 @@ __global__ void __launch_bounds__(256, EMIT ? 4 : 6) k_l7_pass(const __grid_cons
   }
   if (EMIT) {
     // decoded once, by the SIZE pass
-    SlotsG sl{dv->slotbuf + rec, dv->slot_stride, in_range};
-    ok = sl[S7_COUNT] != 0;
+    const SlotsG sl(dv->slotbuf + rec, dv->slot_stride, in_range);
+    ok = sl.ok();
     l7_tail<1>(p, dv, dyn, rec, warp, lane, ok, frame, base, len, sl);
     return;
   }
@@ -649,8 +683,6 @@ __global__ void __launch_bounds__(256, EMIT ? 4 : 6) k_l7_pass(const __grid_cons
   // (same interleaving as a per-thread local array, without the zero / fill / copy-out round trip).
   // Threads past the last record own a spare column too (slot_stride >= nrec + 4096 > grid size).
   SlotsW sl{dv->slotbuf + rec, dv->slot_stride};
-#pragma unroll 4
-  for (int i = 0; i <= S7_COUNT; i++) sl[i] = 0;
   if (in_range) {
     if (!(p.repair && rec >= p.frame_bad[frame])) {
       ok = pb_interp(base, len, s_tbl, L7_MAXF, sl);
@@ -659,11 +691,10 @@ __global__ void __launch_bounds__(256, EMIT ? 4 : 6) k_l7_pass(const __grid_cons
           atomicMin(&p.frame_bad[frame], rec);
           dyn->stats.need_repair = 1;
         }
-#pragma unroll 4
-        for (int i = 0; i < S7_COUNT; i++) sl[i] = 0;
+        sl.clear();
       }
     }
-    sl[S7_COUNT] = ok ? 1 : 0;
+    sl.finish(ok);
   }
   l7_tail<0>(p, dv, dyn, rec, warp, lane, ok, frame, base, len, sl);
 }

@@ -227,7 +227,9 @@ typedef struct dfgpu_cfg {
   uint32_t max_batch_records;  /* 0 => max_batch_bytes / 64                     */
   uint32_t flow_tag_cache_flush_timeout; /* s; 0 => 1800 (ingester/config/config.go:59) */
   uint32_t flow_tag_cache_max_size;      /* 0 => 1<<18 (config.go:60); the device
-                                  set never evicts: it is sized >= 8x this       */
+                                  set never evicts: it holds 6x this many 32-byte
+                                  slots (field + field_value + app_service keys at
+                                  load <= 1/2) and reports DFGPU_ENOMEM when full */
   uint32_t trace_id_index_disabled;      /* TraceIdWithIndex.Disabled (config.go:201) */
   uint32_t reserved[7];
 } dfgpu_cfg;

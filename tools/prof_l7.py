@@ -30,7 +30,7 @@ def main():
     wl = synth.gen(a.msg, a.records, seed=1000)
     cfg = abi.Cfg()
     cfg.max_batch_bytes = wl.nbytes + (1 << 20)
-    cfg.flow_tag_cache_max_size = 1 << 20
+    cfg.flow_tag_cache_max_size = int(os.environ.get("FT_CACHE", 1 << 19))
     eng = Engine(0, cfg)
     eng.load_synth(synth)
     dev = torch.from_numpy(wl.data).cuda()
