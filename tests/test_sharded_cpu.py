@@ -82,8 +82,8 @@ def _worker(rank, port, out_q):
             glob.load_synth(synth)
         seen_remote = set()
         T = abi.TABLE_L7_CUSTOM_FIELD_VALUE
-        for step in range(3):
-            shards = [synth.gen(abi.DFGPU_MSG_PROTOCOLLOG, 4000, seed=50 + step, vtap_mod=WORLD, vtap_rem=r)
+        for step in range(2):
+            shards = [synth.gen(abi.DFGPU_MSG_PROTOCOLLOG, 2500, seed=50 + step, vtap_mod=WORLD, vtap_rem=r)
                       for r in range(WORLD)]
             for r, wl in enumerate(shards):
                 assert all(shard_of(v, WORLD) == r for v in wl.frames["vtap_id"])
