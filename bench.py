@@ -128,6 +128,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(index):
+    """Run this rank's host threads (and, by first touch, place its pinned staging buffers) on the CPUs
+    local to its GPU's PCIe root, like a NUMA-aware ingester deployment would.  Returns what it did."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c < ncpu]
+        if cpus and len(cpus) < ncpu:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {index}"
+        return "no narrower affinity reported"
+    except Exception as ex:  # noqa: BLE001
+        return f"unbound ({type(ex).__name__})"
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -234,6 +253,7 @@ def main():
         print(json.dumps({"error": "no CUDA device: libdfgpu has no CPU fallback"}))
         return 2
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local)  # before any pinned allocation: first touch places the staging buffers
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from deepflow_b200.native import Engine
@@ -293,15 +313,17 @@ def main():
 
     streams = [torch.cuda.ExternalStream(e.stream, device=local) for e in engines]
     tstream = torch.cuda.Stream(device=local)  # timing stream: start event before, end event after every decoder
+    # clocks / throttle reasons: sampled from the first warm-up step to the end of the e2e leg (the
+    # value leg alone lasts ~0.1 s, less than nvidia-smi needs to start on an 8-GPU box)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(a.warmup):
         resident_step()
     for e in engines:
         e.sync()
         e.profile_enable(True)
-    sampler = ClockSampler(local)
     launches0 = sum(e.launch_count for e in engines)
     barrier()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(tstream)
     for st in streams:
@@ -317,7 +339,6 @@ def main():
         e.sync()
     tstream.synchronize()
     barrier()
-    clocks = sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
     emit_ms, emit_n, emit_in = 0.0, 0, 0
     stage_ms = {}
@@ -396,6 +417,7 @@ def main():
         e.sync()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
 
     # per-step byte accounting for e2e (H2D = staging buffers + frame tables; D2H = column blocks)
     bytes_per_row = out_b_last / max(1, rows_last)
@@ -433,7 +455,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer (f64 casts only at pack)",
                 "data": "synthetic", "config": dict(cfg_common, mean_wire_bytes=in_bytes / nrec_step,
                                                     packed_bytes_per_row=bytes_per_row, gen_seconds=gen_s,
-                                                    decoders_per_gpu=len(engines),
+                                                    decoders_per_gpu=len(engines), host_affinity=numa,
                                                     tag_merge=(None if merge is None else {
                                                         "collective": "all_gather of emitted flow_tag key fingerprints, "
                                                                       "once per e2e step (NCCL)",
