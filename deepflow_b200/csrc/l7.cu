@@ -31,6 +31,7 @@ struct L7Host {  // host mirror kept in ctx->ft
   uint8_t* d_row_flag = nullptr;
   size_t row_flag_cap = 0;
   uint64_t* d_slotbuf = nullptr;
+  uint32_t* d_rec_row = nullptr;
   size_t slot_cap = 0;
   uint32_t epoch = 0;
 };
@@ -546,8 +547,12 @@ int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s) {
     h->d_slotbuf = nullptr;
     size_t cap = (size_t)ctx->bp.nrec + ctx->bp.nrec / 8 + 4096;
     CU(cudaMalloc(&h->d_slotbuf, cap * (S7_COUNT + 2) * sizeof(uint64_t)));  // + 2 presence words
+    if (h->d_rec_row) CU(cudaFree(h->d_rec_row));
+    h->d_rec_row = nullptr;
+    CU(cudaMalloc(&h->d_rec_row, cap * sizeof(uint32_t)));
     h->slot_cap = cap;
   }
+  h->dev.rec_row = h->d_rec_row;
   h->dev.slotbuf = h->d_slotbuf;
   h->dev.slot_stride = (uint32_t)h->slot_cap;
   h->dev.epoch = h->epoch;
@@ -777,6 +782,7 @@ extern "C" void dfgpu_l7_free_state(dfgpu_ctx* ctx) {
   cudaFree(h->d_ft_arena);
   cudaFree(h->d_row_flag);
   cudaFree(h->d_slotbuf);
+  cudaFree(h->d_rec_row);
   cudaFree(h->d_dev);
   delete h;
   ctx->ft = nullptr;

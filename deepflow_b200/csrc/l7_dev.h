@@ -41,6 +41,7 @@ struct L7Dev {
   // the presence bitmap of the slots (bit 63 of the second word: the record decoded)
   uint64_t* slotbuf;
   uint32_t slot_stride;
+  uint32_t* rec_row;  // [records] row of the record in l7_flow_log (0xffffffff: none), EMIT pass -> l7_kg.cu
 };
 
 

@@ -1,0 +1,130 @@
+/*
+ * l7_kg.cu — SmartEncoding of the L7 rows, one lane per (record, SIDE).
+ *   KnowledgeGraph.FillL7   flow_log/log_data/l7_flow_log.go:599-613 -> kg.cuh kg_fill_side
+ *                           (KnowledgeGraph.fill l4_flow_log.go:536-728)
+ *   QueryProcessInfo use    l7_flow_log.go:589-596
+ * SmartEncoding is a chain of ~6 dependent dictionary probes per endpoint, walked at ~10 of 32
+ * lanes active; it was 0.82 ms of the 1.50 ms EMIT pass (ablation, profiles/).  The two endpoints of
+ * a record are independent except for the loopback "borrow the peer's pod" step, so each gets its own
+ * lane: twice the chains in flight per SM, half the state per thread (40 registers -> 48 warps/SM).
+ * The pair exchanges (is_loopback, pod) with one shuffle.  Inputs come from the slot buffer the SIZE
+ * pass wrote, the row index from the EMIT pass (rec_row).
+ */
+#include "l7_dev.h"
+
+namespace dfgpu {
+
+namespace {
+struct Slots {  // one record's column of the slot-major buffer (see SlotsG in l7_pass.cu)
+  const uint64_t* p;
+  size_t stride;
+  uint64_t m0, m1;
+  __device__ __forceinline__ Slots(const uint64_t* col, size_t st, bool valid) : p(col), stride(st) {
+    m0 = valid ? __ldg(p + (size_t)S7_COUNT * stride) : 0ull;
+    m1 = valid ? __ldg(p + (size_t)(S7_COUNT + 1) * stride) : 0ull;
+  }
+  __device__ __forceinline__ uint64_t operator[](int i) const {
+    const uint64_t m = i < 64 ? m0 >> i : m1 >> (i - 64);
+    return (m & 1) ? __ldg(p + (size_t)i * stride) : 0ull;
+  }
+};
+template <class T>
+__device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, T v) {
+  reinterpret_cast<T*>(p.arena + p.fix_off[col])[row] = v;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(256, 6) k_l7_kg(const __grid_constant__ BatchParams p) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t rec = t >> 1;
+  const int s = (int)(t & 1);
+  const DynState* dyn = p.dyn;
+  const L7Dev* dv = reinterpret_cast<const L7Dev*>(p.ext);
+  if ((dyn->stats.need_repair && !p.repair) || dyn->overflow) return;
+  const bool in_range = rec < p.nrec;
+  const uint32_t row = in_range ? dv->rec_row[rec] : 0xffffffffu;
+  const bool ok = row != 0xffffffffu;  // both lanes of a pair agree
+  const Slots sl(dv->slotbuf + rec, dv->slot_stride, ok);
+  const uint8_t* base = p.in + (ok ? p.rec_off[rec] : 0);
+  const uint32_t vtap_id = sl_u32(sl, S7_VTAP_ID);
+
+  KGSideIn in;
+  in.v6 = sl_u32(sl, S7_IS_IPV6) == 1;
+  in.vip = sl_u32(sl, s ? S7_VIP_DST : S7_VIP_SRC) == 1;
+  in.l3_epc = sl_i32(sl, s ? S7_EPC_DST : S7_EPC_SRC);
+  in.ip.ip4 = sl_u32(sl, s ? S7_IP_DST : S7_IP_SRC);
+  {
+    const uint64_t r6 = sl[s ? S7_IP6_DST : S7_IP6_SRC];
+    const uint32_t n6 = (uint32_t)(r6 >> 32);
+    in.ip.ip6len = n6;
+#pragma unroll
+    for (int i = 0; i < 16; i++) in.ip.ip6[i] = (uint32_t)i < n6 ? __ldg(base + (uint32_t)r6 + i) : 0;
+  }
+  in.mac = sl[s ? S7_MAC_DST : S7_MAC_SRC];
+  in.gpid = sl_u32(sl, s ? S7_GPID_1 : S7_GPID_0);
+  in.vtap_id = (uint16_t)vtap_id;
+  in.port = s ? (uint16_t)sl_u32(sl, S7_PORT_DST) : (uint16_t)0;
+  in.tap_side = sl_u32(sl, S7_TAP_SIDE);
+  in.protocol = (uint8_t)sl_u32(sl, S7_PROTOCOL);
+  in.server_side = s == 1;
+  {  // :556-567 with the partner lane (the pair sits in adjacent lanes of one warp)
+    const uint32_t my_pod = sl_u32(sl, s ? S7_POD_1 : S7_POD_0);
+    const bool my_lb = ok && is_loopback(in.v6, in.ip);
+    const uint32_t other_pod = __shfl_xor_sync(0xffffffffu, my_pod, 1);
+    const bool other_lb = __shfl_xor_sync(0xffffffffu, (int)my_lb, 1) != 0;
+    uint32_t pod0 = s ? other_pod : my_pod, pod1 = s ? my_pod : other_pod;
+    uint8_t ts0 = 0, ts1 = 0;
+    kg_peer_pods(s ? other_lb : my_lb, s ? my_lb : other_lb, pod0, pod1, ts0, ts1);
+    in.pod = s ? pod1 : pod0;
+    in.tag_source = s ? ts1 : ts0;
+  }
+  if (!ok) return;
+  KGSide k;
+  kg_fill_side(p.dict, in, k);
+
+  uint32_t gpid = in.gpid;
+  const uint32_t pid = sl_u32(sl, s ? S7_PID_1 : S7_PID_0);
+  if (pid != 0 && gpid == 0) {  // l7_flow_log.go:589-596
+    gpid = t64_getz(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)vtap_id << 32 | (uint64_t)pid);
+    k.tag_source |= TS_PROCESSID;
+  }
+  // the _0 / _1 columns of a pair are adjacent in the schema (auto_* come in blocks of four)
+  static_assert(L7C_REGION_ID_1 == L7C_REGION_ID_0 + 1 && L7C_AZ_ID_1 == L7C_AZ_ID_0 + 1 &&
+                    L7C_HOST_ID_1 == L7C_HOST_ID_0 + 1 && L7C_L3_DEVICE_TYPE_1 == L7C_L3_DEVICE_TYPE_0 + 1 &&
+                    L7C_L3_DEVICE_ID_1 == L7C_L3_DEVICE_ID_0 + 1 && L7C_POD_NODE_ID_1 == L7C_POD_NODE_ID_0 + 1 &&
+                    L7C_POD_NS_ID_1 == L7C_POD_NS_ID_0 + 1 && L7C_POD_GROUP_ID_1 == L7C_POD_GROUP_ID_0 + 1 &&
+                    L7C_POD_ID_1 == L7C_POD_ID_0 + 1 && L7C_POD_CLUSTER_ID_1 == L7C_POD_CLUSTER_ID_0 + 1 &&
+                    L7C_L3_EPC_ID_1 == L7C_L3_EPC_ID_0 + 1 && L7C_EPC_ID_1 == L7C_EPC_ID_0 + 1 &&
+                    L7C_SUBNET_ID_1 == L7C_SUBNET_ID_0 + 1 && L7C_SERVICE_ID_1 == L7C_SERVICE_ID_0 + 1 &&
+                    L7C_AUTO_INSTANCE_ID_1 == L7C_AUTO_INSTANCE_ID_0 + 4 &&
+                    L7C_AUTO_SERVICE_TYPE_1 == L7C_AUTO_SERVICE_TYPE_0 + 4 &&
+                    L7C_TAG_SOURCE_1 == L7C_TAG_SOURCE_0 + 1 && L7C_GPROCESS_ID_1 == L7C_GPROCESS_ID_0 + 1,
+                "column pairs");
+  st<uint16_t>(p, L7C_REGION_ID_0 + s, row, k.region_id);
+  st<uint16_t>(p, L7C_AZ_ID_0 + s, row, k.az_id);
+  st<uint16_t>(p, L7C_HOST_ID_0 + s, row, k.host_id);
+  st<uint8_t>(p, L7C_L3_DEVICE_TYPE_0 + s, row, k.l3_device_type);
+  st<uint32_t>(p, L7C_L3_DEVICE_ID_0 + s, row, k.l3_device_id);
+  st<uint32_t>(p, L7C_POD_NODE_ID_0 + s, row, k.pod_node_id);
+  st<uint16_t>(p, L7C_POD_NS_ID_0 + s, row, k.pod_ns_id);
+  st<uint32_t>(p, L7C_POD_GROUP_ID_0 + s, row, k.pod_group_id);
+  st<uint32_t>(p, L7C_POD_ID_0 + s, row, k.pod_id);
+  st<uint16_t>(p, L7C_POD_CLUSTER_ID_0 + s, row, k.pod_cluster_id);
+  st<int32_t>(p, L7C_L3_EPC_ID_0 + s, row, k.l3_epc_id);
+  st<int32_t>(p, L7C_EPC_ID_0 + s, row, k.epc_id);
+  st<uint16_t>(p, L7C_SUBNET_ID_0 + s, row, k.subnet_id);
+  st<uint32_t>(p, L7C_SERVICE_ID_0 + s, row, k.service_id);
+  st<uint32_t>(p, L7C_AUTO_INSTANCE_ID_0 + 4 * s, row, k.auto_instance_id);
+  st<uint8_t>(p, L7C_AUTO_INSTANCE_TYPE_0 + 4 * s, row, k.auto_instance_type);
+  st<uint32_t>(p, L7C_AUTO_SERVICE_ID_0 + 4 * s, row, k.auto_service_id);
+  st<uint8_t>(p, L7C_AUTO_SERVICE_TYPE_0 + 4 * s, row, k.auto_service_type);
+  st<uint8_t>(p, L7C_TAG_SOURCE_0 + s, row, k.tag_source);
+  st<uint32_t>(p, L7C_GPROCESS_ID_0 + s, row, gpid);
+  if (s == 0) st<uint16_t>(p, L7C_TEAM_ID, row, (uint16_t)p.frames[p.rec_frame[rec]].team_id);
+}
+
+void launch_l7_kg(const BatchParams& p, cudaStream_t s) {
+  if (p.nrec) k_l7_kg<<<(unsigned)(((uint64_t)p.nrec * 2 + 255) / 256), 256, 0, s>>>(p);
+}
+
+}  // namespace dfgpu

@@ -415,7 +415,10 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
       if (lane == 0 && m) atomicAdd(&dyn->stats.l7_counts[c], __popc(m));
     }
   }
-  if (!ok) return;
+  if (!ok) {
+    if (rec < p.nrec) dv->rec_row[rec] = 0xffffffffu;  // no row: l7_kg.cu skips the record
+    return;
+  }
   const uint32_t wb = warp < p.nwarps ? warp : 0;
 #define WBASE(s) ((uint64_t)p.warp_base[(size_t)(s) * p.nwarps + wb] + ex[s])
   const uint32_t row = (uint32_t)WBASE(L7S_ROWS);
@@ -426,7 +429,10 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   const uint32_t vtap_id = sl_u32(sl, S7_VTAP_ID);
   const SRef ip6_src = sref(base, sl, S7_IP6_SRC), ip6_dst = sref(base, sl, S7_IP6_DST);
 
-  // ---- KnowledgeGraph.FillL7 :599-613 ---------------------------------------------------
+  // SmartEncoding (KnowledgeGraph.FillL7: the 39 KG columns, team_id, gprocess_id_0/1) runs right after
+  // this pass with one lane per (record, side): l7_kg.cu.  It needs the row of every record.
+  dv->rec_row[rec] = row;
+#if 0
   KG k;
   {
     KGInput in;
@@ -509,6 +515,7 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   st<uint8_t>(p, L7C_TAG_SOURCE_0, row, k.tag_source[0]);
   st<uint8_t>(p, L7C_TAG_SOURCE_1, row, k.tag_source[1]);
   st<uint16_t>(p, L7C_TEAM_ID, row, (uint16_t)fr.team_id);
+#endif
 
   // ---- L7Base.Fill :514-582 ---------------------------------------------------------------
   const uint64_t tap_port = sl[S7_TAP_PORT];
@@ -535,11 +542,9 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   st<uint32_t>(p, L7C_RESP_TCP_SEQ, row, sl_u32(sl, S7_RESP_TCP_SEQ));
   st<int64_t>(p, L7C_START_TIME, row, (int64_t)sl[S7_START_TIME] / 1000);
   st<int64_t>(p, L7C_END_TIME, row, (int64_t)end_time / 1000);
-  st<uint32_t>(p, L7C_GPROCESS_ID_0, row, gpid0);
-  st<uint32_t>(p, L7C_GPROCESS_ID_1, row, gpid1);
   st<uint8_t>(p, L7C_BIZ_TYPE, row, (uint8_t)sl_u32(sl, S7_BIZ_TYPE));
-  st<int32_t>(p, L7C_PROCESS_ID_0, row, (int32_t)pid0);
-  st<int32_t>(p, L7C_PROCESS_ID_1, row, (int32_t)pid1);
+  st<int32_t>(p, L7C_PROCESS_ID_0, row, (int32_t)sl_u32(sl, S7_PID_0));
+  st<int32_t>(p, L7C_PROCESS_ID_1, row, (int32_t)sl_u32(sl, S7_PID_1));
   st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_REQUEST, row, sl[S7_SYS_REQ]);
   st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_RESPONSE, row, sl[S7_SYS_RESP]);
   st<uint32_t>(p, L7C_SYSCALL_THREAD_0, row, sl_u32(sl, S7_THREAD_0));
@@ -739,12 +744,15 @@ __global__ void k_l7_trace_scan(const BatchParams p) {
   if (threadIdx.x == 0) p.dyn->stats.last_trace_id_index = carry;
 }
 
+void launch_l7_kg(const BatchParams& p, cudaStream_t s);  // l7_kg.cu
+
 void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s) {
   if (!emit) {
     if (p.nrec) k_l7_pass<0><<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
     k_l7_trace_scan<<<1, 1024, 0, s>>>(p);
   } else if (p.nrec) {
     k_l7_pass<1><<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
+    launch_l7_kg(p, s);
   }
 }
 
