@@ -160,18 +160,21 @@ def measured_peak_hbm():
 def output_bytes(batch):
     """Exact size of the packed l7_flow_log column block (what the EMIT kernel writes)."""
     cols, nrows = batch.columns(abi.TABLE_L7_FLOW_LOG)
-    total = 0
+    total = strings = 0
     for c in cols:
         t = c.ch_type
         if t in (abi.CH_STR, abi.CH_LC_STR_ROWS):
             total += nrows * 16 + c.buf.nbytes
+            strings += c.buf.nbytes
         elif t in (abi.CH_ARR_STR, abi.CH_ARR_LC_STR):
             total += nrows * 8 + c.pos.nbytes + c.buf.nbytes
+            strings += c.buf.nbytes
         elif t in (abi.CH_ARR_UINT16, abi.CH_ARR_FLOAT64):
             total += nrows * 8 + c.values.nbytes
+            strings += c.values.nbytes
         else:
             total += nrows * c.elem_size + (nrows if c.nulls is not None else 0)
-    return total, nrows
+    return total, nrows, strings
 
 
 def cpu_port_run(synth, sample_records, threads, seed, warm=True):
@@ -355,8 +358,23 @@ def main():
     b = engines[last_i % len(engines)].fetch()
     cnt = b.counters()
     assert cnt.error_count == 0 and cnt.count == subs[last_i].nrecords, (cnt.error_count, cnt.count)
-    out_b_last, rows_last = output_bytes(b)
+    out_b_last, rows_last, str_b_last = output_bytes(b)
     b.release()
+
+    # ---- roofline leg: the dominant kernel timed alone -------------------------------------------------
+    # In the value leg the decoders' kernels share the SMs, so a kernel's event time there contains its
+    # neighbours.  One more pass of one decoder by itself: CUDA events of the library, on its stream,
+    # right around every EMIT launch.
+    main_eng.sync()
+    main_eng.profile_enable(True)
+    for i, w in enumerate(subs):
+        main_eng.stage_ptr(MSG, dev_data[i].data_ptr(), w.nbytes, w.frames.ctypes.data, len(w.frames))
+        main_eng.run()
+    main_eng.sync()
+    solo_stage_ms, solo_runs = main_eng.profile_stages()
+    solo_emit_ms, solo_emit_n, _ = main_eng.profile_read()
+    main_eng.profile_enable(False)
+    main_eng.fetch().release()
 
     # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H per sub-batch -------------
     d2h_total = [0]
@@ -437,19 +455,31 @@ def main():
         value = total_recs_step * a.steps / (dev_ms_max / 1000.0)
         e2e_value = total_recs_step * a.steps / (e2e_ms_max / 1000.0)
         peak, peak_src = measured_peak_hbm()
-        # algorithmic bytes of one EMIT launch (SURVEY §8d B_L7): wire + 4 B length prefix per
-        # record + every byte of the packed block + 32 B per dictionary probe (12 / record)
-        alg_per_rec = in_bytes / nrec_step + bytes_per_row + 32 * 12
-        emit_launch_s = emit_ms / 1000.0 / max(1, emit_n)
-        recs_per_launch = nrec_step * a.steps / max(1, emit_n)
+        # Dominant kernel = the EMIT/pack pass.  Its algorithmic bytes per record: every byte of the packed
+        # row it writes (all of the block except the 41 SmartEncoding columns the KG kernel writes: 116 B)
+        # + the string / array bytes it copies out of the wire record.  The slot buffer it also reads is an
+        # artefact of this design, not compulsory traffic, and is NOT counted.
+        str_per_row = str_b_last / max(1, rows_last)
+        alg_per_rec = (bytes_per_row - 116) + str_per_row
+        emit_launch_s = solo_emit_ms / 1000.0 / max(1, solo_emit_n)
+        recs_per_launch = nrec_step / max(1, solo_emit_n)
         achieved = alg_per_rec * recs_per_launch / emit_launch_s / 1e9 if emit_launch_s > 0 else 0.0
+        # the whole per-record path (SURVEY §8d B_L7: wire + 4 + packed row + 32 B x 12 probes) over the
+        # three kernels that carry it (SIZE/decode, EMIT, SmartEncoding)
+        path_bytes = in_bytes / nrec_step + bytes_per_row + 32 * 12
+        path_ms = solo_stage_ms.get("size_pass", 0) + solo_stage_ms.get("emit_pass", 0)
+        path_achieved = path_bytes * nrec_step / (path_ms / 1000.0) / 1e9 if path_ms else 0.0
         roof = {"bound": "hbm", "kernel": "k_l7_pass<EMIT>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_record": alg_per_rec, "launches_timed": emit_n,
-                "avg_launch_ms": emit_ms / max(1, emit_n),
-                # share of the summed per-stage CUDA-event time of all decoders (they overlap on the device)
-                "share_of_device_time": emit_ms / sum(stage_ms.values()) if stage_ms else None,
-                "stage_ms_per_step": {k: v / a.steps for k, v in stage_ms.items()}}
+                "algorithmic_bytes_per_record": alg_per_rec, "launches_timed": solo_emit_n,
+                "avg_launch_ms": solo_emit_ms / max(1, solo_emit_n),
+                "timed": "one decoder alone (kernels of concurrent decoders would overlap the events)",
+                "share_of_device_time": solo_emit_ms / sum(solo_stage_ms.values()) if solo_stage_ms else None,
+                "stage_ms_per_step_one_decoder": solo_stage_ms,
+                "path": {"kernels": "k_l7_pass<SIZE> + k_l7_pass<EMIT> + k_l7_kg",
+                         "algorithmic_bytes_per_record": path_bytes, "ms_per_step": path_ms,
+                         "achieved": path_achieved, "frac": path_achieved / peak},
+                "stage_ms_per_step_all_decoders": {k: v / a.steps for k, v in stage_ms.items()}}
         line = {"metric": METRIC, "value": value, "unit": "records/s", "n_gpus": a.gpus, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer (f64 casts only at pack)",

@@ -17,6 +17,7 @@ using namespace dfgpu;
 namespace dfgpu {
 void launch_l4_pass(const BatchParams& p, int emit, cudaStream_t s);
 void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s);
+void launch_l7_kg(const BatchParams& p, cudaStream_t s);
 struct FlowTagDev;
 int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s);
 int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s);
@@ -316,7 +317,11 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
   }
   if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 1, s);
   else launch_l7_pass(bp, 1, s);
-  if (pe1) CU(cudaEventRecord(pe1, s));
+  if (pe1) CU(cudaEventRecord(pe1, s));  // the profile events bracket the EMIT kernel alone
+  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG && bp.nrec) {
+    launch_l7_kg(bp, s);  // SmartEncoding columns, one lane per (record, side)
+    ctx->launches++;
+  }
   ctx->mark(5);
   if (bp.nrec) ctx->launches++;
   if (ctx->cur_msg != DFGPU_MSG_PROTOCOLLOG) {  // L7 commits after its flow_tag stage

@@ -34,7 +34,10 @@ __device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, 
 }
 }  // namespace
 
-__global__ void __launch_bounds__(256, 6) k_l7_kg(const __grid_constant__ BatchParams p) {
+#ifndef L7_KG_MIN_BLOCKS
+#define L7_KG_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_constant__ BatchParams p) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t rec = t >> 1;
   const int s = (int)(t & 1);

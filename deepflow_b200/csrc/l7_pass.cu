@@ -432,90 +432,6 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   // SmartEncoding (KnowledgeGraph.FillL7: the 39 KG columns, team_id, gprocess_id_0/1) runs right after
   // this pass with one lane per (record, side): l7_kg.cu.  It needs the row of every record.
   dv->rec_row[rec] = row;
-#if 0
-  KG k;
-  {
-    KGInput in;
-    in.v6 = v6;
-    in.vip[0] = sl_u32(sl, S7_VIP_SRC) == 1;
-    in.vip[1] = sl_u32(sl, S7_VIP_DST) == 1;
-    in.l3_epc[0] = sl_i32(sl, S7_EPC_SRC);
-    in.l3_epc[1] = sl_i32(sl, S7_EPC_DST);
-    in.ip[0].ip4 = sl_u32(sl, S7_IP_SRC);
-    in.ip[1].ip4 = sl_u32(sl, S7_IP_DST);
-    in.ip[0].ip6len = ip6_src.n;
-    in.ip[1].ip6len = ip6_dst.n;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      in.ip[0].ip6[i] = (uint32_t)i < ip6_src.n ? ldb(ip6_src.p + i) : 0;
-      in.ip[1].ip6[i] = (uint32_t)i < ip6_dst.n ? ldb(ip6_dst.p + i) : 0;
-    }
-    in.mac[0] = sl[S7_MAC_SRC];
-    in.mac[1] = sl[S7_MAC_DST];
-    in.gpid[0] = sl_u32(sl, S7_GPID_0);
-    in.gpid[1] = sl_u32(sl, S7_GPID_1);
-    in.pod_id[0] = sl_u32(sl, S7_POD_0);
-    in.pod_id[1] = sl_u32(sl, S7_POD_1);
-    in.vtap_id = (uint16_t)vtap_id;
-    in.port = (uint16_t)sl_u32(sl, S7_PORT_DST);
-    in.tap_side = tap_side;
-    in.protocol = (uint8_t)sl_u32(sl, S7_PROTOCOL);
-#ifdef ABL_NO_KG
-    memset(&k, 0, sizeof k);
-#else
-    kg_fill(p.dict, in, k);
-#endif
-  }
-  uint32_t gpid0 = sl_u32(sl, S7_GPID_0), gpid1 = sl_u32(sl, S7_GPID_1);
-  const uint32_t pid0 = sl_u32(sl, S7_PID_0), pid1 = sl_u32(sl, S7_PID_1);
-  if (pid0 != 0 && gpid0 == 0) {  // :589-592
-    gpid0 = t64_getz(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)vtap_id << 32 | (uint64_t)pid0);
-    k.tag_source[0] |= TS_PROCESSID;
-  }
-  if (pid1 != 0 && gpid1 == 0) {
-    gpid1 = t64_getz(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)vtap_id << 32 | (uint64_t)pid1);
-    k.tag_source[1] |= TS_PROCESSID;
-  }
-  st<uint16_t>(p, L7C_REGION_ID_0, row, k.region_id[0]);
-  st<uint16_t>(p, L7C_REGION_ID_1, row, k.region_id[1]);
-  st<uint16_t>(p, L7C_AZ_ID_0, row, k.az_id[0]);
-  st<uint16_t>(p, L7C_AZ_ID_1, row, k.az_id[1]);
-  st<uint16_t>(p, L7C_HOST_ID_0, row, k.host_id[0]);
-  st<uint16_t>(p, L7C_HOST_ID_1, row, k.host_id[1]);
-  st<uint8_t>(p, L7C_L3_DEVICE_TYPE_0, row, k.l3_device_type[0]);
-  st<uint8_t>(p, L7C_L3_DEVICE_TYPE_1, row, k.l3_device_type[1]);
-  st<uint32_t>(p, L7C_L3_DEVICE_ID_0, row, k.l3_device_id[0]);
-  st<uint32_t>(p, L7C_L3_DEVICE_ID_1, row, k.l3_device_id[1]);
-  st<uint32_t>(p, L7C_POD_NODE_ID_0, row, k.pod_node_id[0]);
-  st<uint32_t>(p, L7C_POD_NODE_ID_1, row, k.pod_node_id[1]);
-  st<uint16_t>(p, L7C_POD_NS_ID_0, row, k.pod_ns_id[0]);
-  st<uint16_t>(p, L7C_POD_NS_ID_1, row, k.pod_ns_id[1]);
-  st<uint32_t>(p, L7C_POD_GROUP_ID_0, row, k.pod_group_id[0]);
-  st<uint32_t>(p, L7C_POD_GROUP_ID_1, row, k.pod_group_id[1]);
-  st<uint32_t>(p, L7C_POD_ID_0, row, k.pod_id[0]);
-  st<uint32_t>(p, L7C_POD_ID_1, row, k.pod_id[1]);
-  st<uint16_t>(p, L7C_POD_CLUSTER_ID_0, row, k.pod_cluster_id[0]);
-  st<uint16_t>(p, L7C_POD_CLUSTER_ID_1, row, k.pod_cluster_id[1]);
-  st<int32_t>(p, L7C_L3_EPC_ID_0, row, k.l3_epc_id[0]);
-  st<int32_t>(p, L7C_L3_EPC_ID_1, row, k.l3_epc_id[1]);
-  st<int32_t>(p, L7C_EPC_ID_0, row, k.epc_id[0]);
-  st<int32_t>(p, L7C_EPC_ID_1, row, k.epc_id[1]);
-  st<uint16_t>(p, L7C_SUBNET_ID_0, row, k.subnet_id[0]);
-  st<uint16_t>(p, L7C_SUBNET_ID_1, row, k.subnet_id[1]);
-  st<uint32_t>(p, L7C_SERVICE_ID_0, row, k.service_id[0]);
-  st<uint32_t>(p, L7C_SERVICE_ID_1, row, k.service_id[1]);
-  st<uint32_t>(p, L7C_AUTO_INSTANCE_ID_0, row, k.auto_instance_id[0]);
-  st<uint8_t>(p, L7C_AUTO_INSTANCE_TYPE_0, row, k.auto_instance_type[0]);
-  st<uint32_t>(p, L7C_AUTO_SERVICE_ID_0, row, k.auto_service_id[0]);
-  st<uint8_t>(p, L7C_AUTO_SERVICE_TYPE_0, row, k.auto_service_type[0]);
-  st<uint32_t>(p, L7C_AUTO_INSTANCE_ID_1, row, k.auto_instance_id[1]);
-  st<uint8_t>(p, L7C_AUTO_INSTANCE_TYPE_1, row, k.auto_instance_type[1]);
-  st<uint32_t>(p, L7C_AUTO_SERVICE_ID_1, row, k.auto_service_id[1]);
-  st<uint8_t>(p, L7C_AUTO_SERVICE_TYPE_1, row, k.auto_service_type[1]);
-  st<uint8_t>(p, L7C_TAG_SOURCE_0, row, k.tag_source[0]);
-  st<uint8_t>(p, L7C_TAG_SOURCE_1, row, k.tag_source[1]);
-  st<uint16_t>(p, L7C_TEAM_ID, row, (uint16_t)fr.team_id);
-#endif
 
   // ---- L7Base.Fill :514-582 ---------------------------------------------------------------
   const uint64_t tap_port = sl[S7_TAP_PORT];
@@ -744,15 +660,12 @@ __global__ void k_l7_trace_scan(const BatchParams p) {
   if (threadIdx.x == 0) p.dyn->stats.last_trace_id_index = carry;
 }
 
-void launch_l7_kg(const BatchParams& p, cudaStream_t s);  // l7_kg.cu
-
 void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s) {
   if (!emit) {
     if (p.nrec) k_l7_pass<0><<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
     k_l7_trace_scan<<<1, 1024, 0, s>>>(p);
   } else if (p.nrec) {
-    k_l7_pass<1><<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
-    launch_l7_kg(p, s);
+    k_l7_pass<1><<<(p.nrec + 255) / 256, 256, 0, s>>>(p);  // api.cu launches l7_kg.cu right after
   }
 }
 
