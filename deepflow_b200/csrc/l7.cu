@@ -103,7 +103,7 @@ struct RowView {  // one packed l7 row, as the flow_tag stage sees it
   SRef app_service, endpoint;
 };
 
-__device__ void load_row(const BatchParams& p, uint32_t row, RowView& v) {
+__device__ __forceinline__ void load_row(const BatchParams& p, uint32_t row, RowView& v) {
   const DynState* dyn = p.dyn;
   auto fix = [&](int col) { return p.arena + p.fix_off[col]; };
   auto aux = [&](int col) { return p.arena + p.aux_off[col]; };
@@ -177,8 +177,11 @@ __device__ __forceinline__ unsigned long long pos_key(const L7Dev* d, uint32_t r
 //   PHASE 1: decide value winners (-> counts), set their time; field + metric keys upsert + atomicMin
 //   PHASE 2: decide field winners (-> counts), set their time
 //   PHASE 3: write rows
+#ifndef FT_P0_MIN_BLOCKS
+#define FT_P0_MIN_BLOCKS 4
+#endif
 template <int PHASE>
-__global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ BatchParams p) {
+__global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_flow_tag(const __grid_constant__ BatchParams p) {
   const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t warp = row >> 5, lane = threadIdx.x & 31;
   DynState* dyn = p.dyn;
@@ -202,9 +205,70 @@ __global__ void __launch_bounds__(256) k_l7_flow_tag(const __grid_constant__ Bat
   }
 
   RowView v;
+  const uint32_t timeout = d->ft_timeout;
+  if (PHASE == 0) {
+    // The steady-state walk (every batch, every row): each string is hashed ONCE and its key probed for
+    // both sides; the first slot of both probes is loaded before either is consumed, and a key that is
+    // present and fresh costs nothing beyond that one 32-byte sector.  The order of the probes is free in
+    // this phase (insertion + atomicMax commute); phases 1-3 below keep the reference's side-major order.
+    if (row < nrows) {
+      load_row(p, row, v);
+      const uint32_t ns = v.n_sides;
+      const int32_t vpc0 = v.vpc[0], vpc1 = v.vpc[1];
+      const uint16_t pns0 = v.pod_ns[0], pns1 = v.pod_ns[1];
+      bool any = false;
+      auto probe2 = [&](uint32_t kind, StrHash hn, StrHash hv, uint8_t ftype, uint32_t metric, uint32_t i) {
+        const U128 f0 = key_fp(d, kind, hn, hv, vpc0, pns0, ftype, v.team);
+        const U128 f1 = key_fp(d, kind, hn, hv, vpc1, pns1, ftype, v.team);
+        TsPeek k0, k1;
+        ts_peek(d->ft, d->ft_mask, f0, k0);
+        if (ns > 1) ts_peek(d->ft, d->ft_mask, f1, k1);
+        if (!ts_peek_fresh(k0, f0, v.time, timeout)) {
+          FtEntry* e = ft_upsert(d, f0, &dyn->stats.ft_full);
+          if (e && ft_candidate(e, v.time, timeout)) {
+            atomicMax(&e->first_pos, pos_key(d, row, 0, metric, i));
+            any = true;
+          }
+        }
+        if (ns > 1 && !ts_peek_fresh(k1, f1, v.time, timeout)) {
+          FtEntry* e = ft_upsert(d, f1, &dyn->stats.ft_full);
+          if (e && ft_candidate(e, v.time, timeout)) {
+            atomicMax(&e->first_pos, pos_key(d, row, 1, metric, i));
+            any = true;
+          }
+        }
+      };
+      const uint32_t n_names = (uint32_t)(v.an_hi - v.an_lo), n_values = (uint32_t)(v.av_hi - v.av_lo);
+      const uint32_t tot_names = n_names + 3, tot_values = n_values + 3;
+      const uint32_t min_len = tot_names > tot_values ? tot_values : tot_names;  // :666-674
+      for (uint32_t i = 0; i < min_len; i++) {
+        const SRef name = attr_name_at(d, v, i), value = attr_value_at(v, i);
+        probe2(KIND_FIELD_VALUE, str_hash(name.p, name.n), str_hash(value.p, value.n), 0, 0, i);
+      }
+      const uint32_t n_metrics = (uint32_t)(v.mn_hi - v.mn_lo);  // :726-742
+      for (uint32_t i = 0; i < n_metrics; i++) {
+        const dfgpu_pos q = v.mn_pos[v.mn_lo + i];
+        probe2(KIND_FIELD, str_hash(v.mn_buf + q.start, (uint32_t)(q.end - q.start)), StrHash{0, 0}, 1, 1, i);
+      }
+      if (v.app_service.n) {  // decoder.go:464-472
+        const U128 fpa =
+            key_fp(d, KIND_APP_SERVICE, str_hash(v.app_service.p, v.app_service.n), StrHash{0, 0}, 0, 0, 0, v.team);
+        TsPeek k;
+        ts_peek(d->ft, d->ft_mask, fpa, k);
+        if (!ts_peek_fresh(k, fpa, v.time_as, timeout)) {
+          FtEntry* e = ft_upsert(d, fpa, &dyn->stats.ft_full);
+          if (e && ft_candidate(e, v.time_as, timeout)) {
+            atomicMax(&e->first_pos, pos_key(d, row, 0, 0, 0));
+            any = true;
+          }
+        }
+      }
+      d->row_flag[row] = any ? 1 : 0;
+    }
+    return;
+  }
   constexpr uint32_t FT_HASH_CACHE = 8;
   StrHash hcache[2 * FT_HASH_CACHE];
-  const uint32_t timeout = d->ft_timeout;
   uint8_t* fa = d->ft_arena;
   const uint64_t* fo = dyn->stats.ft_off;
 

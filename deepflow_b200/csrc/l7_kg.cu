@@ -6,11 +6,13 @@
  * SmartEncoding is a chain of ~6 dependent dictionary probes per endpoint, walked at ~10 of 32
  * lanes active; it was 0.82 ms of the 1.50 ms EMIT pass (ablation, profiles/).  The two endpoints of
  * a record are independent except for the loopback "borrow the peer's pod" step, so each gets its own
- * lane: twice the chains in flight per SM, half the state per thread (40 registers -> 48 warps/SM).
+ * lane: twice the chains in flight per SM, half the state per thread.  The per-side routine is
+ * kg_side.cuh: register-only (no by-reference structs, no byte arrays), first probes issued together.
  * The pair exchanges (is_loopback, pod) with one shuffle.  Inputs come from the slot buffer the SIZE
  * pass wrote, the row index from the EMIT pass (rec_row).
  */
 #include "l7_dev.h"
+#include "kg_side.cuh"
 
 namespace dfgpu {
 
@@ -35,7 +37,7 @@ __device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, 
 }  // namespace
 
 #ifndef L7_KG_MIN_BLOCKS
-#define L7_KG_MIN_BLOCKS 6
+#define L7_KG_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_constant__ BatchParams p) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_co
   const uint8_t* base = p.in + (ok ? p.rec_off[rec] : 0);
   const uint32_t vtap_id = sl_u32(sl, S7_VTAP_ID);
 
-  KGSideIn in;
+  kgs::SideIn in;
   in.v6 = sl_u32(sl, S7_IS_IPV6) == 1;
   in.vip = sl_u32(sl, s ? S7_VIP_DST : S7_VIP_SRC) == 1;
   in.l3_epc = sl_i32(sl, s ? S7_EPC_DST : S7_EPC_SRC);
@@ -59,9 +61,15 @@ __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_co
   {
     const uint64_t r6 = sl[s ? S7_IP6_DST : S7_IP6_SRC];
     const uint32_t n6 = (uint32_t)(r6 >> 32);
-    in.ip.ip6len = n6;
-#pragma unroll
-    for (int i = 0; i < 16; i++) in.ip.ip6[i] = (uint32_t)i < n6 ? __ldg(base + (uint32_t)r6 + i) : 0;
+    in.ip.len6 = n6;
+    uint64_t lo = 0, hi = 0;  // zero padded, like copy(key[4:], ipv6)
+    const uint8_t* q = base + (uint32_t)r6;
+    for (uint32_t i = 0; i < (n6 < 16 ? n6 : 16u); i++) {
+      const uint64_t v = (uint64_t)__ldg(q + i) << ((i & 7) * 8);
+      if (i < 8) lo |= v; else hi |= v;
+    }
+    in.ip.lo = lo;
+    in.ip.hi = hi;
   }
   in.mac = sl[s ? S7_MAC_DST : S7_MAC_SRC];
   in.gpid = sl_u32(sl, s ? S7_GPID_1 : S7_GPID_0);
@@ -72,7 +80,7 @@ __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_co
   in.server_side = s == 1;
   {  // :556-567 with the partner lane (the pair sits in adjacent lanes of one warp)
     const uint32_t my_pod = sl_u32(sl, s ? S7_POD_1 : S7_POD_0);
-    const bool my_lb = ok && is_loopback(in.v6, in.ip);
+    const bool my_lb = ok && kgs::loopback(in.v6, in.ip);
     const uint32_t other_pod = __shfl_xor_sync(0xffffffffu, my_pod, 1);
     const bool other_lb = __shfl_xor_sync(0xffffffffu, (int)my_lb, 1) != 0;
     uint32_t pod0 = s ? other_pod : my_pod, pod1 = s ? my_pod : other_pod;
@@ -83,12 +91,12 @@ __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_co
   }
   if (!ok) return;
   KGSide k;
-  kg_fill_side(p.dict, in, k);
+  kgs::fill_side(p.dict, in, k);
 
   uint32_t gpid = in.gpid;
   const uint32_t pid = sl_u32(sl, s ? S7_PID_1 : S7_PID_0);
   if (pid != 0 && gpid == 0) {  // l7_flow_log.go:589-596
-    gpid = t64_getz(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)vtap_id << 32 | (uint64_t)pid);
+    gpid = kgs::t64_z(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)vtap_id << 32 | (uint64_t)pid);
     k.tag_source |= TS_PROCESSID;
   }
   // the _0 / _1 columns of a pair are adjacent in the schema (auto_* come in blocks of four)

@@ -38,11 +38,13 @@ __device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, 
   reinterpret_cast<T*>(p.arena + p.fix_off[col])[row] = v;
 }
 __device__ __forceinline__ void st_ip6(const BatchParams& p, int col, uint32_t row, SRef s) {
-  uint32_t w[4] = {0, 0, 0, 0};
-  uint8_t* b = reinterpret_cast<uint8_t*>(w);
-  uint32_t n = s.n > 16 ? 16 : s.n;
-  for (uint32_t i = 0; i < n; i++) b[i] = ldb(s.p + i);
-  reinterpret_cast<uint4*>(p.arena + p.fix_off[col])[row] = make_uint4(w[0], w[1], w[2], w[3]);
+  uint64_t lo = 0, hi = 0;  // bytes 0..7 / 8..15 (no byte-indexed local array: that would live in local memory)
+  const uint32_t n = s.n > 16 ? 16 : s.n;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint64_t v = (uint64_t)ldb(s.p + i) << ((i & 7) * 8);
+    if (i < 8) lo |= v; else hi |= v;
+  }
+  reinterpret_cast<ulonglong2*>(p.arena + p.fix_off[col])[row] = make_ulonglong2(lo, hi);
 }
 template <class T>
 __device__ __forceinline__ void st_nullable(const BatchParams& p, int col, uint32_t row, bool has, T v) {
@@ -101,7 +103,7 @@ struct L7EmitSink {
 };
 
 // streams fields 16..19 of ONE ExtendedInfo occurrence (already validated by pb_interp)
-__device__ __noinline__ void walk_ext_range(const uint8_t* p, uint32_t n, L7EmitSink& sink) {
+__device__ __forceinline__ void walk_ext_range(const uint8_t* p, uint32_t n, L7EmitSink& sink) {
   Rd r{p, 0, n};
   while (r.i < r.l) {
     uint32_t f, wt;
@@ -145,60 +147,48 @@ __device__ __noinline__ void l7_arrays_slow(const uint8_t* base, uint32_t len, L
   dec_app_proto_log(base, len, scratch, sink);
 }
 
-// The derived (post-Fill) view of one record: every output string and nullable.
-struct L7Row {
-  SRef str[22];  // streams 0..21
+// The derived (post-Fill) view of one record: the scalars of L7FlowLog.Fill + fillL7FlowLog
+// (l7_flow_log.go:363-452).  Scalars only — the 22 output strings are produced one at a time by
+// l7_str() where they are sized / copied, so nothing here is indexed dynamically and the whole view
+// stays in registers (ncu, round 1: an SRef[22] + size arrays cost a 1016-byte stack frame per thread,
+// 154 MB of live frames > L2, and 2x the algorithmic DRAM traffic).
+struct L7Hdr {
+  bool has_req, has_resp, has_ext, has_trace, two_ids;
   uint8_t type, is_tls, is_async, is_reversed, l7_protocol, response_status;
-  bool has_request_id, has_response_code, has_request_length, has_response_length, has_sql_rows;
-  uint64_t request_id, sql_rows;
-  int32_t response_code;
-  int64_t request_length, response_length;
+  bool has_request_id, has_response_code, has_request_length, has_response_length;
+  uint32_t request_id, sql_rows;
+  int32_t response_code, request_length, response_length;
   uint32_t n_pseudo, pseudo_name_bytes, pseudo_value_bytes;
-  bool trace_nonempty;
+  SRef exc;       // response_exception (wire value or the protocol's description of the code)
+  SRef trace_id;  // first of trace_ids, else the legacy trace_id
   uint64_t trace_hash;
 };
 
-// L7FlowLog.Fill + fillL7FlowLog over the decoded slots; strings only referenced
 template <class S>
-__device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const S& sl, L7Row& o) {
+__device__ __forceinline__ void l7_hdr(const L7Dev* dv, const uint8_t* base, const S& sl, L7Hdr& o) {
   const SRef none{nullptr, 0};
-#pragma unroll
-  for (int i = 0; i < 22; i++) o.str[i] = none;
-  const bool has_req = sl[S7_REQ_CNT] != 0, has_resp = sl[S7_RESP_CNT] != 0, has_ext = sl[S7_EXT_CNT] != 0,
-             has_trace = sl[S7_TRACE_CNT] != 0;
+  o.has_req = sl[S7_REQ_CNT] != 0;
+  o.has_resp = sl[S7_RESP_CNT] != 0;
+  o.has_ext = sl[S7_EXT_CNT] != 0;
+  o.has_trace = sl[S7_TRACE_CNT] != 0;
   const uint32_t flags = sl_u32(sl, S7_FLAGS);
   o.type = (uint8_t)sl_u32(sl, S7_HEAD_MSG_TYPE);
   o.is_tls = (flags & 1) ? 1 : 0;
   o.is_async = (flags & 2) ? 1 : 0;
   o.is_reversed = (flags & 4) ? 1 : 0;
   o.l7_protocol = (uint8_t)sl_u32(sl, S7_HEAD_PROTO);
-  o.str[L7V_BIZ_CODE] = sref(base, sl, S7_BIZ_CODE);
-  o.str[L7V_BIZ_SCENARIO] = sref(base, sl, S7_BIZ_SCENARIO);
-  o.str[L7V_BIZ_RESPONSE_CODE] = sref(base, sl, S7_BIZ_RESPONSE_CODE);
-  o.str[L7V_KNAME_0] = sref(base, sl, S7_KNAME_0);
-  o.str[L7V_KNAME_1] = sref(base, sl, S7_KNAME_1);
-  if (has_ext && sl_len(sl, S7_PROTOCOL_STR)) o.str[L7V_BIZ_PROTOCOL] = sref(base, sl, S7_PROTOCOL_STR);
-  else o.str[L7V_BIZ_PROTOCOL] = cs_ref(dv, dv->proto_cs[o.l7_protocol][o.is_tls]);
-  o.str[L7V_VERSION] = sref(base, sl, S7_VERSION);
   o.response_status = 5;  // STATUS_UNKNOWN
-  o.request_length = (int64_t)sl_i32(sl, S7_REQ_LEN);
-  o.response_length = (int64_t)sl_i32(sl, S7_RESP_LEN);
-  o.sql_rows = (uint64_t)sl_u32(sl, S7_ROW_EFFECT);
-  o.has_sql_rows = o.sql_rows != 0;
+  o.request_length = sl_i32(sl, S7_REQ_LEN);
+  o.response_length = sl_i32(sl, S7_RESP_LEN);
+  o.sql_rows = sl_u32(sl, S7_ROW_EFFECT);
   o.has_request_length = o.has_response_length = o.has_response_code = o.has_request_id = false;
   o.response_code = 0;
   o.request_id = 0;
-  if (has_req) {  // :379-387
-    o.str[L7V_REQUEST_DOMAIN] = sref(base, sl, S7_DOMAIN);
-    o.str[L7V_REQUEST_RESOURCE] = sref(base, sl, S7_RESOURCE);
-    o.str[L7V_REQUEST_TYPE] = sref(base, sl, S7_REQ_TYPE);
-    if (o.request_length != -1 && o.type != 1) o.has_request_length = true;
-    o.str[L7V_ENDPOINT] = sref(base, sl, S7_ENDPOINT);
-  }
-  if (has_resp) {  // :389-409
+  o.exc = none;
+  if (o.has_req && o.request_length != -1 && o.type != 1) o.has_request_length = true;  // :379-387
+  if (o.has_resp) {  // :389-409
     o.response_status = (uint8_t)sl_u32(sl, S7_RESP_STATUS);
     if (o.type != 0) {
-      o.str[L7V_RESPONSE_RESULT] = sref(base, sl, S7_RESULT);
       const int32_t code = sl_i32(sl, S7_RESP_CODE);
       o.response_code = code;
       SRef exc = sref(base, sl, S7_EXCEPTION);
@@ -231,39 +221,33 @@ __device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const S& sl, L7R
           default: break;  // h.ResponseException = l.Resp.Exception (empty)
         }
       }
-      o.str[L7V_RESPONSE_EXCEPTION] = exc;
+      o.exc = exc;
       if (o.response_code != -32768) o.has_response_code = true;
       if (o.response_length != -1) o.has_response_length = true;
     }
   }
   o.n_pseudo = o.pseudo_name_bytes = o.pseudo_value_bytes = 0;
-  if (has_ext) {  // :411-433
-    o.request_id = (uint64_t)sl_u32(sl, S7_REQUEST_ID);
+  if (o.has_ext) {  // :411-433
+    o.request_id = sl_u32(sl, S7_REQUEST_ID);
     if (o.request_id != 0) o.has_request_id = true;
-    o.str[L7V_APP_SERVICE] = sref(base, sl, S7_SERVICE_NAME);
-    o.str[L7V_X_REQUEST_ID_0] = sref(base, sl, S7_X_REQUEST_ID_0);
-    o.str[L7V_X_REQUEST_ID_1] = sref(base, sl, S7_X_REQUEST_ID_1);
-    o.str[L7V_HTTP_PROXY_CLIENT] = sref(base, sl, S7_CLIENT_IP);
     uint32_t n;
     if ((n = sl_len(sl, S7_USER_AGENT))) { o.n_pseudo++; o.pseudo_name_bytes += 15; o.pseudo_value_bytes += n; }
     if ((n = sl_len(sl, S7_REFERER))) { o.n_pseudo++; o.pseudo_name_bytes += 12; o.pseudo_value_bytes += n; }
     if ((n = sl_len(sl, S7_RPC_SERVICE))) { o.n_pseudo++; o.pseudo_name_bytes += 11; o.pseudo_value_bytes += n; }
   }
   SRef trace_id = none;
-  if (has_trace) {  // :434-438 + fillTraceIds :344-360
-    o.str[L7V_SPAN_ID] = sref(base, sl, S7_SPAN_ID);
+  o.two_ids = false;
+  if (o.has_trace) {  // :434-438 + fillTraceIds :344-360
     const uint32_t n_ids = (uint32_t)sl[S7_TRACE_IDS_N];
     if (n_ids > 0) trace_id = sref(base, sl, S7_TRACE_IDS_0);
-    if (n_ids > 1) o.str[L7V_TRACE_ID_2] = sref(base, sl, S7_TRACE_IDS_1);
+    o.two_ids = n_ids > 1;
     if (trace_id.n == 0) trace_id = sref(base, sl, S7_TRACE_ID);
-    o.str[L7V_PARENT_SPAN_ID] = sref(base, sl, S7_PARENT_SPAN_ID);
   }
-  o.str[L7V_TRACE_ID] = trace_id;
-  o.trace_nonempty = trace_id.n != 0;
-  o.trace_hash = o.trace_nonempty ? djb_hash(17, trace_id.p, trace_id.n) : 0;
+  o.trace_id = trace_id;
+  o.trace_hash = trace_id.n != 0 ? djb_hash(17, trace_id.p, trace_id.n) : 0;
   switch (o.l7_protocol) {  // :438-451
     case 100:
-      if (has_req) {
+      if (o.has_req) {
         SRef rt = sref(base, sl, S7_REQ_TYPE);
         bool supported = str_eq(rt, "Fetch") || str_eq(rt, "Produce") || str_eq(rt, "JoinGroup") ||
                          str_eq(rt, "LeaveGroup") || str_eq(rt, "SyncGroup");
@@ -275,6 +259,66 @@ __device__ void l7_derive(const L7Dev* dv, const uint8_t* base, const S& sl, L7R
       }
       break;
     case 43: o.has_request_id = true; break;
+  }
+}
+
+// Output string `i` (stream order L7V_*) of the row.  `i` is a compile-time constant at every call
+// site (fully unrolled loops), so the switch folds away.
+template <class S>
+__device__ __forceinline__ SRef l7_str(const int i, const L7Dev* dv, const uint8_t* base, const S& sl,
+                                       const L7Hdr& h) {
+  const SRef none{nullptr, 0};
+  switch (i) {
+    case L7V_BIZ_CODE: return sref(base, sl, S7_BIZ_CODE);
+    case L7V_BIZ_SCENARIO: return sref(base, sl, S7_BIZ_SCENARIO);
+    case L7V_BIZ_RESPONSE_CODE: return sref(base, sl, S7_BIZ_RESPONSE_CODE);
+    case L7V_KNAME_0: return sref(base, sl, S7_KNAME_0);
+    case L7V_KNAME_1: return sref(base, sl, S7_KNAME_1);
+    case L7V_BIZ_PROTOCOL:
+      if (h.has_ext && sl_len(sl, S7_PROTOCOL_STR)) return sref(base, sl, S7_PROTOCOL_STR);
+      return cs_ref(dv, dv->proto_cs[h.l7_protocol][h.is_tls]);
+    case L7V_VERSION: return sref(base, sl, S7_VERSION);
+    case L7V_REQUEST_TYPE: return h.has_req ? sref(base, sl, S7_REQ_TYPE) : none;
+    case L7V_REQUEST_DOMAIN: return h.has_req ? sref(base, sl, S7_DOMAIN) : none;
+    case L7V_REQUEST_RESOURCE: return h.has_req ? sref(base, sl, S7_RESOURCE) : none;
+    case L7V_ENDPOINT: return h.has_req ? sref(base, sl, S7_ENDPOINT) : none;
+    case L7V_RESPONSE_EXCEPTION: return h.exc;
+    case L7V_RESPONSE_RESULT: return (h.has_resp && h.type != 0) ? sref(base, sl, S7_RESULT) : none;
+    case L7V_HTTP_PROXY_CLIENT: return h.has_ext ? sref(base, sl, S7_CLIENT_IP) : none;
+    case L7V_X_REQUEST_ID_0: return h.has_ext ? sref(base, sl, S7_X_REQUEST_ID_0) : none;
+    case L7V_X_REQUEST_ID_1: return h.has_ext ? sref(base, sl, S7_X_REQUEST_ID_1) : none;
+    case L7V_TRACE_ID: return h.trace_id;
+    case L7V_TRACE_ID_2: return (h.has_trace && h.two_ids) ? sref(base, sl, S7_TRACE_IDS_1) : none;
+    case L7V_SPAN_ID: return h.has_trace ? sref(base, sl, S7_SPAN_ID) : none;
+    case L7V_PARENT_SPAN_ID: return h.has_trace ? sref(base, sl, S7_PARENT_SPAN_ID) : none;
+    case L7V_APP_SERVICE: return h.has_ext ? sref(base, sl, S7_SERVICE_NAME) : none;
+    default: return none;  // app_instance: only the OTel import fills it
+  }
+}
+__device__ __forceinline__ int l7_str_col(const int i) {
+  switch (i) {
+    case L7V_BIZ_CODE: return L7C_BIZ_CODE;
+    case L7V_BIZ_SCENARIO: return L7C_BIZ_SCENARIO;
+    case L7V_BIZ_RESPONSE_CODE: return L7C_BIZ_RESPONSE_CODE;
+    case L7V_KNAME_0: return L7C_PROCESS_KNAME_0;
+    case L7V_KNAME_1: return L7C_PROCESS_KNAME_1;
+    case L7V_BIZ_PROTOCOL: return L7C_BIZ_PROTOCOL;
+    case L7V_VERSION: return L7C_VERSION;
+    case L7V_REQUEST_TYPE: return L7C_REQUEST_TYPE;
+    case L7V_REQUEST_DOMAIN: return L7C_REQUEST_DOMAIN;
+    case L7V_REQUEST_RESOURCE: return L7C_REQUEST_RESOURCE;
+    case L7V_ENDPOINT: return L7C_ENDPOINT;
+    case L7V_RESPONSE_EXCEPTION: return L7C_RESPONSE_EXCEPTION;
+    case L7V_RESPONSE_RESULT: return L7C_RESPONSE_RESULT;
+    case L7V_HTTP_PROXY_CLIENT: return L7C_HTTP_PROXY_CLIENT;
+    case L7V_X_REQUEST_ID_0: return L7C_X_REQUEST_ID_0;
+    case L7V_X_REQUEST_ID_1: return L7C_X_REQUEST_ID_1;
+    case L7V_TRACE_ID: return L7C_TRACE_ID;
+    case L7V_TRACE_ID_2: return L7C_TRACE_ID_2;
+    case L7V_SPAN_ID: return L7C_SPAN_ID;
+    case L7V_PARENT_SPAN_ID: return L7C_PARENT_SPAN_ID;
+    case L7V_APP_SERVICE: return L7C_APP_SERVICE;
+    default: return L7C_APP_INSTANCE;
   }
 }
 
@@ -332,46 +376,55 @@ struct SlotsW {
 static_assert(S7_COUNT <= 64 + 63, "presence bitmap: two words, bit 63 of the second is the ok flag");
 
 // Everything after the decode: row build, sizes (SIZE pass) or column stores (EMIT pass).
-// S is the private slot array (SIZE) or SlotsG (EMIT).
+// S is SlotsW (SIZE) or SlotsG (EMIT).  Called convergently by every lane of the warp (warp scans);
+// lanes without a row carry ok = false and contribute zero sizes.
 template <int EMIT, class S>
 __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, DynState* dyn, const uint32_t rec,
                                         const uint32_t warp, const uint32_t lane, const bool ok, const uint32_t frame,
                                         const uint8_t* base, const uint32_t len, const S& sl) {
   // AppProtoLogsData.IsValid() (datatype/pb/flow_log.go:82-89) cannot fail: Base and
   // Base.Head are pre-allocated.
-  L7Row w;
-  l7_derive(dv, base, sl, w);
+  L7Hdr w;
+  l7_hdr(dv, base, sl, w);
 
   const uint32_t n_an = (uint32_t)sl[S7_ATTR_NAMES], b_an = (uint32_t)(sl[S7_ATTR_NAMES] >> 32);
   const uint32_t n_av = (uint32_t)sl[S7_ATTR_VALUES], b_av = (uint32_t)(sl[S7_ATTR_VALUES] >> 32);
   const uint32_t n_mn = (uint32_t)sl[S7_METRICS_NAMES], b_mn = (uint32_t)(sl[S7_METRICS_NAMES] >> 32);
   const uint32_t n_mv = (uint32_t)sl[S7_METRICS_VALUES];
-  uint32_t sz[L7S_COUNT];
-  sz[L7S_ROWS] = ok ? 1u : 0u;
-#pragma unroll
-  for (int i = 0; i < 22; i++) sz[L7S_STR0 + i] = ok ? w.str[i].n : 0u;
-  sz[L7S_AN_ELEMS] = ok ? w.n_pseudo + n_an : 0u;
-  sz[L7S_AN_BYTES] = ok ? w.pseudo_name_bytes + b_an : 0u;
-  sz[L7S_AV_ELEMS] = ok ? w.n_pseudo + n_av : 0u;
-  sz[L7S_AV_BYTES] = ok ? w.pseudo_value_bytes + b_av : 0u;
-  sz[L7S_MN_ELEMS] = ok ? n_mn : 0u;
-  sz[L7S_MN_BYTES] = ok ? b_mn : 0u;
-  sz[L7S_MV_ELEMS] = ok ? n_mv : 0u;
+  const uint32_t z_rows = ok ? 1u : 0u;
+  const uint32_t z_an_e = ok ? w.n_pseudo + n_an : 0u, z_an_b = ok ? w.pseudo_name_bytes + b_an : 0u;
+  const uint32_t z_av_e = ok ? w.n_pseudo + n_av : 0u, z_av_b = ok ? w.pseudo_value_bytes + b_av : 0u;
+  const uint32_t z_mn_e = ok ? n_mn : 0u, z_mn_b = ok ? b_mn : 0u, z_mv_e = ok ? n_mv : 0u;
   const uint32_t tap_side = sl_u32(sl, S7_TAP_SIDE);
   const uint32_t tside = ok ? tapside_code(tap_side) : 0;
-  const bool has_trace = ok && w.trace_nonempty;
+  const bool has_trace = ok && w.trace_id.n != 0;
   const uint32_t trace_mask = __ballot_sync(0xffffffffu, has_trace);
+  const bool wr = lane == 0 && warp < p.nwarps;
 
   if (!EMIT) {
+#define WTOT(s, v)                                                 \
+  {                                                                \
+    const uint32_t t_ = warp_sum(v);                               \
+    if (wr) p.warp_tot[(size_t)(s) * p.nwarps + warp] = t_;        \
+  }
+    WTOT(L7S_ROWS, z_rows)
 #pragma unroll
-    for (int s = 0; s < L7S_COUNT; s++) {
-      uint32_t t = warp_sum(sz[s]);
-      if (lane == 0 && warp < p.nwarps) p.warp_tot[(size_t)s * p.nwarps + warp] = t;
+    for (int i = 0; i < 22; i++) {
+      const uint32_t n = ok ? l7_str(i, dv, base, sl, w).n : 0u;
+      WTOT(L7S_STR0 + i, n)
     }
+    WTOT(L7S_AN_ELEMS, z_an_e)
+    WTOT(L7S_AN_BYTES, z_an_b)
+    WTOT(L7S_AV_ELEMS, z_av_e)
+    WTOT(L7S_AV_BYTES, z_av_b)
+    WTOT(L7S_MN_ELEMS, z_mn_e)
+    WTOT(L7S_MN_BYTES, z_mn_b)
+    WTOT(L7S_MV_ELEMS, z_mv_e)
+#undef WTOT
     // last record of the warp carrying a trace id: feeds the lastTraceIdIndex carry
     int last = trace_mask ? 31 - __clz(trace_mask) : 0;
     uint64_t h = __shfl_sync(0xffffffffu, w.trace_hash, last);
-    if (lane == 0 && warp < p.nwarps) {
+    if (wr) {
       p.warp_tot[(size_t)L7S_TRACE_HAS * p.nwarps + warp] = trace_mask ? 1 : 0;
       p.warp_tot[(size_t)L7S_TRACE_LO * p.nwarps + warp] = (uint32_t)h;
       p.warp_tot[(size_t)L7S_TRACE_HI * p.nwarps + warp] = (uint32_t)(h >> 32);
@@ -381,20 +434,19 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   }
 
   // ---- EMIT ---------------------------------------------------------------------------
-  uint32_t ex[L7S_COUNT];
-#pragma unroll
-  for (int s = 0; s < L7S_COUNT; s++) ex[s] = warp_excl_scan(sz[s]);
+  const uint32_t wb = warp < p.nwarps ? warp : 0;
+#define WBASE(s, e) ((uint64_t)p.warp_base[(size_t)(s) * p.nwarps + wb] + (e))
+  const uint32_t row = (uint32_t)WBASE(L7S_ROWS, warp_excl_scan(z_rows));
   // trace_id_index (ParseTraceIdIndex :296-310): hash, or previous valid hash + 1
   uint64_t trace_index = 0;
   {
-    const uint32_t wb0 = warp < p.nwarps ? warp : 0;
-    uint64_t carry = (uint64_t)p.warp_base[(size_t)L7S_TRACE_HI * p.nwarps + wb0] << 32 |
-                     p.warp_base[(size_t)L7S_TRACE_LO * p.nwarps + wb0];
+    uint64_t carry = (uint64_t)p.warp_base[(size_t)L7S_TRACE_HI * p.nwarps + wb] << 32 |
+                     p.warp_base[(size_t)L7S_TRACE_LO * p.nwarps + wb];
     uint32_t before = trace_mask & ((1u << lane) - 1);
     int src = before ? 31 - __clz(before) : 0;
     uint64_t prev = __shfl_sync(0xffffffffu, w.trace_hash, src);
     if (!before) prev = carry;
-    trace_index = p.cfg_trace_disabled ? 0 : (w.trace_nonempty ? w.trace_hash : prev + 1);
+    trace_index = p.cfg_trace_disabled ? 0 : (w.trace_id.n != 0 ? w.trace_hash : prev + 1);
   }
   // updateCounter decoder.go:498-525 (one atomic per class per warp)
   {
@@ -415,117 +467,108 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
       if (lane == 0 && m) atomicAdd(&dyn->stats.l7_counts[c], __popc(m));
     }
   }
-  if (!ok) {
-    if (rec < p.nrec) dv->rec_row[rec] = 0xffffffffu;  // no row: l7_kg.cu skips the record
-    return;
-  }
-  const uint32_t wb = warp < p.nwarps ? warp : 0;
-#define WBASE(s) ((uint64_t)p.warp_base[(size_t)(s) * p.nwarps + wb] + ex[s])
-  const uint32_t row = (uint32_t)WBASE(L7S_ROWS);
-  const dfgpu_frame fr = p.frames[frame];
-  const bool v6 = sl_u32(sl, S7_IS_IPV6) == 1;
-  const uint64_t end_time = sl[S7_END_TIME];
-  const uint32_t time_s = (uint32_t)(end_time / 1000000000ull);
-  const uint32_t vtap_id = sl_u32(sl, S7_VTAP_ID);
-  const SRef ip6_src = sref(base, sl, S7_IP6_SRC), ip6_dst = sref(base, sl, S7_IP6_DST);
-
   // SmartEncoding (KnowledgeGraph.FillL7: the 39 KG columns, team_id, gprocess_id_0/1) runs right after
-  // this pass with one lane per (record, side): l7_kg.cu.  It needs the row of every record.
-  dv->rec_row[rec] = row;
+  // this pass with one lane per (record, side): l7_kg.cu.  It needs the row of every record
+  // (0xffffffff: no row, the record is skipped).
+  if (rec < p.nrec) dv->rec_row[rec] = ok ? row : 0xffffffffu;
 
-  // ---- L7Base.Fill :514-582 ---------------------------------------------------------------
-  const uint64_t tap_port = sl[S7_TAP_PORT];
-  st<uint32_t>(p, L7C_TIME, row, time_s);
-  st<uint32_t>(p, L7C_IP4_0, row, v6 ? 0u : sl_u32(sl, S7_IP_SRC));
-  st<uint32_t>(p, L7C_IP4_1, row, v6 ? 0u : sl_u32(sl, S7_IP_DST));
-  st_ip6(p, L7C_IP6_0, row, v6 ? ip6_src : SRef{nullptr, 0});
-  st_ip6(p, L7C_IP6_1, row, v6 ? ip6_dst : SRef{nullptr, 0});
-  st<uint8_t>(p, L7C_IS_IPV4, row, v6 ? 0 : 1);
-  st<uint8_t>(p, L7C_PROTOCOL, row, (uint8_t)sl_u32(sl, S7_PROTOCOL));
-  st<uint16_t>(p, L7C_CLIENT_PORT, row, (uint16_t)sl_u32(sl, S7_PORT_SRC));
-  st<uint16_t>(p, L7C_SERVER_PORT, row, (uint16_t)sl_u32(sl, S7_PORT_DST));
-  st<uint64_t>(p, L7C_FLOW_ID, row, sl[S7_FLOW_ID]);
-  st<uint8_t>(p, L7C_CAPTURE_NETWORK_TYPE_ID, row, (uint8_t)sl_u32(sl, S7_TAP_TYPE));
-  const uint8_t tap_port_type = (uint8_t)(tap_port >> 60);
-  st<uint8_t>(p, L7C_NAT_SOURCE, row, (uint8_t)((tap_port >> 36) & 0xf));
-  st<uint8_t>(p, L7C_CAPTURE_NIC_TYPE, row, tap_port_type);
-  st<uint16_t>(p, L7C_SIGNAL_SOURCE, row, tap_port_type == 8 ? 4 : tap_port_type == 7 ? 3 : 0);
-  st<uint8_t>(p, L7C_TUNNEL_TYPE, row, (uint8_t)((tap_port >> 32) & 0xf));
-  st<uint32_t>(p, L7C_CAPTURE_NIC, row, (uint32_t)tap_port);
-  st<uint8_t>(p, L7C_OBSERVATION_POINT, row, dyn->lc_rank[LC7_TAPSIDE][tside]);
-  st<uint16_t>(p, L7C_AGENT_ID, row, (uint16_t)vtap_id);
-  st<uint32_t>(p, L7C_REQ_TCP_SEQ, row, sl_u32(sl, S7_REQ_TCP_SEQ));
-  st<uint32_t>(p, L7C_RESP_TCP_SEQ, row, sl_u32(sl, S7_RESP_TCP_SEQ));
-  st<int64_t>(p, L7C_START_TIME, row, (int64_t)sl[S7_START_TIME] / 1000);
-  st<int64_t>(p, L7C_END_TIME, row, (int64_t)end_time / 1000);
-  st<uint8_t>(p, L7C_BIZ_TYPE, row, (uint8_t)sl_u32(sl, S7_BIZ_TYPE));
-  st<int32_t>(p, L7C_PROCESS_ID_0, row, (int32_t)sl_u32(sl, S7_PID_0));
-  st<int32_t>(p, L7C_PROCESS_ID_1, row, (int32_t)sl_u32(sl, S7_PID_1));
-  st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_REQUEST, row, sl[S7_SYS_REQ]);
-  st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_RESPONSE, row, sl[S7_SYS_RESP]);
-  st<uint32_t>(p, L7C_SYSCALL_THREAD_0, row, sl_u32(sl, S7_THREAD_0));
-  st<uint32_t>(p, L7C_SYSCALL_THREAD_1, row, sl_u32(sl, S7_THREAD_1));
-  st<uint64_t>(p, L7C_SYSCALL_COROUTINE_0, row, sl[S7_CORO_0]);
-  st<uint64_t>(p, L7C_SYSCALL_COROUTINE_1, row, sl[S7_CORO_1]);
-  st<uint32_t>(p, L7C_SYSCALL_CAP_SEQ_0, row, sl_u32(sl, S7_CAP_SEQ_0));
-  st<uint32_t>(p, L7C_SYSCALL_CAP_SEQ_1, row, sl_u32(sl, S7_CAP_SEQ_1));
-  // ---- L7FlowLog block ----------------------------------------------------------------------
-  {
-    uint32_t count = p.persist->id_counter + row + 1;  // genID l4_flow_log.go:949-953
-    st<uint64_t>(p, L7C__ID, row,
-                 (uint64_t)time_s << 32 | (uint64_t)(p.dict.analyzer_id & 0x3ff) << 22 | ((uint64_t)count & 0x3fffff));
-  }
-  st<uint8_t>(p, L7C_L7_PROTOCOL, row, w.l7_protocol);
-  st<uint8_t>(p, L7C_TYPE, row, w.type);
-  st<uint8_t>(p, L7C_IS_TLS, row, w.is_tls);
-  st<uint8_t>(p, L7C_IS_ASYNC, row, w.is_async);
-  st<uint8_t>(p, L7C_IS_REVERSED, row, w.is_reversed);
-  st_nullable<uint64_t>(p, L7C_REQUEST_ID, row, w.has_request_id, w.request_id);
-  st<uint8_t>(p, L7C_RESPONSE_STATUS, row, w.response_status);
-  st_nullable<int32_t>(p, L7C_RESPONSE_CODE, row, w.has_response_code, w.response_code);
-  st<uint64_t>(p, L7C_TRACE_ID_INDEX, row, trace_index);
-  st_nullable<uint8_t>(p, L7C_SPAN_KIND, row, false, 0);
-  st<uint64_t>(p, L7C_RESPONSE_DURATION, row, sl[S7_HEAD_RRT] / 1000);
-  st_nullable<int64_t>(p, L7C_REQUEST_LENGTH, row, w.has_request_length, w.request_length);
-  st_nullable<int64_t>(p, L7C_RESPONSE_LENGTH, row, w.has_response_length, w.response_length);
-  st_nullable<uint64_t>(p, L7C_SQL_AFFECTED_ROWS, row, w.has_sql_rows, w.sql_rows);
-  st<uint8_t>(p, L7C_DIRECTION_SCORE, row, (uint8_t)sl_u32(sl, S7_DIRECTION_SCORE));
-  st<uint32_t>(p, L7C_CAPTURED_REQUEST_BYTE, row, sl_u32(sl, S7_CAP_REQ_BYTE));
-  st<uint32_t>(p, L7C_CAPTURED_RESPONSE_BYTE, row, sl_u32(sl, S7_CAP_RESP_BYTE));
-
-  // ---- the 22 per-row string columns: Pos + bytes -------------------------------------------
-  {
-    const int cols[22] = {L7C_BIZ_CODE, L7C_BIZ_SCENARIO, L7C_BIZ_RESPONSE_CODE, L7C_PROCESS_KNAME_0,
-                          L7C_PROCESS_KNAME_1, L7C_BIZ_PROTOCOL, L7C_VERSION, L7C_REQUEST_TYPE,
-                          L7C_REQUEST_DOMAIN, L7C_REQUEST_RESOURCE, L7C_ENDPOINT, L7C_RESPONSE_EXCEPTION,
-                          L7C_RESPONSE_RESULT, L7C_HTTP_PROXY_CLIENT, L7C_X_REQUEST_ID_0, L7C_X_REQUEST_ID_1,
-                          L7C_TRACE_ID, L7C_TRACE_ID_2, L7C_SPAN_ID, L7C_PARENT_SPAN_ID, L7C_APP_SERVICE,
-                          L7C_APP_INSTANCE};
-#pragma unroll 1
-    for (int i = 0; i < 22; i++) {
-      uint64_t off = WBASE(L7S_STR0 + i);
-      uint32_t n = w.str[i].n;
-      reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[cols[i]])[row] = dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
-#ifndef ABL_NO_STRCOPY
-      if (n) copy_bytes(p.arena + dyn->var_buf_off[i] + off, w.str[i].p, n);
-#endif
+  if (ok) {
+    const bool v6 = sl_u32(sl, S7_IS_IPV6) == 1;
+    const uint64_t end_time = sl[S7_END_TIME];
+    const uint32_t time_s = (uint32_t)(end_time / 1000000000ull);
+    const uint32_t vtap_id = sl_u32(sl, S7_VTAP_ID);
+    // ---- L7Base.Fill :514-582 ---------------------------------------------------------------
+    const uint64_t tap_port = sl[S7_TAP_PORT];
+    st<uint32_t>(p, L7C_TIME, row, time_s);
+    st<uint32_t>(p, L7C_IP4_0, row, v6 ? 0u : sl_u32(sl, S7_IP_SRC));
+    st<uint32_t>(p, L7C_IP4_1, row, v6 ? 0u : sl_u32(sl, S7_IP_DST));
+    st_ip6(p, L7C_IP6_0, row, v6 ? sref(base, sl, S7_IP6_SRC) : SRef{nullptr, 0});
+    st_ip6(p, L7C_IP6_1, row, v6 ? sref(base, sl, S7_IP6_DST) : SRef{nullptr, 0});
+    st<uint8_t>(p, L7C_IS_IPV4, row, v6 ? 0 : 1);
+    st<uint8_t>(p, L7C_PROTOCOL, row, (uint8_t)sl_u32(sl, S7_PROTOCOL));
+    st<uint16_t>(p, L7C_CLIENT_PORT, row, (uint16_t)sl_u32(sl, S7_PORT_SRC));
+    st<uint16_t>(p, L7C_SERVER_PORT, row, (uint16_t)sl_u32(sl, S7_PORT_DST));
+    st<uint64_t>(p, L7C_FLOW_ID, row, sl[S7_FLOW_ID]);
+    st<uint8_t>(p, L7C_CAPTURE_NETWORK_TYPE_ID, row, (uint8_t)sl_u32(sl, S7_TAP_TYPE));
+    const uint8_t tap_port_type = (uint8_t)(tap_port >> 60);
+    st<uint8_t>(p, L7C_NAT_SOURCE, row, (uint8_t)((tap_port >> 36) & 0xf));
+    st<uint8_t>(p, L7C_CAPTURE_NIC_TYPE, row, tap_port_type);
+    st<uint16_t>(p, L7C_SIGNAL_SOURCE, row, tap_port_type == 8 ? 4 : tap_port_type == 7 ? 3 : 0);
+    st<uint8_t>(p, L7C_TUNNEL_TYPE, row, (uint8_t)((tap_port >> 32) & 0xf));
+    st<uint32_t>(p, L7C_CAPTURE_NIC, row, (uint32_t)tap_port);
+    st<uint8_t>(p, L7C_OBSERVATION_POINT, row, dyn->lc_rank[LC7_TAPSIDE][tside]);
+    st<uint16_t>(p, L7C_AGENT_ID, row, (uint16_t)vtap_id);
+    st<uint32_t>(p, L7C_REQ_TCP_SEQ, row, sl_u32(sl, S7_REQ_TCP_SEQ));
+    st<uint32_t>(p, L7C_RESP_TCP_SEQ, row, sl_u32(sl, S7_RESP_TCP_SEQ));
+    st<int64_t>(p, L7C_START_TIME, row, (int64_t)sl[S7_START_TIME] / 1000);
+    st<int64_t>(p, L7C_END_TIME, row, (int64_t)end_time / 1000);
+    st<uint8_t>(p, L7C_BIZ_TYPE, row, (uint8_t)sl_u32(sl, S7_BIZ_TYPE));
+    st<int32_t>(p, L7C_PROCESS_ID_0, row, (int32_t)sl_u32(sl, S7_PID_0));
+    st<int32_t>(p, L7C_PROCESS_ID_1, row, (int32_t)sl_u32(sl, S7_PID_1));
+    st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_REQUEST, row, sl[S7_SYS_REQ]);
+    st<uint64_t>(p, L7C_SYSCALL_TRACE_ID_RESPONSE, row, sl[S7_SYS_RESP]);
+    st<uint32_t>(p, L7C_SYSCALL_THREAD_0, row, sl_u32(sl, S7_THREAD_0));
+    st<uint32_t>(p, L7C_SYSCALL_THREAD_1, row, sl_u32(sl, S7_THREAD_1));
+    st<uint64_t>(p, L7C_SYSCALL_COROUTINE_0, row, sl[S7_CORO_0]);
+    st<uint64_t>(p, L7C_SYSCALL_COROUTINE_1, row, sl[S7_CORO_1]);
+    st<uint32_t>(p, L7C_SYSCALL_CAP_SEQ_0, row, sl_u32(sl, S7_CAP_SEQ_0));
+    st<uint32_t>(p, L7C_SYSCALL_CAP_SEQ_1, row, sl_u32(sl, S7_CAP_SEQ_1));
+    // ---- L7FlowLog block ----------------------------------------------------------------------
+    {
+      uint32_t count = p.persist->id_counter + row + 1;  // genID l4_flow_log.go:949-953
+      st<uint64_t>(p, L7C__ID, row,
+                   (uint64_t)time_s << 32 | (uint64_t)(p.dict.analyzer_id & 0x3ff) << 22 | ((uint64_t)count & 0x3fffff));
     }
+    st<uint8_t>(p, L7C_L7_PROTOCOL, row, w.l7_protocol);
+    st<uint8_t>(p, L7C_TYPE, row, w.type);
+    st<uint8_t>(p, L7C_IS_TLS, row, w.is_tls);
+    st<uint8_t>(p, L7C_IS_ASYNC, row, w.is_async);
+    st<uint8_t>(p, L7C_IS_REVERSED, row, w.is_reversed);
+    st_nullable<uint64_t>(p, L7C_REQUEST_ID, row, w.has_request_id, (uint64_t)w.request_id);
+    st<uint8_t>(p, L7C_RESPONSE_STATUS, row, w.response_status);
+    st_nullable<int32_t>(p, L7C_RESPONSE_CODE, row, w.has_response_code, w.response_code);
+    st<uint64_t>(p, L7C_TRACE_ID_INDEX, row, trace_index);
+    st_nullable<uint8_t>(p, L7C_SPAN_KIND, row, false, 0);
+    st<uint64_t>(p, L7C_RESPONSE_DURATION, row, sl[S7_HEAD_RRT] / 1000);
+    st_nullable<int64_t>(p, L7C_REQUEST_LENGTH, row, w.has_request_length, (int64_t)w.request_length);
+    st_nullable<int64_t>(p, L7C_RESPONSE_LENGTH, row, w.has_response_length, (int64_t)w.response_length);
+    st_nullable<uint64_t>(p, L7C_SQL_AFFECTED_ROWS, row, w.sql_rows != 0, (uint64_t)w.sql_rows);
+    st<uint8_t>(p, L7C_DIRECTION_SCORE, row, (uint8_t)sl_u32(sl, S7_DIRECTION_SCORE));
+    st<uint32_t>(p, L7C_CAPTURED_REQUEST_BYTE, row, sl_u32(sl, S7_CAP_REQ_BYTE));
+    st<uint32_t>(p, L7C_CAPTURED_RESPONSE_BYTE, row, sl_u32(sl, S7_CAP_RESP_BYTE));
     // events: always empty on this path (only the OTel import fills it)
     reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[L7C_EVENTS])[row] = dfgpu_pos{0, 0};
   }
+
+  // ---- the 22 per-row string columns: Pos + bytes (one string live at a time) ----------------
+#pragma unroll
+  for (int i = 0; i < 22; i++) {
+    const SRef s = l7_str(i, dv, base, sl, w);
+    const uint32_t n = ok ? s.n : 0u;
+    const uint64_t off = WBASE(L7S_STR0 + i, warp_excl_scan(n));
+    if (ok) {
+      reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[l7_str_col(i)])[row] =
+          dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
+#ifndef ABL_NO_STRCOPY
+      if (n) copy_bytes(p.arena + dyn->var_buf_off[i] + off, s.p, n);
+#endif
+    }
+  }
   // ---- arrays: cumulative END offsets per row, then the elements ---------------------------
-  const uint64_t an_e = WBASE(L7S_AN_ELEMS), an_b = WBASE(L7S_AN_BYTES);
-  const uint64_t av_e = WBASE(L7S_AV_ELEMS), av_b = WBASE(L7S_AV_BYTES);
-  const uint64_t mn_e = WBASE(L7S_MN_ELEMS), mn_b = WBASE(L7S_MN_BYTES);
-  const uint64_t mv_e = WBASE(L7S_MV_ELEMS);
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_NAMES])[row] = an_e + sz[L7S_AN_ELEMS];
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_VALUES])[row] = av_e + sz[L7S_AV_ELEMS];
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_NAMES])[row] = mn_e + sz[L7S_MN_ELEMS];
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_VALUES])[row] = mv_e + sz[L7S_MV_ELEMS];
+  const uint64_t an_e = WBASE(L7S_AN_ELEMS, warp_excl_scan(z_an_e)), an_b = WBASE(L7S_AN_BYTES, warp_excl_scan(z_an_b));
+  const uint64_t av_e = WBASE(L7S_AV_ELEMS, warp_excl_scan(z_av_e)), av_b = WBASE(L7S_AV_BYTES, warp_excl_scan(z_av_b));
+  const uint64_t mn_e = WBASE(L7S_MN_ELEMS, warp_excl_scan(z_mn_e)), mn_b = WBASE(L7S_MN_BYTES, warp_excl_scan(z_mn_b));
+  const uint64_t mv_e = WBASE(L7S_MV_ELEMS, warp_excl_scan(z_mv_e));
+#undef WBASE
+  if (!ok) return;
+  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_NAMES])[row] = an_e + z_an_e;
+  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_VALUES])[row] = av_e + z_av_e;
+  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_NAMES])[row] = mn_e + z_mn_e;
+  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_VALUES])[row] = mv_e + z_mv_e;
 #ifdef ABL_NO_ARRAYS
   if (false) {
 #else
-  if (sz[L7S_AN_ELEMS] | sz[L7S_AV_ELEMS] | sz[L7S_MN_ELEMS] | sz[L7S_MV_ELEMS]) {
+  if (z_an_e | z_av_e | z_mn_e | z_mv_e) {
 #endif
     L7EmitSink sink;
     sink.an_pos = reinterpret_cast<dfgpu_pos*>(p.arena + dyn->var_pos_off[L7V_ATTR_NAMES]) + an_e;
@@ -539,7 +582,7 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
     sink.mn_off = mn_b;
     sink.mv = reinterpret_cast<uint64_t*>(p.arena + dyn->var_buf_off[L7V_METRICS_VALUES]) + mv_e;
     // pseudo attributes first, in the reference's order (:418-429)
-    if (sl[S7_EXT_CNT]) {
+    if (w.has_ext) {
       SRef ua = sref(base, sl, S7_USER_AGENT), rf = sref(base, sl, S7_REFERER), rpc = sref(base, sl, S7_RPC_SERVICE);
       if (ua.n) {
         SRef nm = cs_ref(dv, CS_ATTR_UA);
@@ -559,21 +602,26 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
     }
     if (n_an | n_av | n_mn | n_mv) {
       if (sl[S7_EXT_CNT] == 1 && sl[S7_BASE_CNT] <= 1) {
-        // the common case: one ext_info occurrence — walk just that range
+        // the common case: one ext_info occurrence — walk just that range (inlined: the sink stays in
+        // registers; it is the tail of the kernel)
         walk_ext_range(base + sl_off(sl, S7_EXT_RANGE), sl_len(sl, S7_EXT_RANGE), sink);
       } else {
-        // ext_info split over several occurrences (merge semantics): full re-walk
-        l7_arrays_slow(base, len, sink);
+        // ext_info split over several occurrences (merge semantics): full re-walk, out of line, on a
+        // copy so that the address of `sink` itself never escapes
+        L7EmitSink cold = sink;
+        l7_arrays_slow(base, len, cold);
       }
     }
   }
-#undef WBASE
 }
 
+#ifndef L7_EMIT_MIN_BLOCKS
+#define L7_EMIT_MIN_BLOCKS 4
+#endif
 template <int EMIT>
 // SIZE pass: 40 registers / 6 CTAs per SM measured fastest (0.77 ms vs 0.92 at 4 and 0.86 at 8 CTAs per
 // 625 k records); EMIT pass: 64 registers / 4 CTAs (80 and 128 registers were slower: 1.65 / 1.99 ms).
-__global__ void __launch_bounds__(256, EMIT ? 4 : 6) k_l7_pass(const __grid_constant__ BatchParams p) {
+__global__ void __launch_bounds__(256, EMIT ? L7_EMIT_MIN_BLOCKS : 6) k_l7_pass(const __grid_constant__ BatchParams p) {
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
   const bool in_range = rec < p.nrec;

@@ -123,6 +123,24 @@ __device__ __forceinline__ FtEntry* ts_find(FtEntry* tbl, uint32_t mask, U128 fp
   return nullptr;
 }
 
+// The first slot of a probe sequence, whole (one 32-byte sector, two loads issued together), so that
+// several probes can be in flight before any is consumed.
+struct TsPeek {
+  unsigned long long lo, hi, first_pos, ts;  // ts = time | state << 32
+};
+__device__ __forceinline__ void ts_peek(const FtEntry* tbl, uint32_t mask, U128 fp, TsPeek& k) {
+  const FtEntry* e = tbl + ((uint32_t)(fp.lo ^ (fp.hi >> 17)) & mask);
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(k.lo), "=l"(k.hi) : "l"(e) : "memory");
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2+16];" : "=l"(k.first_pos), "=l"(k.ts) : "l"(e) : "memory");
+}
+// the key sits in its first slot, has been emitted, and its lru time has not expired: nothing to do
+__device__ __forceinline__ bool ts_peek_fresh(const TsPeek& k, U128 fp, uint32_t now, uint32_t timeout) {
+  if (k.lo != fp.lo || k.hi != fp.hi) return false;
+  const uint32_t time = (uint32_t)k.ts, state = (uint32_t)(k.ts >> 32);
+  if (state == 0) return false;
+  return !((uint32_t)(time + timeout) < now);
+}
+
 // lru semantics (l7_flow_log.go:693-701, app_service_tag_writer.go:100-108): emit when
 // the key is new, or when old + CacheFlushTimeout < time (uint32 arithmetic)
 __device__ __forceinline__ bool ts_candidate(const FtEntry* e, uint32_t now, uint32_t timeout) {

@@ -50,6 +50,9 @@ def main():
         for k, v in st.items():
             print(f"  {k:10s} {v / n:8.3f} ms  {100 * v / tot:5.1f} %")
         print(f"  total      {tot / n:8.3f} ms  -> {wl.nrecords / (tot / n) / 1e3:.1f} M rec/s")
+        ems, en, _ = eng.profile_read()  # the EMIT kernel alone (emit_pass = EMIT + SmartEncoding)
+        if en:
+            print(f"  EMIT kernel alone {ems / en:8.3f} ms, SmartEncoding kernel {(st['emit_pass'] - ems) / n:8.3f} ms")
     eng.close()
 
 
