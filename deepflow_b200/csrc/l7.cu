@@ -610,7 +610,7 @@ int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s) {
     if (h->d_slotbuf) CU(cudaFree(h->d_slotbuf));
     h->d_slotbuf = nullptr;
     size_t cap = (size_t)ctx->bp.nrec + ctx->bp.nrec / 8 + 4096;
-    CU(cudaMalloc(&h->d_slotbuf, cap * (S7_COUNT + 2) * sizeof(uint64_t)));  // + 2 presence words
+    CU(cudaMalloc(&h->d_slotbuf, cap * (S7_COUNT + 3) * sizeof(uint64_t)));  // + 2 presence words + the trace-id hash
     if (h->d_rec_row) CU(cudaFree(h->d_rec_row));
     h->d_rec_row = nullptr;
     CU(cudaMalloc(&h->d_rec_row, cap * sizeof(uint32_t)));

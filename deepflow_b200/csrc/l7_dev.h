@@ -36,9 +36,10 @@ struct L7Dev {
   uint8_t* ft_arena;
   uint64_t ft_arena_bytes;
   uint8_t* row_flag;  // [nrows] set by flow_tag phase 0: the row has a new/expired key
-  // decoded slots of every record, slot-major ([S7_COUNT + 2][slot_stride], coalesced): written by the
+  // decoded slots of every record, slot-major ([S7_COUNT + 3][slot_stride], coalesced): written by the
   // SIZE pass so that the EMIT pass does not decode the record a second time; the two extra rows are
-  // the presence bitmap of the slots (bit 63 of the second word: the record decoded)
+  // the presence bitmap of the slots (bit 63 of the second word: the record decoded), the third the DJB
+  // hash of the record's trace id
   uint64_t* slotbuf;
   uint32_t slot_stride;
   uint32_t* rec_row;  // [records] row of the record in l7_flow_log (0xffffffff: none), EMIT pass -> l7_kg.cu

@@ -23,8 +23,21 @@ __device__ __forceinline__ SRef cs_tbl(const L7Dev* d, uint32_t base, int32_t id
   if (idx >= 0 && idx < n) return cs_ref(d, base + (uint32_t)idx);
   return SRef{nullptr, 0};
 }
+// DJBHash (libs/utils/hash.go:37-43) over n bytes; the bytes come out of aligned 8-byte blocks (one load
+// per 8 bytes instead of one per byte; a block is only touched when it holds a byte of the string)
 __device__ __forceinline__ uint64_t djb_hash(uint64_t h, const uint8_t* p, uint32_t n) {
-  for (uint32_t i = 0; i < n; i++) h = ((h << 5) + h) + (uint64_t)ldb(p + i);
+  if (!n) return h;
+  const unsigned long long* sb = reinterpret_cast<const unsigned long long*>((uintptr_t)p & ~(uintptr_t)7);
+  uint32_t o = (uint32_t)(uintptr_t)p & 7u;
+  unsigned long long cur = __ldg(sb) >> (o * 8);
+  for (uint32_t i = 0; i < n; i++) {
+    h = ((h << 5) + h) + (uint64_t)(cur & 0xff);
+    cur >>= 8;
+    if (++o == 8 && i + 1 < n) {
+      o = 0;
+      cur = __ldg(++sb);
+    }
+  }
   return h;
 }
 __device__ bool str_eq(SRef s, const char* lit) {
@@ -51,34 +64,56 @@ __device__ __forceinline__ void st_nullable(const BatchParams& p, int col, uint3
   reinterpret_cast<T*>(p.arena + p.fix_off[col])[row] = has ? v : T(0);
   (p.arena + p.aux_off[col])[row] = has ? 0 : 1;
 }
-// String bytes -> column buffer.  Source and destination have arbitrary alignment.  Short strings go
-// byte by byte; longer ones byte-align the destination, then move 8 bytes per load/store pair (the
-// source word is funnelled out of two aligned 8-byte blocks).  Ablation (profiles/): the byte loops
-// were 0.33 + part of 0.41 ms of the 1.62 ms EMIT pass.
-__device__ __noinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, uint32_t n) {
-  if (n < 16) {
-    for (uint32_t i = 0; i < n; i++) dst[i] = ldb(src + i);
+// String bytes -> column buffer.  Source and destination have arbitrary alignment.  Every source byte
+// comes out of an aligned 8-byte block (a block is only touched when it holds a byte of the string, and
+// the first blocks are requested together); bytes are then STORED from registers.  ncu, round 1: the
+// byte-by-byte load/store loop for strings < 16 B was 24 % of the EMIT pass's stall samples, the head /
+// tail byte loops of longer strings another 8 %.
+__device__ __forceinline__ void store_bytes(uint8_t* dst, unsigned long long w, uint32_t n) {  // n <= 8
+  for (uint32_t i = 0; i < n; i++) {
+    dst[i] = (uint8_t)w;
+    w >>= 8;
+  }
+}
+__device__ __noinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, uint32_t n) {  // n > 0
+  const unsigned long long* sb = reinterpret_cast<const unsigned long long*>((uintptr_t)src & ~(uintptr_t)7);
+  const uint32_t so = (uint32_t)(uintptr_t)src & 7u, sh = so * 8u;
+  const uint32_t nblk = (so + n + 7u) >> 3;  // blocks holding source bytes (>= 1)
+  const unsigned long long b0 = __ldg(sb);
+  const unsigned long long b1 = nblk > 1 ? __ldg(sb + 1) : 0ull;
+  const unsigned long long w0 = sh ? (b0 >> sh) | (b1 << (64 - sh)) : b0;  // source bytes 0..7
+  if (n <= 16) {
+    const unsigned long long b2 = nblk > 2 ? __ldg(sb + 2) : 0ull;
+    const unsigned long long w1 = sh ? (b1 >> sh) | (b2 << (64 - sh)) : b1;  // source bytes 8..15
+    store_bytes(dst, w0, n < 8 ? n : 8u);
+    if (n > 8) store_bytes(dst + 8, w1, n - 8);
     return;
   }
+  // byte-align the destination from the first word, then move 8 bytes per load/store pair
   const uint32_t head = (uint32_t)(0u - (uint32_t)(uintptr_t)dst) & 7u;
-  for (uint32_t i = 0; i < head; i++) dst[i] = ldb(src + i);
+  store_bytes(dst, w0, head);
   const uint8_t* s = src + head;
   uint8_t* d = dst + head;
   const uint32_t m = n - head;
-  const unsigned long long* sb = reinterpret_cast<const unsigned long long*>((uintptr_t)s & ~(uintptr_t)7);
-  const uint32_t sh = ((uint32_t)(uintptr_t)s & 7u) * 8u;
-  unsigned long long cur = __ldg(sb);
+  const unsigned long long* sb2 = reinterpret_cast<const unsigned long long*>((uintptr_t)s & ~(uintptr_t)7);
+  const uint32_t sh2 = ((uint32_t)(uintptr_t)s & 7u) * 8u;
+  unsigned long long cur = sb2 == sb ? b0 : b1;  // head <= 7: s lies in block 0 or 1
   uint32_t k = 0;
   for (; k + 8 <= m; k += 8) {
     // the next block is touched only if it holds a valid source byte
-    const bool need = sh != 0 || k + 8 < m;
-    const unsigned long long nxt = need ? __ldg(sb + 1) : 0ull;
-    const unsigned long long w = sh ? (cur >> sh) | (nxt << (64 - sh)) : cur;
+    const bool need = sh2 != 0 || k + 8 < m;
+    const unsigned long long nxt = need ? __ldg(sb2 + 1) : 0ull;
+    const unsigned long long w = sh2 ? (cur >> sh2) | (nxt << (64 - sh2)) : cur;
     *reinterpret_cast<unsigned long long*>(d + k) = w;
     cur = nxt;
-    sb++;
+    sb2++;
   }
-  for (; k < m; k++) d[k] = ldb(s + k);
+  const uint32_t r = m - k;  // 0..7 tail bytes; `cur` is the block holding source byte k
+  if (r) {
+    const bool need = sh2 + r * 8u > 64u;  // the tail runs into the next block
+    const unsigned long long nxt = need ? __ldg(sb2 + 1) : 0ull;
+    store_bytes(d + k, sh2 ? (cur >> sh2) | (nxt << (64 - sh2)) : cur, r);
+  }
 }
 template <class S>
 __device__ __forceinline__ SRef sref(const uint8_t* base, const S& sl, int i) {
@@ -244,7 +279,8 @@ __device__ __forceinline__ void l7_hdr(const L7Dev* dv, const uint8_t* base, con
     if (trace_id.n == 0) trace_id = sref(base, sl, S7_TRACE_ID);
   }
   o.trace_id = trace_id;
-  o.trace_hash = trace_id.n != 0 ? djb_hash(17, trace_id.p, trace_id.n) : 0;
+  // the SIZE pass hashes the trace id (ParseTraceIdIndex :296-310) and leaves the value for the EMIT pass
+  o.trace_hash = trace_id.n == 0 ? 0 : S::kHashSaved ? sl.saved_hash() : djb_hash(17, trace_id.p, trace_id.n);
   switch (o.l7_protocol) {  // :438-451
     case 100:
       if (o.has_req) {
@@ -339,6 +375,9 @@ struct SlotsG {
     m1 = valid ? __ldg(p + (size_t)(S7_COUNT + 1) * stride) : 0ull;
   }
   __device__ __forceinline__ bool ok() const { return (m1 >> 63) != 0; }
+  static constexpr bool kHashSaved = true;  // row S7_COUNT + 2: DJB hash of the record's trace id
+  __device__ __forceinline__ uint64_t saved_hash() const { return __ldg(p + (size_t)(S7_COUNT + 2) * stride); }
+  __device__ __forceinline__ void save_hash(uint64_t) const {}
   __device__ __forceinline__ uint64_t operator[](int i) const {
     const uint64_t m = i < 64 ? m0 >> i : m1 >> (i - 64);
     return (m & 1) ? __ldg(p + (size_t)i * stride) : 0ull;
@@ -368,6 +407,9 @@ struct SlotsW {
   __device__ __forceinline__ Ref operator[](int i) { return Ref{this, i}; }
   __device__ __forceinline__ uint64_t operator[](int i) const { return get(i); }
   __device__ __forceinline__ void clear() { m0 = m1 = 0; }
+  static constexpr bool kHashSaved = false;
+  __device__ __forceinline__ uint64_t saved_hash() const { return 0; }
+  __device__ __forceinline__ void save_hash(uint64_t h) const { p[(size_t)(S7_COUNT + 2) * stride] = h; }
   __device__ __forceinline__ void finish(bool ok) {
     p[(size_t)S7_COUNT * stride] = m0;
     p[(size_t)(S7_COUNT + 1) * stride] = m1 | (uint64_t)(ok ? 1 : 0) << 63;
@@ -430,6 +472,7 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
       p.warp_tot[(size_t)L7S_TRACE_HI * p.nwarps + warp] = (uint32_t)(h >> 32);
     }
     lc_note(dyn->stats.lc_first[LC7_TAPSIDE], tside, rec, ok);
+    if (has_trace) sl.save_hash(w.trace_hash);
     return;
   }
 
@@ -615,6 +658,9 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   }
 }
 
+#ifndef L7_PREFETCH
+#define L7_PREFETCH 0  // bit 0: SIZE pass, bit 1: EMIT pass
+#endif
 #ifndef L7_EMIT_MIN_BLOCKS
 #define L7_EMIT_MIN_BLOCKS 4
 #endif
@@ -638,6 +684,13 @@ __global__ void __launch_bounds__(256, EMIT ? L7_EMIT_MIN_BLOCKS : 6) k_l7_pass(
     base = p.in + p.rec_off[rec];
     len = p.rec_len[rec];
   }
+#if L7_PREFETCH
+  // all 128-byte lines of the record are requested before the walk touches the first: the walk is a
+  // chain of dependent reads, this turns all but the first line's miss into an L2 hit
+  if (L7_PREFETCH & (EMIT ? 2 : 1))
+    for (uint32_t x = 0; x < len && x < 2048u; x += 128u)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + x));
+#endif
   if (EMIT) {
     // decoded once, by the SIZE pass
     const SlotsG sl(dv->slotbuf + rec, dv->slot_stride, in_range);
