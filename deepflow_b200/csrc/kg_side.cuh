@@ -68,23 +68,28 @@ constexpr uint64_t FOUND = 1ull << 32;
 
 struct Pre {  // the first entry of a probe sequence, loaded ahead of its use
   uint4 e;
-  uint32_t s;
 };
 __device__ __forceinline__ Pre t64_pre(const DevDict& d, uint32_t tid, uint64_t key, bool want) {
   Pre r;
-  r.s = t64_slot(tid, key, d.t64_mask);
-  r.e = want ? __ldg(reinterpret_cast<const uint4*>(d.t64 + r.s)) : make_uint4(0, 0, 0, TID_EMPTY);
+  const uint32_t s = t64_slot(tid, key, d.t64_mask);
+  r.e = want ? __ldg(reinterpret_cast<const uint4*>(d.t64 + s)) : make_uint4(0, 0, 0, TID_EMPTY);
   return r;
 }
-__device__ __forceinline__ uint64_t t64_fin(const DevDict& d, uint32_t tid, uint64_t key, Pre pre) {
-  uint4 raw = pre.e;
-  uint32_t s = pre.s;
+// the rest of the sequence (linear probing past a foreign key): rare, out of line
+__device__ __noinline__ uint64_t t64_more(const T64Entry* t, uint32_t mask, uint32_t tid, uint64_t key) {
+  uint32_t s = t64_slot(tid, key, mask);
   for (;;) {
+    s = (s + 1) & mask;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(t + s));
     if (raw.w == TID_EMPTY) return 0;
     if (raw.w == tid && ((uint64_t)raw.y << 32 | raw.x) == key) return FOUND | raw.z;
-    s = (s + 1) & d.t64_mask;
-    raw = __ldg(reinterpret_cast<const uint4*>(d.t64 + s));
   }
+}
+__device__ __forceinline__ uint64_t t64_fin(const DevDict& d, uint32_t tid, uint64_t key, Pre pre) {
+  const uint4 raw = pre.e;
+  if (raw.w == TID_EMPTY) return 0;
+  if (raw.w == tid && ((uint64_t)raw.y << 32 | raw.x) == key) return FOUND | raw.z;
+  return t64_more(d.t64, d.t64_mask, tid, key);
 }
 __device__ __forceinline__ uint64_t t64_get(const DevDict& d, uint32_t tid, uint64_t key) {
   return t64_fin(d, tid, key, t64_pre(d, tid, key, true));
@@ -235,105 +240,33 @@ __device__ __forceinline__ void apply(const DevDict& d, uint64_t h, KGSide& o) {
   }
 }
 
-// grpc_service.go:138-193
-__device__ __forceinline__ uint32_t pod_service(const DevDict& d, uint32_t pod_id, uint32_t pod_node_id,
-                                                uint32_t pod_cluster_id, uint32_t pod_group_id, int32_t epc, bool v6,
-                                                const IpV a, uint8_t protocol, uint16_t server_port, Pre pre4) {
-  if (server_port == 0) protocol = 0;
-  const uint32_t sp = to_service_protocol(protocol);
+// ---- services (:713-727) ------------------------------------------------------------------------------
+// QueryPodService (grpc_service.go:138-193) and QueryCustomService (:195-323) are priority lists of
+// look-ups whose keys all follow from the endpoint's Info: every first probe is issued before any is
+// consumed (up to 11 sectors in flight per lane, executed by the whole warp), then the answers are taken
+// in the reference's order.  Only customServicePodService (keyed by the pod-service answer) and the
+// "does the address still belong to this pod" re-check (:150-158) stay dependent.
+__device__ __noinline__ uint32_t custom_service_ip6(const DevDict& d, int32_t epc, uint64_t lo, uint64_t hi,
+                                                    uint32_t server_port, uint32_t sp) {
   uint32_t sid = 0;
-  if (pod_id != 0) {
-    sid = t64_z(d, TID_PS_GROUPPORT, key_podx_port(pod_group_id, sp, server_port));
-    if (sid == 0) {
-      const uint64_t h = reget(d, v6, a, epc, pre4);
-      if (h && hit_pod_id(d, h) != pod_id) return 0;
-    }
-  } else if (pod_node_id != 0 && server_port != 0) {
-    sid = t64_z(d, TID_PS_CLUSTERPORT, key_podx_port(pod_cluster_id, sp, server_port));
-  }
-  if (sid != 0) return sid;
-  if (epc <= 0) return 0;
-  if (v6) return t6_z(d, T6_PS_IP6PORT, a, epc, server_port, sp);
-  return t64_z(d, TID_PS_IP4PORT0 + sp, key_epc_ip4_port(epc, a.ip4, server_port));
-}
-
-// grpc_service.go:195-323, the address-keyed tail (rare: only when custom services are configured)
-__device__ __noinline__ uint32_t custom_service_ip(const DevDict& d, int32_t epc, bool v6, uint32_t ip4, uint64_t lo,
-                                                   uint64_t hi, uint32_t server_port, uint32_t sp) {
-  uint32_t sid = 0;
-  if (v6) {
-    if (d.counts6[T6_CS_IP6PORT]) {
-      sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6PORT, lo, hi, epc, server_port, sp);
-      if (sid) return sid;
-    }
-    if (d.counts6[T6_CS_IP6] && server_port != 0) {
-      sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6, lo, hi, epc, 0, 0);
-      if (sid) return sid;
-    }
-    if (d.counts6[T6_CS_IP6PORT]) {
-      sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6PORT, lo, hi, 0, server_port, sp);
-      if (sid) return sid;
-    }
-    if (d.counts6[T6_CS_IP6] && server_port != 0) sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6, lo, hi, 0, 0, 0);
-    return sid;
-  }
-  if (d.counts[TID_CS_IP4PORT0 + sp]) {
-    sid = t64_z(d, TID_CS_IP4PORT0 + sp, key_epc_ip4_port(epc, ip4, (uint16_t)server_port));
+  if (d.counts6[T6_CS_IP6PORT]) {
+    sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6PORT, lo, hi, epc, server_port, sp);
     if (sid) return sid;
   }
-  if (d.counts[TID_CS_IP4] && server_port != 0) {
-    sid = t64_z(d, TID_CS_IP4, key_epc_ip4_port(epc, ip4, 0));  // genEpcIDIP4Key(.., protocol 0)
+  if (d.counts6[T6_CS_IP6] && server_port != 0) {
+    sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6, lo, hi, epc, 0, 0);
     if (sid) return sid;
   }
-  if (d.counts[TID_CS_IP4PORT0 + sp]) {
-    sid = t64_z(d, TID_CS_IP4PORT0 + sp, key_epc_ip4_port(0, ip4, (uint16_t)server_port));
+  if (d.counts6[T6_CS_IP6PORT]) {
+    sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6PORT, lo, hi, 0, server_port, sp);
     if (sid) return sid;
   }
-  if (d.counts[TID_CS_IP4] && server_port != 0) sid = t64_z(d, TID_CS_IP4, key_epc_ip4_port(0, ip4, 0));
+  if (d.counts6[T6_CS_IP6] && server_port != 0) sid = (uint32_t)t6_get(d.t6, d.t6_mask, T6_CS_IP6, lo, hi, 0, 0, 0);
   return sid;
 }
-__device__ __forceinline__ uint32_t custom_service(const DevDict& d, int32_t epc, bool v6, const IpV a,
-                                                   uint16_t server_port, uint32_t pod_service_id,
-                                                   uint32_t pod_group_id, uint32_t l3_device_id, uint32_t pod_id,
-                                                   uint32_t pod_cluster_id, uint8_t l3_device_type, uint8_t protocol) {
-  if (epc < 0) return 0;
-  if (server_port == 0) protocol = 0;
-  const uint32_t sp = to_service_protocol(protocol);
-  if (pod_service_id != 0 && d.counts[TID_CS_PODSVC]) {
-    const uint32_t v = t64_z(d, TID_CS_PODSVC, pod_service_id);
-    if (v) return v;
-  }
-  if (pod_group_id != 0 && d.counts[TID_CS_PODGROUP]) {
-    const uint32_t v = t64_z(d, TID_CS_PODGROUP, pod_group_id);
-    if (v) return v;
-  }
-  if (pod_id != 0 && d.counts[TID_CS_POD]) {
-    const uint32_t v = t64_z(d, TID_CS_POD, pod_id);
-    if (v) return v;
-  }
-  if (pod_cluster_id != 0 && server_port != 0) {
-    if (d.counts[TID_CS_CLUSTERPORT]) {
-      const uint32_t v = t64_z(d, TID_CS_CLUSTERPORT, key_podx_port(pod_cluster_id, sp, server_port));
-      if (v) return v;
-    }
-    if (d.counts[TID_CS_CLUSTER]) {
-      const uint32_t v = t64_z(d, TID_CS_CLUSTER, (uint64_t)pod_cluster_id << 32);
-      if (v) return v;
-    }
-  }
-  if (l3_device_id != 0 && l3_device_type == 1 && d.counts[TID_CS_CHOST]) {  // VMDevice
-    const uint32_t v = t64_z(d, TID_CS_CHOST, l3_device_id);
-    if (v) return v;
-  }
-  if (l3_device_id != 0 && l3_device_type == 6 && d.counts[TID_CS_HOST]) {  // HostDevice
-    const uint32_t v = t64_z(d, TID_CS_HOST, l3_device_id);
-    if (v) return v;
-  }
-  const bool any = v6 ? (d.counts6[T6_CS_IP6PORT] | d.counts6[T6_CS_IP6]) != 0
-                      : (d.counts[TID_CS_IP4PORT0 + sp] | d.counts[TID_CS_IP4]) != 0;
-  if (!any) return 0;
-  return custom_service_ip(d, epc, v6, a.ip4, a.lo, a.hi, server_port, sp);
-}
+
+struct SideIn;
+__device__ __forceinline__ void services(const DevDict& d, const SideIn& in, KGSide& o, Pre pre_ip4);
 
 struct SideIn {
   bool v6, vip;
@@ -442,15 +375,88 @@ __device__ __forceinline__ void fill_side(const DevDict& d, const SideIn& in, KG
   }
   apply(d, h, o);  // :677-704
   o.l3_epc_id = in.l3_epc;
-  // :713-719
-  if (o.l3_device_type == 11 || o.pod_id != 0 || (in.server_side && o.pod_node_id != 0))
-    o.service_id = pod_service(d, o.pod_id, o.pod_node_id, o.pod_cluster_id, o.pod_group_id, in.l3_epc, in.v6, in.ip,
-                               in.protocol, in.port, pre_ip4);
-  // :721-727
+  services(d, in, o, pre_ip4);  // :713-727
+}
+
+__device__ __forceinline__ void services(const DevDict& d, const SideIn& in, KGSide& o, Pre pre_ip4) {
+  const int32_t epc = in.l3_epc;
+  const uint16_t port = in.port;
+  const uint32_t sp = to_service_protocol(port == 0 ? (uint8_t)0 : in.protocol);  // both queries: port 0 => protocol 0
+  const uint32_t ip4 = in.ip.ip4;
+  // ---- keys + first probes -----------------------------------------------------------------------------
+  const bool want_ps = o.l3_device_type == 11 || o.pod_id != 0 || (in.server_side && o.pod_node_id != 0);
+  const bool ps_group = o.pod_id != 0, ps_cluster = o.pod_id == 0 && o.pod_node_id != 0 && port != 0;
+  const uint32_t ps1_tid = ps_group ? TID_PS_GROUPPORT : TID_PS_CLUSTERPORT;
+  const uint64_t ps1_key = key_podx_port(ps_group ? o.pod_group_id : o.pod_cluster_id, sp, port);
+  const uint64_t ps2_key = key_epc_ip4_port(epc, ip4, port);
+  const Pre p_ps1 = t64_pre(d, ps1_tid, ps1_key, want_ps && (ps_group || ps_cluster));
+  const Pre p_ps2 = t64_pre(d, TID_PS_IP4PORT0 + sp, ps2_key, want_ps && !in.v6 && epc > 0);
+  const bool cs = epc >= 0;
+  const bool w_pg = cs && o.pod_group_id != 0 && d.counts[TID_CS_PODGROUP] != 0;
+  const bool w_pod = cs && o.pod_id != 0 && d.counts[TID_CS_POD] != 0;
+  const bool w_clp = cs && o.pod_cluster_id != 0 && port != 0 && d.counts[TID_CS_CLUSTERPORT] != 0;
+  const bool w_cl = cs && o.pod_cluster_id != 0 && port != 0 && d.counts[TID_CS_CLUSTER] != 0;
+  const uint32_t host_tid = o.l3_device_type == 1 ? TID_CS_CHOST : TID_CS_HOST;  // VMDevice / HostDevice
+  const bool w_host = cs && o.l3_device_id != 0 &&
+                      ((o.l3_device_type == 1 && d.counts[TID_CS_CHOST] != 0) ||
+                       (o.l3_device_type == 6 && d.counts[TID_CS_HOST] != 0));
+  const bool w_ipp = cs && !in.v6 && d.counts[TID_CS_IP4PORT0 + sp] != 0;
+  const bool w_ip = cs && !in.v6 && d.counts[TID_CS_IP4] != 0 && port != 0;
+  const uint64_t k_clp = key_podx_port(o.pod_cluster_id, sp, port), k_cl = (uint64_t)o.pod_cluster_id << 32;
+  const uint64_t k_i1 = ps2_key, k_i2 = key_epc_ip4_port(epc, ip4, 0);  // genEpcIDIP4Key(.., protocol 0)
+  const uint64_t k_i3 = key_epc_ip4_port(0, ip4, port), k_i4 = key_epc_ip4_port(0, ip4, 0);
+  const Pre c_pg = t64_pre(d, TID_CS_PODGROUP, o.pod_group_id, w_pg);
+  const Pre c_pod = t64_pre(d, TID_CS_POD, o.pod_id, w_pod);
+  const Pre c_clp = t64_pre(d, TID_CS_CLUSTERPORT, k_clp, w_clp);
+  const Pre c_cl = t64_pre(d, TID_CS_CLUSTER, k_cl, w_cl);
+  const Pre c_host = t64_pre(d, host_tid, o.l3_device_id, w_host);
+  const Pre c_i1 = t64_pre(d, TID_CS_IP4PORT0 + sp, k_i1, w_ipp);
+  const Pre c_i2 = t64_pre(d, TID_CS_IP4, k_i2, w_ip);
+  const Pre c_i3 = t64_pre(d, TID_CS_IP4PORT0 + sp, k_i3, w_ipp);
+  const Pre c_i4 = t64_pre(d, TID_CS_IP4, k_i4, w_ip);
+
+  // ---- QueryPodService :138-193 ---------------------------------------------------------------------
+  uint32_t sid = 0;
+  if (want_ps) {
+    bool dead = false;
+    if (ps_group) {
+      sid = (uint32_t)t64_fin(d, ps1_tid, ps1_key, p_ps1);
+      if (sid == 0) {  // :150-158 the address now belongs to another pod: no service
+        const uint64_t h = reget(d, in.v6, in.ip, epc, pre_ip4);
+        dead = h != 0 && hit_pod_id(d, h) != o.pod_id;
+      }
+    } else if (ps_cluster) {
+      sid = (uint32_t)t64_fin(d, ps1_tid, ps1_key, p_ps1);
+    }
+    if (sid == 0 && !dead && epc > 0)
+      sid = in.v6 ? t6_z(d, T6_PS_IP6PORT, in.ip, epc, port, sp)
+                  : (uint32_t)t64_fin(d, TID_PS_IP4PORT0 + sp, ps2_key, p_ps2);
+    if (dead) sid = 0;
+  }
+  o.service_id = sid;
   get_auto_instance(o.pod_id, in.gpid, o.pod_node_id, o.l3_device_id, o.subnet_id, o.l3_device_type, o.l3_epc_id,
                     o.auto_instance_id, o.auto_instance_type);
-  const uint32_t custom = custom_service(d, in.l3_epc, in.v6, in.ip, in.port, o.service_id, o.pod_group_id,
-                                         o.l3_device_id, o.pod_id, o.pod_cluster_id, o.l3_device_type, in.protocol);
+  // ---- QueryCustomService :195-323 ------------------------------------------------------------------
+  uint32_t custom = 0;
+  if (cs) {
+    if (sid != 0 && d.counts[TID_CS_PODSVC]) custom = t64_z(d, TID_CS_PODSVC, sid);
+    if (!custom && w_pg) custom = (uint32_t)t64_fin(d, TID_CS_PODGROUP, o.pod_group_id, c_pg);
+    if (!custom && w_pod) custom = (uint32_t)t64_fin(d, TID_CS_POD, o.pod_id, c_pod);
+    if (!custom && w_clp) custom = (uint32_t)t64_fin(d, TID_CS_CLUSTERPORT, k_clp, c_clp);
+    if (!custom && w_cl) custom = (uint32_t)t64_fin(d, TID_CS_CLUSTER, k_cl, c_cl);
+    if (!custom && w_host) custom = (uint32_t)t64_fin(d, host_tid, o.l3_device_id, c_host);
+    if (!custom) {
+      if (in.v6) {
+        if (d.counts6[T6_CS_IP6PORT] | d.counts6[T6_CS_IP6])
+          custom = custom_service_ip6(d, epc, in.ip.lo, in.ip.hi, port, sp);
+      } else {
+        if (w_ipp) custom = (uint32_t)t64_fin(d, TID_CS_IP4PORT0 + sp, k_i1, c_i1);
+        if (!custom && w_ip) custom = (uint32_t)t64_fin(d, TID_CS_IP4, k_i2, c_i2);
+        if (!custom && w_ipp) custom = (uint32_t)t64_fin(d, TID_CS_IP4PORT0 + sp, k_i3, c_i3);
+        if (!custom && w_ip) custom = (uint32_t)t64_fin(d, TID_CS_IP4, k_i4, c_i4);
+      }
+    }
+  }
   get_auto_service(custom, o.service_id, o.pod_group_id, in.gpid, o.pod_cluster_id, o.l3_device_id, o.subnet_id,
                    o.l3_device_type, o.pod_group_type, o.l3_epc_id, o.auto_service_id, o.auto_service_type);
 }
