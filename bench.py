@@ -147,6 +147,19 @@ def bind_near_gpu(index):
         return f"unbound ({type(ex).__name__})"
 
 
+def ncu_traffic(kernel, recs_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json names the capture), scaled to this launch's record
+    count.  None when no capture is recorded: ncu cannot run inside the bench."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(p))[kernel]
+        b = (t["dram_bytes_read"] + t["dram_bytes_write"]) * recs_per_launch / t["records_per_launch"]
+        return b, t["source"]
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -469,8 +482,10 @@ def main():
         path_bytes = in_bytes / nrec_step + bytes_per_row + 32 * 12
         path_ms = solo_stage_ms.get("size_pass", 0) + solo_stage_ms.get("emit_pass", 0)
         path_achieved = path_bytes * nrec_step / (path_ms / 1000.0) / 1e9 if path_ms else 0.0
+        traffic, traffic_src = ncu_traffic("k_l7_pass<EMIT>", recs_per_launch)
         roof = {"bound": "hbm", "kernel": "k_l7_pass<EMIT>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_record": alg_per_rec, "launches_timed": solo_emit_n,
                 "avg_launch_ms": solo_emit_ms / max(1, solo_emit_n),
                 "timed": "one decoder alone (kernels of concurrent decoders would overlap the events)",

@@ -721,44 +721,54 @@ __global__ void __launch_bounds__(256, EMIT ? L7_EMIT_MIN_BLOCKS : 6) k_l7_pass(
   l7_tail<0>(p, dv, dyn, rec, warp, lane, ok, frame, base, len, sl);
 }
 
-// "last valid" carry of lastTraceIdIndex across warps (single CTA)
-__global__ void k_l7_trace_scan(const BatchParams p) {
-  __shared__ int sh[1024];
-  __shared__ unsigned long long carry;
-  const uint32_t* has = p.warp_tot + (size_t)L7S_TRACE_HAS * p.nwarps;
-  const uint32_t* lo = p.warp_tot + (size_t)L7S_TRACE_LO * p.nwarps;
-  const uint32_t* hi = p.warp_tot + (size_t)L7S_TRACE_HI * p.nwarps;
-  uint32_t* olo = p.warp_base + (size_t)L7S_TRACE_LO * p.nwarps;
-  uint32_t* ohi = p.warp_base + (size_t)L7S_TRACE_HI * p.nwarps;
-  if (threadIdx.x == 0) carry = p.persist->last_trace_id_index;
-  __syncthreads();
-  for (uint32_t base = 0; base < p.nwarps; base += blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    int v = (i < p.nwarps && has[i]) ? (int)threadIdx.x : -1;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
-      int t = threadIdx.x >= d ? sh[threadIdx.x - d] : -1;
-      __syncthreads();
-      if (t > sh[threadIdx.x]) sh[threadIdx.x] = t;
-      __syncthreads();
-    }
-    // exclusive: the carry INTO warp i is the last valid among warps < i
-    int prev = threadIdx.x > 0 ? sh[threadIdx.x - 1] : -1;
-    unsigned long long c = carry;
-    if (prev >= 0) c = (unsigned long long)hi[base + prev] << 32 | lo[base + prev];
-    if (i < p.nwarps) {
-      olo[i] = (uint32_t)c;
-      ohi[i] = (uint32_t)(c >> 32);
-    }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) {
-      int last = sh[threadIdx.x];
-      if (last >= 0) carry = (unsigned long long)hi[base + last] << 32 | lo[base + last];
-    }
-    __syncthreads();
+// "last valid" carry of lastTraceIdIndex across warps (single CTA): the carry INTO warp i is the hash of
+// the last warp j < i that saw a trace id, else the value persisted by the previous batch.  Chunk per
+// thread + one block-wide max-scan of "last valid warp of my chunk" (same shape as k_slot_scan).
+__global__ void __launch_bounds__(1024) k_l7_trace_scan(const BatchParams p) {
+  __shared__ int wmax[32];
+  const uint32_t n = p.nwarps;
+  const uint32_t* has = p.warp_tot + (size_t)L7S_TRACE_HAS * n;
+  const uint32_t* lo_in = p.warp_tot + (size_t)L7S_TRACE_LO * n;
+  const uint32_t* hi_in = p.warp_tot + (size_t)L7S_TRACE_HI * n;
+  uint32_t* olo = p.warp_base + (size_t)L7S_TRACE_LO * n;
+  uint32_t* ohi = p.warp_base + (size_t)L7S_TRACE_HI * n;
+  const unsigned long long carry0 = p.persist->last_trace_id_index;
+  const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+  int last = -1;
+  for (uint32_t i = lo; i < hi; i++)
+    if (has[i]) last = (int)i;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = last;  // inclusive max-scan inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o && t > inc) inc = t;
   }
-  if (threadIdx.x == 0) p.dyn->stats.last_trace_id_index = carry;
+  if (lane == 31) wmax[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < (blockDim.x >> 5) ? wmax[lane] : -1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o && t > w) w = t;
+    }
+    const int excl = __shfl_up_sync(0xffffffffu, w, 1);
+    wmax[lane] = lane ? excl : -1;  // last valid warp before this warp of threads
+    if (lane == 31)
+      p.dyn->stats.last_trace_id_index = w >= 0 ? (unsigned long long)hi_in[w] << 32 | lo_in[w] : carry0;
+  }
+  __syncthreads();
+  int prev = __shfl_up_sync(0xffffffffu, inc, 1);  // last valid before my chunk, inside my warp
+  if (lane == 0) prev = -1;
+  int run = prev > wmax[wid] ? prev : wmax[wid];
+  for (uint32_t i = lo; i < hi; i++) {
+    const unsigned long long c = run >= 0 ? (unsigned long long)hi_in[run] << 32 | lo_in[run] : carry0;
+    olo[i] = (uint32_t)c;
+    ohi[i] = (uint32_t)(c >> 32);
+    if (has[i]) run = (int)i;
+  }
 }
 
 void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s) {
