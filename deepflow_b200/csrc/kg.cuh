@@ -390,26 +390,12 @@ DF_KG_SIDE_LOOP
   }
 }
 
-// ---- the same routine, one SIDE at a time -------------------------------------------------------
+// ---- one SIDE at a time ------------------------------------------------------------------------
 // KnowledgeGraph.fill treats its two endpoints independently except for one step: a loopback
 // endpoint without a pod borrows the peer's pod (:556-567, side 0 first).  (The "reuse the agent
 // info found for side 0" shortcut :651-660 is only a cache: the agent is looked up by vtap id, the
-// same for both sides.)  l7_kg.cu runs one lane per (record, side): twice the lanes in flight for the
-// same dependent probe chains, half the per-thread state.
-struct KGSideIn {
-  bool v6, vip;
-  int32_t l3_epc;
-  IpAddr ip;
-  uint64_t mac;
-  uint32_t gpid;
-  uint32_t pod;       // after kg_peer_pods
-  uint8_t tag_source; // TS_PEER when the pod was borrowed
-  uint16_t vtap_id;
-  uint16_t port;      // side 1: server port; side 0: 0 (:714-727)
-  uint32_t tap_side;
-  uint8_t protocol;
-  bool server_side;   // side 1 also matches pod-node services (:717-719)
-};
+// same for both sides.)  l7_kg.cu runs one lane per (record, side) through kg_side.cuh; these are the
+// pieces it shares with this file.
 struct KGSide {
   uint16_t region_id, az_id, host_id;
   uint8_t l3_device_type;
@@ -435,102 +421,6 @@ DF_HD void kg_peer_pods(bool lb0, bool lb1, uint32_t& pod0, uint32_t& pod1, uint
     ts1 |= TS_PEER;
     pod1 = pod0;
   }
-}
-
-DF_HD void kg_fill_side(const DevDict& d, const KGSideIn& in, KGSide& o) {
-  o.region_id = o.az_id = o.host_id = 0;
-  o.l3_device_type = 0;
-  o.l3_device_id = o.pod_node_id = 0;
-  o.pod_ns_id = 0;
-  o.pod_group_id = 0;
-  o.pod_group_type = 0;
-  o.pod_id = 0;
-  o.pod_cluster_id = 0;
-  o.epc_id = 0;
-  o.subnet_id = 0;
-  o.service_id = 0;
-  o.tag_source = in.tag_source;
-  uint32_t pod = in.pod;
-  bool by_mac = in.vip, by_agent = false;
-  if (in.tap_side == 4) {  // Local :570-585
-    if (is_local_ip(in.v6, in.ip)) {
-      if (in.mac != 0) by_mac = true; else by_agent = true;
-    }
-  } else if (in.tap_side == 41 || in.tap_side == 42) {  // ClientProcess / ServerProcess :586-598
-    if (in.mac != 0) by_mac = true;
-    else if (is_local_ip(in.v6, in.ip)) by_agent = true;
-  }
-  const uint64_t l3mac = in.mac | (uint64_t)(int64_t)in.l3_epc << 48;
-  if (in.gpid != 0 && pod == 0) {  // :601-614
-    uint32_t gi;
-    if (t64_find(d.t64, d.t64_mask, TID_GPROC, in.gpid, gi)) {
-      const uint64_t vp = d.gp_vals[gi];
-      const uint32_t p = (uint32_t)vp;
-      if (p != 0 && (uint16_t)(vp >> 32) == in.vtap_id) {
-        pod = p;
-        o.tag_source |= TS_GPID;
-      }
-    }
-  }
-  InfoVal info;
-  bool has = false;
-  if (pod != 0) {  // :617-624
-    o.tag_source |= TS_PODID;
-    has = query_pod(d, pod, info);
-  }
-  if (!has) {  // :626-666
-    if (by_mac) {
-      o.tag_source |= TS_MAC;
-      has = query_mac(d, l3mac, info);
-    }
-    if (!has && by_agent) {
-      o.tag_source |= TS_AGENT;
-      uint32_t vi;
-      if (t64_find(d.t64, d.t64_mask, TID_VTAP, in.vtap_id, vi)) {
-        const DVtap& v = d.vtaps[vi];
-        IpAddr a;
-        a.ip4 = v.ip4;
-        for (int i = 0; i < 16; i++) a.ip6[i] = v.ip6[i];
-        a.ip6len = v.has_ip6 ? 16 : 0;
-        has = reget_info_from_ip(d, !v.is_v4, a, v.epc, info);
-      }
-    }
-    if (!has) {
-      o.tag_source |= TS_EPCIP;
-      has = reget_info_from_ip(d, in.v6, in.ip, in.l3_epc, info);
-    }
-  }
-  if (in.l3_epc > 0) {  // :668-675 L2 epc through the mac table
-    InfoVal l2;
-    if (query_mac(d, l3mac, l2)) o.epc_id = l2.l2_epc;
-  }
-  if (has) {  // :677-704
-    o.region_id = (uint16_t)info.region_id;
-    o.az_id = (uint16_t)info.az_id;
-    o.host_id = (uint16_t)info.host_id;
-    o.l3_device_type = (uint8_t)info.device_type;
-    o.l3_device_id = info.device_id;
-    o.pod_node_id = info.pod_node_id;
-    o.pod_ns_id = (uint16_t)info.pod_ns_id;
-    o.pod_group_id = info.pod_group_id;
-    o.pod_group_type = info.pod_group_type;
-    o.pod_id = info.pod_id;
-    o.pod_cluster_id = (uint16_t)info.pod_cluster_id;
-    o.subnet_id = (uint16_t)info.subnet_id;
-  }
-  o.l3_epc_id = in.l3_epc;
-  // :713-719
-  if (o.l3_device_type == 11 || o.pod_id != 0 || (in.server_side && o.pod_node_id != 0))
-    o.service_id = query_pod_service(d, o.pod_id, o.pod_node_id, o.pod_cluster_id, o.pod_group_id, in.l3_epc, in.v6,
-                                     in.ip, in.protocol, in.port);
-  // :721-727
-  get_auto_instance(o.pod_id, in.gpid, o.pod_node_id, o.l3_device_id, o.subnet_id, o.l3_device_type, o.l3_epc_id,
-                    o.auto_instance_id, o.auto_instance_type);
-  const uint32_t custom = query_custom_service(d, in.l3_epc, in.v6, in.ip, in.port, o.service_id, o.pod_group_id,
-                                               o.l3_device_id, o.pod_id, o.pod_cluster_id, o.l3_device_type,
-                                               in.protocol);
-  get_auto_service(custom, o.service_id, o.pod_group_id, in.gpid, o.pod_cluster_id, o.l3_device_id, o.subnet_id,
-                   o.l3_device_type, o.pod_group_type, o.l3_epc_id, o.auto_service_id, o.auto_service_type);
 }
 
 }  // namespace dfgpu

@@ -1,6 +1,6 @@
 /*
  * l7_kg.cu — SmartEncoding of the L7 rows, one lane per (record, SIDE).
- *   KnowledgeGraph.FillL7   flow_log/log_data/l7_flow_log.go:599-613 -> kg.cuh kg_fill_side
+ *   KnowledgeGraph.FillL7   flow_log/log_data/l7_flow_log.go:599-613 -> kg_side.cuh kgs::fill_side
  *                           (KnowledgeGraph.fill l4_flow_log.go:536-728)
  *   QueryProcessInfo use    l7_flow_log.go:589-596
  * SmartEncoding is a chain of ~6 dependent dictionary probes per endpoint, walked at ~10 of 32

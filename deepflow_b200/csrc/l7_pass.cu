@@ -592,9 +592,7 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
     if (ok) {
       reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[l7_str_col(i)])[row] =
           dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
-#ifndef ABL_NO_STRCOPY
       if (n) copy_bytes(p.arena + dyn->var_buf_off[i] + off, s.p, n);
-#endif
     }
   }
   // ---- arrays: cumulative END offsets per row, then the elements ---------------------------
@@ -608,11 +606,7 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_ATTRIBUTE_VALUES])[row] = av_e + z_av_e;
   reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_NAMES])[row] = mn_e + z_mn_e;
   reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_VALUES])[row] = mv_e + z_mv_e;
-#ifdef ABL_NO_ARRAYS
-  if (false) {
-#else
   if (z_an_e | z_av_e | z_mn_e | z_mv_e) {
-#endif
     L7EmitSink sink;
     sink.an_pos = reinterpret_cast<dfgpu_pos*>(p.arena + dyn->var_pos_off[L7V_ATTR_NAMES]) + an_e;
     sink.an_buf = p.arena + dyn->var_buf_off[L7V_ATTR_NAMES];
