@@ -10,12 +10,17 @@ vtap_id % N == rank shard of the firehose (weak scaling: 10 M records per GPU);
 per-record work has no collective — the only exchange is the all-gather of newly
 emitted flow_tag keys after every e2e step (deepflow_b200/sharded.py).
 
-  value     device-resident: inputs already in HBM, kernels only (CUDA events on the
-            library's stream)
+  value     device-resident: inputs already in HBM, kernels only; every decoder context of
+            the GPU (default 3, like the ingester's decoder goroutines) runs its share of
+            the sub-batches on its own stream, timed by CUDA events on a timing stream that
+            waits for all of them
   e2e       through the C ABI with HOST buffers: pinned H2D of every sub-batch, all
             kernels, D2H of every column block, inside the timed region
-  roofline  the dominant kernel (EMIT/pack pass): algorithmic bytes / its CUDA-event
-            time vs the measured HBM peak
+  roofline  the dominant kernel (EMIT/pack pass), timed live in a separate leg where ONE
+            decoder runs alone (CUDA events on its stream around each launch):
+            algorithmic bytes / average launch time vs the measured HBM peak; `traffic` is
+            the DRAM bytes of one launch from the committed ncu capture (profiles/);
+            `path` = the same for SIZE + EMIT + SmartEncoding over SURVEY §8(d)'s bytes
   cpu_baseline   the CPU oracle (a C++ restatement of the Go path) on a bounded sample
 
 --impl reference times that CPU restatement with all host threads instead (the Go
