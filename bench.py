@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--pods", type=int, default=100_000, help="dictionary size P (SURVEY §8d)")
     ap.add_argument("--decoders", type=int, default=3, help="contexts per GPU in the e2e leg (DecoderQueueCount)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-native-leg", action="store_true", help="skip the second e2e leg (native_strings=1)")
     return ap.parse_args()
 
 
@@ -182,10 +183,10 @@ def output_bytes(batch):
     for c in cols:
         t = c.ch_type
         if t in (abi.CH_STR, abi.CH_LC_STR_ROWS):
-            total += nrows * 16 + c.buf.nbytes
+            total += (0 if c.native else nrows * 16) + c.buf.nbytes
             strings += c.buf.nbytes
         elif t in (abi.CH_ARR_STR, abi.CH_ARR_LC_STR):
-            total += nrows * 8 + c.pos.nbytes + c.buf.nbytes
+            total += nrows * 8 + (0 if c.native else c.pos.nbytes) + c.buf.nbytes
             strings += c.buf.nbytes
         elif t in (abi.CH_ARR_UINT16, abi.CH_ARR_FLOAT64):
             total += nrows * 8 + c.values.nbytes
@@ -400,7 +401,7 @@ def main():
     from deepflow_b200.sharded import FLOW_TAG_TABLES, TagMerge
     merge = TagMerge(device=torch.device("cuda", local)) if world > 1 else None
 
-    def e2e_step():
+    def e2e_step(engines=engines):
         err = []
         new_fps, new_times = [], []
 
@@ -455,18 +456,52 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    # ---- e2e again with dfgpu_cfg.native_strings (first step): String / Array(String)
+    # columns cross PCIe in ClickHouse native encoding, their Position arrays stay on the GPU ------------
+    e2e_nat_s = nat_bytes_per_row = None
+    if not a.no_native_leg:
+        for e in engines:
+            e.sync()
+        ncfg = abi.Cfg()
+        ncfg.max_batch_bytes = cfg.max_batch_bytes
+        ncfg.flow_tag_cache_max_size = cfg.flow_tag_cache_max_size
+        ncfg.native_strings = 1
+        nat_engines = [Engine(local, ncfg) for _ in range(len(engines))]
+        for e in nat_engines:
+            e.load_synth(synth)
+        for _ in range(a.warmup):
+            e2e_step(nat_engines)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step(nat_engines)
+        for e in nat_engines:
+            e.sync()
+        barrier()
+        e2e_nat_s = time.perf_counter() - t0
+        w = subs[-1]
+        nb = nat_engines[0].submit(w)
+        nc = nb.counters()
+        assert nc.error_count == 0 and nc.count == w.nrecords, (nc.error_count, nc.count)
+        nat_out_b, nat_rows, _ = output_bytes(nb)
+        nat_bytes_per_row = nat_out_b / max(1, nat_rows)
+        nb.release()
+        for e in nat_engines:
+            e.close()
+
     # per-step byte accounting for e2e (H2D = staging buffers + frame tables; D2H = column blocks)
     bytes_per_row = out_b_last / max(1, rows_last)
     d2h_per_step = int(bytes_per_row * nrec_step)
     h2d_per_step = int(in_bytes + sum(w.frames.nbytes for w in subs))
 
     # ---- max over ranks ----------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=f"cuda:{local}")
+    times = torch.tensor([dev_ms, e2e_s * 1000.0, (e2e_nat_s or 0.0) * 1000.0], dtype=torch.float64,
+                         device=f"cuda:{local}")
     recs = torch.tensor([float(nrec_step)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(recs, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = times.tolist()
+    dev_ms_max, e2e_ms_max, e2e_nat_ms_max = times.tolist()
     total_recs_step = recs.item()
 
     if rank == 0:
@@ -514,6 +549,13 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": h2d_per_step,
                         "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms_max / a.steps},
                 "gpu_launches": int(launches_value), "clocks": clocks, "roofline": roof}
+        if e2e_nat_s:
+            line["e2e_native_strings"] = {
+                "value": total_recs_step * a.steps / (e2e_nat_ms_max / 1000.0), "unit": "records/s",
+                "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": int(nat_bytes_per_row * nrec_step),
+                "ms_per_step": e2e_nat_ms_max / a.steps,
+                "what": "same call, dfgpu_cfg.native_strings=1: String / Array(String) columns leave the GPU as "
+                        "ClickHouse native column data (uvarint length + bytes), no Position arrays over PCIe"}
         if not a.no_cpu_baseline:
             build.build_oracle()
             v, n, dt = cpu_port_run(synth, 400_000, 1, 4242)

@@ -87,7 +87,8 @@ class GeoEntry(C.Structure):
 class Cfg(C.Structure):
     _fields_ = [("max_batch_bytes", C.c_uint64), ("max_batch_records", C.c_uint32),
                 ("flow_tag_cache_flush_timeout", C.c_uint32), ("flow_tag_cache_max_size", C.c_uint32),
-                ("trace_id_index_disabled", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+                ("trace_id_index_disabled", C.c_uint32), ("native_strings", C.c_uint32),
+                ("reserved", C.c_uint32 * 6)]
 
 
 class Counters(C.Structure):
@@ -122,6 +123,8 @@ class Column:
         t = c.ch_type
         self.values = self.buf = self.pos = self.arr_offsets = self.nulls = None
         self.dict = None
+        # dfgpu_cfg.native_strings: buf is the ClickHouse native encoding (uvarint length + bytes per value)
+        self.native = t in (CH_STR, CH_LC_STR_ROWS, CH_ARR_STR, CH_ARR_LC_STR) and not c.pos and self.nrows > 0
         if t in (CH_STR, CH_LC_STR_ROWS):
             self.buf = _np_from(c.data, c.data_bytes, np.uint8)
             self.pos = _np_from(c.pos, self.nrows * 16, np.int64).reshape(-1, 2)
@@ -151,7 +154,37 @@ class Column:
     # -- value-level view used by the parity tests ---------------------------------
     def strings(self):
         b = self.buf.tobytes()
+        if self.native:  # decode the native stream
+            out, i = [], 0
+            while i < len(b):
+                n = shift = 0
+                while True:
+                    c = b[i]
+                    i += 1
+                    n |= (c & 0x7F) << shift
+                    shift += 7
+                    if c < 0x80:
+                        break
+                out.append(b[i:i + n])
+                i += n
+            return out
         return [b[s:e] for s, e in self.pos]
+
+    def native_bytes(self):
+        """The ClickHouse native encoding of a String / Array(String) column's values
+        (ch-go ColStr.EncodeColumn: per value uvarint(len) + bytes)."""
+        if self.native:
+            return self.buf.tobytes()
+        out = bytearray()
+        b = self.buf.tobytes()
+        for s, e in self.pos:
+            n = int(e - s)
+            while n >= 0x80:
+                out.append((n & 0x7F) | 0x80)
+                n >>= 7
+            out.append(n)
+            out += b[s:e]
+        return bytes(out)
 
     def rows(self):
         """Row-wise python values (slow; tests only)."""

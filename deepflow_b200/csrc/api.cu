@@ -257,7 +257,10 @@ static bool is_array(int ch) {
 }
 
 // fixed region of the arena for `rows` rows; returns its size
-static uint64_t plan_fixed(const TableSchema& s, uint32_t rows, uint64_t* fix_off, uint64_t* aux_off) {
+// native_str (dfgpu_cfg.native_strings): String columns carry no Position array in the host-bound part of the
+// arena (k_finish puts the device-only ones behind var_end)
+static uint64_t plan_fixed(const TableSchema& s, uint32_t rows, uint64_t* fix_off, uint64_t* aux_off,
+                           bool native_str = false) {
   uint64_t cur = 0;
   for (int c = 0; c < s.ncols; c++) {
     const ColSpec& cs = s.cols[c];
@@ -265,7 +268,8 @@ static uint64_t plan_fixed(const TableSchema& s, uint32_t rows, uint64_t* fix_of
     size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
     cur += align_up((size_t)rows * es, 256);
     aux_off[c] = cur;
-    cur += align_up((size_t)rows * aux_bytes_per_row(cs.ch_type), 256);
+    const bool str_pos = cs.ch_type == DFGPU_CH_STR || cs.ch_type == DFGPU_CH_LC_STR_ROWS;
+    if (!(native_str && str_pos)) cur += align_up((size_t)rows * aux_bytes_per_row(cs.ch_type), 256);
   }
   return cur;
 }
@@ -463,9 +467,11 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
   // the kernels index [slot][nwarps] with stride nwarps (not warp_cap): both halves are
   // large enough because nslots <= MAX_SLOTS and nwarps <= warp_cap.
   const bool is_metrics = ctx->cur_msg == DFGPU_MSG_METRICS;
-  uint64_t fixed = is_metrics ? 0 : plan_fixed(*sch, nrec, bp.fix_off, bp.aux_off);
+  bp.native_str = (ctx->cfg.native_strings && ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) ? 1u : 0u;
+  uint64_t fixed = is_metrics ? 0 : plan_fixed(*sch, nrec, bp.fix_off, bp.aux_off, bp.native_str != 0);
   bp.var_base = fixed;
   uint64_t want = fixed + 2 * (uint64_t)ctx->cur_nbytes + (uint64_t)nrec * 96 + (1u << 20);
+  if (bp.native_str) want += (uint64_t)nrec * (23 * 16 + 32);  // device-only Positions + length prefixes
   if (is_metrics) want = metrics_arena_need(nrec, ctx->cur_nbytes);
   if (want > ctx->arena_cap) {
     if (ctx->d_arena) CU(cudaFree(ctx->d_arena));
@@ -629,7 +635,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
     if (!repair && !grow) break;
     if (attempt >= 3) return fail(ctx, DFGPU_ENOMEM, "could not size the output arena");
     if (grow) {
-      uint64_t want = d->var_end + (1u << 20);
+      uint64_t want = (d->dev_end > d->var_end ? d->dev_end : d->var_end) + (1u << 20);
       CU(cudaFree(ctx->d_arena));
       ctx->d_arena = nullptr;
       CU(cudaMalloc(&ctx->d_arena, (size_t)want));
@@ -673,6 +679,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
     size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
     if (es && nrows) CU(cudaMemcpyAsync(hb + bp.fix_off[c], bp.arena + bp.fix_off[c], (size_t)nrows * es, cudaMemcpyDeviceToHost, s));
     size_t ab = aux_bytes_per_row(cs.ch_type);
+    if (bp.native_str && (cs.ch_type == DFGPU_CH_STR || cs.ch_type == DFGPU_CH_LC_STR_ROWS)) ab = 0;  // no Positions
     if (ab && nrows) CU(cudaMemcpyAsync(hb + bp.aux_off[c], bp.arena + bp.aux_off[c], (size_t)nrows * ab, cudaMemcpyDeviceToHost, s));
   }
   if (!dense && total > bp.var_base)
@@ -703,7 +710,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
       case DFGPU_CH_STR:
       case DFGPU_CH_LC_STR_ROWS: {
         int v = stream_of_col++;
-        col.pos = (const dfgpu_pos*)(hb + bp.aux_off[c]);
+        col.pos = bp.native_str ? nullptr : (const dfgpu_pos*)(hb + bp.aux_off[c]);
         col.data = hb + d->var_buf_off[v];
         col.data_bytes = d->stats.var_bytes[v];
         break;
@@ -721,7 +728,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
       case DFGPU_CH_ARR_LC_STR: {
         int v = stream_of_col++;
         col.arr_offsets = (const uint64_t*)(hb + bp.aux_off[c]);
-        col.pos = (const dfgpu_pos*)(hb + d->var_pos_off[v]);
+        col.pos = bp.native_str ? nullptr : (const dfgpu_pos*)(hb + d->var_pos_off[v]);
         col.data = hb + d->var_buf_off[v];
         col.data_bytes = d->stats.var_bytes[v];
         col.nelems = d->stats.var_total[v];

@@ -217,13 +217,24 @@ __global__ void k_finish(const BatchParams p) {
       uint64_t elems = s.slot_elems >= 0 ? slot_total[s.slot_elems] : nrows;
       uint64_t bytes = s.slot_bytes >= 0 ? slot_total[s.slot_bytes] : elems * s.elem_size;
       d->var_pos_off[v] = cur;
-      if (s.has_pos) cur += (elems * 16 + 255) & ~255ull;
+      if (s.has_pos && !p.native_str) cur += (elems * 16 + 255) & ~255ull;
       d->var_buf_off[v] = cur;
       cur += (bytes + 255) & ~255ull;
       d->stats.var_total[v] = elems;
       d->stats.var_bytes[v] = bytes;
     }
     d->var_end = cur;
+    if (p.native_str) {
+      // native strings: the Position arrays (one per value of every string stream) are device-only
+      // working state of the flow_tag stage; they sit behind everything that is copied to the host
+      for (uint32_t v = 0; v < p.nstreams; v++) {
+        const StreamSpec s = p.streams[v];
+        if (s.slot_bytes < 0) continue;  // not a string stream
+        d->var_pos_off[v] = cur;
+        cur += (d->stats.var_total[v] * 16 + 255) & ~255ull;
+      }
+    }
+    d->dev_end = cur;
     d->overflow = cur > p.arena_bytes ? 1 : 0;
   }
   // rank of each LowCardinality code by first appearance (ch-go builds the

@@ -49,7 +49,8 @@ void l7_streams(BatchParams& bp) {
   bp.streams[L7V_ATTR_VALUES] = StreamSpec{L7S_AV_ELEMS, L7S_AV_BYTES, 1, 1};
   bp.streams[L7V_METRICS_NAMES] = StreamSpec{L7S_MN_ELEMS, L7S_MN_BYTES, 1, 1};
   bp.streams[L7V_METRICS_VALUES] = StreamSpec{L7S_MV_ELEMS, -1, 8, 0};
-  bp.streams[L7V_EVENTS] = StreamSpec{-1, -1, 0, 0};
+  // events: always empty; native encoding = one zero length byte per row
+  bp.streams[L7V_EVENTS] = StreamSpec{-1, -1, (uint8_t)(bp.native_str ? 1 : 0), 0};
 }
 
 int l7_lc_space(int) { return LC7_TAPSIDE; }
@@ -128,8 +129,11 @@ __device__ __forceinline__ void load_row(const BatchParams& p, uint32_t row, Row
   v.an_buf = p.arena + dyn->var_buf_off[L7V_ATTR_NAMES];
   v.av_buf = p.arena + dyn->var_buf_off[L7V_ATTR_VALUES];
   v.mn_buf = p.arena + dyn->var_buf_off[L7V_METRICS_NAMES];
-  dfgpu_pos sp = reinterpret_cast<const dfgpu_pos*>(aux(L7C_APP_SERVICE))[row];
-  dfgpu_pos ep = reinterpret_cast<const dfgpu_pos*>(aux(L7C_ENDPOINT))[row];
+  // the Positions of the per-row strings: column aux region, or (native strings) the device-only region
+  const uint8_t* sp_base = p.native_str ? p.arena + dyn->var_pos_off[L7V_APP_SERVICE] : aux(L7C_APP_SERVICE);
+  const uint8_t* ep_base = p.native_str ? p.arena + dyn->var_pos_off[L7V_ENDPOINT] : aux(L7C_ENDPOINT);
+  dfgpu_pos sp = reinterpret_cast<const dfgpu_pos*>(sp_base)[row];
+  dfgpu_pos ep = reinterpret_cast<const dfgpu_pos*>(ep_base)[row];
   v.app_service = SRef{p.arena + dyn->var_buf_off[L7V_APP_SERVICE] + sp.start, (uint32_t)(sp.end - sp.start)};
   v.endpoint = SRef{p.arena + dyn->var_buf_off[L7V_ENDPOINT] + ep.start, (uint32_t)(ep.end - ep.start)};
 }

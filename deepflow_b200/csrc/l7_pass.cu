@@ -75,6 +75,14 @@ __device__ __forceinline__ void store_bytes(uint8_t* dst, unsigned long long w, 
     w >>= 8;
   }
 }
+// uvarint length prefix of the ClickHouse native String encoding (dfgpu_cfg.native_strings)
+__device__ __forceinline__ void put_varint(uint8_t* dst, uint32_t n) {
+  while (n >= 0x80u) {
+    *dst++ = (uint8_t)(n | 0x80u);
+    n >>= 7;
+  }
+  *dst = (uint8_t)n;
+}
 __device__ __noinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, uint32_t n) {  // n > 0
   const unsigned long long* sb = reinterpret_cast<const unsigned long long*>((uintptr_t)src & ~(uintptr_t)7);
   const uint32_t so = (uint32_t)(uintptr_t)src & 7u, sh = so * 8u;
@@ -126,9 +134,14 @@ struct L7EmitSink {
   dfgpu_pos* av_pos; uint8_t* av_buf; uint64_t av_off;  // attribute_values
   dfgpu_pos* mn_pos; uint8_t* mn_buf; uint64_t mn_off;  // metrics_names
   uint64_t* mv;                                          // metrics_values (f64 bit patterns)
+  uint32_t nat;                                          // native strings: uvarint length before every element
   __device__ __forceinline__ void put(dfgpu_pos*& pos, uint8_t* buf, uint64_t& off, const uint8_t* s, uint32_t n) {
+    if (nat) {
+      put_varint(buf + off, n);
+      off += pb_vsize(n);
+    }
     *pos++ = dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
-    copy_bytes(buf + off, s, n);
+    if (n) copy_bytes(buf + off, s, n);
     off += n;
   }
   __device__ __forceinline__ void attr_name(const uint8_t* s, uint32_t n) { put(an_pos, an_buf, an_off, s, n); }
@@ -200,7 +213,7 @@ struct L7Hdr {
 };
 
 template <class S>
-__device__ __forceinline__ void l7_hdr(const L7Dev* dv, const uint8_t* base, const S& sl, L7Hdr& o) {
+__device__ __forceinline__ void l7_hdr(const L7Dev* dv, const uint8_t* base, const S& sl, L7Hdr& o, const uint32_t nat) {
   const SRef none{nullptr, 0};
   o.has_req = sl[S7_REQ_CNT] != 0;
   o.has_resp = sl[S7_RESP_CNT] != 0;
@@ -266,9 +279,11 @@ __device__ __forceinline__ void l7_hdr(const L7Dev* dv, const uint8_t* base, con
     o.request_id = sl_u32(sl, S7_REQUEST_ID);
     if (o.request_id != 0) o.has_request_id = true;
     uint32_t n;
-    if ((n = sl_len(sl, S7_USER_AGENT))) { o.n_pseudo++; o.pseudo_name_bytes += 15; o.pseudo_value_bytes += n; }
-    if ((n = sl_len(sl, S7_REFERER))) { o.n_pseudo++; o.pseudo_name_bytes += 12; o.pseudo_value_bytes += n; }
-    if ((n = sl_len(sl, S7_RPC_SERVICE))) { o.n_pseudo++; o.pseudo_name_bytes += 11; o.pseudo_value_bytes += n; }
+    // nat: every element carries its uvarint length in the stream (names are < 128 bytes: one byte)
+    const uint32_t pv = nat ? ~0u : 0u;
+    if ((n = sl_len(sl, S7_USER_AGENT))) { o.n_pseudo++; o.pseudo_name_bytes += 15 + nat; o.pseudo_value_bytes += n + (pb_vsize(n) & pv); }
+    if ((n = sl_len(sl, S7_REFERER))) { o.n_pseudo++; o.pseudo_name_bytes += 12 + nat; o.pseudo_value_bytes += n + (pb_vsize(n) & pv); }
+    if ((n = sl_len(sl, S7_RPC_SERVICE))) { o.n_pseudo++; o.pseudo_name_bytes += 11 + nat; o.pseudo_value_bytes += n + (pb_vsize(n) & pv); }
   }
   SRef trace_id = none;
   o.two_ids = false;
@@ -426,8 +441,9 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
                                         const uint8_t* base, const uint32_t len, const S& sl) {
   // AppProtoLogsData.IsValid() (datatype/pb/flow_log.go:82-89) cannot fail: Base and
   // Base.Head are pre-allocated.
+  const uint32_t nat = p.native_str ? 1u : 0u;  // ClickHouse native String encoding (dfgpu_cfg.native_strings)
   L7Hdr w;
-  l7_hdr(dv, base, sl, w);
+  l7_hdr(dv, base, sl, w, nat);
 
   const uint32_t n_an = (uint32_t)sl[S7_ATTR_NAMES], b_an = (uint32_t)(sl[S7_ATTR_NAMES] >> 32);
   const uint32_t n_av = (uint32_t)sl[S7_ATTR_VALUES], b_av = (uint32_t)(sl[S7_ATTR_VALUES] >> 32);
@@ -452,7 +468,8 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
     WTOT(L7S_ROWS, z_rows)
 #pragma unroll
     for (int i = 0; i < 22; i++) {
-      const uint32_t n = ok ? l7_str(i, dv, base, sl, w).n : 0u;
+      const uint32_t sn = l7_str(i, dv, base, sl, w).n;
+      const uint32_t n = ok ? sn + (nat ? pb_vsize(sn) : 0u) : 0u;
       WTOT(L7S_STR0 + i, n)
     }
     WTOT(L7S_AN_ELEMS, z_an_e)
@@ -580,19 +597,25 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
     st<uint32_t>(p, L7C_CAPTURED_REQUEST_BYTE, row, sl_u32(sl, S7_CAP_REQ_BYTE));
     st<uint32_t>(p, L7C_CAPTURED_RESPONSE_BYTE, row, sl_u32(sl, S7_CAP_RESP_BYTE));
     // events: always empty on this path (only the OTel import fills it)
-    reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[L7C_EVENTS])[row] = dfgpu_pos{0, 0};
+    if (nat) (p.arena + dyn->var_buf_off[L7V_EVENTS])[row] = 0;  // uvarint(0)
+    else reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[L7C_EVENTS])[row] = dfgpu_pos{0, 0};
   }
 
   // ---- the 22 per-row string columns: Pos + bytes (one string live at a time) ----------------
 #pragma unroll
   for (int i = 0; i < 22; i++) {
     const SRef s = l7_str(i, dv, base, sl, w);
-    const uint32_t n = ok ? s.n : 0u;
+    const uint32_t vs = nat ? pb_vsize(s.n) : 0u;  // length prefix
+    const uint32_t n = ok ? s.n + vs : 0u;
     const uint64_t off = WBASE(L7S_STR0 + i, warp_excl_scan(n));
     if (ok) {
-      reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[l7_str_col(i)])[row] =
-          dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
-      if (n) copy_bytes(p.arena + dyn->var_buf_off[i] + off, s.p, n);
+      // Position of the value's bytes: the column's aux region, or (native) the device-only array the
+      // flow_tag stage reads
+      dfgpu_pos* pos = reinterpret_cast<dfgpu_pos*>(p.arena + (nat ? dyn->var_pos_off[i] : p.aux_off[l7_str_col(i)]));
+      pos[row] = dfgpu_pos{(int64_t)(off + vs), (int64_t)(off + vs + s.n)};
+      uint8_t* dst = p.arena + dyn->var_buf_off[i] + off;
+      if (nat) put_varint(dst, s.n);
+      if (s.n) copy_bytes(dst + vs, s.p, s.n);
     }
   }
   // ---- arrays: cumulative END offsets per row, then the elements ---------------------------
@@ -608,6 +631,7 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
   reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L7C_METRICS_VALUES])[row] = mv_e + z_mv_e;
   if (z_an_e | z_av_e | z_mn_e | z_mv_e) {
     L7EmitSink sink;
+    sink.nat = nat;
     sink.an_pos = reinterpret_cast<dfgpu_pos*>(p.arena + dyn->var_pos_off[L7V_ATTR_NAMES]) + an_e;
     sink.an_buf = p.arena + dyn->var_buf_off[L7V_ATTR_NAMES];
     sink.an_off = an_b;
@@ -701,7 +725,7 @@ __global__ void __launch_bounds__(256, EMIT ? L7_EMIT_MIN_BLOCKS : 6) k_l7_pass(
   SlotsW sl{dv->slotbuf + rec, dv->slot_stride};
   if (in_range) {
     if (!(p.repair && rec >= p.frame_bad[frame])) {
-      ok = pb_interp(base, len, s_tbl, L7_MAXF, sl);
+      ok = pb_interp(base, len, s_tbl, L7_MAXF, sl, p.native_str ? ~0u : 0u);
       if (!ok) {
         if (!p.repair) {
           atomicMin(&p.frame_bad[frame], rec);

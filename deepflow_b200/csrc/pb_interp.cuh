@@ -47,9 +47,15 @@ __device__ __forceinline__ uint32_t pb_digits(uint64_t v) {
 // Returns false on any error the generated Unmarshal would return.
 // SW: the slot store — a private uint64_t array, or a view that writes straight into a slot-major
 // global buffer (anything whose operator[] yields a uint64_t lvalue).
+// uvarint size of a length prefix (ClickHouse native String encoding)
+__device__ __forceinline__ uint32_t pb_vsize(uint32_t n) {
+  return 1u + (n >= 0x80u) + (n >= 0x4000u) + (n >= 0x200000u) + (n >= 0x10000000u);
+}
+// len_prefix_mask: ~0u when repeated strings are to be SIZED in native encoding (their byte count then
+// includes one uvarint length prefix per element, dfgpu_cfg.native_strings), else 0.
 template <class SW>
 __device__ __forceinline__ bool pb_interp(const uint8_t* rec, uint32_t len, const uint32_t* __restrict__ tbl,
-                                          uint32_t maxf, SW& slots) {
+                                          uint32_t maxf, SW& slots, const uint32_t len_prefix_mask = 0u) {
   uint32_t stack_end[PB_MAX_DEPTH];
   uint32_t stack_msg[PB_MAX_DEPTH];
   uint32_t depth = 0, msg = 0, end = len;
@@ -95,7 +101,7 @@ __device__ __forceinline__ bool pb_interp(const uint8_t* rec, uint32_t len, cons
         continue;
       }
       if (kind == PK_STR) slots[slot] = (uint64_t)off | (uint64_t)n << 32;
-      else if (kind == PK_RSTR_CNT) slots[slot] += 1 + ((uint64_t)n << 32);
+      else if (kind == PK_RSTR_CNT) slots[slot] += 1 + ((uint64_t)(n + (pb_vsize(n) & len_prefix_mask)) << 32);
       else if (kind == PK_RSTR_FIRST2) {
         uint64_t c = slots[slot + 2];
         if (c < 2) slots[slot + c] = (uint64_t)off | (uint64_t)n << 32;

@@ -39,9 +39,10 @@ struct DynState {  // per batch, device resident, read back by fetch
   BatchStats stats;
   uint64_t var_pos_off[MAX_VAR];
   uint64_t var_buf_off[MAX_VAR];
-  uint64_t var_end;       // first free byte after the last stream
+  uint64_t var_end;       // first free byte after the last stream that goes back to the host
   uint32_t overflow;      // var region does not fit the arena
   uint32_t pad;
+  uint64_t dev_end;       // first free byte of the arena (>= var_end: device-only regions follow var_end)
   uint8_t lc_rank[LC_SPACES][256];
   uint64_t trace_carry_hash;  // scratch
 };
@@ -72,6 +73,7 @@ struct BatchParams {
   uint32_t nstreams;
   uint32_t n_lc;
   uint32_t cfg_trace_disabled;
+  uint32_t native_str;  // dfgpu_cfg.native_strings (l7_flow_log only): strings leave as uvarint(len) + bytes
   const void* ext;  // message-type specific device state (L7Dev)
   StreamSpec streams[MAX_VAR];
   DevDict dict;

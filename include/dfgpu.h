@@ -108,7 +108,9 @@ typedef struct dfgpu_col {
   const void* data;      /* fixed: nrows elems | STR: Buf | ARR_*: elem values
                             or Buf | LC_STR: keys | NULLABLE: Values           */
   uint64_t data_bytes;
-  const dfgpu_pos* pos;  /* STR: nrows entries; ARR_STR/ARR_LC_STR: nelems     */
+  const dfgpu_pos* pos;  /* STR: nrows entries; ARR_STR/ARR_LC_STR: nelems;
+                            NULL when data is the native-encoded stream
+                            (dfgpu_cfg.native_strings)                          */
   const uint64_t* arr_offsets; /* ARR_*: nrows cumulative element END offsets  */
   uint64_t nelems;       /* ARR_*: total element count                         */
   const uint8_t* nulls;  /* NULLABLE_*: nrows bytes, 1 = NULL                  */
@@ -231,7 +233,16 @@ typedef struct dfgpu_cfg {
                                   slots (field + field_value + app_service keys at
                                   load <= 1/2) and reports DFGPU_ENOMEM when full */
   uint32_t trace_id_index_disabled;      /* TraceIdWithIndex.Disabled (config.go:201) */
-  uint32_t reserved[7];
+  uint32_t native_strings;     /* SURVEY 8(f) N1, first step.  1 => the String and Array(String)
+                                  columns of l7_flow_log leave the GPU in ClickHouse NATIVE
+                                  column encoding (per value: uvarint length, then the bytes =
+                                  what ch-go ColStr.EncodeColumn appends) instead of the ch-go
+                                  container (Buf + 16-byte Position per value): dfgpu_col.pos is
+                                  NULL, data/data_bytes is the encoded stream, arr_offsets stay.
+                                  The Position arrays never cross PCIe (-45 % D2H bytes per row).
+                                  The Go side wraps such a column in a proto.ColInput whose
+                                  EncodeColumn appends data verbatim.        */
+  uint32_t reserved[6];
 } dfgpu_cfg;
 
 /* decoder.Counter (decoder.go:60-80) for one submit; the shim adds them up.   */
