@@ -240,6 +240,8 @@ typedef struct dfgpu_cfg {
                                   container (Buf + 16-byte Position per value): dfgpu_col.pos is
                                   NULL, data/data_bytes is the encoded stream, arr_offsets stay.
                                   The Position arrays never cross PCIe (-45 % D2H bytes per row).
+                                  LC_STR_ROWS / ARR_LC_STR columns carry the same stream; the shim
+                                  walks its length prefixes to Append into the LowCardinality column.
                                   The Go side wraps such a column in a proto.ColInput whose
                                   EncodeColumn appends data verbatim.        */
   uint32_t reserved[6];
