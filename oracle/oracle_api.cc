@@ -237,6 +237,12 @@ const char* oracle_kat_tapside(uint32_t v) {
 }
 int oracle_kat_is_local_ip(int v6, uint32_t ip4, const uint8_t* ip6, uint32_t len) { return IsLocalIP(v6, ip4, ip6, len); }
 int oracle_kat_is_loopback(int v6, uint32_t ip4, const uint8_t* ip6, uint32_t len) { return IsLoopback(v6, ip4, ip6, len); }
+// L7Protocol.String(isTLS) (datatype/flow.go:623-803), NUL terminated copy
+const char* oracle_kat_l7_protocol_string(uint32_t p, int tls) {
+  static thread_local std::string s;
+  s = std::string(L7ProtocolString((uint8_t)p, tls != 0));
+  return s.c_str();
+}
 uint64_t oracle_kat_djb(uint64_t base, const char* s, uint32_t n) { return DJBHash(base, std::string_view(s, n)); }
 // libs/lru/lru_test.go TestKeys + eviction order: add keys[0..n) to a cache of `cap`,
 // touch `touch` (AddOrGet) when >= 0, then list the keys oldest -> newest.
