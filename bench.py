@@ -460,8 +460,9 @@ def main():
     # columns cross PCIe in ClickHouse native encoding, their Position arrays stay on the GPU ------------
     e2e_nat_s = nat_bytes_per_row = None
     if not a.no_native_leg:
-        for e in engines:
+        for e in engines:  # everything that needed them is measured: free their device + pinned memory first
             e.sync()
+            e.close()
         ncfg = abi.Cfg()
         ncfg.max_batch_bytes = cfg.max_batch_bytes
         ncfg.flow_tag_cache_max_size = cfg.flow_tag_cache_max_size
