@@ -237,6 +237,28 @@ const char* oracle_kat_tapside(uint32_t v) {
 }
 int oracle_kat_is_local_ip(int v6, uint32_t ip4, const uint8_t* ip6, uint32_t len) { return IsLocalIP(v6, ip4, ip6, len); }
 int oracle_kat_is_loopback(int v6, uint32_t ip4, const uint8_t* ip6, uint32_t len) { return IsLoopback(v6, ip4, ip6, len); }
+// common.GetAutoInstance / GetAutoService / IsPodServiceIP (ingester/common/common.go:160-198): out = {id, type}
+void oracle_kat_auto_instance(uint32_t pod, uint32_t gpid, uint32_t pod_node, uint32_t l3dev, uint32_t subnet,
+                              uint32_t l3type, int32_t l3epc, uint32_t* out) {
+  uint32_t id = 0;
+  uint8_t type = 0;
+  GetAutoInstance(pod, gpid, pod_node, l3dev, subnet, (uint8_t)l3type, l3epc, id, type);
+  out[0] = id;
+  out[1] = type;
+}
+void oracle_kat_auto_service(uint32_t custom, uint32_t pod_service, uint32_t pod_group, uint32_t gpid,
+                             uint32_t pod_cluster, uint32_t l3dev, uint32_t subnet, uint32_t l3type,
+                             uint32_t pod_group_type, int32_t l3epc, uint32_t* out) {
+  uint32_t id = 0;
+  uint8_t type = 0;
+  GetAutoService(custom, pod_service, pod_group, gpid, pod_cluster, l3dev, subnet, (uint8_t)l3type,
+                 (uint8_t)pod_group_type, l3epc, id, type);
+  out[0] = id;
+  out[1] = type;
+}
+int oracle_kat_is_pod_service_ip(uint32_t device_type, uint32_t pod, uint32_t pod_node) {
+  return IsPodServiceIP((uint8_t)device_type, pod, pod_node) ? 1 : 0;
+}
 // L7Protocol.String(isTLS) (datatype/flow.go:623-803), NUL terminated copy
 const char* oracle_kat_l7_protocol_string(uint32_t p, int tls) {
   static thread_local std::string s;

@@ -156,3 +156,54 @@ def test_l7_protocol_strings_match_reference_switch(built):
     assert want.pop(121) == ["TLS", "TLS"] and "proto_cs[121][0] = d.proto_cs[121][1] = CS_PROTO_TLS" in src
     assert dev == {k: v[0] for k, v in want.items()}
     assert all(v[1] == v[0] + "_TLS" for v in want.values())
+
+
+def test_auto_instance_service_type_codes_match_trident_enums(built):
+    """common.GetAutoInstance / GetAutoService / IsPodServiceIP (ingester/common/common.go:137-198) return
+    trident.AutoServiceType / DeviceType codes; the values are MACHINE-EXTRACTED from message/trident.proto
+    (tests/golden/proto_fields.json "trident.proto:enums") — the Go source names them by enum, and its inline
+    comment for POD_SERVICE ("// 12") is stale: the proto says 11."""
+    import json
+    import os
+    l = lib()
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proto_fields.json")))
+    A, D = g["trident.proto:enums"]["AutoServiceType"], g["trident.proto:enums"]["DeviceType"]
+    POD, POD_NODE = A["AUTO_SERVICE_TYPE_POD"], A["AUTO_SERVICE_TYPE_POD_NODE"]
+    POD_SERVICE, POD_CLUSTER = A["AUTO_SERVICE_TYPE_POD_SERVICE"], A["AUTO_SERVICE_TYPE_POD_CLUSTER"]
+    CUSTOM, PROCESS = A["AUTO_SERVICE_TYPE_CUSTOM_SERVICE"], A["AUTO_SERVICE_TYPE_PROCESS"]
+    IP, INTERNET = A["AUTO_SERVICE_TYPE_IP"], A["AUTO_SERVICE_TYPE_INTERNET_IP"]
+    assert (POD, POD_NODE, POD_SERVICE, POD_CLUSTER, CUSTOM, PROCESS, IP, INTERNET) == (10, 14, 11, 103, 104, 120, 255, 0)
+    out = (C.c_uint32 * 2)()
+
+    def inst(pod, gp, node, dev, subnet, l3type, epc):
+        l.oracle_kat_auto_instance(pod, gp, node, dev, subnet, l3type, C.c_int32(epc), out)
+        return out[0], out[1]
+
+    def svc(custom, ps, pg, gp, pc, dev, subnet, l3type, pgtype, epc):
+        l.oracle_kat_auto_service(custom, ps, pg, gp, pc, dev, subnet, l3type, pgtype, C.c_int32(epc), out)
+        return out[0], out[1]
+
+    # the priority chains of common.go:160-191, one step at a time
+    assert inst(7, 8, 9, 10, 11, 1, 5) == (7, POD)
+    assert inst(0, 8, 9, 10, 11, 1, 5) == (8, PROCESS)
+    assert inst(0, 0, 9, 10, 11, 1, 5) == (9, POD_NODE)
+    assert inst(0, 0, 0, 10, 11, 6, 5) == (10, 6)           # l3 device: its own device type
+    assert inst(0, 0, 0, 0, 11, 6, -2) == (0, INTERNET)     # EPC_FROM_INTERNET
+    assert inst(0, 0, 0, 0, 11, 6, 5) == (11, IP)
+    assert svc(1, 2, 3, 4, 5, 6, 7, 1, 130, 5) == (1, CUSTOM)
+    assert svc(0, 2, 3, 4, 5, 6, 7, 1, 130, 5) == (2, POD_SERVICE)
+    assert svc(0, 0, 3, 4, 5, 6, 7, 1, 130, 5) == (3, 130)  # pod group: its own pod_group_type
+    assert svc(0, 0, 0, 4, 5, 6, 7, 1, 130, 5) == (4, PROCESS)
+    assert svc(0, 0, 0, 0, 5, 6, 7, 1, 130, 5) == (5, POD_CLUSTER)
+    assert svc(0, 0, 0, 0, 0, 6, 7, 1, 130, 5) == (6, 1)
+    assert svc(0, 0, 0, 0, 0, 0, 7, 1, 130, -2) == (0, INTERNET)
+    assert svc(0, 0, 0, 0, 0, 0, 7, 1, 130, 5) == (7, IP)
+    ps = D["DEVICE_TYPE_POD_SERVICE"]
+    assert ps == 11 and (D["DEVICE_TYPE_VM"], D["DEVICE_TYPE_HOST_DEVICE"]) == (1, 6)  # custom service chost / host
+    assert l.oracle_kat_is_pod_service_ip(ps, 0, 0) == 1 and l.oracle_kat_is_pod_service_ip(1, 0, 0) == 0
+    assert l.oracle_kat_is_pod_service_ip(1, 3, 0) == 1 and l.oracle_kat_is_pod_service_ip(1, 0, 4) == 1
+    # dictionary snapshot enums the builder switches on (include/dfgpu.h: dfgpu_service.type / protocol, dfgpu_cidr.type)
+    assert g["trident.proto:enums"]["ServiceType"] == {"POD_SERVICE_NODE": 1, "POD_SERVICE_POD_GROUP": 2,
+                                                         "POD_SERVICE_IP": 3, "LB_SERVICE": 4, "CUSTOM_SERVICE": 7}
+    assert g["trident.proto:enums"]["ServiceProtocol"] == {"ANY": 0, "TCP_SERVICE": 1, "UDP_SERVICE": 2}
+    assert g["trident.proto:enums"]["CidrType"] == {"WAN": 1, "LAN": 2}

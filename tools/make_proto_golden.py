@@ -35,10 +35,24 @@ def parse(path):
     return msgs
 
 
+def parse_enums(path, wanted):
+    """{enum: {NAME: value}} of the named enums (SmartEncoding type codes come from trident.proto)."""
+    src = open(path, encoding="utf-8").read()
+    out = {}
+    for m in re.finditer(r"enum\s+(\w+)\s*\{(.*?)\}", src, re.S):
+        if m.group(1) in wanted:
+            body = re.sub(r"//[^\n]*", "", m.group(2))
+            out[m.group(1)] = {k: int(v) for k, v in re.findall(r"(\w+)\s*=\s*(-?\d+)\s*;", body)}
+    return out
+
+
 def main():
     out = {}
     for name in ("flow_log.proto", "metric.proto"):
         out[name] = parse(os.path.join(REF, "message", name))
+    out["trident.proto:enums"] = parse_enums(os.path.join(REF, "message", "trident.proto"),
+                                             {"AutoServiceType", "DeviceType", "ServiceType", "ServiceProtocol",
+                                              "CidrType"})
     with open(OUT, "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)
     print(OUT, {k: len(v) for k, v in out.items()})
