@@ -1,0 +1,601 @@
+"""A SECOND, independent restatement of SmartEncoding (SURVEY A5 + A5d), in Python, written straight from the Go
+source — not from oracle/ — as SURVEY §8(c) asks for the part of the path no reference test pins:
+  table build    updateInterfaceInfos grpc_platformdata.go:1494-1684, updateCidrInfos :1422-1492,
+                 updateGprocessInfos :2008-2028, updateVtapIps :1760-1791, updatePodIps :1861-1942,
+                 NewServiceTable / addPodServiceIp / addCustomService grpc_service.go:325-534
+  queries        QueryIPV4Infos/IPV6Infos :292-326 (+ queryIPV4Cidr :825-861, queryEpcIDBaseInfo :658-673),
+                 queryMacInfo :607-617, QueryPodIdInfo :376-382, QueryGprocessInfo :2047-2052,
+                 QueryPodService grpc_service.go:138-193, QueryCustomService :195-323
+  fill           KnowledgeGraph.fill flow_log/log_data/l4_flow_log.go:536-728, FillL4 :730-745,
+                 FillL7 l7_flow_log.go:599-613 (+ QueryProcessInfo use :589-596),
+                 GetAutoInstance / GetAutoService / IsPodServiceIP ingester/common/common.go:137-198,
+                 IsLoopback / IsLocalIP libs/utils/utils.go:116-130 over Go's net.IP predicates
+Go maps are Python dicts (assignment = last wins), Go integer keys are reproduced as integers (so the key
+collisions of the uint64 packings are reproduced too).  Test infrastructure only (tests/test_kg_crosscheck_cpu.py)."""
+import ctypes as C
+import ipaddress
+
+from deepflow_b200 import abi
+
+M64 = (1 << 64) - 1
+EPC_FROM_INTERNET, EPC_UNKNOWN = -2, 0
+IF_TYPE_WAN = 3  # libs/datatype/platform.go:31
+TS_GPID, TS_PODID, TS_MAC, TS_EPCIP, TS_PEER, TS_AGENT, TS_PROCESSID = 1, 2, 4, 8, 16, 32, 64  # tag.go:255-266
+
+
+# ---- the snapshot structs of include/dfgpu.h ------------------------------------------------------------
+class Interface(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("device_type", "device_id", "if_type", "epc_id", "launch_server_id",
+                                          "region_id")] + [("mac", C.c_uint64)] + \
+               [(n, C.c_uint32) for n in ("pod_node_id", "az_id", "pod_group_id", "pod_ns_id", "pod_id",
+                                          "pod_cluster_id", "vtap_id", "pod_group_type", "ip_res_off", "ip_res_cnt")]
+
+
+class IpResource(C.Structure):
+    _fields_ = [("ip", abi.Ip), ("subnet_id", C.c_uint32)]
+
+
+class Cidr(C.Structure):
+    _fields_ = [("prefix", abi.Ip), ("prefix_len", C.c_uint32), ("type", C.c_uint32), ("epc_id", C.c_int32),
+                ("subnet_id", C.c_uint32), ("region_id", C.c_uint32), ("az_id", C.c_uint32)]
+
+
+class GProcess(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("gprocess_id", "vtap_id", "pod_id", "pid")]
+
+
+class VtapIp(C.Structure):
+    _fields_ = [("vtap_id", C.c_uint32), ("epc_id", C.c_uint32), ("ip", abi.Ip), ("pod_cluster_id", C.c_uint32),
+                ("team_id", C.c_uint32)]
+
+
+class PodIp(C.Structure):
+    _fields_ = [("pod_id", C.c_uint32), ("epc_id", C.c_uint32), ("ip", abi.Ip), ("pod_node_ip", abi.Ip)] + \
+               [(n, C.c_uint32) for n in ("pod_cluster_id", "pod_ns_id", "pod_group_id", "pod_group_type")]
+
+
+class Service(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "type", "id", "pod_cluster_id", "epc_id", "protocol", "pod_group_ids_off", "pod_group_ids_cnt", "ips_off",
+        "ips_cnt", "server_ports_off", "server_ports_cnt", "pod_service_ids_off", "pod_service_ids_cnt",
+        "chost_ids_off", "chost_ids_cnt", "host_ids_off", "host_ids_cnt", "pod_ids_off", "pod_ids_cnt")]
+
+
+def _arr(ptr, n, T):
+    return C.cast(ptr, C.POINTER(T * int(n))).contents if n else []
+
+
+def _s32(v):
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+class Info:  # grpc.Info :64-90, the members the path reads
+    __slots__ = ("epc", "l2_epc", "host_id", "region", "device_type", "device_id", "subnet", "pod_node", "pod_ns",
+                 "pod_group", "pod_group_type", "pod_id", "pod_cluster", "az", "dup")
+
+    def __init__(self, **kw):
+        for s in self.__slots__:
+            setattr(self, s, 0)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def copy(self):
+        i = Info()
+        for s in self.__slots__:
+            setattr(i, s, getattr(self, s))
+        return i
+
+
+def _ip_of(x):  # dfgpu_ip -> ("4", u32) | ("6", 16 bytes) | None  (what net.ParseIP + To4 made of the string)
+    if not x.valid:
+        return None
+    return ("6", bytes(x.ip6)) if x.is_v6 else ("4", int(x.ip4))
+
+
+# keys of grpc_service.go:62-120
+def k_epc_ip4_port(epc, ip4, port):
+    return ((epc << 48) | (ip4 << 16) | port) & M64
+
+
+def k_epc_ip4(epc, ip4, proto):
+    return ((epc << 48) | (ip4 << 16) | proto) & M64
+
+
+def k_podx_port(i, proto, port):
+    return ((i << 32) | (proto << 16) | port) & M64
+
+
+def k_podx(i, proto):
+    return ((i << 32) | (proto << 16)) & M64
+
+
+def to_service_protocol(p):  # :127-136
+    return 1 if p == 6 else 2 if p == 17 else 0
+
+
+class Platform:
+    def __init__(self, snap):
+        s = snap
+        self.region_id, self.analyzer_id = int(s.region_id), int(s.analyzer_id)
+        self.ip4, self.ip6, self.mac, self.base, self.pod = {}, {}, {}, {}, {}
+        self.cidr4, self.cidr6 = {}, {}
+        ipres = _arr(s.ip_resources, s.n_ip_resources, IpResource)
+        for f in _arr(s.interfaces, s.n_interfaces, Interface):  # updateInterfaceInfos
+            epc = _s32(f.epc_id)
+            if epc == 0:
+                epc = EPC_FROM_INTERNET
+            self.base.setdefault(epc, f.region_id)
+            common = dict(epc=epc, host_id=f.launch_server_id, region=f.region_id, device_type=f.device_type,
+                          device_id=f.device_id, pod_node=f.pod_node_id, pod_ns=f.pod_ns_id, pod_group=f.pod_group_id,
+                          pod_group_type=f.pod_group_type & 0xFF, pod_id=f.pod_id, pod_cluster=f.pod_cluster_id,
+                          az=f.az_id)
+            first_subnet = 0
+            wan = f.if_type == IF_TYPE_WAN
+            for k in range(f.ip_res_cnt):
+                r = ipres[f.ip_res_off + k]
+                if first_subnet == 0:
+                    first_subnet = r.subnet_id
+                ip = _ip_of(r.ip)
+                if ip is None:
+                    if r.ip.is_v6:
+                        continue  # ParseIP failed
+                    ip = ("4", 0)
+                info = Info(subnet=r.subnet_id, **common)
+                if ip[0] == "4":
+                    self.ip4[(epc, ip[1])] = info
+                    if f.pod_id > 0:
+                        self.pod[f.pod_id] = info
+                    if wan:
+                        self.ip4[(0, ip[1])] = Info(epc=epc)
+                else:
+                    self.ip6[(epc, ip[1])] = info
+                    if f.pod_id > 0:
+                        self.pod[f.pod_id] = info
+                    if wan:
+                        self.ip6[(0, ip[1])] = Info(epc=epc)
+            if f.mac != 0:
+                key = (f.mac | (epc << 48)) & M64
+                if key in self.mac:
+                    self.mac[key].dup += 1
+                else:  # the literal has no PodNSID
+                    m = Info(subnet=first_subnet, l2_epc=epc, **common)
+                    m.pod_ns = 0
+                    self.mac[key] = m
+        order = 0
+        for c in _arr(s.cidrs, s.n_cidrs, Cidr):  # updateCidrInfos
+            p = _ip_of(c.prefix)
+            if p is None:
+                continue
+            epc = EPC_FROM_INTERNET if c.epc_id == 0 else int(c.epc_id)
+            self.base.setdefault(epc, c.region_id)
+            if p[0] == "4":
+                net = ipaddress.ip_network((p[1], c.prefix_len), strict=False)
+            else:
+                net = ipaddress.ip_network((p[1], c.prefix_len), strict=False)
+            ci = (c.prefix_len, order, net, c.subnet_id, c.region_id, c.az_id)
+            order += 1
+            tbl = self.cidr4 if p[0] == "4" else self.cidr6
+            tbl.setdefault(epc, []).append(ci)
+            if c.type == 1:  # CidrType_WAN: also searchable without an epc
+                tbl.setdefault(0, []).append(ci)
+        for tbl in (self.cidr4, self.cidr6):  # longest prefix first (sort.Slice: ties assumed not to matter)
+            for epc in tbl:
+                tbl[epc].sort(key=lambda x: (-x[0], x[1]))
+        self.gp, self.vtap_pid = {}, {}
+        for g in _arr(s.gprocesses, s.n_gprocesses, GProcess):  # updateGprocessInfos
+            if g.pid != 0:
+                self.vtap_pid[(g.vtap_id << 32) | g.pid] = g.gprocess_id
+            if g.vtap_id == 0 or g.gprocess_id == 0 or g.pod_id == 0:
+                continue
+            self.gp[g.gprocess_id] = (g.vtap_id << 32) | g.pod_id
+        self.vtap = {}
+        for v in _arr(s.vtap_ips, s.n_vtap_ips, VtapIp):  # updateVtapIps
+            epc = _s32(v.epc_id)
+            if epc == 0:
+                epc = EPC_FROM_INTERNET
+            ip = _ip_of(v.ip)
+            d = {"epc": epc, "is_v4": True, "ip4": 0, "ip6": None}
+            if ip is not None:
+                if ip[0] == "4":
+                    d["ip4"] = ip[1]
+                else:
+                    d["is_v4"], d["ip6"] = False, ip[1]
+            self.vtap[v.vtap_id & 0xFFFF] = d
+        self._services(s)
+        for p in _arr(s.pod_ips, s.n_pod_ips, PodIp):  # updatePodIps (after the tables above are live)
+            if p.pod_id in self.pod:
+                continue
+            epc = _s32(p.epc_id)
+            if epc == 0:
+                epc = EPC_FROM_INTERNET
+            ip = _ip_of(p.ip) or _ip_of(p.pod_node_ip)
+            info = Info()
+            if ip is not None:
+                q = self.query_ip4(epc, ip[1]) if ip[0] == "4" else self.query_ip6(epc, ip[1])
+                if q is not None:
+                    info = q.copy()
+            info.pod_id, info.pod_cluster, info.pod_ns = p.pod_id, p.pod_cluster_id, p.pod_ns_id
+            info.pod_group, info.pod_group_type, info.epc = p.pod_group_id, p.pod_group_type & 0xFF, epc
+            info.dup = 0
+            self.pod[p.pod_id] = info
+
+    def _services(self, s):  # NewServiceTable
+        u32 = _arr(s.u32_pool, s.n_u32_pool, C.c_uint32)
+        ips = _arr(s.ip_pool, s.n_ip_pool, abi.Ip)
+        self.ps_ip4 = [dict(), dict(), dict()]
+        self.ps_ip6, self.ps_cluster_port, self.ps_group_port = {}, {}, {}
+        self.cs_ip4_port = [dict(), dict(), dict()]
+        self.cs_ip6_port, self.cs_ip4, self.cs_ip6 = {}, {}, {}
+        self.cs_cluster_port, self.cs_cluster = {}, {}
+        self.cs_podsvc, self.cs_podgroup, self.cs_pod, self.cs_chost, self.cs_host = {}, {}, {}, {}, {}
+        for v in _arr(s.services, s.n_services, Service):
+            proto, sid = v.protocol, v.id
+            ports = [u32[v.server_ports_off + j] & 0xFFFF for j in range(v.server_ports_cnt)]
+            if v.type == 1:  # POD_SERVICE_NODE
+                for port in ports + [0]:
+                    self.ps_cluster_port[k_podx_port(v.pod_cluster_id, proto, port)] = sid
+                    self.ps_cluster_port[k_podx_port(v.pod_cluster_id, 0, port)] = sid
+            elif v.type == 2:  # POD_SERVICE_POD_GROUP
+                if v.pod_group_ids_cnt == 0:
+                    continue
+                g = u32[v.pod_group_ids_off]
+                for port in ports + [0]:
+                    self.ps_group_port[k_podx_port(g, proto, port)] = sid
+                    self.ps_group_port[k_podx_port(g, 0, port)] = sid
+            elif v.type == 3:  # POD_SERVICE_IP: addPodServiceIp
+                if proto > 2:
+                    continue
+                epc = _s32(v.epc_id)
+                for i in range(v.ips_cnt):
+                    ip = _ip_of(ips[v.ips_off + i])
+                    if ip is None:
+                        continue
+                    for port in ports + [0]:
+                        if ip[0] == "4":
+                            self.ps_ip4[proto][k_epc_ip4_port(epc, ip[1], port)] = sid
+                            self.ps_ip4[0][k_epc_ip4_port(epc, ip[1], port)] = sid
+                        else:
+                            self.ps_ip6[(ip[1], epc, port, proto)] = sid
+                            self.ps_ip6[(ip[1], epc, port, 0)] = sid
+            elif v.type == 7:  # CUSTOM_SERVICE: addCustomService
+                epc = _s32(v.epc_id)
+                for tbl, off, cnt in ((self.cs_podsvc, v.pod_service_ids_off, v.pod_service_ids_cnt),
+                                      (self.cs_podgroup, v.pod_group_ids_off, v.pod_group_ids_cnt),
+                                      (self.cs_pod, v.pod_ids_off, v.pod_ids_cnt),
+                                      (self.cs_chost, v.chost_ids_off, v.chost_ids_cnt),
+                                      (self.cs_host, v.host_ids_off, v.host_ids_cnt)):
+                    for i in range(cnt):
+                        tbl[u32[off + i]] = sid
+                if v.pod_cluster_id != 0:
+                    if not ports:
+                        for pr in (proto, 0):
+                            self.cs_cluster[k_podx(v.pod_cluster_id, pr)] = sid
+                            self.cs_cluster_port[k_podx_port(v.pod_cluster_id, pr, 0)] = sid
+                    else:
+                        for port in ports + [0]:
+                            self.cs_cluster_port[k_podx_port(v.pod_cluster_id, proto, port)] = sid
+                            self.cs_cluster_port[k_podx_port(v.pod_cluster_id, 0, port)] = sid
+                    continue
+                if v.ips_cnt == 0:
+                    continue
+                ip = _ip_of(ips[v.ips_off])
+                if ip is None or proto > 2:
+                    continue
+                if not ports:
+                    for pr in (proto, 0):
+                        if ip[0] == "4":
+                            self.cs_ip4[k_epc_ip4(epc, ip[1], pr)] = sid
+                            self.cs_ip4_port[pr][k_epc_ip4_port(epc, ip[1], 0)] = sid
+                        else:
+                            self.cs_ip6[(ip[1], epc, pr)] = sid
+                            self.cs_ip6_port[(ip[1], epc, 0, pr)] = sid
+                    continue
+                for port in ports + [0]:
+                    for pr in (proto, 0):
+                        if ip[0] == "4":
+                            self.cs_ip4_port[pr][k_epc_ip4_port(epc, ip[1], port)] = sid
+                        else:
+                            self.cs_ip6_port[(ip[1], epc, port, pr)] = sid
+
+    # ---- queries ---------------------------------------------------------------------------------------
+    def _base(self, epc):  # queryEpcIDBaseInfo
+        if epc == EPC_UNKNOWN:
+            return self.region_id
+        return self.base.get(epc)
+
+    def query_ip4(self, epc, ip4):
+        if epc == EPC_FROM_INTERNET:
+            return None
+        info = self.ip4.get((epc, ip4))
+        if info is None:
+            addr = ipaddress.IPv4Address(ip4)
+            for _plen, _o, net, subnet, region, az in self.cidr4.get(epc, ()):
+                if addr in net:
+                    info = Info(subnet=subnet, region=region, az=az)
+                    break
+        if info is not None:
+            return info
+        r = self._base(epc)
+        return None if r is None else Info(region=r)
+
+    def query_ip6(self, epc, ip6):  # ip6: the wire bytes (any length)
+        if epc == EPC_FROM_INTERNET:
+            return None
+        key = (bytes(ip6) + bytes(16))[:16]  # copy(key[4:], ipv6)
+        info = self.ip6.get((epc, key))
+        if info is None and len(ip6) == 16:
+            addr = ipaddress.IPv6Address(bytes(ip6))
+            if addr.ipv4_mapped is None:  # IPNet.Contains: a v4-mapped address is compared as 4 bytes -> no v6 net
+                for _plen, _o, net, subnet, region, az in self.cidr6.get(epc, ()):
+                    if addr in net:
+                        info = Info(subnet=subnet, region=region, az=az)
+                        break
+        if info is not None:
+            return info
+        r = self._base(epc)
+        return None if r is None else Info(region=r)
+
+    def reget(self, v6, ip6, ip4, epc):  # common.RegetInfoFromIP
+        return self.query_ip6(epc, ip6) if v6 else self.query_ip4(epc, ip4)
+
+    def query_mac(self, key):
+        i = self.mac.get(key & M64)
+        return None if i is None or i.dup > 0 else i
+
+    def query_pod_service(self, pod, pod_node, pod_cluster, pod_group, epc, v6, ip4, ip6, protocol, port):
+        if port == 0:
+            protocol = 0
+        sp = to_service_protocol(protocol)
+        sid = 0
+        if pod != 0:
+            sid = self.ps_group_port.get(k_podx_port(pod_group, sp, port), 0)
+            if sid == 0:
+                info = self.reget(v6, ip6, ip4, epc)
+                if info is not None and info.pod_id != pod:
+                    return sid
+        elif pod_node != 0 and port != 0:
+            sid = self.ps_cluster_port.get(k_podx_port(pod_cluster, sp, port), 0)
+        if sid != 0:
+            return sid
+        if epc <= 0:
+            return 0
+        if v6:
+            return self.ps_ip6.get(((bytes(ip6) + bytes(16))[:16], epc, port, sp), 0)
+        return self.ps_ip4[sp].get(k_epc_ip4_port(epc, ip4, port), 0)
+
+    def query_custom_service(self, epc, v6, ip4, ip6, port, pod_service, pod_group, l3_device_id, pod, pod_cluster,
+                             l3_device_type, protocol):
+        if epc < 0:
+            return 0
+        if port == 0:
+            protocol = 0
+        sp = to_service_protocol(protocol)
+        for key, tbl in ((pod_service, self.cs_podsvc), (pod_group, self.cs_podgroup), (pod, self.cs_pod)):
+            if key != 0 and tbl:
+                s = tbl.get(key, 0)
+                if s != 0:
+                    return s
+        if pod_cluster != 0 and port != 0:
+            if self.cs_cluster_port:
+                s = self.cs_cluster_port.get(k_podx_port(pod_cluster, sp, port), 0)
+                if s > 0:
+                    return s
+            if self.cs_cluster:
+                s = self.cs_cluster.get(k_podx(pod_cluster, 0), 0)
+                if s > 0:
+                    return s
+        if l3_device_id != 0 and l3_device_type == 1 and self.cs_chost:
+            s = self.cs_chost.get(l3_device_id, 0)
+            if s != 0:
+                return s
+        if l3_device_id != 0 and l3_device_type == 6 and self.cs_host:
+            s = self.cs_host.get(l3_device_id, 0)
+            if s != 0:
+                return s
+        s = 0
+        if v6:
+            k6 = (bytes(ip6) + bytes(16))[:16]
+            if self.cs_ip6_port:
+                s = self.cs_ip6_port.get((k6, epc, port, sp), 0)
+                if s > 0:
+                    return s
+            if self.cs_ip6 and port != 0:
+                s = self.cs_ip6.get((k6, epc, 0), 0)
+                if s > 0:
+                    return s
+            if self.cs_ip6_port:
+                s = self.cs_ip6_port.get((k6, 0, port, sp), 0)
+                if s > 0:
+                    return s
+            if self.cs_ip6 and port != 0:
+                s = self.cs_ip6.get((k6, 0, 0), 0)
+            return s
+        if self.cs_ip4_port[sp]:
+            s = self.cs_ip4_port[sp].get(k_epc_ip4_port(epc, ip4, port), 0)
+            if s > 0:
+                return s
+        if self.cs_ip4 and port != 0:
+            s = self.cs_ip4.get(k_epc_ip4(epc, ip4, 0), 0)
+            if s > 0:
+                return s
+        if self.cs_ip4_port[sp]:
+            s = self.cs_ip4_port[sp].get(k_epc_ip4_port(0, ip4, port), 0)
+            if s > 0:
+                return s
+        if self.cs_ip4 and port != 0:
+            s = self.cs_ip4.get(k_epc_ip4(0, ip4, 0), 0)
+        return s
+
+
+# ---- Go net.IP predicates (the byte slice the wire carried, any length) -----------------------------------
+def _go_ip(v6, ip4, ip6):
+    """-> ipaddress object as Go's methods see it, or None for a slice that is neither 4 nor 16 bytes."""
+    if not v6:
+        return ipaddress.IPv4Address(ip4)
+    b = bytes(ip6)
+    if len(b) == 4:
+        return ipaddress.IPv4Address(b)
+    if len(b) == 16:
+        a = ipaddress.IPv6Address(b)
+        return a.ipv4_mapped if a.ipv4_mapped is not None else a  # To4()
+    return None
+
+
+def is_loopback(v6, ip4, ip6):  # utils.IsLoopback
+    if not v6:
+        return (ip4 & 0xFF000000) == 0x7F000000
+    a = _go_ip(True, 0, ip6)
+    if a is None:
+        return False
+    if a.version == 4:
+        return int(a) >> 24 == 127
+    return a == ipaddress.IPv6Address("::1")
+
+
+def is_local_ip(v6, ip4, ip6):  # utils.IsLocalIP = !IsGlobalUnicast
+    a = _go_ip(v6, ip4, ip6)
+    if a is None:
+        return True
+    if a.version == 4:
+        i = int(a)
+        gu = not (i == 0xFFFFFFFF or i == 0 or i >> 24 == 127 or (i >> 28) == 0xE or (i >> 16) == 0xA9FE)
+    else:
+        b = a.packed
+        gu = not (a == ipaddress.IPv6Address("::") or a == ipaddress.IPv6Address("::1") or b[0] == 0xFF or
+                  (b[0] == 0xFE and (b[1] & 0xC0) == 0x80))
+    return not gu
+
+
+def marshal_epc(v):  # MarshalInt32WithSpecialID tag.go:560-565
+    if v > 0 or v == -1 or v == -2:
+        return v
+    return v & 0xFFFF
+
+
+def auto_instance(pod, gp, pod_node, l3dev, subnet, l3type, l3epc):
+    if pod > 0:
+        return pod, 10
+    if gp > 0:
+        return gp, 120
+    if pod_node > 0:
+        return pod_node, 14
+    if l3dev > 0:
+        return l3dev, l3type
+    if l3epc == EPC_FROM_INTERNET:
+        return 0, 0
+    return subnet, 255
+
+
+def auto_service(custom, pod_service, pod_group, gp, pod_cluster, l3dev, subnet, l3type, pod_group_type, l3epc):
+    if custom > 0:
+        return custom, 104
+    if pod_service > 0:
+        return pod_service, 11
+    if pod_group > 0:
+        return pod_group, pod_group_type
+    if gp > 0:
+        return gp, 120
+    if pod_cluster > 0:
+        return pod_cluster, 103
+    if l3dev > 0:
+        return l3dev, l3type
+    if l3epc == EPC_FROM_INTERNET:
+        return 0, 0
+    return subnet, 255
+
+
+def fill(pd, v6, vip, epc, ip4, ip6, mac, gpid, vtap_id, pod, port, tap_side, protocol):
+    """KnowledgeGraph.fill; every per-side argument is a pair (side 0, side 1).  Returns {column: value}."""
+    pod = list(pod)
+    ts = [0, 0]
+    by_mac = [bool(vip[0]), bool(vip[1])]
+    by_agent = [False, False]
+    if is_loopback(v6, ip4[0], ip6[0]) and pod[0] == 0 and pod[1] != 0:
+        ts[0] |= TS_PEER
+        pod[0] = pod[1]
+    if is_loopback(v6, ip4[1], ip6[1]) and pod[1] == 0 and pod[0] != 0:
+        ts[1] |= TS_PEER
+        pod[1] = pod[0]
+    if tap_side == 4:  # Local
+        for s in (0, 1):
+            if is_local_ip(v6, ip4[s], ip6[s]):
+                if mac[s] != 0:
+                    by_mac[s] = True
+                else:
+                    by_agent[s] = True
+    elif tap_side in (41, 42):  # ClientProcess / ServerProcess
+        for s in (0, 1):
+            if mac[s] != 0:
+                by_mac[s] = True
+            elif is_local_ip(v6, ip4[s], ip6[s]):
+                by_agent[s] = True
+    l3mac = [(mac[s] | (epc[s] << 48)) & M64 for s in (0, 1)]
+    for s in (0, 1):
+        if gpid[s] != 0 and pod[s] == 0:
+            vp = pd.gp.get(gpid[s])
+            if vp is not None and (vp & 0xFFFFFFFF) != 0 and ((vp >> 32) & 0xFFFF) == vtap_id:
+                pod[s] = vp & 0xFFFFFFFF
+                ts[s] |= TS_GPID
+    info = [None, None]
+    for s in (0, 1):
+        if pod[s] != 0:
+            ts[s] |= TS_PODID
+            info[s] = pd.pod.get(pod[s])
+    agent = None
+    for s in (0, 1):
+        if info[s] is not None:
+            continue
+        if by_mac[s]:
+            ts[s] |= TS_MAC
+            info[s] = pd.query_mac(l3mac[s])
+        if info[s] is None and by_agent[s]:
+            ts[s] |= TS_AGENT
+            if s == 1 and by_agent[0] and agent is not None:
+                info[1] = agent
+            else:
+                v = pd.vtap.get(vtap_id)
+                if v is not None:
+                    got = pd.reget(not v["is_v4"], v["ip6"] or b"", v["ip4"], v["epc"])
+                    info[s] = got
+                    if s == 0:
+                        agent = got
+        if info[s] is None:
+            ts[s] |= TS_EPCIP
+            info[s] = pd.reget(v6, ip6[s], ip4[s], epc[s])
+    l2 = [pd.query_mac(l3mac[s]) if epc[s] > 0 else None for s in (0, 1)]
+    o = {}
+    for s in (0, 1):
+        i = info[s]
+        g = (lambda n: getattr(i, n)) if i is not None else (lambda n: 0)
+        o[f"region_id_{s}"] = g("region") & 0xFFFF
+        o[f"az_id_{s}"] = g("az") & 0xFFFF
+        o[f"host_id_{s}"] = g("host_id") & 0xFFFF
+        o[f"l3_device_type_{s}"] = g("device_type") & 0xFF
+        o[f"l3_device_id_{s}"] = g("device_id")
+        o[f"pod_node_id_{s}"] = g("pod_node")
+        o[f"pod_ns_id_{s}"] = g("pod_ns") & 0xFFFF
+        o[f"pod_group_id_{s}"] = g("pod_group")
+        o[f"pod_id_{s}"] = g("pod_id")
+        o[f"pod_cluster_id_{s}"] = g("pod_cluster") & 0xFFFF
+        o[f"subnet_id_{s}"] = g("subnet") & 0xFFFF
+        o[f"l3_epc_id_{s}"] = epc[s]
+        o[f"epc_id_{s}"] = l2[s].l2_epc if l2[s] is not None else 0
+        pgt = g("pod_group_type")
+        srv_port = port if s == 1 else 0
+        sid = 0
+        if o[f"l3_device_type_{s}"] == 11 or o[f"pod_id_{s}"] != 0 or (s == 1 and o["pod_node_id_1"] != 0):
+            sid = pd.query_pod_service(o[f"pod_id_{s}"], o[f"pod_node_id_{s}"], o[f"pod_cluster_id_{s}"],
+                                       o[f"pod_group_id_{s}"], epc[s], v6, ip4[s], ip6[s], protocol, srv_port)
+        o[f"service_id_{s}"] = sid
+        o[f"auto_instance_id_{s}"], o[f"auto_instance_type_{s}"] = auto_instance(
+            o[f"pod_id_{s}"], gpid[s], o[f"pod_node_id_{s}"], o[f"l3_device_id_{s}"], o[f"subnet_id_{s}"],
+            o[f"l3_device_type_{s}"], epc[s])
+        custom = pd.query_custom_service(epc[s], v6, ip4[s], ip6[s], srv_port, sid, o[f"pod_group_id_{s}"],
+                                         o[f"l3_device_id_{s}"], o[f"pod_id_{s}"], o[f"pod_cluster_id_{s}"],
+                                         o[f"l3_device_type_{s}"], protocol)
+        o[f"auto_service_id_{s}"], o[f"auto_service_type_{s}"] = auto_service(
+            custom, sid, o[f"pod_group_id_{s}"], gpid[s], o[f"pod_cluster_id_{s}"], o[f"l3_device_id_{s}"],
+            o[f"subnet_id_{s}"], o[f"l3_device_type_{s}"], pgt, epc[s])
+        o[f"tag_source_{s}"] = ts[s]
+    return o

@@ -1,0 +1,210 @@
+"""SmartEncoding cross-check ("a second independent Python restatement of A5 on small inputs"):
+the oracle's 38 KnowledgeGraph columns + gprocess ids of l7_flow_log and l4_flow_log against
+tests/kg_second_opinion.py — a restatement written straight from the Go source, sharing no code with oracle/ —
+on generated batches over the synthetic dictionary (WAN / LAN CIDRs, duplicate MACs, pods known only through
+pod_ips, gprocess infos, agent addresses, pod / custom services, IPv6).  Inputs are decoded with Google's protobuf
+runtime, not with the oracle's decoder."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import kg_second_opinion as K
+import pb_schema as P
+from deepflow_b200 import abi
+
+KG_COLS = ["region_id", "az_id", "host_id", "l3_device_type", "l3_device_id", "pod_node_id", "pod_ns_id",
+           "pod_group_id", "pod_id", "pod_cluster_id", "l3_epc_id", "epc_id", "subnet_id", "service_id",
+           "auto_instance_id", "auto_instance_type", "auto_service_id", "auto_service_type", "tag_source"]
+
+
+def _records(wl):
+    out = []
+    for f in wl.frames:
+        o, end = int(f["offset"]), int(f["offset"]) + int(f["len"])
+        while o < end:
+            n = int.from_bytes(bytes(wl.data[o:o + 4]), "little")
+            out.append(bytes(wl.data[o + 4:o + 4 + n]))
+            o += 4 + n
+    return out
+
+
+def _platform(synth):
+    from deepflow_b200.synth import lib
+    snap = lib().synth_dict(synth._h).contents
+    return K.Platform(snap)
+
+
+def _check(cols, n, want_rows, extra=()):
+    by = {c.name: c for c in cols}
+    problems = []
+    for name in [f"{c}_{s}" for c in KG_COLS for s in (0, 1)] + list(extra):
+        got = by[name].values
+        for r in range(n):
+            w = want_rows[r][name]
+            g = int(got[r])
+            if by[name].ch_type == abi.CH_INT32:
+                w = K._s32(w)
+            if g != w:
+                problems.append(f"row {r} {name}: oracle {g} != second opinion {w}")
+                if len(problems) > 20:
+                    return problems
+    return problems
+
+
+@pytest.mark.parametrize("seed,nrec", [(11, 3000), (12, 1500)])
+def test_l7_knowledge_graph_columns(synth, built, seed, nrec):
+    from oracle_binding import Oracle
+    pd = _platform(synth)
+    wl = synth.gen(abi.DFGPU_MSG_PROTOCOLLOG, nrec, seed=seed)
+    ora = Oracle(abi.Cfg())
+    ora.load_synth(synth)
+    try:
+        ora.submit(wl)
+        cols, n = ora.columns(abi.TABLE_L7_FLOW_LOG)
+        recs = _records(wl)
+        assert n == len(recs) == nrec
+        cls = P.classes()["AppProtoLogsData"]
+        want = []
+        for raw in recs:
+            m = cls()
+            m.ParseFromString(raw)
+            b = m.base
+            vtap = b.vtap_id & 0xFFFF
+            o = K.fill(pd, b.is_ipv6 == 1, (b.is_vip_interface_src == 1, b.is_vip_interface_dst == 1),
+                       (b.l3_epc_id_src, b.l3_epc_id_dst), (b.ip_src, b.ip_dst), (b.ip6_src, b.ip6_dst),
+                       (b.mac_src, b.mac_dst), (b.gpid_0, b.gpid_1), vtap, (b.pod_id_0, b.pod_id_1),
+                       b.port_dst & 0xFFFF, b.tap_side, b.protocol & 0xFF)
+            for s, pid, gp in ((0, b.process_id_0, b.gpid_0), (1, b.process_id_1, b.gpid_1)):
+                o[f"gprocess_id_{s}"] = gp
+                if pid != 0 and gp == 0:  # l7_flow_log.go:589-596
+                    o[f"gprocess_id_{s}"] = pd.vtap_pid.get((vtap << 32) | pid, 0)
+                    o[f"tag_source_{s}"] |= K.TS_PROCESSID
+            want.append(o)
+        problems = _check(cols, n, want, extra=("gprocess_id_0", "gprocess_id_1"))
+        assert not problems, "\n".join(problems)
+        # the batch must actually exercise the interesting paths
+        ts = np.concatenate([c.values for c in cols if c.name in ("tag_source_0", "tag_source_1")])
+        for bit in (K.TS_PODID, K.TS_MAC, K.TS_EPCIP, K.TS_PEER, K.TS_AGENT, K.TS_PROCESSID) + \
+                ((K.TS_GPID,) if nrec >= 3000 else ()):
+            assert (ts & bit).any(), f"tag_source bit {bit} never set"
+        assert (next(c for c in cols if c.name == "auto_service_type_1").values == 104).any()  # custom services
+    finally:
+        ora.close()
+
+
+def test_l4_knowledge_graph_columns(synth, built):
+    from oracle_binding import Oracle
+    pd = _platform(synth)
+    wl = synth.gen(abi.DFGPU_MSG_TAGGEDFLOW, 1500, seed=21)
+    ora = Oracle(abi.Cfg())
+    ora.load_synth(synth)
+    try:
+        ora.submit(wl)
+        cols, n = ora.columns(abi.TABLE_L4_FLOW_LOG)
+        recs = _records(wl)
+        assert n == len(recs) == 1500
+        cls = P.classes()["TaggedFlow"]
+        want = []
+        for raw in recs:
+            m = cls()
+            m.ParseFromString(raw)
+            f = m.flow
+            k, a, b = f.flow_key, f.metrics_peer_src, f.metrics_peer_dst
+            o = K.fill(pd, f.eth_type == 0x86DD, (a.is_vip_interface == 1, b.is_vip_interface == 1),
+                       (K.marshal_epc(a.l3_epc_id), K.marshal_epc(b.l3_epc_id)), (k.ip_src, k.ip_dst),
+                       (k.ip6_src, k.ip6_dst), (k.mac_src, k.mac_dst), (a.gpid, b.gpid), k.vtap_id & 0xFFFF, (0, 0),
+                       k.port_dst & 0xFFFF, f.tap_side, k.proto & 0xFF)  # FillL4 :730-745
+            want.append(o)
+        problems = _check(cols, n, want)
+        assert not problems, "\n".join(problems)
+    finally:
+        ora.close()
+
+
+def test_l7_service_lookups_targeted(synth, built):
+    """Generated traffic rarely lands on a pod-service key.  Records are re-addressed so that the server side
+    hits every service table on purpose (pod-group+port, node cluster+port, cluster ip+port, the custom-service
+    priority list with and without port / epc), re-serialised with Google's protobuf runtime, and compared again."""
+    from oracle_binding import Oracle
+    from deepflow_b200.synth import Workload
+    pd = _platform(synth)
+    base = synth.gen(abi.DFGPU_MSG_PROTOCOLLOG, 1200, seed=31)
+    cls = P.classes()["AppProtoLogsData"]
+    msgs = []
+    for raw in _records(base):
+        m = cls()
+        m.ParseFromString(raw)
+        msgs.append(m)
+    ipproto = {0: 47, 1: 6, 2: 17}  # ServiceProtocol -> an IP protocol that maps to it (47: neither TCP nor UDP)
+    pods_by_group, node_infos = {}, []
+    for pid, inf in pd.pod.items():
+        pods_by_group.setdefault(inf.pod_group, pid)
+    for (epc, ip), inf in pd.ip4.items():
+        if inf.pod_id == 0 and inf.pod_node != 0 and epc > 0:
+            node_infos.append((epc, ip, inf))
+    plans = []
+    for k in list(pd.ps_group_port)[:150]:
+        g, sp, port = k >> 32, (k >> 16) & 0xFFFF, k & 0xFFFF
+        if g in pods_by_group:
+            plans.append(("group", pods_by_group[g], sp, port))
+    for epc, ip, inf in node_infos[:150]:
+        for k in pd.ps_cluster_port:
+            if k >> 32 == inf.pod_cluster:
+                plans.append(("node", epc, ip, (k >> 16) & 0xFFFF, k & 0xFFFF))
+                break
+    for sp in (0, 1, 2):
+        for k in list(pd.ps_ip4[sp])[:60] + list(pd.cs_ip4_port[sp])[:60]:
+            plans.append(("ip", K._s32(k >> 48 if (k >> 48) < 0x8000 else (k >> 48) - 0x10000), (k >> 16) & 0xFFFFFFFF, sp,
+                          k & 0xFFFF))
+    for k in list(pd.cs_ip4)[:60]:
+        plans.append(("ip", K._s32(k >> 48 if (k >> 48) < 0x8000 else (k >> 48) - 0x10000), (k >> 16) & 0xFFFFFFFF, 1, 4321))
+    for pid in list(pd.cs_pod)[:60]:
+        plans.append(("pod", pid))
+    assert len(plans) > 200, len(plans)
+    used = []
+    for m, plan in zip(msgs, plans):
+        b = m.base
+        b.is_ipv6, b.tap_side, b.mac_dst, b.gpid_1, b.process_id_1, b.is_vip_interface_dst = 0, 0, 0, 0, 0, 0
+        if plan[0] == "group":
+            b.pod_id_1, b.protocol, b.port_dst = plan[1], ipproto[plan[2]], plan[3]
+        elif plan[0] == "node":
+            b.pod_id_1, b.l3_epc_id_dst, b.ip_dst, b.protocol, b.port_dst = 0, plan[1], plan[2], ipproto[plan[3]], plan[4]
+        elif plan[0] == "ip":
+            b.pod_id_1, b.l3_epc_id_dst, b.ip_dst, b.protocol, b.port_dst = 0, max(plan[1], 1), plan[2], ipproto[plan[3]], plan[4]
+        else:
+            b.pod_id_1 = plan[1]
+        used.append(m)
+    buf = bytearray()
+    for m in used:
+        raw = m.SerializeToString()
+        buf += len(raw).to_bytes(4, "little") + raw
+    fr = base.frames[:1].copy()
+    fr["offset"], fr["len"] = 0, len(buf)
+    wl = Workload(np.frombuffer(bytes(buf), np.uint8).copy(), fr, None, base.msg_type)
+    ora = Oracle(abi.Cfg())
+    ora.load_synth(synth)
+    try:
+        ora.submit(wl)
+        cols, n = ora.columns(abi.TABLE_L7_FLOW_LOG)
+        assert n == len(used) and ora.counters().error_count == 0
+        want = []
+        for m in used:
+            b = m.base
+            vtap = b.vtap_id & 0xFFFF
+            o = K.fill(pd, b.is_ipv6 == 1, (b.is_vip_interface_src == 1, b.is_vip_interface_dst == 1),
+                       (b.l3_epc_id_src, b.l3_epc_id_dst), (b.ip_src, b.ip_dst), (b.ip6_src, b.ip6_dst),
+                       (b.mac_src, b.mac_dst), (b.gpid_0, b.gpid_1), vtap, (b.pod_id_0, b.pod_id_1),
+                       b.port_dst & 0xFFFF, b.tap_side, b.protocol & 0xFF)
+            for s, pid, gp in ((0, b.process_id_0, b.gpid_0), (1, b.process_id_1, b.gpid_1)):
+                if pid != 0 and gp == 0:
+                    o[f"tag_source_{s}"] |= K.TS_PROCESSID
+            want.append(o)
+        problems = _check(cols, n, want)
+        assert not problems, "\n".join(problems)
+        by = {c.name: c for c in cols}
+        assert int((by["service_id_1"].values != 0).sum()) > 100          # pod services found
+        assert int((by["auto_service_type_1"].values == 104).sum()) > 30   # custom services found
+        assert int((by["auto_service_type_1"].values == 11).sum()) > 60    # pod service as auto service
+    finally:
+        ora.close()
