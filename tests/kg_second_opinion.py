@@ -599,3 +599,180 @@ def fill(pd, v6, vip, epc, ip4, ip6, mac, gpid, vtap_id, pod, port, tap_side, pr
             o[f"subnet_id_{s}"], o[f"l3_device_type_{s}"], pgt, epc[s])
         o[f"tag_source_{s}"] = ts[s]
     return o
+
+
+# =====================================================================================================================
+# flow_metrics twin: Tag.ReadFromPB (libs/flow-metrics/tag.go:1176-1240), getPlatformInfos + DocumentExpand
+# (ingester/flow_metrics/unmarshaller/handle_document.go:41-306), Tag.TableID (tag.go:920-931).  Code bits and table
+# codes come from the machine-extracted tests/golden/metrics_columns.json, passed in as `bits` / `tables`.
+# =====================================================================================================================
+TABLE_ORDER = ["NETWORK", "NETWORK_MAP", "APPLICATION", "APPLICATION_MAP", "TRAFFIC_POLICY"]  # tag.go:509-517
+_MAIN = ["RegionID", "HostID", "L3Device", "SubnetID", "PodNodeID", "AZID", "PodGroupID", "PodNSID", "PodID",
+         "PodClusterID", "ServiceID", "Resource"]
+
+
+def read_tag(f, code, bits, tables):
+    t = {"code": code, "v6": f.is_ipv6 != 0}
+    path = code & bits["IPPath"] != 0
+    if t["v6"]:
+        t["ip6"] = (bytes(f.ip) + bytes(16))[:16]
+        t["ip61"] = (bytes(f.ip1) + bytes(16))[:16] if path else bytes(16)
+        t["ip"] = t["ip1"] = 0
+    else:
+        t["ip"] = int.from_bytes((bytes(f.ip) + bytes(4))[:4], "big")
+        t["ip1"] = int.from_bytes((bytes(f.ip1) + bytes(4))[:4], "big") if path else 0
+        t["ip6"] = t["ip61"] = b""
+    t["mac"], t["mac1"] = f.mac, f.mac1
+    t["epc"], t["epc1"] = marshal_epc(f.l3_epc_id), marshal_epc(f.l3_epc_id1)
+    d = f.direction & 7
+    t["role"] = 0 if d == 1 else 1 if d == 2 else 2 if d == 4 else 3  # ToRole: client / server / local / rest
+    t["tap_side"], t["protocol"] = f.tap_side & 0xFF, f.protocol & 0xFF
+    t["server_port"], t["vtap"] = f.server_port & 0xFFFF, f.vtap_id & 0xFFFF
+    if path:
+        t["code"] |= bits["GPIDPath"] | bits["SignalSource"]
+    elif code != tables["TRAFFIC_POLICY"]:
+        t["code"] |= bits["GPID"] | bits["SignalSource"]
+    t["gpid"], t["gpid1"] = f.gpid, f.gpid1
+    t["pod"] = t["pod1"] = 0
+    if f.pod_id != 0:
+        if path and t["role"] == 1:
+            t["pod1"] = f.pod_id
+        else:
+            t["pod"] = f.pod_id
+    t["signal_source"] = f.signal_source & 0xFFFF
+    t["ts"] = t["ts1"] = 0
+    for k in ("region", "host", "dev_id", "dev_type", "subnet", "pod_node", "pod_ns", "az", "pod_group", "pod_cluster",
+              "service", "ai_id", "ai_type", "as_id", "as_type"):
+        t[k] = t[k + "1"] = 0
+    return t
+
+
+def _is_multicast(v6, ip4, ip6):
+    a = _go_ip(v6, ip4, ip6)
+    if a is None:
+        return False
+    return (int(a) >> 28) == 0xE if a.version == 4 else a.packed[0] == 0xFF
+
+
+def _side_info(pd, t, s):
+    """One side of getPlatformInfos; s = "" (0 side) or "1"."""
+    o = "1" if s == "" else ""
+    v6 = t["v6"]
+    ip4, ip6 = t["ip" + s], t["ip6" + s]
+    info = None
+    if is_loopback(v6, ip4, ip6) and t["pod" + s] == 0 and t["pod" + o] != 0:
+        t["ts" + s] |= TS_PEER
+        t["pod" + s] = t["pod" + o]
+    if t["gpid" + s] != 0 and t["pod" + s] == 0:
+        vp = pd.gp.get(t["gpid" + s])
+        if vp is not None and (vp & 0xFFFFFFFF) != 0 and ((vp >> 32) & 0xFFFF) == t["vtap"]:
+            t["pod" + s] = vp & 0xFFFFFFFF
+            t["ts" + s] |= TS_GPID
+    if t["pod" + s] != 0:
+        info = pd.pod.get(t["pod" + s])
+        t["ts" + s] |= TS_PODID
+    if info is None:
+        if t["mac" + s] != 0:
+            t["ts" + s] |= TS_MAC
+            info = pd.query_mac(t["mac" + s] | (t["epc" + s] << 48))
+        if info is None:
+            by_agent = t["tap_side"] in (4, 41, 42) and is_local_ip(v6, ip4, ip6)
+            if by_agent:
+                t["ts" + s] |= TS_AGENT
+                v = pd.vtap.get(t["vtap"])
+                if v is not None:
+                    info = pd.reget(not v["is_v4"], v["ip6"] or b"", v["ip4"], v["epc"])
+            else:
+                t["ts" + s] |= TS_EPCIP
+                info = pd.reget(v6, ip6, ip4, t["epc" + s])
+    return info
+
+
+def _apply(t, s, i):
+    t["region" + s], t["host" + s], t["dev_id" + s] = i.region & 0xFFFF, i.host_id & 0xFFFF, i.device_id
+    t["dev_type" + s], t["subnet" + s], t["pod_node" + s] = i.device_type & 0xFF, i.subnet & 0xFFFF, i.pod_node
+    t["pod_ns" + s], t["az" + s], t["pod_group" + s] = i.pod_ns & 0xFFFF, i.az & 0xFFFF, i.pod_group
+    t["pod" + s], t["pod_cluster" + s] = i.pod_id, i.pod_cluster & 0xFFFF
+    return i.pod_group_type
+
+
+def doc_expand(pd, t, meter_id, bits, my_region, default_org=True):
+    """DocumentExpand; returns False when the document is dropped (region filter)."""
+    edge_code = bits["IPPath"] | bits["L3EpcIDPath"]
+    suffix = (1 if t["code"] & bits["ACLGID"] else 0) | (2 if t["code"] & 0xFFFFF00000 else 0) | \
+             (4 if t["code"] & bits["ServerPort"] else 0)
+    if meter_id == 4 and suffix == 1:  # ACL_ID usage meter, acl-only suffix: not expanded
+        return True
+    if t["code"] & bits["ServerPort"] == bits["ServerPort"]:
+        t["code"] |= bits["IsKeyService"]
+    edge = t["code"] & edge_code == edge_code
+    info = _side_info(pd, t, "") if t["epc"] != EPC_FROM_INTERNET else None
+    info1 = _side_info(pd, t, "1") if edge and t["epc1"] != EPC_FROM_INTERNET else None
+    if edge:
+        for n in _MAIN:
+            t["code"] |= bits[n + "Path"]
+    else:
+        for n in _MAIN:
+            t["code"] |= bits[n]
+    v6 = t["v6"]
+    pgt = pgt1 = 0
+    if info1 is not None:
+        pgt1 = _apply(t, "1", info1)
+        if t["dev_type1"] == 11 or t["pod1"] != 0 or t["pod_node1"] != 0:
+            t["service1"] = pd.query_pod_service(t["pod1"], t["pod_node1"], t["pod_cluster1"], t["pod_group1"], t["epc1"],
+                                                 v6, t["ip1"], t["ip61"], t["protocol"], t["server_port"])
+        if info is None and _is_multicast(v6, t["ip"], t["ip6"]):
+            t["region"], t["subnet"], t["az"] = t["region1"], t["subnet1"], t["az1"]
+            t["ts"] |= TS_PEER
+        if default_org and my_region != 0 and t["region1"] != 0 and t["tap_side"] == 2 and t["region1"] != my_region:
+            return False
+    t["ai_id1"], t["ai_type1"] = auto_instance(t["pod1"], t["gpid1"], t["pod_node1"], t["dev_id1"], t["subnet1"],
+                                               t["dev_type1"], t["epc1"])
+    c1 = pd.query_custom_service(t["epc1"], v6, t["ip1"], t["ip61"], t["server_port"], t["service1"], t["pod_group1"],
+                                 t["dev_id1"], t["pod1"], t["pod_cluster1"], t["dev_type1"], t["protocol"])
+    t["as_id1"], t["as_type1"] = auto_service(c1, t["service1"], t["pod_group1"], t["gpid1"], t["pod_cluster1"],
+                                              t["dev_id1"], t["subnet1"], t["dev_type1"], pgt1, t["epc1"])
+    if info is not None:
+        pgt = _apply(t, "", info)
+        if t["dev_type"] == 11 or t["pod"] != 0 or t["pod_node"] != 0:
+            if t["server_port"] > 0 and not (t["code"] & edge_code):
+                t["service"] = pd.query_pod_service(t["pod"], t["pod_node"], t["pod_cluster"], t["pod_group"], t["epc"],
+                                                    v6, t["ip"], t["ip6"], t["protocol"], t["server_port"])
+            elif t["dev_type"] == 11 or t["pod"] != 0:
+                t["service"] = pd.query_pod_service(t["pod"], t["pod_node"], t["pod_cluster"], t["pod_group"], t["epc"],
+                                                    v6, t["ip"], t["ip6"], t["protocol"], 0)
+        if info1 is None and edge and _is_multicast(v6, t["ip1"], t["ip61"]):
+            t["region1"], t["subnet1"], t["az1"] = t["region"], t["subnet"], t["az"]
+            t["ts1"] |= TS_PEER
+        if default_org and my_region != 0 and t["region"] != 0:
+            if edge:
+                if t["tap_side"] == 1 and t["region"] != my_region:
+                    return False
+            elif t["region"] != my_region:
+                return False
+    t["ai_id"], t["ai_type"] = auto_instance(t["pod"], t["gpid"], t["pod_node"], t["dev_id"], t["subnet"], t["dev_type"],
+                                             t["epc"])
+    sport = t["server_port"] if not (t["code"] & edge_code) else 0
+    c0 = pd.query_custom_service(t["epc"], v6, t["ip"], t["ip6"], sport, t["service"], t["pod_group"], t["dev_id"],
+                                 t["pod"], t["pod_cluster"], t["dev_type"], t["protocol"])
+    t["as_id"], t["as_type"] = auto_service(c0, t["service"], t["pod_group"], t["gpid"], t["pod_cluster"], t["dev_id"],
+                                            t["subnet"], t["dev_type"], pgt, t["epc"])
+    if t["signal_source"] == 4:  # OTel
+        if t["tap_side"] == 50 and t["server_port"] == 0:  # ServerApp
+            t["server_port"] = 65535
+        for k in ("epc", "epc1"):
+            if t[k] == EPC_FROM_INTERNET:
+                t[k] = EPC_UNKNOWN
+        for k in ("as_type", "as_type1", "ai_type", "ai_type1"):
+            if t[k] == 0:
+                t[k] = 255
+    return True
+
+
+def table_index(code, second, bits, tables):
+    """Tag.TableID: index into the 5 minute tables (+5 for per-second documents), or None."""
+    c = code & ~bits["MAC"] & ~bits["MACPath"]
+    for i, name in enumerate(TABLE_ORDER):
+        if c == tables[name]:
+            return i + (5 if second else 0)
+    return None

@@ -208,3 +208,74 @@ def test_l7_service_lookups_targeted(synth, built):
         assert int((by["auto_service_type_1"].values == 11).sum()) > 60    # pod service as auto service
     finally:
         ora.close()
+
+
+def test_metrics_document_expand_and_routing(synth, built):
+    """flow_metrics twin (A10): Tag.ReadFromPB + DocumentExpand + Tag.TableID restated a second time in Python
+    against the oracle — which of the 9 tables every Document goes to (or that it is dropped), and the
+    SmartEncoding-derived tag columns of its row."""
+    import json
+    import os
+    from oracle_binding import Oracle
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_columns.json")))
+    bits, tables = dict(g["code_bits"]), dict(g["table_codes"])
+    pd = _platform(synth)
+    wl = synth.gen(abi.DFGPU_MSG_METRICS, 4000, seed=41)
+    ora = Oracle(abi.Cfg())
+    ora.load_synth(synth)
+    try:
+        ora.submit(wl)
+        cls = P.classes()["Document"]
+        meter_of_table = {0: 1, 1: 1, 2: 5, 3: 5, 4: 4}  # network* -> Flow, application* -> App, traffic_policy -> Usage
+        rows = {i: [] for i in range(9)}
+        dropped = 0
+        for raw in _records(wl):
+            m = cls()
+            m.ParseFromString(raw)
+            t = K.read_tag(m.tag.field, m.tag.code, bits, tables)
+            mid = m.meter.meter_id
+            if not K.doc_expand(pd, t, mid, bits, pd.region_id & 0xFFFF):
+                dropped += 1
+                continue
+            ti = K.table_index(t["code"], (m.flags & 1) == 1, bits, tables)
+            # inputs the reference leaves undefined (DESIGN §3.6): a meter the table does not store, a per-second
+            # traffic_policy document -> counted as dropped by the library
+            if ti is None or ti > 8 or meter_of_table[ti % 5] != mid:
+                dropped += 1
+                continue
+            rows[ti].append(t)
+        single = {"region_id": "region", "host_id": "host", "l3_device_id": "dev_id", "l3_device_type": "dev_type",
+                  "subnet_id": "subnet", "pod_node_id": "pod_node", "pod_ns_id": "pod_ns", "az_id": "az",
+                  "pod_group_id": "pod_group", "pod_id": "pod", "pod_cluster_id": "pod_cluster", "service_id": "service",
+                  "auto_instance_id": "ai_id", "auto_instance_type": "ai_type", "auto_service_id": "as_id",
+                  "auto_service_type": "as_type", "tag_source": "ts", "l3_epc_id": "epc", "gprocess_id": "gpid"}
+        problems, compared = [], 0
+        for ti in range(9):
+            cols, n = ora.columns(abi.TABLE_METRICS_BASE + ti)
+            if n != len(rows[ti]):
+                problems.append(f"table {ti}: oracle {n} rows != second opinion {len(rows[ti])}")
+                continue
+            by = {c.name: c for c in cols}
+            for name, key in single.items():
+                for cname, k in ((name, key), (name + "_0", key), (name + "_1", key + "1")):
+                    if cname not in by:
+                        continue
+                    got = by[cname].values
+                    for r, t in enumerate(rows[ti]):
+                        w = t[k]
+                        if by[cname].ch_type == abi.CH_INT32:
+                            w = K._s32(w)
+                        compared += 1
+                        if int(got[r]) != w:
+                            problems.append(f"table {ti} row {r} {cname}: oracle {int(got[r])} != second opinion {w}")
+                            if len(problems) > 20:
+                                break
+            if "server_port" in by:
+                for r, t in enumerate(rows[ti]):
+                    if int(by["server_port"].values[r]) != t["server_port"]:
+                        problems.append(f"table {ti} row {r} server_port")
+        assert not problems, "\n".join(problems[:25])
+        assert compared > 50_000 and all(len(rows[i]) > 50 for i in range(9) if i != 9)
+        assert dropped == ora.counters().drop_count and dropped > 100
+    finally:
+        ora.close()
