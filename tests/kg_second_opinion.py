@@ -776,3 +776,128 @@ def table_index(code, second, bits, tables):
         if c == tables[name]:
             return i + (5 if second else 0)
     return None
+
+
+# ---- the rest of the flow_metrics row: Tag.AppendToColumnBlock (tag_column_block.go:521-721) and the meters'
+# ReadFromPB + AppendToColumnBlock (basic_meter.go, basic_meter_column_block.go, app_meter*.go, usage_meter*.go) ----
+_TAPSIDE = {0: "rest", 1: "c", 2: "s", 4: "local", 9: "c-nd", 10: "s-nd", 17: "c-hv", 18: "s-hv", 25: "c-gw-hv",
+            26: "s-gw-hv", 33: "c-gw", 34: "s-gw", 41: "c-p", 42: "s-p", 49: "c-app", 50: "s-app", 48: "app"}
+U64 = (1 << 64) - 1
+U32 = (1 << 32) - 1
+
+
+def read_tag_rest(t, f, team_id):
+    """The Tag members ReadFromPB sets that SmartEncoding does not look at."""
+    t["tid"], t["acl_gid"] = f.global_thread_id & 0xFF, f.acl_gid & 0xFFFF
+    tp = f.tap_port
+    t["capture_nic"], t["capture_nic_type"] = tp & U32, (tp >> 60) & 0xFF
+    t["nat_source"], t["tunnel_type"] = (tp >> 36) & 0xF, (tp >> 32) & 0xF
+    t["tap_type"], t["l7_protocol"] = f.tap_type & 0xFF, f.l7_protocol & 0xFF
+    t["app_service"], t["app_instance"], t["endpoint"] = f.app_service.encode(), f.app_instance.encode(), f.endpoint.encode()
+    t["biz_type"], t["tunnel_ip_id"], t["team_id"] = f.biz_type & 0xFF, f.server_port & 0xFFFF, team_id
+
+
+def tag_columns(t, time, bits):
+    c, o = t["code"], {"time": time, "_tid": t["tid"]}
+    has = lambda n: c & bits[n] != 0  # noqa: E731
+    pairs = (("AZID", "az_id", "az"), ("HostID", "host_id", "host"), ("PodClusterID", "pod_cluster_id", "pod_cluster"),
+             ("PodGroupID", "pod_group_id", "pod_group"), ("PodID", "pod_id", "pod"), ("PodNodeID", "pod_node_id", "pod_node"),
+             ("PodNSID", "pod_ns_id", "pod_ns"), ("RegionID", "region_id", "region"), ("ServiceID", "service_id", "service"),
+             ("SubnetID", "subnet_id", "subnet"), ("L3EpcID", "l3_epc_id", "epc"), ("GPID", "gprocess_id", "gpid"))
+    for bit, col, key in pairs:
+        if has(bit):
+            o[col] = t[key]
+        if has(bit + "Path"):
+            o[col + "_0"], o[col + "_1"] = t[key], t[key + "1"]
+    if has("ACLGID"):
+        o["acl_gid"] = t["acl_gid"]
+    if has("Direction"):
+        o["role"] = t["role"]
+    ip6 = t["ip6"] if t["v6"] else bytes(16)
+    ip61 = t["ip61"] if t["v6"] else bytes(16)
+    if has("IP"):
+        o["ip4"], o["ip6"], o["is_ipv4"], o["tag_source"] = t["ip"], ip6, 0 if t["v6"] else 1, t["ts"]
+    if has("IPPath"):
+        o["ip4_0"], o["ip4_1"], o["ip6_0"], o["ip6_1"] = t["ip"], t["ip1"], ip6, ip61
+        o["is_ipv4"], o["tag_source_0"], o["tag_source_1"] = 0 if t["v6"] else 1, t["ts"], t["ts1"]
+    if has("IsKeyService"):
+        o["is_key_service"] = 0  # Tag.IsKeyService is never set on this path
+    if has("L3Device"):
+        o["l3_device_id"], o["l3_device_type"] = t["dev_id"], t["dev_type"]
+    if has("L3DevicePath"):
+        o["l3_device_id_0"], o["l3_device_id_1"] = t["dev_id"], t["dev_id1"]
+        o["l3_device_type_0"], o["l3_device_type_1"] = t["dev_type"], t["dev_type1"]
+    if has("L7Protocol"):
+        o["l7_protocol"], o["app_service"], o["app_instance"] = t["l7_protocol"], t["app_service"], t["app_instance"]
+        o["endpoint"], o["biz_type"] = t["endpoint"], t["biz_type"]
+    if has("Protocol"):
+        o["protocol"] = t["protocol"]
+    if has("Resource"):
+        o["auto_instance_id"], o["auto_instance_type"] = t["ai_id"], t["ai_type"]
+        o["auto_service_id"], o["auto_service_type"] = t["as_id"], t["as_type"]
+    if has("ResourcePath"):
+        for n, s in (("0", ""), ("1", "1")):
+            o["auto_instance_id_" + n], o["auto_instance_type_" + n] = t["ai_id" + s], t["ai_type" + s]
+            o["auto_service_id_" + n], o["auto_service_type_" + n] = t["as_id" + s], t["as_type" + s]
+    if has("SignalSource"):
+        o["signal_source"] = t["signal_source"]
+    if has("ServerPort"):
+        o["server_port"] = t["server_port"]
+    if has("TunnelIPID"):
+        o["tunnel_ip_id"] = t["tunnel_ip_id"]
+    if has("TAPPort"):
+        o["capture_nic_type"], o["tunnel_type"] = t["capture_nic_type"], t["tunnel_type"]
+        o["capture_nic"], o["nat_source"] = t["capture_nic"], t["nat_source"]
+    if has("TAPSide"):
+        o["observation_point"] = _TAPSIDE[t["tap_side"]].encode()
+    if has("TAPType"):
+        o["capture_network_type_id"] = t["tap_type"]
+    if has("VTAPID"):
+        o["agent_id"], o["team_id"] = t["vtap"], t["team_id"]
+    return o
+
+
+def flow_meter_columns(p):
+    tr, la, pe, an = p.traffic, p.latency, p.performance, p.anomaly
+    o = {"packet_tx": tr.packet_tx, "packet_rx": tr.packet_rx, "packet": (tr.packet_tx + tr.packet_rx) & U64,
+         "byte_tx": tr.byte_tx, "byte_rx": tr.byte_rx, "byte": (tr.byte_tx + tr.byte_rx) & U64,
+         "l3_byte_tx": tr.l3_byte_tx, "l3_byte_rx": tr.l3_byte_rx, "l4_byte_tx": tr.l4_byte_tx, "l4_byte_rx": tr.l4_byte_rx,
+         "new_flow": tr.new_flow, "closed_flow": tr.closed_flow, "l7_request": tr.l7_request, "l7_response": tr.l7_response,
+         "syn_count": tr.syn, "synack_count": tr.synack, "direction_score": tr.direction_score & 0xFF}
+    for n in ("rtt", "rtt_client", "rtt_server", "srt", "art", "rrt", "cit"):
+        o[n + "_sum"] = float(getattr(la, n + "_sum"))
+        o[n + "_count"] = getattr(la, n + "_count")
+        o[n + "_max"] = getattr(la, n + "_max")
+    o.update({"retrans_tx": pe.retrans_tx, "retrans_rx": pe.retrans_rx, "retrans": (pe.retrans_tx + pe.retrans_rx) & U64,
+              "zero_win_tx": pe.zero_win_tx, "zero_win_rx": pe.zero_win_rx,
+              "zero_win": (pe.zero_win_tx + pe.zero_win_rx) & U64, "retrans_syn": pe.retrans_syn,
+              "retrans_synack": pe.retrans_synack})
+    cef = (an.client_ack_miss + an.client_source_port_reuse + an.client_establish_reset) & U64
+    sef = (an.server_syn_miss + an.server_reset + an.server_queue_lack + an.server_establish_reset) & U64
+    o.update({"client_rst_flow": an.client_rst_flow, "server_rst_flow": an.server_rst_flow,
+              "server_syn_miss": an.server_syn_miss, "client_ack_miss": an.client_ack_miss,
+              "client_half_close_flow": an.client_half_close_flow, "server_half_close_flow": an.server_half_close_flow,
+              "client_source_port_reuse": an.client_source_port_reuse, "server_reset": an.server_reset,
+              "server_queue_lack": an.server_queue_lack, "client_establish_other_rst": an.client_establish_reset,
+              "server_establish_other_rst": an.server_establish_reset, "tcp_timeout": an.tcp_timeout,
+              "client_establish_fail": cef, "server_establish_fail": sef, "tcp_establish_fail": (cef + sef) & U64,
+              "tcp_transfer_fail": (an.client_rst_flow + an.server_rst_flow + an.server_queue_lack + an.tcp_timeout) & U64,
+              "tcp_rst_fail": (an.client_establish_reset + an.server_establish_reset + an.server_reset +
+                               an.client_rst_flow + an.server_rst_flow) & U64,
+              "l7_client_error": an.l7_client_error, "l7_server_error": an.l7_server_error, "l7_timeout": an.l7_timeout,
+              "l7_error": (an.l7_client_error + an.l7_server_error) & U32, "ooo_tx": an.client_ooo, "ooo_rx": an.server_ooo,
+              "flow_load": p.flow_load.load})
+    return o
+
+
+def app_meter_columns(p):
+    return {"request": p.traffic.request, "response": p.traffic.response, "direction_score": p.traffic.direction_score & 0xFF,
+            "rrt_max": p.latency.rrt_max, "rrt_sum": float(p.latency.rrt_sum), "rrt_count": p.latency.rrt_count,
+            "client_error": p.anomaly.client_error, "server_error": p.anomaly.server_error, "timeout": p.anomaly.timeout,
+            "error": (p.anomaly.client_error + p.anomaly.server_error) & U32}
+
+
+def usage_meter_columns(p):
+    return {"packet_tx": p.packet_tx, "packet_rx": p.packet_rx, "packet": (p.packet_tx + p.packet_rx) & U64,
+            "byte_tx": p.byte_tx, "byte_rx": p.byte_rx, "byte": (p.byte_tx + p.byte_rx) & U64,
+            "l3_byte_tx": p.l3_byte_tx, "l3_byte_rx": p.l3_byte_rx, "l4_byte_tx": p.l4_byte_tx, "l4_byte_rx": p.l4_byte_rx}

@@ -279,3 +279,73 @@ def test_metrics_document_expand_and_routing(synth, built):
         assert dropped == ora.counters().drop_count and dropped > 100
     finally:
         ora.close()
+
+
+def test_metrics_full_rows(synth, built):
+    """EVERY column of every row of the 9 flow_metrics tables (tag columns in GenTagColumns order + the meter's
+    columns) from the second restatement: Tag.AppendToColumnBlock, the three meters' ReadFromPB + AppendToColumnBlock."""
+    import json
+    import os
+    from oracle_binding import Oracle
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_columns.json")))
+    bits, tables = dict(g["code_bits"]), dict(g["table_codes"])
+    pd = _platform(synth)
+    wl = synth.gen(abi.DFGPU_MSG_METRICS, 3000, seed=43)
+    ora = Oracle(abi.Cfg())
+    ora.load_synth(synth)
+    try:
+        ora.submit(wl)
+        cls = P.classes()["Document"]
+        meter_of_table = {0: 1, 1: 1, 2: 5, 3: 5, 4: 4}
+        rows = {i: [] for i in range(9)}
+        for fr in wl.frames:
+            o, end = int(fr["offset"]), int(fr["offset"]) + int(fr["len"])
+            while o < end:
+                n = int.from_bytes(bytes(wl.data[o:o + 4]), "little")
+                raw = bytes(wl.data[o + 4:o + 4 + n])
+                o += 4 + n
+                m = cls()
+                m.ParseFromString(raw)
+                t = K.read_tag(m.tag.field, m.tag.code, bits, tables)
+                K.read_tag_rest(t, m.tag.field, int(fr["team_id"]) & 0xFFFF)
+                mid = m.meter.meter_id
+                if not K.doc_expand(pd, t, mid, bits, pd.region_id & 0xFFFF):
+                    continue
+                ti = K.table_index(t["code"], (m.flags & 1) == 1, bits, tables)
+                if ti is None or ti > 8 or meter_of_table[ti % 5] != mid:
+                    continue
+                row = K.tag_columns(t, m.timestamp, bits)
+                meter = K.flow_meter_columns(m.meter.flow) if mid == 1 else \
+                    K.app_meter_columns(m.meter.app) if mid == 5 else K.usage_meter_columns(m.meter.usage)
+                assert not (set(row) & set(meter)) or mid == 5  # application tables: direction_score only in the meter
+                row.update(meter)
+                rows[ti].append(row)
+        problems, compared = [], 0
+        for ti in range(9):
+            cols, n = ora.columns(abi.TABLE_METRICS_BASE + ti)
+            assert n == len(rows[ti]), (ti, n, len(rows[ti]))
+            names = [c.name for c in cols]
+            assert len(set(names)) == len(names)
+            got = {c.name: c.rows() for c in cols}
+            for r, want in enumerate(rows[ti]):
+                if r == 0:
+                    assert set(want) == set(names), (ti, sorted(set(want) ^ set(names)))
+                for name, w in want.items():
+                    gv = got[name][r]
+                    if isinstance(w, float):
+                        ok = np.float64(gv).tobytes() == np.float64(w).tobytes()
+                    else:
+                        if isinstance(w, int) and w >= 1 << 31 and next(c for c in cols if c.name == name).ch_type == abi.CH_INT32:
+                            w -= 1 << 32
+                        if name.startswith("l3_epc_id"):
+                            w = K._s32(w)
+                        ok = gv == w
+                    compared += 1
+                    if not ok:
+                        problems.append(f"table {ti} row {r} {name}: oracle {gv!r} != second opinion {w!r}")
+                if len(problems) > 15:
+                    break
+        assert not problems, "\n".join(problems[:15])
+        assert compared > 100_000
+    finally:
+        ora.close()
