@@ -349,3 +349,112 @@ def test_metrics_full_rows(synth, built):
         assert compared > 100_000
     finally:
         ora.close()
+
+
+def _merge_into(acc, other):
+    """Meter.ConcurrentMerge on the protobuf messages themselves (field widths = the wire schema's):
+    wrapping sums, `_max` / direction_score keep the maximum, Anomaly.client_ooo / server_ooo are ASSIGNED
+    (basic_meter.go:94-113, 277-315, 417-424, 556-577, 707-709; app_meter.go:153-265; usage_meter.go)."""
+    from google.protobuf.descriptor import FieldDescriptor as FD
+    for fd in acc.DESCRIPTOR.fields:
+        a, b = getattr(acc, fd.name), getattr(other, fd.name)
+        if fd.message_type is not None:
+            _merge_into(a, b)
+            continue
+        mask = (1 << 32) - 1 if fd.type == FD.TYPE_UINT32 else (1 << 64) - 1
+        if fd.name.endswith("_max"):
+            v = max(a, b)
+        elif fd.name == "direction_score":
+            v = max(a & 0xFF, b & 0xFF)
+        elif fd.name in ("client_ooo", "server_ooo"):
+            v = b
+        else:
+            v = (a + b) & mask
+        setattr(acc, fd.name, v)
+
+
+@pytest.mark.parametrize("bucket", [60, 86400])
+def test_metrics_reduce_second_opinion(synth, built, bucket):
+    """The reduce operator (A9): rows of one table grouped by (time bucket, every tag column) in first-appearance
+    order, meters folded with ConcurrentMerge in input order, the derived *_fail columns kept from the first row."""
+    import copy
+    import json
+    import os
+    from oracle_binding import Oracle
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_columns.json")))
+    bits, tables = dict(g["code_bits"]), dict(g["table_codes"])
+    pd = _platform(synth)
+    from deepflow_b200.synth import Workload
+    base = synth.gen(abi.DFGPU_MSG_METRICS, 2500, seed=47)
+    # the same documents three times in one submit: every group gets >= 3 rows (first / last / sum / max rules)
+    data = np.concatenate([base.data] * 3)
+    frames = np.concatenate([base.frames] * 3).copy()
+    for r in range(3):
+        frames["offset"][r * len(base.frames):(r + 1) * len(base.frames)] += r * base.data.nbytes
+    wl = Workload(data, frames, None, base.msg_type)
+    ora = Oracle(abi.Cfg())
+    ora.load_synth(synth)
+    try:
+        ora.submit(wl)
+        cls = P.classes()["Document"]
+        meter_of_table = {0: 1, 1: 1, 2: 5, 3: 5, 4: 4}
+        rows = {i: [] for i in range(9)}
+        for fr in wl.frames:
+            o, end = int(fr["offset"]), int(fr["offset"]) + int(fr["len"])
+            while o < end:
+                n = int.from_bytes(bytes(wl.data[o:o + 4]), "little")
+                m = cls()
+                m.ParseFromString(bytes(wl.data[o + 4:o + 4 + n]))
+                o += 4 + n
+                t = K.read_tag(m.tag.field, m.tag.code, bits, tables)
+                K.read_tag_rest(t, m.tag.field, int(fr["team_id"]) & 0xFFFF)
+                mid = m.meter.meter_id
+                if not K.doc_expand(pd, t, mid, bits, pd.region_id & 0xFFFF):
+                    continue
+                ti = K.table_index(t["code"], (m.flags & 1) == 1, bits, tables)
+                if ti is None or ti > 8 or meter_of_table[ti % 5] != mid:
+                    continue
+                rows[ti].append((K.tag_columns(t, m.timestamp, bits), m.meter))
+        merged_rows = compared = 0
+        for ti in range(9):
+            groups, order = {}, []
+            for tags, meter in rows[ti]:
+                tags = dict(tags, time=tags["time"] // bucket * bucket)
+                key = tuple(sorted((k, v) for k, v in tags.items()))
+                if key not in groups:
+                    groups[key] = [tags, copy.deepcopy(meter), meter]  # tags, accumulator, first row's meter
+                    order.append(key)
+                else:
+                    _merge_into(groups[key][1], meter)
+                    merged_rows += 1
+            assert ora.metrics_reduce(abi.TABLE_METRICS_BASE + ti, bucket) == 0
+            cols, n = ora.columns(abi.TABLE_METRICS_REDUCED)
+            assert n == len(order), (ti, n, len(order))
+            got = {c.name: c.rows() for c in cols}
+            for r, key in enumerate(order):
+                tags, acc, first = groups[key]
+                mid = meter_of_table[ti % 5]
+                if mid == 1:
+                    want = K.flow_meter_columns(acc.flow)
+                    f1 = K.flow_meter_columns(first.flow)
+                    for c in ("client_establish_fail", "server_establish_fail", "tcp_establish_fail", "tcp_transfer_fail",
+                              "tcp_rst_fail"):
+                        want[c] = f1[c]  # set by ReadFromPB only; ConcurrentMerge does not touch them
+                elif mid == 5:
+                    want = K.app_meter_columns(acc.app)
+                else:
+                    want = K.usage_meter_columns(acc.usage)
+                want = dict(tags, **want)
+                for name, w in want.items():
+                    gv = got[name][r]
+                    if isinstance(w, float):
+                        ok = np.float64(gv).tobytes() == np.float64(w).tobytes()
+                    else:
+                        if name.startswith("l3_epc_id"):
+                            w = K._s32(w)
+                        ok = gv == w
+                    compared += 1
+                    assert ok, f"table {ti} group {r} {name}: oracle {gv!r} != second opinion {w!r}"
+        assert compared > 100_000 and merged_rows > 3000, (compared, merged_rows)
+    finally:
+        ora.close()
