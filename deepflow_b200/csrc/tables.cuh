@@ -26,12 +26,12 @@
 #define DF_HD inline
 #define DF_HD_NOINLINE inline
 #endif
-// The dictionary probes and the SmartEncoding routine are compiled two ways:
-//  * out of line (default): inside the big row-building kernels they must not bloat the instruction
-//    stream (ncu: 31 % instruction-fetch stalls when everything was inlined);
-//  * DF_KG_INLINE: inside the dedicated SmartEncoding kernel (l7_kg.cu) everything is inlined and
-//    the two sides are unrolled so that the per-record state stays in registers instead of going
-//    through by-reference structs in local memory (ncu: 3.8 GB of local traffic per 625 k records).
+// The dictionary probes and the record-wise SmartEncoding routine (kg.cuh kg_fill: the L4 pass and the
+// flow_metrics pass) are compiled OUT OF LINE: inside the big row-building kernels they must not bloat the
+// instruction stream (ncu: 31 % instruction-fetch stalls when everything was inlined).  DF_KG_INLINE (all
+// inline, sides unrolled) is kept as a build option for experiments; the L7 path does not use these functions
+// any more — its dedicated kernel (l7_kg.cu) runs the register-only, one-side-per-lane restatement in
+// kg_side.cuh.
 #ifdef DF_KG_INLINE
 #define DF_KG_FN static DF_HD
 #define DF_KG_SIDE_LOOP _Pragma("unroll")
