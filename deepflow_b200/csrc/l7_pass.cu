@@ -1,15 +1,17 @@
 /*
  * l7_pass.cu — the L7 flow-log kernel: AppProtoLogsData record -> one l7_flow_log
  * row.  One thread per record, a warp = 32 consecutive records (coalesced column
- * stores).  Decode runs through the table-driven interpreter (pb_interp.cuh) into
- * per-thread slots; the row build reads the slots.  Replaces, fused:
+ * stores).  The SIZE pass decodes ONCE through the table-driven interpreter
+ * (pb_interp.cuh) straight into a slot-major global buffer and sizes the variable
+ * columns; the EMIT pass builds the row from those slots and copies the strings.
+ * Replaces, fused:
  *   decode          gogo Unmarshal via SimpleDecoder.ReadPB (simple_codec.go:229-248)
  *   row build       ProtoLogToL7FlowLog  flow_log/log_data/l7_flow_log.go:638-644,
  *                   L7FlowLog.Fill :312-342, L7Base.Fill :514-597, fillL7FlowLog :363-452,
  *                   fillTraceIds :344-360, fillExceptionDesc :463-488 (exception_desc.go),
  *                   L7Protocol.String datatype/flow.go:623-803,
  *                   ParseTraceIdIndex :296-310 -> DJBHash libs/utils/hash.go:37-43
- *   SmartEncoding   KnowledgeGraph.FillL7 :599-613 -> kg.cuh ; QueryProcessInfo :589-596
+ *   SmartEncoding   KnowledgeGraph.FillL7 :599-613, QueryProcessInfo :589-596 -> its own kernel, l7_kg.cu
  *   column pack     L7FlowLog.AppendToColumnBlock l7_column_block.go:167-208,376-422
  *   counters        updateCounter decoder.go:498-525
  */
@@ -683,8 +685,9 @@ __device__ __forceinline__ void l7_tail(const BatchParams& p, const L7Dev* dv, D
 #define L7_EMIT_MIN_BLOCKS 4
 #endif
 template <int EMIT>
-// SIZE pass: 40 registers / 6 CTAs per SM measured fastest (0.77 ms vs 0.92 at 4 and 0.86 at 8 CTAs per
-// 625 k records); EMIT pass: 64 registers / 4 CTAs (80 and 128 registers were slower: 1.65 / 1.99 ms).
+// SIZE pass: 40 registers / 6 CTAs per SM measured fastest (0.73 ms per 625 k records; 4 and 8 CTAs: +20 % / +12 %);
+// EMIT pass: 64 registers / 4 CTAs (0.67 ms; 3 / 5 / 6 CTAs per SM: 0.78 / 0.80 / 0.83 ms before the last round of
+// changes).
 __global__ void __launch_bounds__(256, EMIT ? L7_EMIT_MIN_BLOCKS : 6) k_l7_pass(const __grid_constant__ BatchParams p) {
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
