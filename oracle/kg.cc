@@ -1,5 +1,8 @@
 /*
  * ORACLE — test infrastructure only.  See kg.h for the reference map.
+ * Parity unpinned by the reference (KnowledgeGraph.fill has no reference test); cross-checked by the second
+ * restatement tests/kg_second_opinion.py (tests/test_kg_crosscheck_cpu.py).  Pinned pieces: MarshalInt32WithSpecialID
+ * (tag_test.go:45-56), TAP-side strings (tag.go:211-233), auto instance / service type codes (trident.proto enums).
  */
 #include "kg.h"
 

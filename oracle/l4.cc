@@ -8,6 +8,9 @@
  *   geo.QueryProvince       flow_log/geo/geo.go:29 ; libs/geo/netmask_tree.go:24-104
  *   AppendToColumnBlock     l4_column_block.go:53-59,145-172,213-223,243-246,272-276,
  *                           410-451,561-593,748-796,848-859 ; ToInput order :822-833
+ * Pinned: the TaggedFlow literal (tagged_flow_test.go:29-103), the column list (machine-extracted from ToInput), the
+ * netmask tree.  Parity unpinned by the reference: the Fill functions, getStatus, genID, AppendToColumnBlock —
+ * cross-checked by tests/test_l4_row_crosscheck_cpu.py.
  */
 #include "l4.h"
 

@@ -11,6 +11,10 @@
  *   column blocks                 l7_column_block.go:114-158,167-208,376-422;
  *                                 flow_tag_column_block.go:50-101;
  *                                 app_service_tag_column_block.go:39-80
+ * Pinned: column lists (machine-extracted from ToInput), L7Protocol.String (machine-extracted switch), exception
+ * tables (generated from exception_desc.go), DJBHash, lru order.  Parity unpinned by the reference: the Fill functions,
+ * GenerateNewFlowTags, AppendToColumnBlock — cross-checked by tests/test_l7_row_crosscheck_cpu.py and
+ * tests/test_flow_tag_crosscheck_cpu.py.
  * Presence of req/resp/trace_info/ext_info follows the wire (a fresh
  * pb.AppProtoLogsData); the reference's pooled objects keep reset-but-non-nil
  * sub-messages after first use (datatype/pb/flow_log.go:37-77), which only

@@ -1,6 +1,10 @@
 /*
  * ORACLE — test infrastructure only.
  * metrics.cc: see metrics.h for the reference map.
+ * Pinned: column names / order / container types and Code / table-code constants (machine-extracted,
+ * tests/golden/metrics_columns.json), MiniTag literals + direction tables (tag_test.go:259-392), meter merge KATs
+ * (basic_meter_test.go:112-135, usage_meter_test.go:57-79).  Parity unpinned by the reference: DocumentExpand, TableID
+ * routing, the meters' AppendToColumnBlock, the reduce — cross-checked by tests/test_kg_crosscheck_cpu.py.
  */
 #include "metrics.h"
 

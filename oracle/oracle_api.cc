@@ -1,5 +1,12 @@
 /*
  * ORACLE — test infrastructure only.
+ * PINNING (what ties this restatement to the reference; full list: DESIGN.md §4).  Pinned by the reference's own
+ * tests / sources: the wire schema (field lists machine-extracted from message/*.proto), every output column list
+ * (machine-extracted from the ToInput functions), tag Code / table codes, trident enums, L7Protocol.String, the
+ * TaggedFlow / MiniTag literals, meter merge KATs, TAP-side strings, DJBHash, lru order, netmask tree, queue
+ * semantics.  PARITY UNPINNED by the reference (it has no tests for them): KnowledgeGraph.fill, DocumentExpand,
+ * GenerateNewFlowTags, every AppendToColumnBlock, genID, getStatus — for these a second, independent Python
+ * restatement (tests/kg_second_opinion.py, tests/test_*_crosscheck_cpu.py) is compared with this oracle instead.
  * oracle_api.cc: C entry points (ctypes) that drive the CPU restatement the way
  *   Decoder.Run / handleTaggedFlow / handleProtoLog   decoder.go:151-234
  *   SimpleDecoder.ReadPB / IsEnd / Failed              libs/codec/simple_codec.go:229-248,400-406

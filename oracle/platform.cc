@@ -1,5 +1,8 @@
 /*
  * ORACLE — test infrastructure only.  See platform.h for the reference map.
+ * Parity unpinned by the reference (no test builds a PlatformInfoTable / ServiceTable); cross-checked by the second
+ * restatement tests/kg_second_opinion.py.  Pinned pieces: Go net.IP predicates (stdlib semantics, KATs in
+ * tests/test_reference_kats_cpu.py), the netmask tree (libs/geo/netmask_tree_test.go).
  */
 #include "platform.h"
 
