@@ -298,6 +298,7 @@ def test_metrics_full_rows(synth, built):
         cls = P.classes()["Document"]
         meter_of_table = {0: 1, 1: 1, 2: 5, 3: 5, 4: 4}
         rows = {i: [] for i in range(9)}
+        svc_cache, svc_rows = {}, []
         for fr in wl.frames:
             o, end = int(fr["offset"]), int(fr["offset"]) + int(fr["len"])
             while o < end:
@@ -314,6 +315,15 @@ def test_metrics_full_rows(synth, built):
                 ti = K.table_index(t["code"], (m.flags & 1) == 1, bits, tables)
                 if ti is None or ti > 8 or meter_of_table[ti % 5] != mid:
                     continue
+                # appServiceTagWrite (unmarshaller.go:309-327): only the two 1m application tables, through an lru
+                # with the 1800 s flush timeout (app_service_tag_writer.go:92-113); below capacity the lru is a dict
+                if ti in (2, 3) and (t["app_service"] or t["app_instance"]):
+                    key = (ti, t["app_service"], t["app_instance"], 1, t["team_id"])
+                    old_time = svc_cache.get(key)
+                    if old_time is None or ((old_time + 1800) & 0xFFFFFFFF) < m.timestamp:
+                        svc_cache[key] = m.timestamp
+                        svc_rows.append((m.timestamp, b"application" if ti == 2 else b"application_map", t["app_service"],
+                                         t["app_instance"], t["team_id"]))
                 row = K.tag_columns(t, m.timestamp, bits)
                 meter = K.flow_meter_columns(m.meter.flow) if mid == 1 else \
                     K.app_meter_columns(m.meter.app) if mid == 5 else K.usage_meter_columns(m.meter.usage)
@@ -347,6 +357,10 @@ def test_metrics_full_rows(synth, built):
                     break
         assert not problems, "\n".join(problems[:15])
         assert compared > 100_000
+        cols, n = ora.columns(abi.TABLE_METRICS_APP_SERVICE)
+        got = list(zip(*[c.rows() for c in cols])) if n else []
+        assert [c.name for c in cols] == ["time", "table", "app_service", "app_instance", "team_id"]
+        assert got == svc_rows and len(svc_rows) > 50, (len(got), len(svc_rows))
     finally:
         ora.close()
 
