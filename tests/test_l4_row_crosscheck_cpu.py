@@ -2,8 +2,8 @@
 TransportLayer / ApplicationLayer / FlowInfo / Metrics .Fill, getStatus, genID, Uint64SliceToString
 (flow_log/log_data/l4_flow_log.go:457-953) and the blocks' AppendToColumnBlock (l4_column_block.go) restated in
 Python from the Go source, fed by Google's protobuf runtime, against every column of the oracle's rows except the
-KnowledgeGraph ones (second opinion: test_kg_crosscheck_cpu.py) and province_0/1 (geo tree: pinned by the
-reference's own netmask-tree tests, test_reference_kats_cpu.py)."""
+KnowledgeGraph ones (second opinion: test_kg_crosscheck_cpu.py); province_0/1 come from a second restatement of the
+netmask geo tree (libs/geo/netmask_tree.go) over the same range table."""
 import numpy as np
 import pytest
 
@@ -101,6 +101,60 @@ def l4_row(m, counter, analyzer_id):
     return o
 
 
+class GeoTree:
+    """geo.NewNetmaskGeoTree / netmaskTree.Query (libs/geo/netmask_tree.go:19-104) a second time."""
+    MINL, MAXL = 16, 32
+    NETMASK = [(~(0xFFFFFFFF >> i)) & 0xFFFFFFFF for i in range(33)]
+
+    @classmethod
+    def first_mask(cls, start, end):
+        ml = cls.MAXL
+        while ml > cls.MINL:
+            if start & (1 << (cls.MAXL - ml)):
+                break
+            inv = lambda m: (~cls.NETMASK[m]) & 0xFFFFFFFF  # noqa: E731
+            if ((start + inv(ml)) & 0xFFFFFFFF) >= end or ((start + inv(ml - 1)) & 0xFFFFFFFF) > end:
+                break
+            ml -= 1
+        return ml
+
+    def __init__(self, entries, names):
+        self.max_mask = [0] * (1 << self.MINL)
+        self.names = names
+        for s, e, _r in entries:  # updateMask
+            start = s
+            while e >= start:
+                ml = self.first_mask(start, e)
+                key = start >> (self.MAXL - self.MINL)
+                if ml > self.max_mask[key]:
+                    self.max_mask[key] = ml
+                start += 1 << (self.MAXL - ml)
+                if start > 0xFFFFFFFF:
+                    break
+        self.cache = {}
+        for s, e, r in entries:
+            ip = s
+            while ip <= e and ip > 0:
+                m = self.max_mask[ip >> 16]
+                self.cache[ip & self.NETMASK[m]] = r
+                ip += 1 << (self.MAXL - m)
+                if ip > 0xFFFFFFFF:
+                    break
+
+    def province(self, ip):
+        m = self.max_mask[ip >> 16]
+        r = self.cache.get(ip & self.NETMASK[m], 0)
+        return self.names[r] if r < len(self.names) else "未知".encode()  # geo/utils.go:35-40
+
+
+def _geo(synth):
+    import ctypes as C
+    e, n, names, nn = synth.geo()
+    ent = C.cast(e, C.POINTER(abi.GeoEntry * n)).contents
+    nm = C.cast(names, C.POINTER(C.c_char_p * nn)).contents
+    return GeoTree([(x.ip_start, x.ip_end, x.region) for x in ent], [bytes(x) for x in nm])
+
+
 @pytest.mark.parametrize("sizes,seed,flags", [([1500, 800], 5, 0), ([1200], 6, S.F_ALL_WIRE)])
 def test_l4_rows_match_second_opinion(synth, built, sizes, seed, flags):
     from oracle_binding import Oracle
@@ -109,7 +163,8 @@ def test_l4_rows_match_second_opinion(synth, built, sizes, seed, flags):
     ora = Oracle(abi.Cfg())
     ora.load_synth(synth)
     cls = P.classes()["TaggedFlow"]
-    skip = KG_PREFIX[:-2] + ("team_id", "province_")
+    skip = KG_PREFIX[:-2] + ("team_id",)
+    geo = _geo(synth)
     try:
         counter, compared = 0, 0
         for k, n in enumerate(sizes):
@@ -125,6 +180,8 @@ def test_l4_rows_match_second_opinion(synth, built, sizes, seed, flags):
                 m.ParseFromString(raw)
                 counter += 1
                 want = l4_row(m, counter, analyzer)
+                k4 = m.flow.flow_key  # Internet.Fill :530-533: looked up by the IPv4 fields whatever the family
+                want["province_0"], want["province_1"] = geo.province(k4.ip_src), geo.province(k4.ip_dst)
                 assert set(want) == set(rows), sorted(set(want) ^ set(rows))
                 for name, w in want.items():
                     g = rows[name][r]
