@@ -97,10 +97,11 @@ class Counters(C.Structure):
                 ("l7_sql_count", C.c_int64), ("l7_nosql_count", C.c_int64), ("l7_rpc_count", C.c_int64),
                 ("l7_mq_count", C.c_int64), ("new_field_count", C.c_int64),
                 ("new_field_value_count", C.c_int64), ("rows", C.c_int64 * TABLE_MAX),
-                ("device_us", C.c_double)]
+                ("device_us", C.c_double), ("flow_tag_unrecorded", C.c_int64), ("flow_tag_evicted", C.c_int64)]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("rows", "device_us")}
+        d = {k: getattr(self, k) for k, _ in self._fields_
+             if k not in ("rows", "device_us", "flow_tag_unrecorded", "flow_tag_evicted")}
         d["rows"] = {i: self.rows[i] for i in range(TABLE_MAX) if self.rows[i]}
         return d
 

@@ -16,9 +16,11 @@ using namespace dfgpu;
 
 namespace dfgpu {
 void launch_l4_pass(const BatchParams& p, int emit, cudaStream_t s);
-void launch_l7_pass(const BatchParams& p, int emit, cudaStream_t s);
-void launch_l7_kg(const BatchParams& p, cudaStream_t s);
-struct FlowTagDev;
+void launch_l7_repair_plan(const BatchParams& p, cudaStream_t s);
+void launch_l7_decode(const BatchParams& p, unsigned grid, cudaStream_t s);
+void launch_l7_strings(const BatchParams& p, unsigned grid, cudaStream_t s);
+void launch_l7_kg(const BatchParams& p, unsigned grid, cudaStream_t s);
+void l7_grids(dfgpu_ctx* ctx, unsigned* decode, unsigned* strings, unsigned* kg);
 int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s);
 int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s);
 int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n);
@@ -27,7 +29,6 @@ int metrics_passes(dfgpu_ctx* ctx, int repair);
 int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t));
 int metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch* b,
                    uint8_t* (*acquire)(dfgpu_ctx*, size_t));
-uint64_t metrics_arena_need(uint32_t nrec, uint64_t nbytes);
 void metrics_free_state(dfgpu_ctx* ctx);
 }  // namespace dfgpu
 
@@ -42,18 +43,64 @@ struct TableSchema {
   int ncols;
 };
 
-template <class T>
-static int ensure_dev(dfgpu_ctx* ctx, T*& p, size_t& cap, size_t want) {
-  if (cap >= want) return 0;
-  if (p) CU(cudaFree(p));
-  p = nullptr;
-  size_t n = std::max(want, cap + cap / 2);
-  CU(cudaMalloc(&p, n * sizeof(T)));
-  cap = n;
+// Arena bytes that hold any batch of `recs` records / `bytes` wire bytes: every row of the widest table
+// (fixed-width columns + 16-byte Positions: l7 ~750 B, l4 ~900 B, flow_metrics ~1100 B per row) + the
+// variable-length streams (<= the wire bytes, twice with their native length prefixes / device-only
+// Positions) + slack.  Larger batches are caught on the device (DynState::overflow) and grown by fetch.
+static uint64_t arena_need(uint64_t recs, uint64_t bytes) { return recs * 1200 + 3 * bytes + (8u << 20); }
+
+// (Re)allocates every device buffer whose size follows the three capacities.  Called by dfgpu_init with
+// the capacities of dfgpu_cfg, and by dfgpu_fetch when the device reported an overflow — never between
+// dfgpu_stage and the final D2H of a batch that fits.
+static int alloc_buffers(dfgpu_ctx* ctx, size_t in_cap, uint32_t rec_cap, size_t arena_cap) {
+  if (in_cap > ctx->d_in_cap) {
+    if (ctx->d_in) CU(cudaFree(ctx->d_in));
+    if (ctx->d_rec_scratch) CU(cudaFree(ctx->d_rec_scratch));
+    ctx->d_in = nullptr;
+    ctx->d_rec_scratch = nullptr;
+    CU(cudaMalloc(&ctx->d_in, in_cap + 64));
+    CU(cudaMalloc(&ctx->d_rec_scratch, (in_cap / 4 + 2) * sizeof(uint32_t)));
+    ctx->d_in_cap = in_cap;
+    ctx->rec_scratch_cap = in_cap / 4 + 2;
+  }
+  if (rec_cap > ctx->rec_cap) {
+    if (ctx->d_rec_u32) CU(cudaFree(ctx->d_rec_u32));
+    if (ctx->d_warp) CU(cudaFree(ctx->d_warp));
+    ctx->d_rec_u32 = nullptr;
+    ctx->d_warp = nullptr;
+    CU(cudaMalloc(&ctx->d_rec_u32, (size_t)rec_cap * 3 * sizeof(uint32_t)));
+    ctx->rec_cap = rec_cap;
+    ctx->warp_cap = (size_t)rec_cap / 32 + 2;
+    CU(cudaMalloc(&ctx->d_warp, ctx->warp_cap * 2 * MAX_SLOTS * sizeof(uint32_t)));
+  }
+  if (arena_cap > ctx->arena_cap) {
+    if (ctx->d_arena) CU(cudaFree(ctx->d_arena));
+    ctx->d_arena = nullptr;
+    CU(cudaMalloc(&ctx->d_arena, arena_cap));
+    ctx->arena_cap = arena_cap;
+  }
+  return 0;
+}
+static int alloc_frames(dfgpu_ctx* ctx, uint32_t nframes) {
+  if (nframes <= ctx->frames_cap) return 0;
+  if (ctx->d_frames) CU(cudaFree(ctx->d_frames));
+  if (ctx->d_frame_u32) CU(cudaFree(ctx->d_frame_u32));
+  if (ctx->h_frame_u32) CU(cudaFreeHost(ctx->h_frame_u32));
+  ctx->d_frames = nullptr;
+  ctx->d_frame_u32 = nullptr;
+  ctx->h_frame_u32 = nullptr;
+  const size_t cap = std::max<size_t>(nframes + nframes / 2, 4096);
+  CU(cudaMalloc(&ctx->d_frames, cap * sizeof(dfgpu_frame)));
+  CU(cudaMalloc(&ctx->d_frame_u32, cap * 5 * sizeof(uint32_t)));  // nrec | base | chain_err | bad | drop
+  CU(cudaHostAlloc(&ctx->h_frame_u32, cap * 2 * sizeof(uint32_t), cudaHostAllocDefault));
+  ctx->frames_cap = (uint32_t)cap;
+  ctx->h_frames_cap = (uint32_t)cap;
   return 0;
 }
 
 extern "C" {
+
+int dfgpu_close(dfgpu_ctx* ctx);
 
 int dfgpu_init(int device, const dfgpu_cfg* cfg, dfgpu_ctx** out) {
   if (!out) return DFGPU_EINVAL;
@@ -80,6 +127,15 @@ int dfgpu_init(int device, const dfgpu_cfg* cfg, dfgpu_ctx** out) {
     return DFGPU_ENODEV;
   }
   memset(ctx->h_persist, 0, sizeof(PersistState));
+  // every device buffer is sized here, from the configured batch capacities: dfgpu_run neither
+  // allocates nor waits for the GPU
+  int rc = alloc_frames(ctx, 4096);
+  if (!rc) rc = alloc_buffers(ctx, (size_t)ctx->cfg.max_batch_bytes, ctx->cfg.max_batch_records,
+                              (size_t)arena_need(ctx->cfg.max_batch_records, ctx->cfg.max_batch_bytes));
+  if (rc) {
+    dfgpu_close(ctx);
+    return rc;
+  }
   *out = ctx;
   return DFGPU_OK;
 }
@@ -101,9 +157,6 @@ int dfgpu_close(dfgpu_ctx* ctx) {
   cudaFree(ctx->d_dyn);
   cudaFree(ctx->d_persist);
   cudaFree(ctx->d_arena);
-  cudaFree(ctx->d_geo_start);
-  cudaFree(ctx->d_geo_end);
-  cudaFree(ctx->d_geo_code);
   cudaFreeHost(ctx->h_dyn);
   cudaFreeHost(ctx->h_persist);
   cudaFreeHost(ctx->h_frame_u32);
@@ -195,34 +248,29 @@ int dfgpu_geo_load(dfgpu_ctx* ctx, const dfgpu_geo_entry* entries, uint64_t n, c
       }
     canon[c] = (uint8_t)first;
   }
-  ctx->geo_names.assign(256, std::string());
-  for (uint32_t c = 0; c < n_names && c < 256; c++) ctx->geo_names[c] = names[c];
-  if (n_names && names[0] != "\xe6\x9c\xaa\xe7\x9f\xa5") {
-    // out-of-range codes decode to the literal "未知"; keep it reachable if names[0] differs
-  }
+  auto g = std::make_shared<GeoTables>();
+  g->names.assign(256, std::string());
+  for (uint32_t c = 0; c < n_names && c < 256; c++) g->names[c] = names[c];
   std::vector<dfgpu_geo_entry> e(entries, entries + n);
   std::stable_sort(e.begin(), e.end(), [](const dfgpu_geo_entry& a, const dfgpu_geo_entry& b) { return a.ip_start < b.ip_start; });
-  std::vector<uint32_t> st(n), en(n);
-  std::vector<uint8_t> code(n);
+  // one buffer: start[n] | end[n] | code[n]
+  std::vector<uint32_t> img(2 * n + (n + 3) / 4 + 1);
+  uint8_t* code = reinterpret_cast<uint8_t*>(img.data() + 2 * n);
   for (uint64_t i = 0; i < n; i++) {
-    st[i] = e[i].ip_start;
-    en[i] = e[i].ip_end;
+    img[i] = e[i].ip_start;
+    img[n + i] = e[i].ip_end;
     code[i] = canon[e[i].region];
   }
-  cudaFree(ctx->d_geo_start);
-  cudaFree(ctx->d_geo_end);
-  cudaFree(ctx->d_geo_code);
-  ctx->d_geo_start = ctx->d_geo_end = nullptr;
-  ctx->d_geo_code = nullptr;
-  ctx->geo_n = (uint32_t)n;
+  g->n = (uint32_t)n;
   if (n) {
-    CU(cudaMalloc(&ctx->d_geo_start, n * 4));
-    CU(cudaMalloc(&ctx->d_geo_end, n * 4));
-    CU(cudaMalloc(&ctx->d_geo_code, n));
-    CU(cudaMemcpy(ctx->d_geo_start, st.data(), n * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_geo_end, en.data(), n * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ctx->d_geo_code, code.data(), n, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&g->d_start, img.size() * 4));
+    CU(cudaMemcpy(g->d_start, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+    g->d_end = g->d_start + n;
+    g->d_code = reinterpret_cast<uint8_t*>(g->d_start + 2 * n);
   }
+  // built aside, swapped in under the lock: a batch staged before this point keeps the old snapshot
+  std::lock_guard<std::mutex> lk(ctx->dict_mu);
+  ctx->geo = g;
   return DFGPU_OK;
 }
 
@@ -256,24 +304,6 @@ static bool is_array(int ch) {
   return ch == DFGPU_CH_ARR_UINT16 || ch == DFGPU_CH_ARR_STR || ch == DFGPU_CH_ARR_LC_STR || ch == DFGPU_CH_ARR_FLOAT64;
 }
 
-// fixed region of the arena for `rows` rows; returns its size
-// native_str (dfgpu_cfg.native_strings): String columns carry no Position array in the host-bound part of the
-// arena (k_finish puts the device-only ones behind var_end)
-static uint64_t plan_fixed(const TableSchema& s, uint32_t rows, uint64_t* fix_off, uint64_t* aux_off,
-                           bool native_str = false) {
-  uint64_t cur = 0;
-  for (int c = 0; c < s.ncols; c++) {
-    const ColSpec& cs = s.cols[c];
-    fix_off[c] = cur;
-    size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
-    cur += align_up((size_t)rows * es, 256);
-    aux_off[c] = cur;
-    const bool str_pos = cs.ch_type == DFGPU_CH_STR || cs.ch_type == DFGPU_CH_LC_STR_ROWS;
-    if (!(native_str && str_pos)) cur += align_up((size_t)rows * aux_bytes_per_row(cs.ch_type), 256);
-  }
-  return cur;
-}
-
 namespace dfgpu {
 void l7_streams(BatchParams& bp);
 }
@@ -292,48 +322,147 @@ static void setup_streams(BatchParams& bp, int msg) {
   }
 }
 
+// per-column bytes per row of the main table, for the device-side layout (k_prepare)
+static void setup_columns(BatchParams& bp, const TableSchema& s) {
+  bp.ncols = (uint32_t)s.ncols;
+  for (int c = 0; c < s.ncols; c++) {
+    const ColSpec& cs = s.cols[c];
+    bp.col_es[c] = (uint8_t)(is_array(cs.ch_type) ? 0 : cs.elem_size);
+    const bool str_pos = cs.ch_type == DFGPU_CH_STR || cs.ch_type == DFGPU_CH_LC_STR_ROWS;
+    // native strings: String columns carry no Position array in the host-bound part of the arena
+    // (k_finish puts the device-only ones behind var_end)
+    bp.col_aux[c] = (uint8_t)((bp.native_str && str_pos) ? 0 : aux_bytes_per_row(cs.ch_type));
+  }
+}
+
+// Everything after framing: planning on the device, the passes of the message type, the commit.
+// repair = 1 when re-running with the frames' cut points known (a record failed to decode).
 static int launch_passes(dfgpu_ctx* ctx, int repair) {
   BatchParams& bp = ctx->bp;
   bp.repair = repair;
   cudaStream_t s = ctx->stream;
-  // reset first-appearance tables (and, in repair mode, nothing else)
+  if (ctx->cur_msg == DFGPU_MSG_METRICS) {
+    launch_prepare(bp, s);
+    ctx->launches++;
+    if (bp.nframes) {
+      launch_frame_fill(bp, s);
+      ctx->launches++;
+    }
+    return metrics_passes(ctx, repair);
+  }
+  // reset first-appearance tables
   CU(cudaMemsetAsync(&ctx->d_dyn->stats.lc_first, 0xff, sizeof(ctx->d_dyn->stats.lc_first), s));
-  if (bp.nrec == 0) {
-    CU(cudaMemsetAsync(&ctx->d_dyn->stats.var_total, 0, sizeof(ctx->d_dyn->stats.var_total), s));
+  const bool l7 = ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG;
+  if (l7) {
+    if (repair) {
+      launch_l7_repair_plan(bp, s);  // rows dropped before every frame, rows the layout is planned for
+      ctx->launches++;
+    } else if (bp.nframes) {
+      CU(cudaMemsetAsync(bp.frame_drop, 0, (size_t)bp.nframes * 4, s));
+    }
   }
-  if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 0, s);
-  else launch_l7_pass(bp, 0, s);
-  ctx->mark(3);
-  if (bp.nrec) {
-    launch_slot_scan(bp, s);
-    ctx->launches += 2;
-  }
-  launch_finish(bp, s);
+  launch_prepare(bp, s);
   ctx->launches++;
+  if (bp.nframes) {
+    launch_frame_fill(bp, s);
+    ctx->launches++;
+  }
+  ctx->mark(2);
+  unsigned g_dec = 0, g_str = 0, g_kg = 0;
+  if (l7) {
+    l7_grids(ctx, &g_dec, &g_str, &g_kg);
+    launch_l7_decode(bp, g_dec, s);  // decode + fixed-width columns + per-warp sizes (+ trace carry scan)
+  } else {
+    launch_l4_pass(bp, 0, s);
+  }
+  ctx->mark(3);
+  launch_slot_scan(bp, s);
+  launch_finish(bp, s);
+  ctx->launches += 4;
   ctx->mark(4);
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-  if (ctx->prof_on && bp.nrec && ctx->prof_used < dfgpu_ctx::PROF_SLOTS) {
+  if (ctx->prof_on && ctx->prof_used < dfgpu_ctx::PROF_SLOTS) {
     pe0 = ctx->prof_ev[2 * ctx->prof_used];
     pe1 = ctx->prof_ev[2 * ctx->prof_used + 1];
     ctx->prof_bytes[ctx->prof_used] = ctx->cur_nbytes;
     ctx->prof_used++;
     CU(cudaEventRecord(pe0, s));
   }
-  if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) launch_l4_pass(bp, 1, s);
-  else launch_l7_pass(bp, 1, s);
-  if (pe1) CU(cudaEventRecord(pe1, s));  // the profile events bracket the EMIT kernel alone
-  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG && bp.nrec) {
-    launch_l7_kg(bp, s);  // SmartEncoding columns, one lane per (record, side)
+  if (l7) launch_l7_strings(bp, g_str, s);
+  else launch_l4_pass(bp, 1, s);
+  if (pe1) CU(cudaEventRecord(pe1, s));  // the profile events bracket the pack kernel alone
+  ctx->launches++;
+  if (l7) {
+    ctx->mark(5);
+    launch_l7_kg(bp, g_kg, s);  // SmartEncoding columns, one lane per (record, side)
     ctx->launches++;
-  }
-  ctx->mark(5);
-  if (bp.nrec) ctx->launches++;
-  if (ctx->cur_msg != DFGPU_MSG_PROTOCOLLOG) {  // L7 commits after its flow_tag stage
+    ctx->mark(6);
+    int rc = l7_flow_tags(ctx, s);  // commits the counters at its end
+    if (rc) return rc;
+  } else {
+    ctx->mark(5);
+    ctx->mark(6);
     launch_commit(bp, 0, s);
     ctx->launches++;
   }
   CU(cudaGetLastError());
   return 0;
+}
+
+// framing + passes of the staged batch
+static int run_pipeline(dfgpu_ctx* ctx) {
+  cudaStream_t s = ctx->stream;
+  const TableSchema* sch = main_schema(ctx->cur_msg);
+  BatchParams& bp = ctx->bp;
+  memset(&bp, 0, sizeof bp);
+  CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
+  const uint32_t nf = ctx->cur_nframes;
+  bp.in = ctx->cur_in;
+  bp.in_bytes = ctx->cur_nbytes;
+  bp.frames = ctx->cur_frames;
+  bp.nframes = nf;
+  bp.frame_nrec = ctx->d_frame_u32;
+  bp.frame_base = ctx->d_frame_u32 + ctx->frames_cap;
+  bp.frame_chain_err = ctx->d_frame_u32 + 2 * (size_t)ctx->frames_cap;
+  bp.frame_bad = ctx->d_frame_u32 + 3 * (size_t)ctx->frames_cap;
+  bp.frame_drop = ctx->d_frame_u32 + 4 * (size_t)ctx->frames_cap;
+  bp.dyn = ctx->d_dyn;
+  bp.persist = ctx->d_persist;
+  bp.dict = ctx->cur_dict->view;
+  if (ctx->cur_geo) {
+    bp.geo.start = ctx->cur_geo->d_start;
+    bp.geo.end = ctx->cur_geo->d_end;
+    bp.geo.code = ctx->cur_geo->d_code;
+    bp.geo.n = ctx->cur_geo->n;
+  }
+  bp.cfg_trace_disabled = ctx->cfg.trace_id_index_disabled;
+  bp.rec_scratch = ctx->d_rec_scratch;
+  bp.rec_cap = ctx->rec_cap;
+  bp.warp_cap = (uint32_t)ctx->warp_cap;
+  bp.rec_off = ctx->d_rec_u32;
+  bp.rec_len = ctx->d_rec_u32 + ctx->rec_cap;
+  bp.rec_frame = ctx->d_rec_u32 + 2 * (size_t)ctx->rec_cap;
+  bp.warp_tot = ctx->d_warp;
+  bp.warp_base = ctx->d_warp + (size_t)MAX_SLOTS * ctx->warp_cap;
+  bp.arena = ctx->d_arena;
+  bp.arena_bytes = ctx->arena_cap;
+  bp.native_str = (ctx->cfg.native_strings && ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) ? 1u : 0u;
+  if (sch) {
+    setup_columns(bp, *sch);
+    setup_streams(bp, ctx->cur_msg);
+  }
+  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
+    int rc = l7_prepare(ctx, s);
+    if (rc) return rc;
+  }
+  ctx->mark(0);
+  if (nf) {
+    CU(cudaMemsetAsync(bp.frame_bad, 0xff, (size_t)nf * 4, s));
+    launch_frame_count(bp, s);  // walks the length chains, leaves the record count on the device
+    ctx->launches += 2;
+  }
+  ctx->mark(1);
+  return launch_passes(ctx, 0);
 }
 
 extern "C" {
@@ -343,7 +472,7 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
   if (!ctx || nframes < 0 || (nframes && !tbl) || (nbytes && !frames)) return DFGPU_EINVAL;
   if (!main_schema(msg_type) && msg_type != DFGPU_MSG_METRICS)
     return fail(ctx, DFGPU_EINVAL, "unsupported msg_type %d", msg_type);
-  if (nbytes >= (1ull << 32)) return fail(ctx, DFGPU_EINVAL, "batch too large (%zu bytes)", nbytes);
+  if (nbytes >= (1ull << 31)) return fail(ctx, DFGPU_EINVAL, "batch too large (%zu bytes)", nbytes);
   CU(cudaSetDevice(ctx->device));
   cudaPointerAttributes attr;
   if (tbl && cudaPointerGetAttributes(&attr, tbl) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
@@ -352,33 +481,34 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
   uint16_t org = nframes ? tbl[0].org_id : 1;
   for (int i = 1; i < nframes; i++)
     if (tbl[i].org_id != org) return fail(ctx, DFGPU_EMIXEDORG, "frames of one submit must share org_id");
-  for (int i = 0; i < nframes; i++)
-    if (tbl[i].offset + tbl[i].len > nbytes) return fail(ctx, DFGPU_EINVAL, "frame %d outside the staging buffer", i);
+  for (int i = 0; i < nframes; i++) {
+    // offset + len may wrap in uint64: compare without the addition
+    if (tbl[i].offset > nbytes || tbl[i].len > nbytes - tbl[i].offset)
+      return fail(ctx, DFGPU_EINVAL, "frame %d outside the staging buffer", i);
+    // frames share framing scratch by byte range: they must be laid out in order, without overlap
+    if (i && tbl[i].offset < tbl[i - 1].offset + tbl[i - 1].len)
+      return fail(ctx, DFGPU_EINVAL, "frame %d overlaps or precedes frame %d (frames must be sorted by offset)", i, i - 1);
+  }
   {
     std::lock_guard<std::mutex> g(ctx->dict_mu);
     auto it = ctx->dicts.find(org);
     if (it == ctx->dicts.end()) return fail(ctx, DFGPU_ENOENT, "no dictionary loaded for org %u", org);
     ctx->cur_dict = it->second;
+    ctx->cur_geo = ctx->geo;
   }
   bool on_device = false;
   if (frames && cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeDevice) on_device = true;
   cudaGetLastError();
-  size_t fcap = ctx->frames_cap;
-  if ((uint32_t)nframes > ctx->frames_cap) {
-    size_t want = (size_t)nframes;
-    if (ctx->d_frames) CU(cudaFree(ctx->d_frames));
-    if (ctx->d_frame_u32) CU(cudaFree(ctx->d_frame_u32));
-    ctx->d_frames = nullptr;
-    ctx->d_frame_u32 = nullptr;
-    fcap = std::max<size_t>(want, 1024);
-    CU(cudaMalloc(&ctx->d_frames, fcap * sizeof(dfgpu_frame)));
-    CU(cudaMalloc(&ctx->d_frame_u32, fcap * 4 * sizeof(uint32_t)));
-    ctx->frames_cap = (uint32_t)fcap;
-  }
+  if (on_device && ((uintptr_t)frames & 7))
+    return fail(ctx, DFGPU_EINVAL, "device-resident frames must be 8-byte aligned");
+  // a batch beyond the configured capacities grows the buffers here, before anything is queued
+  if ((uint32_t)nframes > ctx->frames_cap && alloc_frames(ctx, (uint32_t)nframes)) return DFGPU_ENODEV;
+  if (nbytes > ctx->d_in_cap &&
+      alloc_buffers(ctx, nbytes + nbytes / 4, ctx->rec_cap, (size_t)arena_need(ctx->rec_cap, nbytes + nbytes / 4)))
+    return DFGPU_ENODEV;
   if (on_device) {
     ctx->cur_in = frames;  // inputs already resident in HBM
   } else {
-    if (ensure_dev(ctx, ctx->d_in, ctx->d_in_cap, nbytes + 64)) return DFGPU_ENODEV;
     if (nbytes) CU(cudaMemcpyAsync(ctx->d_in, frames, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->cur_in = ctx->d_in;
   }
@@ -394,13 +524,12 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
   return DFGPU_OK;
 }
 
+// Queues every kernel of the staged batch on the context's stream and returns: no allocation, no
+// synchronisation, no device->host copy (the record count and everything sized by it stay on the device).
 int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
   if (!ctx || !ctx->staged) return fail(ctx, DFGPU_EINVAL, "dfgpu_run without dfgpu_stage");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  const TableSchema* sch = main_schema(ctx->cur_msg);
-  BatchParams& bp = ctx->bp;
-  memset(&bp, 0, sizeof bp);
   ctx->id_counter_out = id_counter;
   ctx->trace_idx_out = trace_id_index;
   if (id_counter || trace_id_index) {
@@ -411,102 +540,9 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
   }
   CU(cudaEventRecord(ctx->ev0, s));
   ctx->stage_open = ctx->prof_on && ctx->stage_used < dfgpu_ctx::PROF_SLOTS && ctx->cur_msg != DFGPU_MSG_METRICS;
-  ctx->mark(0);
-  CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
-  uint32_t nf = ctx->cur_nframes;
-  bp.in = ctx->cur_in;
-  bp.frames = ctx->cur_frames;
-  bp.nframes = nf;
-  bp.frame_nrec = ctx->d_frame_u32;
-  bp.frame_base = ctx->d_frame_u32 + ctx->frames_cap;
-  bp.frame_chain_err = ctx->d_frame_u32 + 2 * (size_t)ctx->frames_cap;
-  bp.frame_bad = ctx->d_frame_u32 + 3 * (size_t)ctx->frames_cap;
-  bp.dyn = ctx->d_dyn;
-  bp.persist = ctx->d_persist;
-  bp.dict = ctx->cur_dict->view;
-  bp.geo.start = ctx->d_geo_start;
-  bp.geo.end = ctx->d_geo_end;
-  bp.geo.code = ctx->d_geo_code;
-  bp.geo.n = ctx->geo_n;
-  bp.cfg_trace_disabled = ctx->cfg.trace_id_index_disabled;
-  if (ensure_dev(ctx, ctx->d_rec_scratch, ctx->rec_scratch_cap, ctx->cur_nbytes / 4 + 2)) return DFGPU_ENODEV;
-  bp.rec_scratch = ctx->d_rec_scratch;
-  if (nf) {
-    CU(cudaMemsetAsync(bp.frame_bad, 0xff, (size_t)nf * 4, s));
-    launch_frame_count(bp, s);
-    ctx->launches += 2;
-  }
-  ctx->mark(1);
-  // the record count sizes every later grid and the arena: one 4-byte round trip
-  CU(cudaMemcpyAsync(&ctx->h_dyn->stats.nrec, &ctx->d_dyn->stats.nrec, 4, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  uint32_t nrec = ctx->h_dyn->stats.nrec;
-  bp.nrec = nrec;
-  bp.nwarps = (nrec + 31) / 32;
-  if (nrec > ctx->rec_cap) {
-    if (ctx->d_rec_u32) CU(cudaFree(ctx->d_rec_u32));
-    ctx->d_rec_u32 = nullptr;
-    size_t cap = std::max<size_t>(nrec, 4096);
-    cap += cap / 4;
-    CU(cudaMalloc(&ctx->d_rec_u32, cap * 3 * sizeof(uint32_t)));
-    ctx->rec_cap = (uint32_t)cap;
-  }
-  bp.rec_off = ctx->d_rec_u32;
-  bp.rec_len = ctx->d_rec_u32 + ctx->rec_cap;
-  bp.rec_frame = ctx->d_rec_u32 + 2 * (size_t)ctx->rec_cap;
-  if (bp.nwarps > ctx->warp_cap) {
-    if (ctx->d_warp) CU(cudaFree(ctx->d_warp));
-    ctx->d_warp = nullptr;
-    size_t cap = std::max<size_t>(bp.nwarps, 1024);
-    cap += cap / 4;
-    CU(cudaMalloc(&ctx->d_warp, cap * 2 * MAX_SLOTS * sizeof(uint32_t)));
-    ctx->warp_cap = cap;
-  }
-  bp.warp_tot = ctx->d_warp;
-  bp.warp_base = ctx->d_warp + (size_t)MAX_SLOTS * ctx->warp_cap;
-  // the kernels index [slot][nwarps] with stride nwarps (not warp_cap): both halves are
-  // large enough because nslots <= MAX_SLOTS and nwarps <= warp_cap.
-  const bool is_metrics = ctx->cur_msg == DFGPU_MSG_METRICS;
-  bp.native_str = (ctx->cfg.native_strings && ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) ? 1u : 0u;
-  uint64_t fixed = is_metrics ? 0 : plan_fixed(*sch, nrec, bp.fix_off, bp.aux_off, bp.native_str != 0);
-  bp.var_base = fixed;
-  uint64_t want = fixed + 2 * (uint64_t)ctx->cur_nbytes + (uint64_t)nrec * 96 + (1u << 20);
-  if (bp.native_str) want += (uint64_t)nrec * (23 * 16 + 32);  // device-only Positions + length prefixes
-  if (is_metrics) want = metrics_arena_need(nrec, ctx->cur_nbytes);
-  if (want > ctx->arena_cap) {
-    if (ctx->d_arena) CU(cudaFree(ctx->d_arena));
-    ctx->d_arena = nullptr;
-    size_t cap = (size_t)(want + want / 4);
-    CU(cudaMalloc(&ctx->d_arena, cap));
-    ctx->arena_cap = cap;
-  }
-  bp.arena = ctx->d_arena;
-  bp.arena_bytes = ctx->arena_cap;
-  if (!is_metrics) setup_streams(bp, ctx->cur_msg);
-  if (nf && nrec) {
-    launch_frame_fill(bp, s);
-    ctx->launches++;
-  }
-  int rc = 0;
-  if (is_metrics) {
-    rc = metrics_passes(ctx, 0);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev1, s));
-    ctx->ran = true;
-    return DFGPU_OK;
-  }
-  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
-    rc = l7_prepare(ctx, s);
-    if (rc) return rc;
-  }
-  ctx->mark(2);
-  rc = launch_passes(ctx, 0);
+  int rc = run_pipeline(ctx);
   if (rc) return rc;
-  if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
-    rc = l7_flow_tags(ctx, s);
-    if (rc) return rc;
-  }
-  ctx->mark(6);
+  ctx->mark(7);
   if (ctx->stage_open) {
     ctx->stage_used++;
     ctx->stage_open = false;
@@ -526,6 +562,7 @@ int dfgpu_sync(dfgpu_ctx* ctx) {
 }  // extern "C"
 
 static uint8_t* host_acquire(dfgpu_ctx* ctx, size_t bytes) {
+  std::unique_lock<std::mutex> lk(ctx->pool_mu);
   size_t best = (size_t)-1;
   for (size_t i = 0; i < ctx->host_pool.size(); i++)
     if (ctx->host_pool[i].cap >= bytes && (best == (size_t)-1 || ctx->host_pool[i].cap < ctx->host_pool[best].cap)) best = i;
@@ -535,6 +572,7 @@ static uint8_t* host_acquire(dfgpu_ctx* ctx, size_t bytes) {
     ctx->host_pool.erase(ctx->host_pool.begin() + best);
     return p;
   }
+  lk.unlock();
   size_t cap = align_up(bytes + bytes / 8 + 4096, 4096);
   uint8_t* p = nullptr;
   if (cudaHostAlloc(&p, cap + 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
@@ -546,6 +584,7 @@ static void host_release(dfgpu_ctx* ctx, uint8_t* p) {
   HostBuf b;
   b.p = p;
   b.cap = *reinterpret_cast<size_t*>(p);
+  std::lock_guard<std::mutex> lk(ctx->pool_mu);
   ctx->host_pool.push_back(b);
 }
 
@@ -589,13 +628,41 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
   cudaStream_t s = ctx->stream;
   BatchParams& bp = ctx->bp;
   const TableSchema* sch = main_schema(ctx->cur_msg);
-  uint32_t nf = ctx->cur_nframes;
-  if (nf > ctx->h_frames_cap) {
-    if (ctx->h_frame_u32) cudaFreeHost(ctx->h_frame_u32);
-    ctx->h_frame_u32 = nullptr;
-    size_t cap = std::max<uint32_t>(nf, 1024);
-    CU(cudaHostAlloc(&ctx->h_frame_u32, cap * 2 * sizeof(uint32_t), cudaHostAllocDefault));
-    ctx->h_frames_cap = (uint32_t)cap;
+  const uint32_t nf = ctx->cur_nframes;
+  // The first (and, for a batch within the configured capacities, only) wait for the GPU: sizes, offsets,
+  // error flags.  A batch that outgrew a device buffer, or in which a record failed to decode, is re-run.
+  for (int attempt = 0;; attempt++) {
+    CU(cudaMemcpyAsync(ctx->h_dyn, ctx->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, s));
+    if (nf) {
+      CU(cudaMemcpyAsync(ctx->h_frame_u32, bp.frame_chain_err, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync(ctx->h_frame_u32 + ctx->h_frames_cap, bp.frame_bad, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    DynState* d = ctx->h_dyn;
+    const bool repair = d->stats.need_repair && !bp.repair;
+    const bool grow = d->overflow != 0;
+    if (!repair && !grow) break;
+    if (attempt >= 4) return fail(ctx, DFGPU_ENOMEM, "could not size the device buffers for this batch");
+    if (grow) {
+      // the batch exceeds dfgpu_cfg.max_batch_records / the arena planned from it: grow once, re-run all
+      uint32_t rec_cap = ctx->rec_cap;
+      if (d->rec_overflow || d->stats.nrec > rec_cap) rec_cap = d->stats.nrec + d->stats.nrec / 4 + 1024;
+      uint64_t arena = std::max<uint64_t>(std::max(d->dev_end, d->var_end) + (16u << 20), arena_need(rec_cap, ctx->cur_nbytes));
+      if (arena <= ctx->arena_cap) arena = ctx->arena_cap + ctx->arena_cap / 2;
+      int rc = alloc_buffers(ctx, ctx->d_in_cap, rec_cap, (size_t)arena);
+      if (rc) return rc;
+      rc = run_pipeline(ctx);
+      if (rc) return rc;
+    } else {
+      // a record failed to decode: everything behind it in its frame is dropped
+      // (decoder.go:206-209); re-derive rows and sizes with the per-frame cut known.
+      const uint32_t keep_nrec = d->stats.nrec;
+      CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
+      CU(cudaMemcpyAsync(&ctx->d_dyn->stats.nrec, &keep_nrec, 4, cudaMemcpyHostToDevice, s));
+      int rc = launch_passes(ctx, 1);
+      if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev1, s));
   }
   if (ctx->cur_msg == DFGPU_MSG_METRICS) {
     dfgpu_batch* b = new dfgpu_batch();
@@ -607,11 +674,6 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
       dfgpu_batch_release(b);
       return rc;
     }
-    if (nf) {
-      CU(cudaMemcpyAsync(ctx->h_frame_u32, bp.frame_chain_err, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
-      CU(cudaMemcpyAsync(ctx->h_frame_u32 + ctx->h_frames_cap, bp.frame_bad, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
-    }
     b->counters.raw_count = nf;
     for (uint32_t f = 0; f < nf; f++)  // ErrDocCount: one per abandoned frame (unmarshaller.go:236-240)
       if (ctx->h_frame_u32[f] || ctx->h_frame_u32[ctx->h_frames_cap + f] != NO_BAD) b->counters.error_count++;
@@ -622,43 +684,9 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
     *out = b;
     return DFGPU_OK;
   }
-  for (int attempt = 0;; attempt++) {
-    CU(cudaMemcpyAsync(ctx->h_dyn, ctx->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, s));
-    if (nf) {
-      CU(cudaMemcpyAsync(ctx->h_frame_u32, bp.frame_chain_err, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
-      CU(cudaMemcpyAsync(ctx->h_frame_u32 + ctx->h_frames_cap, bp.frame_bad, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
-    }
-    CU(cudaStreamSynchronize(s));
-    DynState* d = ctx->h_dyn;
-    bool repair = d->stats.need_repair && !bp.repair;
-    bool grow = d->overflow != 0;
-    if (!repair && !grow) break;
-    if (attempt >= 3) return fail(ctx, DFGPU_ENOMEM, "could not size the output arena");
-    if (grow) {
-      uint64_t want = (d->dev_end > d->var_end ? d->dev_end : d->var_end) + (1u << 20);
-      CU(cudaFree(ctx->d_arena));
-      ctx->d_arena = nullptr;
-      CU(cudaMalloc(&ctx->d_arena, (size_t)want));
-      ctx->arena_cap = (size_t)want;
-      bp.arena = ctx->d_arena;
-      bp.arena_bytes = ctx->arena_cap;
-    }
-    // a record failed to decode: everything behind it in its frame is dropped
-    // (decoder.go:206-209); re-derive sizes with the per-frame cut known.
-    uint32_t keep_nrec = d->stats.nrec;
-    CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
-    CU(cudaMemcpyAsync(&ctx->d_dyn->stats.nrec, &keep_nrec, 4, cudaMemcpyHostToDevice, s));
-    int rc = launch_passes(ctx, (repair || bp.repair) ? 1 : 0);
-    if (rc) return rc;
-    if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
-      rc = l7_flow_tags(ctx, s);
-      if (rc) return rc;
-    }
-    CU(cudaEventRecord(ctx->ev1, s));
-  }
   DynState* d = ctx->h_dyn;
   uint32_t nrows = d->stats.nrows;
-  uint64_t total = d->var_end ? d->var_end : bp.var_base;
+  uint64_t total = d->var_end ? d->var_end : d->var_base;
   dfgpu_batch* b = new dfgpu_batch();
   b->ctx = ctx;
   b->msg_type = ctx->cur_msg;
@@ -672,18 +700,18 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
   // D2H.  Common case (every record produced a row): the fixed region was planned for exactly these
   // rows, so the whole used arena is dense -> ONE copy instead of ~150 small ones.  Otherwise: per
   // column only the rows that exist; streams only their used bytes.
-  const bool dense = nrows == bp.nrec && nrows > 0;
+  const bool dense = nrows > 0 && (nrows == d->stats.nrec || (d->plan_valid && nrows == d->plan_rows));
   if (dense) CU(cudaMemcpyAsync(hb, bp.arena, (size_t)total, cudaMemcpyDeviceToHost, s));
   for (int c = 0; c < sch->ncols && !dense; c++) {
     const ColSpec& cs = sch->cols[c];
     size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
-    if (es && nrows) CU(cudaMemcpyAsync(hb + bp.fix_off[c], bp.arena + bp.fix_off[c], (size_t)nrows * es, cudaMemcpyDeviceToHost, s));
+    if (es && nrows) CU(cudaMemcpyAsync(hb + d->fix_off[c], bp.arena + d->fix_off[c], (size_t)nrows * es, cudaMemcpyDeviceToHost, s));
     size_t ab = aux_bytes_per_row(cs.ch_type);
     if (bp.native_str && (cs.ch_type == DFGPU_CH_STR || cs.ch_type == DFGPU_CH_LC_STR_ROWS)) ab = 0;  // no Positions
-    if (ab && nrows) CU(cudaMemcpyAsync(hb + bp.aux_off[c], bp.arena + bp.aux_off[c], (size_t)nrows * ab, cudaMemcpyDeviceToHost, s));
+    if (ab && nrows) CU(cudaMemcpyAsync(hb + d->aux_off[c], bp.arena + d->aux_off[c], (size_t)nrows * ab, cudaMemcpyDeviceToHost, s));
   }
-  if (!dense && total > bp.var_base)
-    CU(cudaMemcpyAsync(hb + bp.var_base, bp.arena + bp.var_base, (size_t)(total - bp.var_base), cudaMemcpyDeviceToHost, s));
+  if (!dense && total > d->var_base)
+    CU(cudaMemcpyAsync(hb + d->var_base, bp.arena + d->var_base, (size_t)(total - d->var_base), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(ctx->h_persist, ctx->d_persist, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (ctx->id_counter_out) *ctx->id_counter_out = ctx->h_persist->id_counter;
@@ -710,7 +738,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
       case DFGPU_CH_STR:
       case DFGPU_CH_LC_STR_ROWS: {
         int v = stream_of_col++;
-        col.pos = bp.native_str ? nullptr : (const dfgpu_pos*)(hb + bp.aux_off[c]);
+        col.pos = bp.native_str ? nullptr : (const dfgpu_pos*)(hb + d->aux_off[c]);
         col.data = hb + d->var_buf_off[v];
         col.data_bytes = d->stats.var_bytes[v];
         break;
@@ -718,7 +746,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
       case DFGPU_CH_ARR_UINT16:
       case DFGPU_CH_ARR_FLOAT64: {
         int v = stream_of_col++;
-        col.arr_offsets = (const uint64_t*)(hb + bp.aux_off[c]);
+        col.arr_offsets = (const uint64_t*)(hb + d->aux_off[c]);
         col.data = hb + d->var_buf_off[v];
         col.data_bytes = d->stats.var_bytes[v];
         col.nelems = d->stats.var_total[v];
@@ -727,7 +755,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
       case DFGPU_CH_ARR_STR:
       case DFGPU_CH_ARR_LC_STR: {
         int v = stream_of_col++;
-        col.arr_offsets = (const uint64_t*)(hb + bp.aux_off[c]);
+        col.arr_offsets = (const uint64_t*)(hb + d->aux_off[c]);
         col.pos = bp.native_str ? nullptr : (const dfgpu_pos*)(hb + d->var_pos_off[v]);
         col.data = hb + d->var_buf_off[v];
         col.data_bytes = d->stats.var_bytes[v];
@@ -735,11 +763,13 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
         break;
       }
       case DFGPU_CH_LC_STR: {
-        col.data = hb + bp.fix_off[c];
+        col.data = hb + d->fix_off[c];
         col.data_bytes = (uint64_t)nrows * cs.elem_size;
         if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) {
-          if (c == L4C_PROVINCE_0) lc_dictionary(b, d->stats.lc_first[LC_PROVINCE_0], ctx->geo_names, col);
-          else if (c == L4C_PROVINCE_1) lc_dictionary(b, d->stats.lc_first[LC_PROVINCE_1], ctx->geo_names, col);
+          static const std::vector<std::string> no_names;
+          const std::vector<std::string>& geo_names = ctx->cur_geo ? ctx->cur_geo->names : no_names;
+          if (c == L4C_PROVINCE_0) lc_dictionary(b, d->stats.lc_first[LC_PROVINCE_0], geo_names, col);
+          else if (c == L4C_PROVINCE_1) lc_dictionary(b, d->stats.lc_first[LC_PROVINCE_1], geo_names, col);
           else {
             static const std::vector<std::string> tap(kTapSideNames, kTapSideNames + 18);
             lc_dictionary(b, d->stats.lc_first[LC_TAPSIDE], tap, col);
@@ -751,9 +781,9 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
         break;
       }
       default: {
-        col.data = hb + bp.fix_off[c];
+        col.data = hb + d->fix_off[c];
         col.data_bytes = (uint64_t)nrows * cs.elem_size;
-        if (aux_bytes_per_row(cs.ch_type) == 1) col.nulls = hb + bp.aux_off[c];
+        if (aux_bytes_per_row(cs.ch_type) == 1) col.nulls = hb + d->aux_off[c];
         break;
       }
     }
@@ -838,14 +868,14 @@ int dfgpu_profile_enable(dfgpu_ctx* ctx, int on) {
   return DFGPU_OK;
 }
 // Sums and resets the stage times of the profiled runs (milliseconds):
-// framing, prepare (+ the nrec round trip), SIZE pass, scans, EMIT pass, flow_tag stage.
+// framing, prepare, decode pass, scans, pack pass, SmartEncoding, flow_tag stage.
 int dfgpu_profile_stages(dfgpu_ctx* ctx, double* ms6, uint64_t* runs) {
   if (!ctx || !ms6) return DFGPU_EINVAL;
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
-  for (int k = 0; k < 6; k++) ms6[k] = 0;
+  for (int k = 0; k < 7; k++) ms6[k] = 0;
   for (int r = 0; r < ctx->stage_used; r++)
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 7; k++) {
       float t = 0;
       CU(cudaEventElapsedTime(&t, ctx->stage_ev[(size_t)r * dfgpu_ctx::STAGE_MARKS + k],
                               ctx->stage_ev[(size_t)r * dfgpu_ctx::STAGE_MARKS + k + 1]));

@@ -9,6 +9,17 @@
 
 using namespace dfgpu;
 
+struct GeoTables {
+  uint32_t* d_start = nullptr;  // one allocation: start[n] | end[n] | code[n]
+  uint32_t* d_end = nullptr;
+  uint8_t* d_code = nullptr;
+  uint32_t n = 0;
+  std::vector<std::string> names;  // by canonical code
+  ~GeoTables() {
+    if (d_start) cudaFree(d_start);
+  }
+};
+
 struct HostBuf {
   uint8_t* p = nullptr;
   size_t cap = 0;
@@ -21,12 +32,10 @@ struct dfgpu_ctx {
   std::string err;
   std::mutex dict_mu;
   std::map<uint16_t, std::shared_ptr<DeviceDict>> dicts;
-  // geo
-  uint32_t* d_geo_start = nullptr;
-  uint32_t* d_geo_end = nullptr;
-  uint8_t* d_geo_code = nullptr;
-  uint32_t geo_n = 0;
-  std::vector<std::string> geo_names;  // by canonical code
+  // geo: an immutable snapshot, swapped under dict_mu (dfgpu_geo_load may run on another thread);
+  // a batch keeps the snapshot it was staged with alive until its fetch is over
+  std::shared_ptr<GeoTables> geo;
+  std::shared_ptr<GeoTables> cur_geo;
 
   // device work buffers
   uint8_t* d_in = nullptr;
@@ -49,6 +58,7 @@ struct dfgpu_ctx {
   PersistState* h_persist = nullptr;
   uint32_t* h_frame_u32 = nullptr;
   uint32_t h_frames_cap = 0;
+  std::mutex pool_mu;  // batches may be released from a writer thread while the decoder thread fetches
   std::vector<HostBuf> host_pool;
 
   // current batch
@@ -72,8 +82,8 @@ struct dfgpu_ctx {
   int prof_used = 0;
   cudaEvent_t prof_ev[2 * PROF_SLOTS] = {nullptr};
   uint64_t prof_bytes[PROF_SLOTS] = {0};
-  // stage marks of every dfgpu_run while profiling: start, framing, prepare, SIZE pass, scans, EMIT, flow_tag
-  static constexpr int STAGE_MARKS = 7;
+  // stage marks of every dfgpu_run while profiling: start, framing, prepare, decode, scans, pack, SmartEncoding, flow_tag
+  static constexpr int STAGE_MARKS = 8;
   std::vector<cudaEvent_t> stage_ev;  // [PROF_SLOTS][STAGE_MARKS], created on enable
   int stage_used = 0;
   bool stage_open = false;

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(32) k_frame_walk(const BatchParams p) {
 // publish (offset, length, frame)
 __global__ void k_frame_fill(const BatchParams p) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= p.nrec) return;
+  if (r >= batch_nrec(p)) return;
   uint32_t lo = 0, hi = p.nframes;  // last frame with frame_base <= r
   while (hi - lo > 1) {
     uint32_t mid = (lo + hi) >> 1;
@@ -160,6 +160,31 @@ __global__ void k_frame_scan(const BatchParams p) {
   if (threadIdx.x == 0) p.dyn->stats.nrec = carry;
 }
 
+// Everything the record count decides, planned on the device right after framing (the host never
+// waits for it): does the record index hold the batch, how many warps of records there are, and where
+// every fixed-width column of the main table lives inside the arena (dense, for exactly nrec rows).
+__global__ void k_prepare(const BatchParams p) {
+  DynState* d = p.dyn;
+  if (threadIdx.x != 0) return;
+  uint32_t nrec = d->stats.nrec;
+  if (nrec > p.rec_cap) {
+    d->rec_overflow = 1;
+    d->overflow = 1;
+    nrec = 0;
+  }
+  d->nwarps = (nrec + 31) / 32;
+  const uint32_t rows = d->plan_valid ? d->plan_rows : nrec;
+  uint64_t cur = 0;
+  for (uint32_t c = 0; c < p.ncols; c++) {
+    d->fix_off[c] = cur;
+    cur += ((uint64_t)rows * p.col_es[c] + 255) & ~255ull;
+    d->aux_off[c] = cur;
+    cur += ((uint64_t)rows * p.col_aux[c] + 255) & ~255ull;
+  }
+  d->var_base = cur;
+  if (cur > p.arena_bytes) d->overflow = 1;
+}
+
 // ---- slot scan: one CTA per slot, exclusive scan over the warps ----------------------
 // Each thread owns a contiguous chunk of the slot's per-warp totals: chunk sums, ONE block-wide scan of
 // the 1024 chunk sums (shuffles), then the chunk is written out.  (The first version scanned 1024
@@ -167,9 +192,9 @@ __global__ void k_frame_scan(const BatchParams p) {
 // barrier latency on an otherwise idle GPU.)
 __global__ void __launch_bounds__(1024) k_slot_scan(const BatchParams p, uint64_t* totals_out) {
   __shared__ uint64_t wsum[32];
-  const uint32_t slot = blockIdx.x, n = p.nwarps;
-  const uint32_t* tot = p.warp_tot + (size_t)slot * n;
-  uint32_t* out = p.warp_base + (size_t)slot * n;
+  const uint32_t slot = blockIdx.x, n = p.dyn->nwarps;
+  const uint32_t* tot = p.warp_tot + (size_t)slot * p.warp_cap;
+  uint32_t* out = p.warp_base + (size_t)slot * p.warp_cap;
   const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
   const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
   uint64_t sum = 0;
@@ -211,7 +236,7 @@ __global__ void k_finish(const BatchParams p) {
   if (threadIdx.x == 0) {
     uint64_t nrows = slot_total[0];
     d->stats.nrows = (uint32_t)nrows;
-    uint64_t cur = p.var_base;
+    uint64_t cur = d->var_base;
     for (uint32_t v = 0; v < p.nstreams; v++) {
       StreamSpec s = p.streams[v];
       uint64_t elems = s.slot_elems >= 0 ? slot_total[s.slot_elems] : nrows;
@@ -235,7 +260,7 @@ __global__ void k_finish(const BatchParams p) {
       }
     }
     d->dev_end = cur;
-    d->overflow = cur > p.arena_bytes ? 1 : 0;
+    if (cur > p.arena_bytes) d->overflow = 1;
   }
   // rank of each LowCardinality code by first appearance (ch-go builds the
   // dictionary in Append order)
@@ -264,12 +289,12 @@ void launch_frame_count(const BatchParams& p, cudaStream_t s) {
   k_frame_walk<<<p.nframes, 32, 0, s>>>(p);
   k_frame_scan<<<1, 1024, 0, s>>>(p);
 }
+void launch_prepare(const BatchParams& p, cudaStream_t s) { k_prepare<<<1, 32, 0, s>>>(p); }
 void launch_frame_fill(const BatchParams& p, cudaStream_t s) {
-  if (!p.nframes || !p.nrec) return;
-  k_frame_fill<<<(p.nrec + 255) / 256, 256, 0, s>>>(p);
+  if (!p.nframes) return;
+  k_frame_fill<<<rec_grid(p), 256, 0, s>>>(p);
 }
 void launch_slot_scan(const BatchParams& p, cudaStream_t s) {
-  if (!p.nrec) return;
   // totals per SLOT land in stats.var_total (scratch until k_finish rewrites it per stream)
   k_slot_scan<<<p.nslots, 1024, 0, s>>>(p, p.dyn->stats.var_total);
 }

@@ -90,7 +90,9 @@ struct BatchStats {
   uint64_t ft_off[32];          // flow_tag table column offsets inside the ft arena
   uint64_t ft_end;              // bytes used in the ft arena
   uint32_t ft_overflow;         // ft arena too small: host grows it and re-runs the writer
-  uint32_t ft_full;             // the device tag set is full (capacity)
+  uint32_t ft_count;            // entries held by the flow_tag set (TagSetState::count): the host schedules rebuilds
+  uint32_t ft_unrecorded;       // cumulative: emissions of keys the saturated set could not store
+  uint32_t ft_evicted;          // cumulative: live entries dropped oldest-first by rebuilds
   uint64_t last_trace_id_index;
   uint32_t lc_first[8][256];    // first record index each LowCardinality code appears at
 };

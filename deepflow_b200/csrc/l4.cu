@@ -20,7 +20,7 @@ namespace {
 
 template <class T>
 __device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, T v) {
-  reinterpret_cast<T*>(p.arena + p.fix_off[col])[row] = v;
+  reinterpret_cast<T*>(p.arena + p.dyn->fix_off[col])[row] = v;
 }
 __device__ __forceinline__ void st_ip6(const BatchParams& p, int col, uint32_t row, const uint8_t* src,
                                        uint32_t len) {
@@ -29,7 +29,7 @@ __device__ __forceinline__ void st_ip6(const BatchParams& p, int col, uint32_t r
   uint8_t* b = reinterpret_cast<uint8_t*>(w);
   uint32_t n = len > 16 ? 16 : len;
   for (uint32_t i = 0; i < n; i++) b[i] = __ldg(src + i);
-  reinterpret_cast<uint4*>(p.arena + p.fix_off[col])[row] = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint4*>(p.arena + p.dyn->fix_off[col])[row] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 struct EmitSink {
@@ -55,7 +55,7 @@ template <int EMIT>
 __global__ void __launch_bounds__(256) k_l4_pass(const __grid_constant__ BatchParams p) {
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t warp = rec >> 5;
-  const bool in_range = rec < p.nrec;
+  const bool in_range = rec < batch_nrec(p);
   DynState* dyn = p.dyn;
   if (EMIT && (dyn->stats.need_repair && !p.repair)) return;  // sizes are stale: host re-runs
   if (EMIT && dyn->overflow) return;
@@ -99,11 +99,11 @@ __global__ void __launch_bounds__(256) k_l4_pass(const __grid_constant__ BatchPa
 
   if (!EMIT) {
     uint32_t t0 = warp_sum(sz_rows), t1 = warp_sum(sz_agg), t2 = warp_sum(sz_acl), t3 = warp_sum(sz_dom);
-    if ((threadIdx.x & 31) == 0 && warp < p.nwarps) {
-      p.warp_tot[0 * p.nwarps + warp] = t0;
-      p.warp_tot[1 * p.nwarps + warp] = t1;
-      p.warp_tot[2 * p.nwarps + warp] = t2;
-      p.warp_tot[3 * p.nwarps + warp] = t3;
+    if ((threadIdx.x & 31) == 0 && warp < p.dyn->nwarps) {
+      p.warp_tot[(size_t)0 * p.warp_cap + warp] = t0;
+      p.warp_tot[(size_t)1 * p.warp_cap + warp] = t1;
+      p.warp_tot[(size_t)2 * p.warp_cap + warp] = t2;
+      p.warp_tot[(size_t)3 * p.warp_cap + warp] = t3;
     }
     lc_note(dyn->stats.lc_first[LC_PROVINCE_0], prov0, rec, ok);
     lc_note(dyn->stats.lc_first[LC_PROVINCE_1], prov1, rec, ok);
@@ -115,11 +115,11 @@ __global__ void __launch_bounds__(256) k_l4_pass(const __grid_constant__ BatchPa
   uint32_t e_rows = warp_excl_scan(sz_rows), e_agg = warp_excl_scan(sz_agg),
            e_acl = warp_excl_scan(sz_acl), e_dom = warp_excl_scan(sz_dom);
   if (!ok) return;
-  const uint32_t wb = warp < p.nwarps ? warp : 0;
-  const uint32_t row = p.warp_base[0 * p.nwarps + wb] + e_rows;
-  const uint64_t agg_off = (uint64_t)p.warp_base[1 * p.nwarps + wb] + e_agg;
-  const uint64_t acl_off = (uint64_t)p.warp_base[2 * p.nwarps + wb] + e_acl;
-  const uint64_t dom_off = (uint64_t)p.warp_base[3 * p.nwarps + wb] + e_dom;
+  const uint32_t wb = warp < p.dyn->nwarps ? warp : 0;
+  const uint32_t row = p.warp_base[(size_t)0 * p.warp_cap + wb] + e_rows;
+  const uint64_t agg_off = (uint64_t)p.warp_base[(size_t)1 * p.warp_cap + wb] + e_agg;
+  const uint64_t acl_off = (uint64_t)p.warp_base[(size_t)2 * p.warp_cap + wb] + e_acl;
+  const uint64_t dom_off = (uint64_t)p.warp_base[(size_t)3 * p.warp_cap + wb] + e_dom;
   const dfgpu_frame fr = p.frames[frame];
 
   const bool v6 = r.eth_type == 0x86DD;  // :956
@@ -319,12 +319,12 @@ __global__ void __launch_bounds__(256) k_l4_pass(const __grid_constant__ BatchPa
 
   // ---- variable-length columns ---------------------------------------------------------
   // aggregated_flow_ids (ColStr): Pos per row + characters in stream 0
-  dfgpu_pos* agg_pos = reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[L4C_AGGREGATED_FLOW_IDS]);
+  dfgpu_pos* agg_pos = reinterpret_cast<dfgpu_pos*>(p.arena + p.dyn->aux_off[L4C_AGGREGATED_FLOW_IDS]);
   agg_pos[row] = dfgpu_pos{(int64_t)agg_off, (int64_t)(agg_off + sz_agg)};
   // acl_gids (ColArr[uint16]): cumulative END offset per row + values in stream 1
-  reinterpret_cast<uint64_t*>(p.arena + p.aux_off[L4C_ACL_GIDS])[row] = acl_off + sz_acl;
+  reinterpret_cast<uint64_t*>(p.arena + p.dyn->aux_off[L4C_ACL_GIDS])[row] = acl_off + sz_acl;
   // request_domain (ColStr)
-  dfgpu_pos* dom_pos = reinterpret_cast<dfgpu_pos*>(p.arena + p.aux_off[L4C_REQUEST_DOMAIN]);
+  dfgpu_pos* dom_pos = reinterpret_cast<dfgpu_pos*>(p.arena + p.dyn->aux_off[L4C_REQUEST_DOMAIN]);
   dom_pos[row] = dfgpu_pos{(int64_t)dom_off, (int64_t)(dom_off + sz_dom)};
   if (sz_dom) {
     uint8_t* dst = p.arena + dyn->var_buf_off[2] + dom_off;
@@ -343,8 +343,7 @@ __global__ void __launch_bounds__(256) k_l4_pass(const __grid_constant__ BatchPa
 }
 
 void launch_l4_pass(const BatchParams& p, int emit, cudaStream_t s) {
-  if (p.nrec == 0) return;
-  dim3 block(256), grid((p.nrec + 255) / 256);
+  dim3 block(256), grid(rec_grid(p));
   if (emit) k_l4_pass<1><<<grid, block, 0, s>>>(p);
   else k_l4_pass<0><<<grid, block, 0, s>>>(p);
 }

@@ -17,6 +17,7 @@
  *   counters        updateCounter decoder.go:498-525
  */
 #include "l7_dev.h"
+#include "l7_tables_host.h"
 
 namespace dfgpu {
 
@@ -25,14 +26,16 @@ struct L7Host {  // host mirror kept in ctx->ft
   L7Dev* d_dev = nullptr;
   uint8_t* d_blob = nullptr;
   uint32_t* d_off = nullptr;
-  FtEntry* d_ft = nullptr;
+  TagSet set;
+  uint8_t* d_import = nullptr;
+  size_t import_cap = 0;
   uint8_t* d_ft_arena = nullptr;
   size_t ft_arena_cap = 0;
-  uint8_t* d_row_flag = nullptr;
-  size_t row_flag_cap = 0;
-  uint64_t* d_slotbuf = nullptr;
-  uint32_t* d_rec_row = nullptr;
-  size_t slot_cap = 0;
+  // per-record hand-over buffers of the decode kernel (one allocation, carved for rec_cap records)
+  uint8_t* d_rec_buf = nullptr;
+  size_t rec_cap = 0;
+  uint64_t* d_raw_scratch = nullptr;
+  unsigned grid_decode = 0, grid_strings = 0, grid_kg = 0;
   uint32_t epoch = 0;
 };
 
@@ -77,9 +80,7 @@ enum {
 };
 
 // find-or-insert in this context's tag set (tagset.cuh)
-__device__ __forceinline__ FtEntry* ft_upsert(const L7Dev* d, U128 fp, uint32_t* full_flag) {
-  return ts_upsert(d->ft, d->ft_mask, fp, full_flag);
-}
+__device__ __forceinline__ FtEntry* ft_upsert(const L7Dev* d, U128 fp) { return ts_upsert(d->ft, d->ft_mask, fp, d->fts); }
 __device__ __forceinline__ FtEntry* ft_find(const L7Dev* d, U128 fp) { return ts_find(d->ft, d->ft_mask, fp); }
 
 // lru semantics (l7_flow_log.go:693-701): emit when the key is new, or when
@@ -106,8 +107,8 @@ struct RowView {  // one packed l7 row, as the flow_tag stage sees it
 
 __device__ __forceinline__ void load_row(const BatchParams& p, uint32_t row, RowView& v) {
   const DynState* dyn = p.dyn;
-  auto fix = [&](int col) { return p.arena + p.fix_off[col]; };
-  auto aux = [&](int col) { return p.arena + p.aux_off[col]; };
+  auto fix = [&](int col) { return p.arena + dyn->fix_off[col]; };
+  auto aux = [&](int col) { return p.arena + dyn->aux_off[col]; };
   int64_t end_us = reinterpret_cast<const int64_t*>(fix(L7C_END_TIME))[row];
   v.time = (uint32_t)(end_us / 1000000);
   v.time_as = reinterpret_cast<const uint32_t*>(fix(L7C_TIME))[row];
@@ -193,12 +194,12 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
   if ((dyn->stats.need_repair && !p.repair) || dyn->overflow) return;
   if (PHASE == 3 && dyn->stats.ft_overflow) return;
   const uint32_t nrows = dyn->stats.nrows;
-  const uint32_t nwarps = p.nwarps;
+  const uint32_t nwarps = dyn->nwarps;
+  const size_t wstride = p.warp_cap;
   // PHASE 0 notes per row whether ANY of its keys is new/expired; in steady state (a
   // saturated tag set) almost no row is, and phases 1-3 skip the row without hashing
   bool active = row < nrows;
   if (PHASE != 0 && active) active = d->row_flag[row] != 0;
-  bool any_candidate = false;
   uint32_t c_fv = 0, b_fvn = 0, b_fvv = 0, c_f = 0, b_fn = 0, c_as = 0, b_as = 0;
 
   // PHASE 3 output cursors
@@ -227,16 +228,20 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
         TsPeek k0, k1;
         ts_peek(d->ft, d->ft_mask, f0, k0);
         if (ns > 1) ts_peek(d->ft, d->ft_mask, f1, k1);
+        // a key the saturated set cannot hold (upsert == nullptr) is emitted by every row that carries
+        // it: duplicates are idempotent in ClickHouse (flow_tag.go:153-160), dropping the batch is not
         if (!ts_peek_fresh(k0, f0, v.time, timeout)) {
-          FtEntry* e = ft_upsert(d, f0, &dyn->stats.ft_full);
-          if (e && ft_candidate(e, v.time, timeout)) {
+          FtEntry* e = ft_upsert(d, f0);
+          if (!e) any = true;
+          else if (ft_candidate(e, v.time, timeout)) {
             atomicMax(&e->first_pos, pos_key(d, row, 0, metric, i));
             any = true;
           }
         }
         if (ns > 1 && !ts_peek_fresh(k1, f1, v.time, timeout)) {
-          FtEntry* e = ft_upsert(d, f1, &dyn->stats.ft_full);
-          if (e && ft_candidate(e, v.time, timeout)) {
+          FtEntry* e = ft_upsert(d, f1);
+          if (!e) any = true;
+          else if (ft_candidate(e, v.time, timeout)) {
             atomicMax(&e->first_pos, pos_key(d, row, 1, metric, i));
             any = true;
           }
@@ -260,14 +265,20 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
         TsPeek k;
         ts_peek(d->ft, d->ft_mask, fpa, k);
         if (!ts_peek_fresh(k, fpa, v.time_as, timeout)) {
-          FtEntry* e = ft_upsert(d, fpa, &dyn->stats.ft_full);
-          if (e && ft_candidate(e, v.time_as, timeout)) {
+          FtEntry* e = ft_upsert(d, fpa);
+          if (!e) any = true;
+          else if (ft_candidate(e, v.time_as, timeout)) {
             atomicMax(&e->first_pos, pos_key(d, row, 0, 0, 0));
             any = true;
           }
         }
       }
       d->row_flag[row] = any ? 1 : 0;
+    }
+    {  // newest lru time of the batch: the clock the rebuild measures expiry against
+      uint32_t tmax = row < nrows ? (v.time > v.time_as ? v.time : v.time_as) : 0u;
+      tmax = __reduce_max_sync(0xffffffffu, tmax);
+      if (lane == 0 && tmax) atomicMax(&d->fts->now, tmax);
     }
     return;
   }
@@ -284,13 +295,13 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
       uint32_t e_f = warp_excl_scan(c_f), e_fn = warp_excl_scan(b_fn), e_as = warp_excl_scan(c_as),
                e_asb = warp_excl_scan(b_as);
       const uint32_t wb = warp < nwarps ? warp : 0;
-      o_fv = (uint64_t)p.warp_base[(size_t)FT_FV_ROWS * nwarps + wb] + e_fv;
-      o_fvn = (uint64_t)p.warp_base[(size_t)FT_FV_NAME_B * nwarps + wb] + e_fvn;
-      o_fvv = (uint64_t)p.warp_base[(size_t)FT_FV_VAL_B * nwarps + wb] + e_fvv;
-      o_f = (uint64_t)p.warp_base[(size_t)FT_F_ROWS * nwarps + wb] + e_f;
-      o_fn = (uint64_t)p.warp_base[(size_t)FT_F_NAME_B * nwarps + wb] + e_fn;
-      o_as = (uint64_t)p.warp_base[(size_t)FT_AS_ROWS * nwarps + wb] + e_as;
-      o_asb = (uint64_t)p.warp_base[(size_t)FT_AS_B * nwarps + wb] + e_asb;
+      o_fv = (uint64_t)p.warp_base[(size_t)FT_FV_ROWS * wstride + wb] + e_fv;
+      o_fvn = (uint64_t)p.warp_base[(size_t)FT_FV_NAME_B * wstride + wb] + e_fvn;
+      o_fvv = (uint64_t)p.warp_base[(size_t)FT_FV_VAL_B * wstride + wb] + e_fvv;
+      o_f = (uint64_t)p.warp_base[(size_t)FT_F_ROWS * wstride + wb] + e_f;
+      o_fn = (uint64_t)p.warp_base[(size_t)FT_F_NAME_B * wstride + wb] + e_fn;
+      o_as = (uint64_t)p.warp_base[(size_t)FT_AS_ROWS * wstride + wb] + e_as;
+      o_asb = (uint64_t)p.warp_base[(size_t)FT_AS_B * wstride + wb] + e_asb;
     }
     if (!active) continue;
     if (walk == 0) load_row(p, row, v);
@@ -315,17 +326,10 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
         }
         U128 fpv = key_fp(d, KIND_FIELD_VALUE, hn, hv, v.vpc[side], v.pod_ns[side], 0, v.team);
         unsigned long long pk = pos_key(d, row, side, 0, i);
-        if (PHASE == 0) {
-          FtEntry* e = ft_upsert(d, fpv, &dyn->stats.ft_full);
-          if (e && ft_candidate(e, v.time, timeout)) {
-            atomicMax(&e->first_pos, pk);
-            any_candidate = true;
-          }
-          continue;
-        }
         FtEntry* e = ft_find(d, fpv);
-        if (!e || e->first_pos != pk) continue;  // not the emitting occurrence
-        if (PHASE == 1) {
+        if (e && e->first_pos != pk) continue;  // not the emitting occurrence (no entry: saturated set, emit)
+        if (PHASE == 1 && !e) atomicAdd(&d->fts->unrecorded, 1u);
+        if (PHASE == 1 && e) {
           e->time = v.time;   // lru Add(key, time)
           e->state = 1;
         }
@@ -356,13 +360,14 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
         if (i >= n_names) continue;
         U128 fpf = key_fp(d, KIND_FIELD, hn, StrHash{0, 0}, v.vpc[side], v.pod_ns[side], 0, v.team);
         if (PHASE == 1) {
-          FtEntry* ef = ft_upsert(d, fpf, &dyn->stats.ft_full);
+          FtEntry* ef = ft_upsert(d, fpf);
           if (ef && ft_candidate(ef, v.time, timeout)) atomicMax(&ef->first_pos, pk);
           continue;
         }
         FtEntry* ef = ft_find(d, fpf);
-        if (!ef || ef->first_pos != pk) continue;
-        if (PHASE == 2) {
+        if (ef && ef->first_pos != pk) continue;
+        if (PHASE == 2 && !ef) atomicAdd(&d->fts->unrecorded, 1u);
+        if (PHASE == 2 && ef) {
           ef->time = v.time;
           ef->state = 1;
         }
@@ -392,18 +397,11 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
         SRef name{v.mn_buf + q.start, (uint32_t)(q.end - q.start)};
         U128 fpf = key_fp(d, KIND_FIELD, str_hash(name.p, name.n), StrHash{0, 0}, v.vpc[side], v.pod_ns[side], 1, v.team);
         unsigned long long pk = pos_key(d, row, side, 1, i);
-        if (PHASE == 0) {  // independent of the value keys: probe right away
-          FtEntry* ef = ft_upsert(d, fpf, &dyn->stats.ft_full);
-          if (ef && ft_candidate(ef, v.time, timeout)) {
-            atomicMax(&ef->first_pos, pk);
-            any_candidate = true;
-          }
-          continue;
-        }
         if (PHASE == 1) continue;
         FtEntry* ef = ft_find(d, fpf);
-        if (!ef || ef->first_pos != pk) continue;
-        if (PHASE == 2) {
+        if (ef && ef->first_pos != pk) continue;
+        if (PHASE == 2 && !ef) atomicAdd(&d->fts->unrecorded, 1u);
+        if (PHASE == 2 && ef) {
           ef->time = v.time;
           ef->state = 1;
         }
@@ -431,16 +429,11 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
     if (v.app_service.n) {
       U128 fpa = key_fp(d, KIND_APP_SERVICE, str_hash(v.app_service.p, v.app_service.n), StrHash{0, 0}, 0, 0, 0, v.team);
       unsigned long long pk = pos_key(d, row, 0, 0, 0);
-      if (PHASE == 0) {
-        FtEntry* e = ft_upsert(d, fpa, &dyn->stats.ft_full);
-        if (e && ft_candidate(e, v.time_as, timeout)) {
-          atomicMax(&e->first_pos, pk);
-          any_candidate = true;
-        }
-      } else {
+      {
         FtEntry* e = ft_find(d, fpa);
-        if (e && e->first_pos == pk) {
-          if (PHASE == 1) {
+        if (!e || e->first_pos == pk) {
+          if (PHASE == 1 && !e) atomicAdd(&d->fts->unrecorded, 1u);
+          if (PHASE == 1 && e) {
             e->time = v.time_as;
             e->state = 1;
           }
@@ -464,7 +457,6 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
       }
     }
   }
-  if (PHASE == 0 && row < nrows) d->row_flag[row] = any_candidate ? 1 : 0;
   if (PHASE == 1 || PHASE == 2) {
     // per-warp totals of the rows/bytes decided in this phase
     uint32_t vals[FT_SLOTS] = {c_fv, b_fvn, b_fvv, c_f, b_fn, c_as, b_as};
@@ -474,13 +466,21 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
       bool mine = (s >= lo && s < hi) || (PHASE == 1 && s >= FT_AS_ROWS);
       if (!mine) continue;
       uint32_t t = warp_sum(vals[s]);
-      if (lane == 0 && warp < nwarps) p.warp_tot[(size_t)s * nwarps + warp] = t;
+      if (lane == 0 && warp < nwarps) p.warp_tot[(size_t)s * wstride + warp] = t;
     }
   }
 }
 
 __global__ void k_l7_ft_clear_pos(FtEntry* t, uint32_t mask) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= mask; i += gridDim.x * blockDim.x) t[i].first_pos = 0;
+}
+
+// the tag set's bookkeeping, for the host (fetch reads DynState)
+__global__ void k_l7_ft_stats(const BatchParams p) {
+  const L7Dev* d = reinterpret_cast<const L7Dev*>(p.ext);
+  p.dyn->stats.ft_count = d->fts->count;
+  p.dyn->stats.ft_unrecorded = d->fts->unrecorded;
+  p.dyn->stats.ft_evicted = d->fts->evicted;
 }
 
 // placement of the three flow_tag tables inside the ft arena
@@ -515,79 +515,65 @@ __global__ void k_l7_ft_layout(const BatchParams p) {
 static int l7_ensure_state(dfgpu_ctx* ctx) {
   if (ctx->ft) return 0;
   L7Host* h = new L7Host();
-  // ---- constant strings ----
-  std::vector<std::string> cs(CS_FIXED_COUNT);
-  cs[CS_ATTR_UA] = "http_user_agent";
-  cs[CS_ATTR_REFERER] = "http_referer";
-  cs[CS_ATTR_RPC] = "rpc_service";
-  cs[CS_FT_APP_SERVICE] = "app_service";
-  cs[CS_FT_ENDPOINT] = "endpoint";
-  cs[CS_FT_APP_INSTANCE] = "app_instance";
-  cs[CS_PROTO_NA] = "N/A";
-  cs[CS_PROTO_TLS] = "TLS";
-  cs[CS_DNS_AVAILABLE] = "available for assignment";
-  cs[CS_DNS_PRIVATE] = "Private Use";
-  cs[CS_KAFKA_UNKNOWN] = DFGPU_EXC_KAFKA_UNKNOWN_SERVER_ERROR;
+  // ---- constant strings + lookup tables (l7_tables_host.h) ----
+  std::vector<std::string> cs;
   L7Dev& d = h->dev;
   memset(&d, 0, sizeof d);
+  l7_build_tables(cs, d.tb);
   {
-    std::vector<uint32_t> t = l7_pb_table();
-    memcpy(d.pb_tbl, t.data(), sizeof d.pb_tbl);
+    std::vector<uint32_t> t = l7_tok_table();
+    memcpy(d.tok_tbl, t.data(), sizeof d.tok_tbl);
   }
-  for (int i = 0; i < 256; i++) d.proto_cs[i][0] = d.proto_cs[i][1] = CS_PROTO_NA;
-  struct PN { int id; const char* name; };
-  static const PN protos[] = {  // L7Protocol.String, datatype/flow.go:623-803
-      {20, "HTTP"}, {21, "HTTP2"}, {40, "Dubbo"}, {41, "gRPC"}, {43, "SofaRPC"}, {44, "FastCGI"}, {45, "bRPC"},
-      {46, "Tars"}, {47, "SOME/IP"}, {48, "ISO-8583"}, {49, "TRIPLE"}, {50, "NetSign"}, {60, "MySQL"},
-      {61, "PostgreSQL"}, {62, "Oracle"}, {63, "Dameng"}, {80, "Redis"}, {81, "MongoDB"}, {82, "Memcached"},
-      {100, "Kafka"}, {101, "MQTT"}, {102, "AMQP"}, {103, "OpenWire"}, {104, "NATS"}, {105, "Pulsar"},
-      {106, "ZMTP"}, {107, "RocketMQ"}, {108, "WebSphereMQ"}, {120, "DNS"}, {127, "Custom"}};
-  for (auto& pn : protos) {
-    d.proto_cs[pn.id][0] = (uint16_t)cs.size();
-    cs.push_back(pn.name);
-    d.proto_cs[pn.id][1] = (uint16_t)cs.size();
-    cs.push_back(std::string(pn.name) + "_TLS");
-  }
-  d.proto_cs[121][0] = d.proto_cs[121][1] = CS_PROTO_TLS;
-  auto add_table = [&](const char* const* t, int n) {
-    uint32_t base = (uint32_t)cs.size();
-    for (int i = 0; i < n; i++) cs.push_back(t[i]);
-    return base;
-  };
-  d.cs_http = add_table(dfgpu_exc_http, DFGPU_EXC_HTTP_LEN);
-  d.cs_dns = add_table(dfgpu_exc_dns, DFGPU_EXC_DNS_LEN);
-  d.cs_dubbo = add_table(dfgpu_exc_dubbo, DFGPU_EXC_DUBBO_LEN);
-  d.cs_kafka = add_table(dfgpu_exc_kafka, DFGPU_EXC_KAFKA_LEN);
-  d.cs_mqtt3 = add_table(dfgpu_exc_mqtt_v3, DFGPU_EXC_MQTT_V3_LEN);
-  d.cs_mqtt5 = add_table(dfgpu_exc_mqtt_v5, DFGPU_EXC_MQTT_V5_LEN);
   std::vector<uint8_t> blob;
   std::vector<uint32_t> off;
-  for (auto& s : cs) {
-    off.push_back((uint32_t)blob.size());
-    blob.insert(blob.end(), s.begin(), s.end());
-  }
-  off.push_back((uint32_t)blob.size());
+  l7_layout_strings(cs, blob, off);
   CU(cudaMalloc(&h->d_blob, blob.size() + 16));
   CU(cudaMalloc(&h->d_off, off.size() * 4));
   CU(cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-  d.cs_blob = h->d_blob;
-  d.cs_off = h->d_off;
-  // ---- device tag set: never evicts, sized for 2x the reference's three LRU capacities ----
-  uint64_t want = (uint64_t)ctx->cfg.flow_tag_cache_max_size * 3 * 2;  // three LRUs, load <= 1/2
-  uint32_t n = 1u << 16;
-  while (n < want && n < (1u << 28)) n <<= 1;
-  CU(cudaMalloc(&h->d_ft, (size_t)n * sizeof(FtEntry)));
-  CU(cudaMemset(h->d_ft, 0, (size_t)n * sizeof(FtEntry)));
-  d.ft = h->d_ft;
-  d.ft_mask = n - 1;
+  d.tb.cs_blob = h->d_blob;
+  d.tb.cs_off = h->d_off;
+  // ---- device tag set: the three LRUs of the reference (field_value, field, app_service) in one table,
+  // 2x their combined capacity; rebuilt (expiry + oldest-first eviction) when more than half full ----
+  if (tagset_create(h->set, (uint64_t)ctx->cfg.flow_tag_cache_max_size * 3 * 2, ctx->cfg.flow_tag_cache_flush_timeout))
+    return fail(ctx, DFGPU_ENOMEM, "flow_tag set allocation failed");
   d.ft_timeout = ctx->cfg.flow_tag_cache_flush_timeout;
   h->ft_arena_cap = 16u << 20;
   CU(cudaMalloc(&h->d_ft_arena, h->ft_arena_cap));
   d.ft_arena = h->d_ft_arena;
   d.ft_arena_bytes = h->ft_arena_cap;
   CU(cudaMalloc(&h->d_dev, sizeof(L7Dev)));
+  // persistent grids: one CTA (or a few) per SM, sized once
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  h->grid_decode = (unsigned)sms * 5;
+  h->grid_strings = (unsigned)sms * 6;
+  h->grid_kg = (unsigned)sms * 4;
+  CU(cudaMalloc(&h->d_raw_scratch, (size_t)h->grid_decode * l7_decode_warps_per_cta() * R7_COUNT * 32 * sizeof(uint64_t)));
+  d.raw_scratch = h->d_raw_scratch;
   ctx->ft = h;
+  return 0;
+}
+
+// per-record buffers, carved from one allocation (first L7 batch of the context, or after the record
+// index grew)
+static int l7_ensure_rec_buffers(dfgpu_ctx* ctx, L7Host* h, size_t cap) {
+  if (cap <= h->rec_cap) return 0;
+  if (h->d_rec_buf) CU(cudaFree(h->d_rec_buf));
+  h->d_rec_buf = nullptr;
+  const size_t per_rec = (size_t)L7REF_COUNT * 8 + 8 + (size_t)L7ARR_COUNT * 4 + 4 + (size_t)L7KG_WORDS * 4 + 4 + 1;
+  CU(cudaMalloc(&h->d_rec_buf, per_rec * cap + 4096));
+  uint8_t* q = h->d_rec_buf;
+  L7Dev& d = h->dev;
+  d.refs = reinterpret_cast<uint64_t*>(q); q += (size_t)L7REF_COUNT * 8 * cap;
+  d.thash = reinterpret_cast<uint64_t*>(q); q += 8 * cap;
+  d.arr = reinterpret_cast<uint32_t*>(q); q += (size_t)L7ARR_COUNT * 4 * cap;
+  d.meta = reinterpret_cast<uint32_t*>(q); q += 4 * cap;
+  d.kgin = reinterpret_cast<uint32_t*>(q); q += (size_t)L7KG_WORDS * 4 * cap;
+  d.rec_row = reinterpret_cast<uint32_t*>(q); q += 4 * cap;
+  d.row_flag = q;
+  d.rec_cap = (uint32_t)cap;
+  h->rec_cap = cap;
   return 0;
 }
 
@@ -596,33 +582,18 @@ int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s) {
   int rc = l7_ensure_state(ctx);
   if (rc) return rc;
   L7Host* h = reinterpret_cast<L7Host*>(ctx->ft);
+  rc = l7_ensure_rec_buffers(ctx, h, ctx->bp.rec_cap);
+  if (rc) return rc;
   h->epoch++;
   if ((h->epoch & 0xffff) == 0) {
     // the 16-bit epoch inside first_pos wrapped: forget every stale candidate
-    k_l7_ft_clear_pos<<<1024, 256, 0, s>>>(h->d_ft, h->dev.ft_mask);
+    k_l7_ft_clear_pos<<<1024, 256, 0, s>>>(h->set.cur, h->set.mask);
     h->epoch = 1;
   }
-  if (ctx->bp.nrec > h->row_flag_cap) {
-    if (h->d_row_flag) CU(cudaFree(h->d_row_flag));
-    h->d_row_flag = nullptr;
-    size_t cap = (size_t)ctx->bp.nrec + ctx->bp.nrec / 4 + 4096;
-    CU(cudaMalloc(&h->d_row_flag, cap));
-    h->row_flag_cap = cap;
-  }
-  h->dev.row_flag = h->d_row_flag;
-  if (ctx->bp.nrec > h->slot_cap) {
-    if (h->d_slotbuf) CU(cudaFree(h->d_slotbuf));
-    h->d_slotbuf = nullptr;
-    size_t cap = (size_t)ctx->bp.nrec + ctx->bp.nrec / 8 + 4096;
-    CU(cudaMalloc(&h->d_slotbuf, cap * (S7_COUNT + 3) * sizeof(uint64_t)));  // + 2 presence words + the trace-id hash
-    if (h->d_rec_row) CU(cudaFree(h->d_rec_row));
-    h->d_rec_row = nullptr;
-    CU(cudaMalloc(&h->d_rec_row, cap * sizeof(uint32_t)));
-    h->slot_cap = cap;
-  }
-  h->dev.rec_row = h->d_rec_row;
-  h->dev.slotbuf = h->d_slotbuf;
-  h->dev.slot_stride = (uint32_t)h->slot_cap;
+  tagset_maybe_rebuild(h->set, s, &ctx->launches);  // between batches, asynchronous
+  h->dev.ft = h->set.cur;
+  h->dev.ft_mask = h->set.mask;
+  h->dev.fts = h->set.d_state;
   h->dev.epoch = h->epoch;
   h->dev.org_id = ctx->cur_org;
   h->dev.ft_arena = h->d_ft_arena;
@@ -632,17 +603,23 @@ int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s) {
   return 0;
 }
 
+void l7_grids(dfgpu_ctx* ctx, unsigned* decode, unsigned* strings, unsigned* kg) {
+  L7Host* h = reinterpret_cast<L7Host*>(ctx->ft);
+  *decode = h->grid_decode;
+  *strings = h->grid_strings;
+  *kg = h->grid_kg;
+}
+
 static void launch_ft_writer(dfgpu_ctx* ctx, cudaStream_t s) {
   BatchParams& bp = ctx->bp;
-  if (!bp.nrec) return;
-  k_l7_flow_tag<3><<<(bp.nrec + 255) / 256, 256, 0, s>>>(bp);
+  k_l7_flow_tag<3><<<rec_grid(bp), 256, 0, s>>>(bp);
   ctx->launches++;
 }
 
 int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s) {
   BatchParams& bp = ctx->bp;
-  if (bp.nrec) {
-    dim3 grid((bp.nrec + 255) / 256), block(256);
+  {
+    dim3 grid(rec_grid(bp)), block(256);
     k_l7_flow_tag<0><<<grid, block, 0, s>>>(bp);
     k_l7_flow_tag<1><<<grid, block, 0, s>>>(bp);
     k_l7_flow_tag<2><<<grid, block, 0, s>>>(bp);
@@ -652,8 +629,9 @@ int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s) {
   k_l7_ft_layout<<<1, 1, 0, s>>>(bp);
   ctx->launches++;
   launch_ft_writer(ctx, s);
+  k_l7_ft_stats<<<1, 1, 0, s>>>(bp);
   launch_commit(bp, 1, s);
-  ctx->launches++;
+  ctx->launches += 2;
   CU(cudaGetLastError());
   return 0;
 }
@@ -698,8 +676,9 @@ int l7_fetch_tables(dfgpu_ctx* ctx, dfgpu_batch* b) {
   L7Host* h = reinterpret_cast<L7Host*>(ctx->ft);
   cudaStream_t s = ctx->stream;
   DynState* d = ctx->h_dyn;
-  if (d->stats.ft_full)
-    return fail(ctx, DFGPU_ENOMEM, "flow_tag device set is full (raise flow_tag_cache_max_size)");
+  h->set.count_seen = d->stats.ft_count;
+  b->counters.flow_tag_unrecorded = d->stats.ft_unrecorded;
+  b->counters.flow_tag_evicted = d->stats.ft_evicted;
   if (d->stats.ft_overflow) {
     // grow the ft arena and re-run only the writer: the emit decisions are already
     // recorded in the tag set and do not change
@@ -800,11 +779,11 @@ int l7_fetch_tables(dfgpu_ctx* ctx, dfgpu_batch* b) {
 
 // ---- multi-GPU tag merge: keys another rank emitted become "seen" here too -----------------------
 __global__ void k_l7_ft_import(FtEntry* tbl, uint32_t mask, const U128* fps, const uint32_t* times, uint32_t n,
-                               uint32_t* full) {
+                               TagSetState* st) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  FtEntry* e = ts_upsert(tbl, mask, fps[i], full);
-  if (!e) return;
+  FtEntry* e = ts_upsert(tbl, mask, fps[i], st);
+  if (!e) return;  // saturated: this rank may emit the key once more (idempotent)
   // the same key may arrive from several ranks: keep the newest emission time
   atomicMax(&e->time, times[i]);
   e->state = 1;
@@ -816,25 +795,22 @@ int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, u
   if (rc) return rc;
   L7Host* h = reinterpret_cast<L7Host*>(ctx->ft);
   cudaStream_t s = ctx->stream;
-  U128* d_fps = nullptr;
-  uint32_t* d_times = nullptr;
-  uint32_t* d_full = nullptr;
-  CU(cudaMalloc(&d_fps, n * 16 + n * 4 + 16));
-  d_times = reinterpret_cast<uint32_t*>(d_fps + n);
-  d_full = d_times + n;
-  cudaError_t e = cudaMemcpyAsync(d_fps, fps, n * 16, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_times, times, n * 4, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_full, 0, 4, s);
-  uint32_t full = 0;
-  if (e == cudaSuccess) {
-    k_l7_ft_import<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->d_ft, h->dev.ft_mask, d_fps, d_times, (uint32_t)n, d_full);
-    ctx->launches++;
-    e = cudaMemcpyAsync(&full, d_full, 4, cudaMemcpyDeviceToHost, s);
+  // the staging buffer of the merge: grown only when a step brings more keys than any step before
+  if (n > h->import_cap) {
+    if (h->d_import) CU(cudaFree(h->d_import));
+    h->d_import = nullptr;
+    const size_t cap = (size_t)n + n / 2 + 4096;
+    CU(cudaMalloc(&h->d_import, cap * 20 + 16));
+    h->import_cap = cap;
   }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(d_fps);
-  if (e != cudaSuccess) return fail(ctx, DFGPU_ENODEV, "tag import failed: %s", cudaGetErrorString(e));
-  if (full) return fail(ctx, DFGPU_ENOMEM, "flow_tag device set is full (raise flow_tag_cache_max_size)");
+  U128* d_fps = reinterpret_cast<U128*>(h->d_import);
+  uint32_t* d_times = reinterpret_cast<uint32_t*>(d_fps + h->import_cap);
+  CU(cudaMemcpyAsync(d_fps, fps, n * 16, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_times, times, n * 4, cudaMemcpyHostToDevice, s));
+  k_l7_ft_import<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->set.cur, h->set.mask, d_fps, d_times, (uint32_t)n, h->set.d_state);
+  ctx->launches++;
+  CU(cudaStreamSynchronize(s));  // the caller's arrays may go away
+  h->set.count_seen += (uint32_t)n;  // upper bound until the next fetch
   return 0;
 }
 
@@ -846,11 +822,11 @@ extern "C" void dfgpu_l7_free_state(dfgpu_ctx* ctx) {
   L7Host* h = reinterpret_cast<L7Host*>(ctx->ft);
   cudaFree(h->d_blob);
   cudaFree(h->d_off);
-  cudaFree(h->d_ft);
+  tagset_destroy(h->set);
   cudaFree(h->d_ft_arena);
-  cudaFree(h->d_row_flag);
-  cudaFree(h->d_slotbuf);
-  cudaFree(h->d_rec_row);
+  cudaFree(h->d_rec_buf);
+  cudaFree(h->d_raw_scratch);
+  cudaFree(h->d_import);
   cudaFree(h->d_dev);
   delete h;
   ctx->ft = nullptr;

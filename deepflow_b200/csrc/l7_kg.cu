@@ -17,22 +17,9 @@
 namespace dfgpu {
 
 namespace {
-struct Slots {  // one record's column of the slot-major buffer (see SlotsG in l7_pass.cu)
-  const uint64_t* p;
-  size_t stride;
-  uint64_t m0, m1;
-  __device__ __forceinline__ Slots(const uint64_t* col, size_t st, bool valid) : p(col), stride(st) {
-    m0 = valid ? __ldg(p + (size_t)S7_COUNT * stride) : 0ull;
-    m1 = valid ? __ldg(p + (size_t)(S7_COUNT + 1) * stride) : 0ull;
-  }
-  __device__ __forceinline__ uint64_t operator[](int i) const {
-    const uint64_t m = i < 64 ? m0 >> i : m1 >> (i - 64);
-    return (m & 1) ? __ldg(p + (size_t)i * stride) : 0ull;
-  }
-};
 template <class T>
 __device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, T v) {
-  reinterpret_cast<T*>(p.arena + p.fix_off[col])[row] = v;
+  reinterpret_cast<T*>(p.arena + p.dyn->fix_off[col])[row] = v;
 }
 }  // namespace
 
@@ -40,30 +27,35 @@ __device__ __forceinline__ void st(const BatchParams& p, int col, uint32_t row, 
 #define L7_KG_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_constant__ BatchParams p) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t rec = t >> 1;
-  const int s = (int)(t & 1);
   const DynState* dyn = p.dyn;
   const L7Dev* dv = reinterpret_cast<const L7Dev*>(p.ext);
   if ((dyn->stats.need_repair && !p.repair) || dyn->overflow) return;
-  const bool in_range = rec < p.nrec;
+  const uint32_t nrec = batch_nrec(p);
+  const size_t cap = dv->rec_cap;
+  // persistent threads: one lane per (record, side)
+  const uint64_t total = (uint64_t)nrec * 2;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < total; base += (uint64_t)gridDim.x * blockDim.x) {
+  const uint64_t t = base + threadIdx.x;  // the loop bound is uniform across the CTA: warps stay whole
+  const uint32_t rec = (uint32_t)(t >> 1);
+  const int s = (int)(t & 1);
+  const bool in_range = rec < nrec;
   const uint32_t row = in_range ? dv->rec_row[rec] : 0xffffffffu;
   const bool ok = row != 0xffffffffu;  // both lanes of a pair agree
-  const Slots sl(dv->slotbuf + rec, dv->slot_stride, ok);
-  const uint8_t* base = p.in + (ok ? p.rec_off[rec] : 0);
-  const uint32_t vtap_id = sl_u32(sl, S7_VTAP_ID);
+  const uint32_t* K = dv->kgin + rec;
+  const uint32_t w0 = ok ? K[L7KG_VTAP_SIDE_PROTO * cap] : 0u, w1 = ok ? K[L7KG_PORT_FLAGS * cap] : 0u;
+  const uint32_t vtap_id = w0 & 0xffffu;
 
   kgs::SideIn in;
-  in.v6 = sl_u32(sl, S7_IS_IPV6) == 1;
-  in.vip = sl_u32(sl, s ? S7_VIP_DST : S7_VIP_SRC) == 1;
-  in.l3_epc = sl_i32(sl, s ? S7_EPC_DST : S7_EPC_SRC);
-  in.ip.ip4 = sl_u32(sl, s ? S7_IP_DST : S7_IP_SRC);
+  in.v6 = (w1 >> 16) & 1u;
+  in.vip = (w1 >> (17 + s)) & 1u;
+  in.l3_epc = ok ? (int32_t)K[(L7KG_EPC_SRC + s) * cap] : 0;
+  in.ip.ip4 = ok ? K[(L7KG_IP_SRC + s) * cap] : 0u;
   {
-    const uint64_t r6 = sl[s ? S7_IP6_DST : S7_IP6_SRC];
+    const unsigned long long r6 = ok ? reinterpret_cast<const unsigned long long*>(dv->refs)[(size_t)(L7REF_IP6_SRC + s) * cap + rec] : 0ull;
     const uint32_t n6 = (uint32_t)(r6 >> 32);
     in.ip.len6 = n6;
     uint64_t lo = 0, hi = 0;  // zero padded, like copy(key[4:], ipv6)
-    const uint8_t* q = base + (uint32_t)r6;
+    const uint8_t* q = p.in + (uint32_t)r6;
     for (uint32_t i = 0; i < (n6 < 16 ? n6 : 16u); i++) {
       const uint64_t v = (uint64_t)__ldg(q + i) << ((i & 7) * 8);
       if (i < 8) lo |= v; else hi |= v;
@@ -71,15 +63,15 @@ __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_co
     in.ip.lo = lo;
     in.ip.hi = hi;
   }
-  in.mac = sl[s ? S7_MAC_DST : S7_MAC_SRC];
-  in.gpid = sl_u32(sl, s ? S7_GPID_1 : S7_GPID_0);
+  in.mac = ok ? (uint64_t)K[(L7KG_MAC_SRC_HI + 2 * s) * cap] << 32 | K[(L7KG_MAC_SRC_LO + 2 * s) * cap] : 0ull;
+  in.gpid = ok ? K[(L7KG_GPID_0 + s) * cap] : 0u;
   in.vtap_id = (uint16_t)vtap_id;
-  in.port = s ? (uint16_t)sl_u32(sl, S7_PORT_DST) : (uint16_t)0;
-  in.tap_side = sl_u32(sl, S7_TAP_SIDE);
-  in.protocol = (uint8_t)sl_u32(sl, S7_PROTOCOL);
+  in.port = s ? (uint16_t)(w1 & 0xffffu) : (uint16_t)0;
+  in.tap_side = (w0 >> 16) & 0xffu;
+  in.protocol = (uint8_t)(w0 >> 24);
   in.server_side = s == 1;
   {  // :556-567 with the partner lane (the pair sits in adjacent lanes of one warp)
-    const uint32_t my_pod = sl_u32(sl, s ? S7_POD_1 : S7_POD_0);
+    const uint32_t my_pod = ok ? K[(L7KG_POD_0 + s) * cap] : 0u;
     const bool my_lb = ok && kgs::loopback(in.v6, in.ip);
     const uint32_t other_pod = __shfl_xor_sync(0xffffffffu, my_pod, 1);
     const bool other_lb = __shfl_xor_sync(0xffffffffu, (int)my_lb, 1) != 0;
@@ -89,12 +81,12 @@ __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_co
     in.pod = s ? pod1 : pod0;
     in.tag_source = s ? ts1 : ts0;
   }
-  if (!ok) return;
+  if (ok) {
   KGSide k;
   kgs::fill_side(p.dict, in, k);
 
   uint32_t gpid = in.gpid;
-  const uint32_t pid = sl_u32(sl, s ? S7_PID_1 : S7_PID_0);
+  const uint32_t pid = K[(L7KG_PID_0 + s) * cap];
   if (pid != 0 && gpid == 0) {  // l7_flow_log.go:589-596
     gpid = kgs::t64_z(p.dict, TID_VTAP_PID, (uint64_t)(uint16_t)vtap_id << 32 | (uint64_t)pid);
     k.tag_source |= TS_PROCESSID;
@@ -131,11 +123,10 @@ __global__ void __launch_bounds__(256, L7_KG_MIN_BLOCKS) k_l7_kg(const __grid_co
   st<uint8_t>(p, L7C_AUTO_SERVICE_TYPE_0 + 4 * s, row, k.auto_service_type);
   st<uint8_t>(p, L7C_TAG_SOURCE_0 + s, row, k.tag_source);
   st<uint32_t>(p, L7C_GPROCESS_ID_0 + s, row, gpid);
-  if (s == 0) st<uint16_t>(p, L7C_TEAM_ID, row, (uint16_t)p.frames[p.rec_frame[rec]].team_id);
+  }
+  }
 }
 
-void launch_l7_kg(const BatchParams& p, cudaStream_t s) {
-  if (p.nrec) k_l7_kg<<<(unsigned)(((uint64_t)p.nrec * 2 + 255) / 256), 256, 0, s>>>(p);
-}
+void launch_l7_kg(const BatchParams& p, unsigned grid, cudaStream_t s) { k_l7_kg<<<grid, 256, 0, s>>>(p); }
 
 }  // namespace dfgpu

@@ -29,7 +29,7 @@ struct MHost {
   MLayout* h_lay = nullptr;  // pinned
   MCand* d_cand = nullptr;
   size_t cand_cap = 0;
-  FtEntry* d_set = nullptr;
+  TagSet as_set;
   uint32_t* d_row_rec = nullptr;
   uint32_t epoch = 0;
   std::vector<ColSpec> cols[MT_TABLE_COUNT];
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) k_m_pass(const __grid_constant__ BatchPar
   __syncthreads();
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
-  const bool in_range = rec < p.nrec;
+  const bool in_range = rec < batch_nrec(p);
   DynState* dyn = p.dyn;
   MLayout* lay = dv->lay;
   if (EMIT && (dyn->stats.need_repair && !p.repair)) return;
@@ -399,17 +399,17 @@ __global__ void __launch_bounds__(256) k_m_pass(const __grid_constant__ BatchPar
   const uint32_t same = __match_any_sync(0xffffffffu, valid ? table : 0xff);
 
   if (!EMIT) {
-    if (lane == 0 && warp < p.nwarps)
-      for (int s = 0; s < M_SLOTS; s++) p.warp_tot[(size_t)s * p.nwarps + warp] = 0;
+    if (lane == 0 && warp < p.dyn->nwarps)
+      for (int s = 0; s < M_SLOTS; s++) p.warp_tot[(size_t)s * p.warp_cap + warp] = 0;
     __syncwarp();
-    if (valid && (int)lane == __ffs(same) - 1 && warp < p.nwarps)
-      p.warp_tot[(size_t)(M_SLOT_ROWS + table) * p.nwarps + warp] = __popc(same);
+    if (valid && (int)lane == __ffs(same) - 1 && warp < p.dyn->nwarps)
+      p.warp_tot[(size_t)(M_SLOT_ROWS + table) * p.warp_cap + warp] = __popc(same);
 #pragma unroll 1
     for (int a = 0; a < 4; a++)
 #pragma unroll 1
       for (int w = 0; w < 3; w++) {
         uint32_t tot = warp_sum(app == a ? t.str[w].n : 0u);
-        if (lane == 0 && warp < p.nwarps) p.warp_tot[(size_t)(M_SLOT_STR + a * 3 + w) * p.nwarps + warp] = tot;
+        if (lane == 0 && warp < p.dyn->nwarps) p.warp_tot[(size_t)(M_SLOT_STR + a * 3 + w) * p.warp_cap + warp] = tot;
       }
     lc_note(&dyn->stats.lc_first[0][0], (uint32_t)(obs < 0 ? 0 : obs) * 256u + tside, rec, obs >= 0);
     const uint32_t n_ok = __popc(__ballot_sync(0xffffffffu, ok)), n_drop = __popc(__ballot_sync(0xffffffffu, ok && !valid));
@@ -432,8 +432,8 @@ __global__ void __launch_bounds__(256) k_m_pass(const __grid_constant__ BatchPar
   MCand cand;
   memset(&cand, 0, sizeof cand);
   if (valid) {
-    const uint32_t wb = warp < p.nwarps ? warp : 0;
-    const uint32_t row = p.warp_base[(size_t)(M_SLOT_ROWS + table) * p.nwarps + wb] + __popc(same & ((1u << lane) - 1));
+    const uint32_t wb = warp < p.dyn->nwarps ? warp : 0;
+    const uint32_t row = p.warp_base[(size_t)(M_SLOT_ROWS + table) * p.warp_cap + wb] + __popc(same & ((1u << lane) - 1));
     const uint64_t tcode = dv->table_code[table];
     uint32_t d = dv->desc_base[table];
     uint8_t* A = p.arena;
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256) k_m_pass(const __grid_constant__ BatchPar
   }
 #define STRCOL(bit, name, which)                                                                         \
   if (tcode & (bit)) {                                                                                   \
-    const uint64_t off = (uint64_t)p.warp_base[(size_t)(M_SLOT_STR + app * 3 + which) * p.nwarps + wb] + e_str[which]; \
+    const uint64_t off = (uint64_t)p.warp_base[(size_t)(M_SLOT_STR + app * 3 + which) * p.warp_cap + wb] + e_str[which]; \
     const uint32_t n = t.str[which].n;                                                                   \
     reinterpret_cast<dfgpu_pos*>(A + lay->aux_off[d])[row] = dfgpu_pos{(int64_t)off, (int64_t)(off + n)}; \
     uint8_t* dst = A + lay->col_off[d] + off;                                                            \
@@ -509,7 +509,7 @@ __global__ void k_m_layout(const BatchParams p) {
   uint64_t cur = 0;
   for (int a = 0; a < 12; a++) lay->str_bytes[a] = tot[M_SLOT_STR + a];
   for (int t = 0; t < MT_TABLE_COUNT; t++) {
-    const uint64_t nrows = p.nrec ? tot[M_SLOT_ROWS + t] : 0;
+    const uint64_t nrows = tot[M_SLOT_ROWS + t];
     lay->nrows[t] = (uint32_t)nrows;
     lay->row_base[t] = t ? lay->row_base[t - 1] + lay->nrows[t - 1] : 0;
     const int app = m_app_index(t);
@@ -519,7 +519,7 @@ __global__ void k_m_layout(const BatchParams p) {
         lay->aux_off[d] = cur;
         cur += (nrows * 16 + 255) & ~255ull;
         lay->col_off[d] = cur;
-        cur += ((p.nrec ? tot[M_SLOT_STR + app * 3 + c.which] : 0) + 255) & ~255ull;
+        cur += (tot[M_SLOT_STR + app * 3 + c.which] + 255) & ~255ull;
       } else {
         lay->col_off[d] = cur;
         cur += (nrows * c.elem + 255) & ~255ull;
@@ -527,22 +527,28 @@ __global__ void k_m_layout(const BatchParams p) {
     }
   }
   lay->end = cur;
-  lay->overflow = cur > p.arena_bytes ? 1 : 0;
+  if (cur > p.arena_bytes) {
+    lay->overflow = 1;
+    p.dyn->overflow = 1;  // dfgpu_fetch grows the arena and re-runs
+    p.dyn->dev_end = cur + (cur >> 3);
+  }
 }
 
 // ---- app_service tags -----------------------------------------------------------------------------
 __global__ void k_m_as_prep(const BatchParams p) {
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
-  if (rec >= p.nrec) return;
+  if (rec >= batch_nrec(p)) return;
   MCand& c = dv->cand[rec];
   if (c.state != 1) return;
   const StrHash a = str_hash(p.in + c.svc_off, c.svc_len), b = str_hash(p.in + c.inst_off, c.inst_len);
   const uint64_t y = (uint64_t)dv->org_id << 24 | (uint64_t)c.team << 8 | c.table;
   const U128 fp = fp_finish(a.a ^ mix64(b.a + y * 0x9E3779B97F4A7C15ull), a.b + mix64(b.b ^ (y * 0xC2B2AE3D27D4EB4Full)));
-  FtEntry* e = ts_upsert(dv->as_set, dv->as_mask, fp, &dv->lay->as_full);
-  if (!e) {
-    c.state = 3;
+  FtEntry* e = ts_upsert(dv->as_set, dv->as_mask, fp, dv->as_state);
+  atomicMax(&dv->as_state->now, c.time);
+  if (!e) {  // saturated set: emit without recording (idempotent duplicate), never fail the batch
+    c.state = 2;
+    atomicAdd(&dv->as_state->unrecorded, 1u);
     return;
   }
   c.slot = (uint32_t)(e - dv->as_set);
@@ -554,7 +560,7 @@ __global__ void k_m_as_prep(const BatchParams p) {
 __global__ void k_m_as_mark(const BatchParams p, uint32_t epoch) {
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
-  if (rec >= p.nrec) return;
+  if (rec >= batch_nrec(p)) return;
   MCand& c = dv->cand[rec];
   if (c.state != 1) return;
   FtEntry* e = dv->as_set + c.slot;
@@ -564,7 +570,7 @@ __global__ void k_m_as_mark(const BatchParams p, uint32_t epoch) {
 __global__ void k_m_as_decide(const BatchParams p, uint32_t epoch, int last) {
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
-  if (rec >= p.nrec) return;
+  if (rec >= batch_nrec(p)) return;
   MCand& c = dv->cand[rec];
   if (c.state != 1) return;
   FtEntry* e = dv->as_set + c.slot;
@@ -582,22 +588,22 @@ __global__ void k_m_as_count(const BatchParams p) {
   const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
   MCand c;
   c.state = 0;
-  if (rec < p.nrec) c = dv->cand[rec];
+  if (rec < batch_nrec(p)) c = dv->cand[rec];
   const bool emit = c.state == 2;
   const uint32_t rows = __popc(__ballot_sync(0xffffffffu, emit));
   const uint32_t b0 = warp_sum(emit ? c.svc_len : 0u), b1 = warp_sum(emit ? c.inst_len : 0u);
-  if (lane == 0 && warp < p.nwarps) {
-    p.warp_tot[0 * (size_t)p.nwarps + warp] = rows;
-    p.warp_tot[1 * (size_t)p.nwarps + warp] = b0;
-    p.warp_tot[2 * (size_t)p.nwarps + warp] = b1;
+  if (lane == 0 && warp < p.dyn->nwarps) {
+    p.warp_tot[0 * (size_t)p.warp_cap + warp] = rows;
+    p.warp_tot[1 * (size_t)p.warp_cap + warp] = b0;
+    p.warp_tot[2 * (size_t)p.warp_cap + warp] = b1;
   }
   lc_note(dv->lay->as_lc_first, emit ? c.table : 0u, rec, emit);
 }
 __global__ void k_m_as_layout(const BatchParams p) {
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
   MLayout* lay = dv->lay;
-  const uint64_t rows = p.nrec ? p.dyn->stats.ft_tot[0] : 0;
-  const uint64_t bytes = p.nrec ? p.dyn->stats.ft_tot[1] : 0, bytes1 = p.nrec ? p.dyn->stats.ft_tot[2] : 0;
+  const uint64_t rows = p.dyn->stats.ft_tot[0];
+  const uint64_t bytes = p.dyn->stats.ft_tot[1], bytes1 = p.dyn->stats.ft_tot[2];
   uint64_t cur = (lay->end + 255) & ~255ull;
   auto take = [&](int i, uint64_t n) {
     lay->as_off[i] = cur;
@@ -614,7 +620,14 @@ __global__ void k_m_as_layout(const BatchParams p) {
   lay->as_bytes[0] = bytes;
   lay->as_bytes[1] = bytes1;
   lay->as_end = cur;
-  if (cur > p.arena_bytes) lay->overflow = 1;
+  lay->as_count = dv->as_state->count;
+  lay->as_unrecorded = dv->as_state->unrecorded;
+  lay->as_evicted = dv->as_state->evicted;
+  if (cur > p.arena_bytes) {
+    lay->overflow = 1;
+    p.dyn->overflow = 1;
+    p.dyn->dev_end = cur + (cur >> 3);
+  }
 }
 __global__ void k_m_as_write(const BatchParams p) {
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
@@ -625,15 +638,15 @@ __global__ void k_m_as_write(const BatchParams p) {
   MCand c;
   c.state = 0;
   c.svc_len = c.inst_len = 0;
-  if (rec < p.nrec) c = dv->cand[rec];
+  if (rec < batch_nrec(p)) c = dv->cand[rec];
   const bool emit = c.state == 2;
   const uint32_t m = __ballot_sync(0xffffffffu, emit);
   const uint32_t eb = warp_excl_scan(emit ? c.svc_len : 0u), eb1 = warp_excl_scan(emit ? c.inst_len : 0u);
   if (!emit) return;
-  const uint32_t wb = warp < p.nwarps ? warp : 0;
-  const uint32_t row = p.warp_base[0 * (size_t)p.nwarps + wb] + __popc(m & ((1u << lane) - 1));
-  const uint64_t off = (uint64_t)p.warp_base[1 * (size_t)p.nwarps + wb] + eb;
-  const uint64_t off1 = (uint64_t)p.warp_base[2 * (size_t)p.nwarps + wb] + eb1;
+  const uint32_t wb = warp < p.dyn->nwarps ? warp : 0;
+  const uint32_t row = p.warp_base[0 * (size_t)p.warp_cap + wb] + __popc(m & ((1u << lane) - 1));
+  const uint64_t off = (uint64_t)p.warp_base[1 * (size_t)p.warp_cap + wb] + eb;
+  const uint64_t off1 = (uint64_t)p.warp_base[2 * (size_t)p.warp_cap + wb] + eb1;
   uint8_t* A = p.arena;
   reinterpret_cast<uint32_t*>(A + lay->as_off[0])[row] = c.time;
   // dictionary rank by first appearance: the other table ranks first only if it appeared earlier
@@ -690,12 +703,8 @@ static int m_ensure_state(dfgpu_ctx* ctx) {
 #undef M
   }
   d.desc_base[MT_TABLE_COUNT] = nd;
-  uint32_t n = 1;
-  while (n < ctx->cfg.flow_tag_cache_max_size * 2u) n <<= 1;
-  CU(cudaMalloc(&h->d_set, (size_t)n * sizeof(FtEntry)));
-  CU(cudaMemset(h->d_set, 0, (size_t)n * sizeof(FtEntry)));
-  d.as_set = h->d_set;
-  d.as_mask = n - 1;
+  if (tagset_create(h->as_set, (uint64_t)ctx->cfg.flow_tag_cache_max_size * 2, ctx->cfg.flow_tag_cache_flush_timeout))
+    return fail(ctx, DFGPU_ENOMEM, "app_service tag set allocation failed");
   d.as_timeout = ctx->cfg.flow_tag_cache_flush_timeout;
   CU(cudaMalloc(&h->d_dev, sizeof(MDev)));
   CU(cudaMalloc(&h->d_lay, sizeof(MLayout)));
@@ -707,7 +716,7 @@ static int m_ensure_state(dfgpu_ctx* ctx) {
 void metrics_free_state(dfgpu_ctx* ctx) {
   MHost* h = reinterpret_cast<MHost*>(ctx->mt);
   if (!h) return;
-  cudaFree(h->d_set);
+  tagset_destroy(h->as_set);
   cudaFree(h->d_dev);
   cudaFree(h->d_lay);
   cudaFree(h->d_cand);
@@ -725,7 +734,7 @@ uint64_t metrics_arena_need(uint32_t nrec, uint64_t nbytes) { return (uint64_t)n
 static uint32_t m_next_epoch(MHost* h, cudaStream_t s) {
   h->epoch++;
   if ((h->epoch & 0xffff) == 0) {
-    k_ts_clear_pos<<<1024, 256, 0, s>>>(h->d_set, h->dev.as_mask);
+    k_ts_clear_pos<<<1024, 256, 0, s>>>(h->as_set.cur, h->as_set.mask);
     h->epoch = 1;
   }
   return h->epoch;
@@ -734,8 +743,7 @@ static uint32_t m_next_epoch(MHost* h, cudaStream_t s) {
 static int m_as_rounds(dfgpu_ctx* ctx, cudaStream_t s, int rounds) {
   MHost* h = reinterpret_cast<MHost*>(ctx->mt);
   BatchParams& bp = ctx->bp;
-  if (!bp.nrec) return 0;
-  dim3 grid((bp.nrec + 255) / 256), block(256);
+  dim3 grid(rec_grid(bp)), block(256);
   for (int r = 0; r < rounds; r++) {
     const uint32_t ep = m_next_epoch(h, s);
     k_m_as_mark<<<grid, block, 0, s>>>(bp, ep);
@@ -748,18 +756,11 @@ static int m_as_emit(dfgpu_ctx* ctx, cudaStream_t s) {
   MHost* h = reinterpret_cast<MHost*>(ctx->mt);
   BatchParams& bp = ctx->bp;
   CU(cudaMemsetAsync(&h->d_lay->as_lc_first, 0xff, sizeof(h->d_lay->as_lc_first), s));
-  if (bp.nrec) {
-    dim3 grid((bp.nrec + 255) / 256), block(256);
-    k_m_as_count<<<grid, block, 0, s>>>(bp);
-    launch_slot_scan_to(bp, 3, ctx->d_dyn->stats.ft_tot, s);
-    ctx->launches += 2;
-  }
+  k_m_as_count<<<rec_grid(bp), 256, 0, s>>>(bp);
+  launch_slot_scan_to(bp, 3, ctx->d_dyn->stats.ft_tot, s);
   k_m_as_layout<<<1, 1, 0, s>>>(bp);
-  if (bp.nrec) {
-    k_m_as_write<<<(bp.nrec + 255) / 256, 256, 0, s>>>(bp);
-    ctx->launches++;
-  }
-  ctx->launches++;
+  k_m_as_write<<<rec_grid(bp), 256, 0, s>>>(bp);
+  ctx->launches += 5;
   return 0;
 }
 
@@ -774,17 +775,21 @@ int metrics_passes(dfgpu_ctx* ctx, int repair) {
   bp.nslots = M_SLOTS;
   bp.nstreams = 0;
   bp.n_lc = 4;
-  bp.var_base = 0;
-  if (bp.nrec > h->cand_cap) {
+  bp.ncols = 0;  // the 9 tables are laid out by k_m_layout, not k_prepare
+  if (bp.rec_cap > h->cand_cap) {  // first metrics batch of this context (or the record index grew)
     if (h->d_cand) CU(cudaFree(h->d_cand));
     h->d_cand = nullptr;
-    size_t cap = (size_t)bp.nrec + bp.nrec / 4 + 4096;
+    size_t cap = (size_t)bp.rec_cap;
     CU(cudaMalloc(&h->d_cand, cap * sizeof(MCand)));
     if (h->d_row_rec) CU(cudaFree(h->d_row_rec));
     h->d_row_rec = nullptr;
     CU(cudaMalloc(&h->d_row_rec, cap * sizeof(uint32_t)));
     h->cand_cap = cap;
   }
+  tagset_maybe_rebuild(h->as_set, s, &ctx->launches);
+  h->dev.as_set = h->as_set.cur;
+  h->dev.as_mask = h->as_set.mask;
+  h->dev.as_state = h->as_set.d_state;
   h->dev.lay = h->d_lay;
   h->dev.cand = h->d_cand;
   h->dev.row_rec = h->d_row_rec;
@@ -794,20 +799,14 @@ int metrics_passes(dfgpu_ctx* ctx, int repair) {
   CU(cudaMemsetAsync(h->d_lay, 0, sizeof(MLayout), s));
   CU(cudaMemsetAsync(&ctx->d_dyn->stats.lc_first, 0xff, sizeof(ctx->d_dyn->stats.lc_first), s));
   CU(cudaMemsetAsync(&ctx->d_dyn->stats.var_total, 0, sizeof(ctx->d_dyn->stats.var_total), s));
-  dim3 grid((bp.nrec + 255) / 256), block(256);
-  if (bp.nrec) {
-    k_m_pass<0><<<grid, block, 0, s>>>(bp);
-    launch_slot_scan(bp, s);
-    ctx->launches += 2;
-  }
+  dim3 grid(rec_grid(bp)), block(256);
+  k_m_pass<0><<<grid, block, 0, s>>>(bp);
+  launch_slot_scan(bp, s);
   launch_finish(bp, s);  // LowCardinality ranks of the 4 observation_point spaces
   k_m_layout<<<1, 1, 0, s>>>(bp);
-  ctx->launches += 2;
-  if (bp.nrec) {
-    k_m_pass<1><<<grid, block, 0, s>>>(bp);
-    k_m_as_prep<<<grid, block, 0, s>>>(bp);
-    ctx->launches += 2;
-  }
+  k_m_pass<1><<<grid, block, 0, s>>>(bp);
+  k_m_as_prep<<<grid, block, 0, s>>>(bp);
+  ctx->launches += 7;
   rc = m_as_rounds(ctx, s, AS_ROUNDS);
   if (rc) return rc;
   rc = m_as_emit(ctx, s);
@@ -821,33 +820,12 @@ int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*
   MHost* h = reinterpret_cast<MHost*>(ctx->mt);
   BatchParams& bp = ctx->bp;
   cudaStream_t s = ctx->stream;
+  // sizes / overflow / repair were settled by dfgpu_fetch (DynState); here: the layout and the
+  // app_service rounds
   for (int attempt = 0;; attempt++) {
     CU(cudaMemcpyAsync(h->h_lay, h->d_lay, sizeof(MLayout), cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(ctx->h_dyn, ctx->d_dyn, sizeof(DynState), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    const bool repair = ctx->h_dyn->stats.need_repair && !bp.repair;
-    if (repair || h->h_lay->overflow) {
-      if (attempt >= 3) return fail(ctx, DFGPU_ENOMEM, "could not size the metrics arena");
-      if (h->h_lay->overflow) {
-        const uint64_t want = std::max(h->h_lay->as_end, h->h_lay->end) + (4u << 20) + 2 * (uint64_t)ctx->cur_nbytes;
-        CU(cudaFree(ctx->d_arena));
-        ctx->d_arena = nullptr;
-        CU(cudaMalloc(&ctx->d_arena, (size_t)want));
-        ctx->arena_cap = (size_t)want;
-        bp.arena = ctx->d_arena;
-        bp.arena_bytes = ctx->arena_cap;
-      }
-      // NOTE: a re-run re-bids app_service keys already stored by the aborted attempt's
-      // rounds; the set is only touched after the EMIT pass, which returns early on
-      // need_repair / overflow, so no key of this batch has been stored yet.
-      const uint32_t keep = ctx->h_dyn->stats.nrec;
-      CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(DynState), s));
-      CU(cudaMemcpyAsync(&ctx->d_dyn->stats.nrec, &keep, 4, cudaMemcpyHostToDevice, s));
-      int rc = metrics_passes(ctx, (repair || bp.repair) ? 1 : 0);
-      if (rc) return rc;
-      continue;
-    }
-    if (h->h_lay->as_full) return fail(ctx, DFGPU_ENOMEM, "app_service tag set is full (flow_tag_cache_max_size)");
+    if (h->h_lay->overflow) return fail(ctx, DFGPU_ENOMEM, "metrics arena overflow after the app_service rounds");
     if (h->h_lay->as_pending) {  // a key re-emits more than AS_ROUNDS times inside one batch: keep going
       if (attempt >= 64) return fail(ctx, DFGPU_ENOMEM, "app_service tag rounds did not converge");
       CU(cudaMemsetAsync(&h->d_lay->as_pending, 0, 4, s));
@@ -859,6 +837,9 @@ int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*
     }
     break;
   }
+  h->as_set.count_seen = h->h_lay->as_count;
+  b->counters.flow_tag_unrecorded = h->h_lay->as_unrecorded;
+  b->counters.flow_tag_evicted = h->h_lay->as_evicted;
   const MLayout& L = *h->h_lay;
   const uint64_t total = std::max<uint64_t>(L.as_end, 256);
   b->host = acquire(ctx, (size_t)total + 64);
@@ -1037,7 +1018,7 @@ __global__ void __launch_bounds__(256) k_red_key(const RedParams q) {
     hi = mix64(hi + (b ^ ((uint64_t)c << 32)));
   }
   const U128 fp = fp_finish(lo, hi);
-  FtEntry* e = ts_upsert(q.set, q.mask, fp, q.full);
+  FtEntry* e = ts_upsert_flag(q.set, q.mask, fp, q.full);
   if (!e) return;
   q.gslot[row] = (uint32_t)(e - q.set);
   atomicMax(&e->first_pos, (unsigned long long)(0xffffffffu - row) + 1);

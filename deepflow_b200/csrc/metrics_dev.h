@@ -237,7 +237,7 @@ struct MLayout {  // written by k_m_finish, read by the EMIT pass and by fetch
   uint64_t as_off[8];            // time, table keys, svc pos, inst pos, team, svc bytes, inst bytes
   uint64_t as_rows, as_bytes[2], as_end;
   uint32_t as_pending;           // candidates left unresolved after the fixed rounds
-  uint32_t as_full;
+  uint32_t as_count, as_unrecorded, as_evicted;  // TagSetState of the app_service set, for the host
   uint32_t as_lc_first[2];
   uint32_t count;                // DocCount: documents that decoded
   uint32_t drop_count;           // DropDocCount
@@ -263,6 +263,7 @@ struct MDev {
   MCand* cand;
   uint32_t* row_rec;  // [row_base[table] + row] -> record index (the reduce re-reads raw meters)
   FtEntry* as_set;
+  TagSetState* as_state;
   uint32_t as_mask, as_timeout, epoch;
   uint16_t org_id;
 };

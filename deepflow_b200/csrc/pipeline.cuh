@@ -40,24 +40,35 @@ struct DynState {  // per batch, device resident, read back by fetch
   uint64_t var_pos_off[MAX_VAR];
   uint64_t var_buf_off[MAX_VAR];
   uint64_t var_end;       // first free byte after the last stream that goes back to the host
-  uint32_t overflow;      // var region does not fit the arena
-  uint32_t pad;
+  uint32_t overflow;      // a device buffer is too small (arena, record index ...): fetch grows it and re-runs
+  uint32_t rec_overflow;  // more records than the record index holds (dfgpu_cfg.max_batch_records)
   uint64_t dev_end;       // first free byte of the arena (>= var_end: device-only regions follow var_end)
   uint8_t lc_rank[LC_SPACES][256];
   uint64_t trace_carry_hash;  // scratch
+  // The record count is only known on the device (framing): everything sized by it is planned there
+  // too (k_prepare), so that dfgpu_run never waits for the GPU.
+  uint32_t nwarps;        // ceil(nrec / 32)
+  uint32_t plan_valid;    // plan_rows holds the row count of the main table (L7 repair pass), else rows = nrec
+  uint32_t plan_rows;
+  uint32_t pad2;
+  uint64_t var_base;      // end of the fixed-width region = start of the variable-length streams
+  uint64_t fix_off[MAX_COLS];  // fixed-width part of column c (values / keys / nullable values)
+  uint64_t aux_off[MAX_COLS];  // nulls (nullable), arr_offsets (arrays), pos (strings)
 };
 
 struct BatchParams {
   const uint8_t* in;
+  uint64_t in_bytes;
   const dfgpu_frame* frames;
   uint32_t nframes;
-  uint32_t nrec;
-  uint32_t nwarps;
+  uint32_t rec_cap;   // capacity of the record index (rec_off / rec_len / rec_frame)
+  uint32_t warp_cap;  // stride of warp_tot / warp_base: [slot][warp_cap]
   int32_t repair;
   uint32_t* frame_nrec;
   uint32_t* frame_base;
   uint32_t* frame_chain_err;
   uint32_t* frame_bad;
+  uint32_t* frame_drop;  // L7: rows dropped in earlier frames (0 unless a record failed to decode)
   uint32_t* rec_off;
   uint32_t* rec_len;
   uint32_t* rec_frame;
@@ -68,7 +79,7 @@ struct BatchParams {
   PersistState* persist;
   uint8_t* arena;
   uint64_t arena_bytes;
-  uint64_t var_base;
+  uint32_t ncols;       // main table (L4 / L7): columns planned by k_prepare
   uint32_t nslots;
   uint32_t nstreams;
   uint32_t n_lc;
@@ -78,14 +89,20 @@ struct BatchParams {
   StreamSpec streams[MAX_VAR];
   DevDict dict;
   DevGeo geo;
-  uint64_t fix_off[MAX_COLS];
-  uint64_t aux_off[MAX_COLS];
+  uint8_t col_es[MAX_COLS];   // bytes per row of the fixed-width part of column c (0: none)
+  uint8_t col_aux[MAX_COLS];  // bytes per row of its aux part (nulls / arr_offsets / pos)
 };
+
+// records found by framing (device side); 0 when the record index overflowed
+__device__ __forceinline__ uint32_t batch_nrec(const BatchParams& p) { return p.dyn->rec_overflow ? 0u : p.dyn->stats.nrec; }
 
 extern const char* const kTapSideNames[18];  // TAPSideEnum.String() texts by canonical code (framing.cu)
 // host launchers of the shared kernels (framing.cu)
 void launch_frame_count(const BatchParams& p, cudaStream_t s);
+void launch_prepare(const BatchParams& p, cudaStream_t s);  // record-count dependent planning (device side)
 void launch_frame_fill(const BatchParams& p, cudaStream_t s);
+// grid of a thread-per-record kernel: covers the record index capacity, CTAs past the batch's records exit
+inline unsigned rec_grid(const BatchParams& p, unsigned block = 256) { return (p.rec_cap + block - 1) / block; }
 void launch_slot_scan(const BatchParams& p, cudaStream_t s);
 // generic: scan `nslots` slot rows of p.warp_tot into p.warp_base, totals to totals_out (device)
 void launch_slot_scan_to(const BatchParams& p, uint32_t nslots, uint64_t* totals_out, cudaStream_t s);

@@ -91,11 +91,47 @@ __device__ __forceinline__ U128 fp_finish(uint64_t lo, uint64_t hi) {
   return r;
 }
 
-// find-or-insert; returns the slot or nullptr when the table is full
-__device__ __forceinline__ FtEntry* ts_upsert(FtEntry* tbl, uint32_t mask, U128 fp, uint32_t* full_flag) {
+// Device-resident bookkeeping of one set (survives across batches).
+struct TagSetState {
+  uint32_t count;       // entries inserted since the last rebuild + entries the rebuild kept
+  uint32_t now;         // newest lru time seen (atomicMax)
+  uint32_t unrecorded;  // emissions whose key could not be stored: the set was saturated (duplicates later)
+  uint32_t evicted;     // live entries dropped oldest-first by rebuilds (beyond what expiry frees)
+  uint32_t expired;     // entries dropped by rebuilds because their lru time had expired (exact: expired == absent)
+  uint32_t rebuilds;
+  uint32_t cutoff_age;  // scratch of a rebuild: entries older than this are dropped
+  uint32_t kept;        // scratch of a rebuild
+  uint32_t hist[64];    // scratch of a rebuild: live entries by age bucket
+};
+constexpr uint32_t TS_MAX_PROBES = 128;
+
+// find-or-insert; returns the slot, or nullptr when no slot is free within TS_MAX_PROBES (saturated set:
+// the caller emits the row anyway — a duplicate flow_tag row is idempotent in ClickHouse,
+// flow_tag.go:153-160 — and the next rebuild makes room)
+__device__ __forceinline__ FtEntry* ts_upsert(FtEntry* tbl, uint32_t mask, U128 fp, TagSetState* st) {
   uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & mask;
-  // a healthy table resolves in a few probes; a long run means it is saturated: give
-  // up, flag it, and let fetch report the capacity error
+  for (uint32_t probes = 0; probes < TS_MAX_PROBES; probes++) {
+    FtEntry* e = tbl + s;
+    unsigned long long lo, hi;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(e) : "memory");
+    if (lo == fp.lo && hi == fp.hi) return e;
+    if ((lo | hi) == 0) {
+      U128 old = cas128(e, U128{0, 0}, fp);
+      if ((old.lo | old.hi) == 0) {
+        atomicAdd(&st->count, 1u);
+        return e;
+      }
+      if (old.lo == fp.lo && old.hi == fp.hi) return e;
+    } else if (lo == 0 || hi == 0) {
+      continue;  // torn read of a concurrent 128-bit publish: re-read this slot
+    }
+    s = (s + 1) & mask;
+  }
+  return nullptr;
+}
+// scratch sets (the reduce's grouping): find-or-insert, flag the caller when the set is too small
+__device__ __forceinline__ FtEntry* ts_upsert_flag(FtEntry* tbl, uint32_t mask, U128 fp, uint32_t* full_flag) {
+  uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & mask;
   for (uint32_t probes = 0; probes < 512; probes++) {
     FtEntry* e = tbl + s;
     unsigned long long lo, hi;
@@ -114,7 +150,7 @@ __device__ __forceinline__ FtEntry* ts_upsert(FtEntry* tbl, uint32_t mask, U128 
 }
 __device__ __forceinline__ FtEntry* ts_find(FtEntry* tbl, uint32_t mask, U128 fp) {
   uint32_t s = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & mask;
-  for (uint32_t probes = 0; probes < 512; probes++) {
+  for (uint32_t probes = 0; probes < TS_MAX_PROBES; probes++) {
     FtEntry* e = tbl + s;
     if (e->fp_lo == fp.lo && e->fp_hi == fp.hi) return e;
     if ((e->fp_lo | e->fp_hi) == 0) return nullptr;
@@ -152,5 +188,23 @@ __device__ __forceinline__ bool ts_candidate(const FtEntry* e, uint32_t now, uin
 __device__ __forceinline__ unsigned long long ts_pos_key(uint32_t epoch, unsigned long long pos) {
   return (unsigned long long)(epoch & 0xffffu) << 48 | (0xffffffffffffull - pos);
 }
+
+// ---- host side: a set with a spare table for rebuilds (tagset.cu) ---------------------------------------
+struct TagSet {
+  FtEntry* cur = nullptr;
+  FtEntry* alt = nullptr;
+  TagSetState* d_state = nullptr;
+  uint32_t mask = 0;
+  uint32_t timeout = 0;
+  uint32_t count_seen = 0;  // TagSetState::count as of the last fetch
+  uint32_t slots() const { return mask + 1; }
+};
+int tagset_create(TagSet& t, uint64_t min_slots, uint32_t timeout);
+void tagset_destroy(TagSet& t);
+// Reclaims slots when the set is more than half full: drops expired entries (exact: an expired key is
+// emitted again exactly like an absent one) and, if the set is still more than a quarter full, the oldest
+// entries by lru time (approximates the reference LRU's eviction, libs/lru/lru.go:52-57; evicted keys
+// are emitted again when they come back).  Asynchronous on `s`; swaps cur / alt.  Returns 1 when it ran.
+int tagset_maybe_rebuild(TagSet& t, cudaStream_t s, uint64_t* launches);
 
 }  // namespace dfgpu

@@ -183,11 +183,12 @@ class Engine:
         return ms.value, int(n.value), int(b.value)
 
     def profile_stages(self):
-        """ms per stage summed over the profiled runs: framing, prepare, SIZE pass, scans, EMIT, flow_tag."""
-        ms = (C.c_double * 6)()
+        """ms per stage summed over the profiled runs: framing, prepare, decode, scans, pack (strings), SmartEncoding,
+        flow_tag."""
+        ms = (C.c_double * 7)()
         n = C.c_uint64()
         self._check(lib().dfgpu_profile_stages(self._h, ms, C.byref(n)), "dfgpu_profile_stages")
-        names = ("framing", "prepare", "size_pass", "scans", "emit_pass", "flow_tag")
+        names = ("framing", "prepare", "decode", "scans", "pack", "smartencoding", "flow_tag")
         return {k: ms[i] for i, k in enumerate(names)}, int(n.value)
 
     @property

@@ -229,9 +229,10 @@ typedef struct dfgpu_cfg {
   uint32_t max_batch_records;  /* 0 => max_batch_bytes / 64                     */
   uint32_t flow_tag_cache_flush_timeout; /* s; 0 => 1800 (ingester/config/config.go:59) */
   uint32_t flow_tag_cache_max_size;      /* 0 => 1<<18 (config.go:60); the device
-                                  set never evicts: it holds 6x this many 32-byte
-                                  slots (field + field_value + app_service keys at
-                                  load <= 1/2) and reports DFGPU_ENOMEM when full */
+                                  set holds 6x this many 32-byte slots (field +
+                                  field_value + app_service keys at load <= 1/2)
+                                  and reclaims them by expiry / oldest-first
+                                  eviction (dfgpu_counters.flow_tag_evicted)      */
   uint32_t trace_id_index_disabled;      /* TraceIdWithIndex.Disabled (config.go:201) */
   uint32_t native_strings;     /* SURVEY 8(f) N1, first step.  1 => the String and Array(String)
                                   columns of l7_flow_log leave the GPU in ClickHouse NATIVE
@@ -259,6 +260,15 @@ typedef struct dfgpu_counters {
   int64_t rows[DFGPU_TABLE_MAX];
   /* device timing of the kernel pipeline of this submit, in microseconds       */
   double device_us;
+  /* flow_tag set pressure (cumulative since dfgpu_init).  The device set holds 6x
+   * flow_tag_cache_max_size slots; when more than half full it is rebuilt between
+   * batches: expired keys are dropped (exact: an expired key is emitted again like an
+   * absent one), then the oldest by lru time (the reference LRU evicts its least
+   * recently used entry, libs/lru/lru.go:52-57; evicted keys are emitted again when they
+   * return).  A key that does not fit a saturated set is emitted without being
+   * recorded (duplicate rows are idempotent in ClickHouse, flow_tag.go:153-160).      */
+  int64_t flow_tag_unrecorded;
+  int64_t flow_tag_evicted;
 } dfgpu_counters;
 
 typedef struct dfgpu_ctx dfgpu_ctx;
@@ -294,8 +304,13 @@ int dfgpu_submit(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nby
 /* The same pipeline split in its three phases, for callers that keep inputs
  * resident in HBM (bench "value" leg) or overlap several contexts:
  *   stage : H2D of frames + frame table (async on the ctx stream)
- *   run   : all kernels (async)
- *   fetch : D2H of the column blocks + counters, then stream sync              */
+ *   run   : all kernels (async: no allocation, no synchronisation, no D2H — the
+ *           record count and everything sized by it stay on the device; every
+ *           buffer was sized at dfgpu_init from dfgpu_cfg.max_batch_*)
+ *   fetch : D2H of the sizes, then of the column blocks + counters, stream sync.
+ *           A batch that outgrew the configured capacities is detected here:
+ *           buffers grow and the batch is re-run (never in steady state).
+ * frames may be device memory (8-byte aligned); the frame table is host memory. */
 int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbytes,
                 const dfgpu_frame* tbl, int nframes);
 int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index);
@@ -310,8 +325,9 @@ uint64_t dfgpu_launch_count(const dfgpu_ctx* ctx);
  * dfgpu_profile_read synchronises, sums and resets.                               */
 int dfgpu_profile_enable(dfgpu_ctx* ctx, int on);
 int dfgpu_profile_read(dfgpu_ctx* ctx, double* emit_ms, uint64_t* launches, uint64_t* in_bytes);
-/* stage breakdown of the profiled runs, ms: framing, prepare, SIZE pass, scans, EMIT pass, flow_tag */
-int dfgpu_profile_stages(dfgpu_ctx* ctx, double* ms6, uint64_t* runs);
+/* stage breakdown of the profiled runs, ms[7]: framing, prepare, decode pass, scans, pack (string / array
+ * columns), SmartEncoding, flow_tag (flow_log message types; L4 packs inside its second pass)            */
+int dfgpu_profile_stages(dfgpu_ctx* ctx, double* ms7, uint64_t* runs);
 int dfgpu_flush(dfgpu_ctx* ctx);
 
 /* Column block of one table of a batch, in ToInput order.  cols may be NULL to

@@ -134,7 +134,7 @@ def test_geo_tianjin_golden(built):
 def test_l7_protocol_strings_match_reference_switch(built):
     """L7Protocol.String(isTLS) for every uint8 value against the table machine-extracted from the reference's
     switch (datatype/flow.go:150-183 constants, :623-803 String; tests/golden/l7_protocols.json,
-    tools/make_l7proto_golden.py) — on the oracle, and on the device-side table literal of l7.cu."""
+    tools/make_l7proto_golden.py) — on the oracle, and on the device-side table literal of l7_tables_host.h."""
     import json
     import os
     import re
@@ -149,11 +149,11 @@ def test_l7_protocol_strings_match_reference_switch(built):
         assert l.oracle_kat_l7_protocol_string(p, 0).decode() == plain, p
         assert l.oracle_kat_l7_protocol_string(p, 1).decode() == tls, p
     # the CUDA side keeps its own literal (name, name + "_TLS"; 121 = "TLS" both ways; the rest "N/A")
-    src = open(os.path.join(here, "..", "deepflow_b200", "csrc", "l7.cu"), encoding="utf-8").read()
+    src = open(os.path.join(here, "..", "deepflow_b200", "csrc", "l7_tables_host.h"), encoding="utf-8").read()
     lit = re.search(r"static const PN protos\[\] = \{(.*?)\};", src, re.S).group(1)
     dev = {int(a): b for a, b in re.findall(r"\{(\d+),\s*\"([^\"]*)\"\}", lit)}
     want = {int(k): v for k, v in g["names"].items()}
-    assert want.pop(121) == ["TLS", "TLS"] and "proto_cs[121][0] = d.proto_cs[121][1] = CS_PROTO_TLS" in src
+    assert want.pop(121) == ["TLS", "TLS"] and "tb.proto_cs[121][0] = tb.proto_cs[121][1] = CS_PROTO_TLS" in src
     assert dev == {k: v[0] for k, v in want.items()}
     assert all(v[1] == v[0] + "_TLS" for v in want.values())
 
