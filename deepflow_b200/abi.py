@@ -88,7 +88,11 @@ class Cfg(C.Structure):
     _fields_ = [("max_batch_bytes", C.c_uint64), ("max_batch_records", C.c_uint32),
                 ("flow_tag_cache_flush_timeout", C.c_uint32), ("flow_tag_cache_max_size", C.c_uint32),
                 ("trace_id_index_disabled", C.c_uint32), ("native_strings", C.c_uint32),
-                ("reserved", C.c_uint32 * 6)]
+                ("rollup_tables", C.c_uint32), ("rollup_max_groups", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+
+
+class RollupRows(C.Structure):
+    _fields_ = [("nrows", C.c_uint64), ("tag_cols", C.c_void_p), ("ntag", C.c_int32), ("raw", C.c_void_p)]
 
 
 class Counters(C.Structure):

@@ -27,8 +27,10 @@ int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, u
 // metrics.cu
 int metrics_passes(dfgpu_ctx* ctx, int repair);
 int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t));
-int metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch* b,
-                   uint8_t* (*acquire)(dfgpu_ctx*, size_t));
+int rollup_add_resident(dfgpu_ctx* ctx, int table, uint32_t bucket);
+int rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket, const dfgpu_rollup_rows* rows);
+int rollup_flush(dfgpu_ctx* ctx, int table, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t));
+void rollup_free_state(dfgpu_ctx* ctx);
 void metrics_free_state(dfgpu_ctx* ctx);
 }  // namespace dfgpu
 
@@ -147,6 +149,7 @@ int dfgpu_close(dfgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   dfgpu_l7_free_state(ctx);
+  rollup_free_state(ctx);
   metrics_free_state(ctx);
   cudaFree(ctx->d_in);
   cudaFree(ctx->d_frames);
@@ -922,23 +925,50 @@ int dfgpu_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times
   return l7_tags_import(ctx, fps, times, n);
 }
 
-int dfgpu_metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch** out) {
-  if (!ctx || !out || bucket_seconds == 0) return DFGPU_EINVAL;
+static int metrics_table_arg(dfgpu_ctx* ctx, int table) {
   if (table < DFGPU_TABLE_METRICS_BASE || table >= DFGPU_TABLE_METRICS_BASE + 9)
     return fail(ctx, DFGPU_EINVAL, "table %d is not a flow_metrics table", table);
-  if (!ctx->metrics_resident) return fail(ctx, DFGPU_ENOENT, "no metrics batch resident on the device");
+  return 0;
+}
+
+int dfgpu_rollup_add(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds) {
+  if (!ctx || bucket_seconds == 0) return DFGPU_EINVAL;
+  if (int rc = metrics_table_arg(ctx, table)) return rc;
+  if (!ctx->metrics_resident) return fail(ctx, DFGPU_ENOENT, "no metrics batch resident on the device (call after dfgpu_submit / dfgpu_fetch)");
+  CU(cudaSetDevice(ctx->device));
+  return rollup_add_resident(ctx, table - DFGPU_TABLE_METRICS_BASE, bucket_seconds);
+}
+
+int dfgpu_rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, const dfgpu_rollup_rows* rows) {
+  if (!ctx || !rows || bucket_seconds == 0 || (rows->nrows && (!rows->tag_cols || !rows->raw))) return DFGPU_EINVAL;
+  if (int rc = metrics_table_arg(ctx, table)) return rc;
+  CU(cudaSetDevice(ctx->device));
+  return rollup_add_rows(ctx, table - DFGPU_TABLE_METRICS_BASE, bucket_seconds, rows);
+}
+
+int dfgpu_rollup_flush(dfgpu_ctx* ctx, int table, dfgpu_batch** out) {
+  if (!ctx || !out) return DFGPU_EINVAL;
+  if (int rc = metrics_table_arg(ctx, table)) return rc;
   CU(cudaSetDevice(ctx->device));
   dfgpu_batch* b = new dfgpu_batch();
   b->ctx = ctx;
   b->msg_type = DFGPU_MSG_METRICS;
   memset(&b->counters, 0, sizeof b->counters);
-  int rc = metrics_reduce(ctx, table - DFGPU_TABLE_METRICS_BASE, bucket_seconds, b, host_acquire);
+  int rc = rollup_flush(ctx, table - DFGPU_TABLE_METRICS_BASE, b, host_acquire);
   if (rc) {
     dfgpu_batch_release(b);
     return rc;
   }
   *out = b;
   return DFGPU_OK;
+}
+
+// one-shot form: the rows of the last metrics submit, reduced and returned (= add + flush; groups an
+// earlier dfgpu_rollup_add left in the table's accumulator are folded in and flushed with them)
+int dfgpu_metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch** out) {
+  int rc = dfgpu_rollup_add(ctx, table, bucket_seconds);
+  if (rc) return rc;
+  return dfgpu_rollup_flush(ctx, table, out);
 }
 
 }  // extern "C"

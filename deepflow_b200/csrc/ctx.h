@@ -95,6 +95,8 @@ struct dfgpu_ctx {
   void* ft = nullptr;
   // flow_metrics state (metrics.cu)
   void* mt = nullptr;
+  // flow_metrics rollup accumulators (rollup.cu)
+  void* ru = nullptr;
   bool metrics_resident = false;  // the arena still holds the tables of the last metrics batch
 };
 

@@ -337,6 +337,11 @@ __global__ void __launch_bounds__(1024) k_l7_trace_scan(const BatchParams p) {
 void launch_l7_repair_plan(const BatchParams& p, cudaStream_t s) { k_l7_repair_plan<<<1, 1024, 0, s>>>(p); }
 
 void launch_l7_decode(const BatchParams& p, unsigned grid, cudaStream_t s) {
+  static bool carve = false;
+  if (!carve) {  // 41 KB of shared memory per CTA, 5 CTAs per SM: ask for the largest shared-memory carve-out
+    cudaFuncSetAttribute(k_l7_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve = true;
+  }
   k_l7_decode<<<grid, A_THREADS, 0, s>>>(p);
   k_l7_trace_scan<<<1, 1024, 0, s>>>(p);
 }

@@ -18,26 +18,9 @@
 #include <algorithm>
 #include <cstring>
 
-#include "metrics_dev.h"
+#include "metrics_host.h"
 
 namespace dfgpu {
-
-struct MHost {
-  MDev dev{};
-  MDev* d_dev = nullptr;
-  MLayout* d_lay = nullptr;
-  MLayout* h_lay = nullptr;  // pinned
-  MCand* d_cand = nullptr;
-  size_t cand_cap = 0;
-  TagSet as_set;
-  uint32_t* d_row_rec = nullptr;
-  uint32_t epoch = 0;
-  std::vector<ColSpec> cols[MT_TABLE_COUNT];
-  // reduce scratch (one allocation, carved per call)
-  uint8_t* d_red = nullptr;
-  size_t red_cap = 0;
-  uint64_t* h_red = nullptr;  // pinned: {groups, str bytes x3}
-};
 
 namespace {
 
@@ -486,6 +469,27 @@ __global__ void __launch_bounds__(256) k_m_pass(const __grid_constant__ BatchPar
       MT_USAGE_METER_COLUMNS(M)
     }
 #undef M
+    // the rollup accumulator (rollup.cu) folds RAW meters: the packed columns hold float64(rtt_sum) etc. and
+    // are lossy above 2^53.  Row-major [row][field] so that one warp reads a row as one contiguous segment.
+    if (dv->raw_tables & (1u << table)) {
+      uint64_t* R = reinterpret_cast<uint64_t*>(A + lay->raw_off[table]) + (size_t)row * dv->raw_nf[table];
+      uint32_t i = 0;
+#define X(name, op) R[i++] = (uint64_t)m.name;
+      if (meter_id == MT_METER_FLOW) {
+        MFlowMeter m;
+        m_read_flow(sl, m);
+        M_FLOW_FIELDS(X)
+      } else if (meter_id == MT_METER_APP) {
+        MAppMeter m;
+        m_read_app(sl, m);
+        M_APP_FIELDS(X)
+      } else {
+        MUsageMeter m;
+        m_read_usage(sl, m);
+        M_USAGE_FIELDS(X)
+      }
+#undef X
+    }
     // appServiceTagWrite unmarshaller.go:309-327: only the 1m application tables
     if ((table == MT_APPLICATION_1M || table == MT_APPLICATION_MAP_1M) && (t.str[0].n | t.str[1].n)) {
       cand.svc_off = (uint32_t)(t.str[0].p - p.in);
@@ -527,6 +531,13 @@ __global__ void k_m_layout(const BatchParams p) {
     }
   }
   lay->end = cur;
+  // raw meters of the tables the rollup is enabled for: device-only, behind the 9 tables (the app_service
+  // tag table follows them; fetch copies the two host-bound ranges separately)
+  for (int t = 0; t < MT_TABLE_COUNT; t++) {
+    lay->raw_off[t] = cur;
+    if (dv->raw_tables & (1u << t)) cur += ((uint64_t)lay->nrows[t] * dv->raw_nf[t] * 8 + 255) & ~255ull;
+  }
+  lay->raw_end = cur;
   if (cur > p.arena_bytes) {
     lay->overflow = 1;
     p.dyn->overflow = 1;  // dfgpu_fetch grows the arena and re-runs
@@ -604,7 +615,7 @@ __global__ void k_m_as_layout(const BatchParams p) {
   MLayout* lay = dv->lay;
   const uint64_t rows = p.dyn->stats.ft_tot[0];
   const uint64_t bytes = p.dyn->stats.ft_tot[1], bytes1 = p.dyn->stats.ft_tot[2];
-  uint64_t cur = (lay->end + 255) & ~255ull;
+  uint64_t cur = (lay->raw_end + 255) & ~255ull;
   auto take = [&](int i, uint64_t n) {
     lay->as_off[i] = cur;
     cur += (n + 255) & ~255ull;
@@ -703,6 +714,16 @@ static int m_ensure_state(dfgpu_ctx* ctx) {
 #undef M
   }
   d.desc_base[MT_TABLE_COUNT] = nd;
+  d.raw_tables = ctx->cfg.rollup_tables & 0x1ffu;
+  for (int t = 0; t < MT_TABLE_COUNT; t++) {
+    uint32_t nf = 0;
+#define X(name, op) nf++;
+    if (d.table_meter[t] == MT_METER_FLOW) { M_FLOW_FIELDS(X) }
+    else if (d.table_meter[t] == MT_METER_APP) { M_APP_FIELDS(X) }
+    else { M_USAGE_FIELDS(X) }
+#undef X
+    d.raw_nf[t] = nf;
+  }
   if (tagset_create(h->as_set, (uint64_t)ctx->cfg.flow_tag_cache_max_size * 2, ctx->cfg.flow_tag_cache_flush_timeout))
     return fail(ctx, DFGPU_ENOMEM, "app_service tag set allocation failed");
   d.as_timeout = ctx->cfg.flow_tag_cache_flush_timeout;
@@ -721,9 +742,7 @@ void metrics_free_state(dfgpu_ctx* ctx) {
   cudaFree(h->d_lay);
   cudaFree(h->d_cand);
   cudaFree(h->d_row_rec);
-  cudaFree(h->d_red);
   cudaFreeHost(h->h_lay);
-  cudaFreeHost(h->h_red);
   delete h;
   ctx->mt = nullptr;
 }
@@ -763,6 +782,8 @@ static int m_as_emit(dfgpu_ctx* ctx, cudaStream_t s) {
   ctx->launches += 5;
   return 0;
 }
+
+int metrics_ensure_state(dfgpu_ctx* ctx) { return m_ensure_state(ctx); }
 
 // all kernels of one metrics batch (after framing); repair = 1 when re-running with known bad records
 int metrics_passes(dfgpu_ctx* ctx, int repair) {
@@ -845,7 +866,12 @@ int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*
   b->host = acquire(ctx, (size_t)total + 64);
   if (!b->host) return fail(ctx, DFGPU_ENOMEM, "pinned host allocation of %llu bytes failed", (unsigned long long)total);
   uint8_t* hb = b->host + 64;
-  CU(cudaMemcpyAsync(hb, bp.arena, (size_t)total, cudaMemcpyDeviceToHost, s));
+  if (L.raw_end > L.end) {  // skip the device-only raw meters between the tables and the app_service table
+    CU(cudaMemcpyAsync(hb, bp.arena, (size_t)L.end, cudaMemcpyDeviceToHost, s));
+    if (total > L.raw_end) CU(cudaMemcpyAsync(hb + L.raw_end, bp.arena + L.raw_end, (size_t)(total - L.raw_end), cudaMemcpyDeviceToHost, s));
+  } else {
+    CU(cudaMemcpyAsync(hb, bp.arena, (size_t)total, cudaMemcpyDeviceToHost, s));
+  }
   CU(cudaStreamSynchronize(s));
   static const std::vector<std::string> tap(kTapSideNames, kTapSideNames + 18);
   b->owned.reserve(16);
@@ -927,453 +953,6 @@ int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*
   }
   b->counters.count = L.count;
   b->counters.drop_count = L.drop_count;
-  return 0;
-}
-
-// ======================================================================================================
-// A9: reduce-by-key.  Rows of one resident table are grouped by (time bucket, every tag column):
-//   key     128-bit fingerprint of the tag columns -> find-or-insert in a scratch set; per group the
-//           first row (atomicMax of the inverted index) and the last row (atomicMax) are kept
-//   rank    groups are numbered in first-appearance order (scan over "row is its group's first row")
-//   gather  counting sort of the row indices by group (atomic slot inside the group; order inside a
-//           group does not matter: sums and maxes commute, first/last rows are known)
-//   merge   one warp per group folds the raw meters (re-read from the input records, not from the
-//           packed columns: rtt_sum etc. are float64 there) with the ConcurrentMerge rules and writes
-//           the tag columns of the first row + the merged meter columns.
-// ======================================================================================================
-struct RedParams {
-  const uint8_t* arena;
-  const uint8_t* in;
-  const uint32_t* rec_off;
-  const uint32_t* rec_len;
-  const uint32_t* row_rec;  // already offset to the table
-  const MDev* dv;
-  const MLayout* lay;
-  int table;
-  uint32_t nrows, nwarps, bucket, nf, ntag, dbase;
-  uint8_t meter;
-  FtEntry* set;
-  uint32_t mask;
-  uint32_t *gslot, *pos, *lead_cnt, *lead_base, *first_row, *last_row, *cnt, *off, *order;
-  uint32_t* slen;  // [3][nrows] string lengths of the group leaders, by rank
-  uint32_t* soff;  // [3][nrows]
-  uint64_t* raw;   // [nf][nrows]
-  uint64_t* totals;  // device: {groups, str bytes 0..2}
-  uint32_t* full;
-  uint8_t* out;
-  const uint64_t* out_off;  // [2 * ncols]: col_off, aux_off of the reduced table
-  uint8_t ops[M_MAX_FIELDS];
-};
-
-__global__ void k_scan_u32(const uint32_t* in, uint32_t* out, const uint64_t* n_dev, uint32_t n_max, uint64_t* total) {
-  __shared__ uint32_t sh[1024];
-  __shared__ uint64_t carry;
-  const uint32_t n = n_dev ? (uint32_t)min((uint64_t)n_max, *n_dev) : n_max;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < n; base += blockDim.x) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < n ? in[i] : 0;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
-      uint32_t t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < n) out[i] = (uint32_t)carry + sh[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry += sh[threadIdx.x];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && total) *total = carry;
-}
-
-__global__ void __launch_bounds__(256) k_red_key(const RedParams q) {
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= q.nrows) return;
-  uint64_t lo = 0x243F6A8885A308D3ull, hi = 0x13198A2E03707344ull;
-  for (uint32_t c = 0; c < q.ntag; c++) {
-    const uint32_t d = q.dbase + c;
-    const MColDesc dc = q.dv->descs[d];
-    uint64_t a = 0, b = 0;
-    if (dc.kind == MK_LCS || dc.kind == MK_STR) {
-      const dfgpu_pos ps = reinterpret_cast<const dfgpu_pos*>(q.arena + q.lay->aux_off[d])[row];
-      const StrHash h = str_hash(q.arena + q.lay->col_off[d] + ps.start, (uint32_t)(ps.end - ps.start));
-      a = h.a;
-      b = h.b;
-    } else {
-      const uint8_t* src = q.arena + q.lay->col_off[d] + (size_t)row * dc.elem;
-      if (dc.elem == 16) {
-        memcpy(&a, src, 8);
-        memcpy(&b, src + 8, 8);
-      } else {
-        for (uint32_t i = 0; i < dc.elem; i++) a |= (uint64_t)src[i] << (8 * i);
-        if (c == 0) a = (uint32_t)a / q.bucket * q.bucket;  // the time column: bucket start
-        b = a * 0x9E3779B97F4A7C15ull;
-      }
-    }
-    lo = mix64(lo ^ (a + c));
-    hi = mix64(hi + (b ^ ((uint64_t)c << 32)));
-  }
-  const U128 fp = fp_finish(lo, hi);
-  FtEntry* e = ts_upsert_flag(q.set, q.mask, fp, q.full);
-  if (!e) return;
-  q.gslot[row] = (uint32_t)(e - q.set);
-  atomicMax(&e->first_pos, (unsigned long long)(0xffffffffu - row) + 1);
-  atomicMax(&e->time, row);
-}
-__global__ void k_red_lead(const RedParams q) {
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t warp = row >> 5, lane = threadIdx.x & 31;
-  bool lead = false;
-  if (row < q.nrows) lead = q.set[q.gslot[row]].first_pos == (unsigned long long)(0xffffffffu - row) + 1;
-  const uint32_t m = __ballot_sync(0xffffffffu, lead);
-  if (lane == 0 && warp < q.nwarps) q.lead_cnt[warp] = __popc(m);
-}
-__global__ void k_red_rank(const RedParams q) {
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t warp = row >> 5, lane = threadIdx.x & 31;
-  bool lead = false;
-  FtEntry* e = nullptr;
-  if (row < q.nrows) {
-    e = q.set + q.gslot[row];
-    lead = e->first_pos == (unsigned long long)(0xffffffffu - row) + 1;
-  }
-  const uint32_t m = __ballot_sync(0xffffffffu, lead);
-  if (!lead) return;
-  const uint32_t rank = q.lead_base[warp] + __popc(m & ((1u << lane) - 1));
-  e->state = rank;
-  q.first_row[rank] = row;
-  q.last_row[rank] = e->time;
-  for (uint32_t c = 0; c < q.ntag; c++) {  // string lengths of the leader (app tables)
-    const uint32_t d = q.dbase + c;
-    const MColDesc dc = q.dv->descs[d];
-    if (dc.kind == MK_LCS || dc.kind == MK_STR) {
-      const dfgpu_pos ps = reinterpret_cast<const dfgpu_pos*>(q.arena + q.lay->aux_off[d])[row];
-      q.slen[(size_t)dc.which * q.nrows + rank] = (uint32_t)(ps.end - ps.start);
-    }
-  }
-}
-__global__ void k_red_count(const RedParams q) {
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= q.nrows) return;
-  const uint32_t rank = q.set[q.gslot[row]].state;
-  q.pos[row] = atomicAdd(&q.cnt[rank], 1u);
-}
-__global__ void k_red_scatter(const RedParams q) {
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= q.nrows) return;
-  const uint32_t rank = q.set[q.gslot[row]].state;
-  q.order[q.off[rank] + q.pos[row]] = row;
-}
-// raw meters of every row, field-major (coalesced): decode the source record again
-__global__ void __launch_bounds__(256) k_red_raw(const RedParams q) {
-  __shared__ uint32_t s_tbl[MM_COUNT * MM_MAXF];
-  for (uint32_t i = threadIdx.x; i < MM_COUNT * MM_MAXF; i += blockDim.x) s_tbl[i] = q.dv->pb_tbl[i];
-  __syncthreads();
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= q.nrows) return;
-  const uint32_t rec = q.row_rec[row];
-  uint64_t sl[MS_COUNT];
-#pragma unroll 1
-  for (int i = 0; i < MS_COUNT; i++) sl[i] = 0;
-  pb_interp(q.in + q.rec_off[rec], q.rec_len[rec], s_tbl, MM_MAXF, sl);
-  uint32_t i = 0;
-#define X(name, op) q.raw[(size_t)(i++) * q.nrows + row] = (uint64_t)m.name;
-  if (q.meter == MT_METER_FLOW) {
-    MFlowMeter m;
-    m_read_flow(sl, m);
-    M_FLOW_FIELDS(X)
-  } else if (q.meter == MT_METER_APP) {
-    MAppMeter m;
-    m_read_app(sl, m);
-    M_APP_FIELDS(X)
-  } else {
-    MUsageMeter m;
-    m_read_usage(sl, m);
-    M_USAGE_FIELDS(X)
-  }
-#undef X
-}
-
-__device__ __forceinline__ uint64_t red_op(uint8_t op, uint64_t a, uint64_t b) {
-  switch (op) {
-    case MOP_S64: return a + b;
-    case MOP_S32: return (uint32_t)((uint32_t)a + (uint32_t)b);
-    case MOP_X32:
-    case MOP_X8: return a < b ? b : a;
-  }
-  return a;  // FST / LST are filled in afterwards
-}
-
-// one warp per group
-__global__ void __launch_bounds__(256) k_red_merge(const RedParams q) {
-  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const uint32_t K = (uint32_t)q.totals[0];
-  if (g >= K) return;
-  const uint32_t n = q.cnt[g], base = q.off[g], first = q.first_row[g], last = q.last_row[g];
-  uint64_t acc[M_MAX_FIELDS];
-#pragma unroll 1
-  for (uint32_t f = 0; f < q.nf; f++) acc[f] = 0;
-  for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t row = q.order[base + i];
-#pragma unroll 1
-    for (uint32_t f = 0; f < q.nf; f++) acc[f] = red_op(q.ops[f], acc[f], q.raw[(size_t)f * q.nrows + row]);
-  }
-#pragma unroll 1
-  for (uint32_t f = 0; f < q.nf; f++) {
-    uint64_t v = acc[f];
-    for (int o = 16; o > 0; o >>= 1) v = red_op(q.ops[f], v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (q.ops[f] == MOP_FST) v = q.raw[(size_t)f * q.nrows + first];
-    if (q.ops[f] == MOP_LST) v = q.raw[(size_t)f * q.nrows + last];
-    acc[f] = v;
-  }
-  const uint64_t* ooff = q.out_off;
-  const uint32_t ncols = q.dv->desc_base[q.table + 1] - q.dbase;
-  // tag columns: copied from the group's first row; the time column becomes the bucket start
-  for (uint32_t c = lane; c < q.ntag; c += 32) {
-    const uint32_t d = q.dbase + c;
-    const MColDesc dc = q.dv->descs[d];
-    if (dc.kind == MK_LCS || dc.kind == MK_STR) {
-      const dfgpu_pos ps = reinterpret_cast<const dfgpu_pos*>(q.arena + q.lay->aux_off[d])[first];
-      const uint32_t len = (uint32_t)(ps.end - ps.start);
-      const uint64_t o = q.soff[(size_t)dc.which * q.nrows + g];
-      reinterpret_cast<dfgpu_pos*>(q.out + ooff[ncols + c])[g] = dfgpu_pos{(int64_t)o, (int64_t)(o + len)};
-      const uint8_t* src = q.arena + q.lay->col_off[d] + ps.start;
-      uint8_t* dst = q.out + ooff[c] + o;
-      for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
-    } else {
-      const uint8_t* src = q.arena + q.lay->col_off[d] + (size_t)first * dc.elem;
-      uint8_t* dst = q.out + ooff[c] + (size_t)g * dc.elem;
-      if (c == 0) {
-        uint32_t t;
-        memcpy(&t, src, 4);
-        t = t / q.bucket * q.bucket;
-        memcpy(dst, &t, 4);
-      } else {
-        for (uint32_t i = 0; i < dc.elem; i++) dst[i] = src[i];
-      }
-    }
-  }
-  if (lane != 0) return;
-  uint32_t i = 0, c = q.ntag;
-#define X(name, op) m.name = (decltype(m.name))acc[i++];
-#define M(name, ch, ctype, expr)                                        \
-  reinterpret_cast<ctype*>(q.out + ooff[c])[g] = (ctype)(expr);         \
-  c++;
-  if (q.meter == MT_METER_FLOW) {
-    MFlowMeter m;
-    M_FLOW_FIELDS(X)
-    MT_FLOW_METER_COLUMNS(M)
-  } else if (q.meter == MT_METER_APP) {
-    MAppMeter m;
-    M_APP_FIELDS(X)
-    MT_APP_METER_COLUMNS(M)
-  } else {
-    MUsageMeter m;
-    M_USAGE_FIELDS(X)
-    MT_USAGE_METER_COLUMNS(M)
-  }
-#undef X
-#undef M
-}
-
-int metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch* b,
-                   uint8_t* (*acquire)(dfgpu_ctx*, size_t)) {
-  MHost* h = reinterpret_cast<MHost*>(ctx->mt);
-  if (!h) return fail(ctx, DFGPU_ENOENT, "no metrics batch resident on the device");
-  cudaStream_t s = ctx->stream;
-  const MLayout& L = *h->h_lay;
-  const uint32_t nrows = L.nrows[table];
-  const auto& cs = h->cols[table];
-  const uint32_t ncols = (uint32_t)cs.size();
-  const int app = m_app_index(table);
-  b->tables.emplace_back();
-  dfgpu_batch::Table& tb = b->tables.back();
-  tb.id = DFGPU_TABLE_METRICS_REDUCED;
-  tb.cols.resize(ncols);
-  if (!h->h_red) CU(cudaHostAlloc(&h->h_red, 8 * sizeof(uint64_t), cudaHostAllocDefault));
-  RedParams q;
-  memset(&q, 0, sizeof q);
-  q.arena = ctx->bp.arena;
-  q.in = ctx->bp.in;
-  q.rec_off = ctx->bp.rec_off;
-  q.rec_len = ctx->bp.rec_len;
-  q.row_rec = h->d_row_rec + L.row_base[table];
-  q.dv = h->d_dev;
-  q.lay = h->d_lay;
-  q.table = table;
-  q.nrows = nrows;
-  q.nwarps = (nrows + 31) / 32;
-  q.bucket = bucket_seconds;
-  q.ntag = h->dev.ntag[table];
-  q.dbase = h->dev.desc_base[table];
-  q.meter = h->dev.table_meter[table];
-  {
-    uint32_t i = 0;
-#define X(name, op) q.ops[i++] = op;
-    if (q.meter == MT_METER_FLOW) { M_FLOW_FIELDS(X) }
-    else if (q.meter == MT_METER_APP) { M_APP_FIELDS(X) }
-    else { M_USAGE_FIELDS(X) }
-#undef X
-    q.nf = i;
-  }
-  uint32_t mask = 1;
-  while (mask < nrows * 2u + 2) mask <<= 1;
-  q.mask = mask - 1;
-  // carve the scratch
-  size_t need = 0;
-  auto carve = [&](size_t bytes) {
-    size_t o = need;
-    need += align_up(bytes + 16, 256);
-    return o;
-  };
-  const size_t n1 = std::max<uint32_t>(nrows, 1);
-  const size_t o_set = carve((size_t)mask * sizeof(FtEntry)), o_gslot = carve(n1 * 4), o_pos = carve(n1 * 4),
-               o_lc = carve((size_t)(q.nwarps + 1) * 4), o_lb = carve((size_t)(q.nwarps + 1) * 4), o_fr = carve(n1 * 4),
-               o_lr = carve(n1 * 4), o_cnt = carve(n1 * 4), o_off = carve(n1 * 4), o_ord = carve(n1 * 4),
-               o_slen = carve(3 * n1 * 4), o_soff = carve(3 * n1 * 4), o_raw = carve((size_t)q.nf * n1 * 8),
-               o_tot = carve(64), o_ooff = carve((size_t)2 * ncols * 8);
-  if (need > h->red_cap) {
-    if (h->d_red) CU(cudaFree(h->d_red));
-    h->d_red = nullptr;
-    CU(cudaMalloc(&h->d_red, need + need / 4));
-    h->red_cap = need + need / 4;
-  }
-  uint8_t* R = h->d_red;
-  q.set = (FtEntry*)(R + o_set);
-  q.gslot = (uint32_t*)(R + o_gslot);
-  q.pos = (uint32_t*)(R + o_pos);
-  q.lead_cnt = (uint32_t*)(R + o_lc);
-  q.lead_base = (uint32_t*)(R + o_lb);
-  q.first_row = (uint32_t*)(R + o_fr);
-  q.last_row = (uint32_t*)(R + o_lr);
-  q.cnt = (uint32_t*)(R + o_cnt);
-  q.off = (uint32_t*)(R + o_off);
-  q.order = (uint32_t*)(R + o_ord);
-  q.slen = (uint32_t*)(R + o_slen);
-  q.soff = (uint32_t*)(R + o_soff);
-  q.raw = (uint64_t*)(R + o_raw);
-  q.totals = (uint64_t*)(R + o_tot);
-  q.full = (uint32_t*)(R + o_tot + 32);
-  q.out_off = (const uint64_t*)(R + o_ooff);
-  CU(cudaMemsetAsync(q.set, 0, (size_t)mask * sizeof(FtEntry), s));
-  CU(cudaMemsetAsync(q.cnt, 0, n1 * 4, s));
-  CU(cudaMemsetAsync(q.slen, 0, 3 * n1 * 4, s));
-  CU(cudaMemsetAsync(q.totals, 0, 64, s));
-  uint64_t K = 0, sbytes[3] = {0, 0, 0};
-  if (nrows) {
-    dim3 grid((nrows + 255) / 256), block(256);
-    k_red_key<<<grid, block, 0, s>>>(q);
-    k_red_lead<<<grid, block, 0, s>>>(q);
-    k_scan_u32<<<1, 1024, 0, s>>>(q.lead_cnt, q.lead_base, nullptr, q.nwarps, q.totals);
-    k_red_rank<<<grid, block, 0, s>>>(q);
-    k_red_count<<<grid, block, 0, s>>>(q);
-    k_scan_u32<<<1, 1024, 0, s>>>(q.cnt, q.off, q.totals, nrows, nullptr);
-    for (int w = 0; w < 3 && app >= 0; w++)
-      k_scan_u32<<<1, 1024, 0, s>>>(q.slen + (size_t)w * nrows, q.soff + (size_t)w * nrows, q.totals, nrows, q.totals + 1 + w);
-    k_red_scatter<<<grid, block, 0, s>>>(q);
-    k_red_raw<<<grid, block, 0, s>>>(q);
-    ctx->launches += 8 + (app >= 0 ? 3 : 0);
-    CU(cudaMemcpyAsync(h->h_red, q.totals, 64, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (((uint32_t*)h->h_red)[8]) return fail(ctx, DFGPU_ENOMEM, "reduce scratch set is full");
-    K = h->h_red[0];
-    for (int w = 0; w < 3; w++) sbytes[w] = h->h_red[1 + w];
-  }
-  // output layout (same column walk as k_m_layout, K rows)
-  std::vector<uint64_t> ooff(2 * (size_t)ncols, 0);
-  uint64_t cur = 0;
-  for (uint32_t c = 0; c < ncols; c++) {
-    const MColDesc& dc = h->dev.descs[q.dbase + c];
-    if (dc.kind == MK_LCS || dc.kind == MK_STR) {
-      ooff[ncols + c] = cur;
-      cur += align_up(K * 16, 256);
-      ooff[c] = cur;
-      cur += align_up(sbytes[dc.which], 256);
-    } else {
-      ooff[c] = cur;
-      cur += align_up(K * dc.elem, 256);
-    }
-  }
-  const uint64_t total = std::max<uint64_t>(cur, 256);
-  uint8_t* d_out = nullptr;
-  CU(cudaMalloc(&d_out, (size_t)total));
-  q.out = d_out;
-  b->host = acquire(ctx, (size_t)total + 64);
-  if (!b->host) {
-    cudaFree(d_out);
-    return fail(ctx, DFGPU_ENOMEM, "pinned host allocation of %llu bytes failed", (unsigned long long)total);
-  }
-  uint8_t* hb = b->host + 64;
-  if (K) {
-    cudaError_t e = cudaMemcpyAsync((void*)q.out_off, ooff.data(), ooff.size() * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) {
-      k_red_merge<<<(unsigned)((K * 32 + 255) / 256), 256, 0, s>>>(q);
-      ctx->launches++;
-      e = cudaMemcpyAsync(hb, d_out, (size_t)total, cudaMemcpyDeviceToHost, s);
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) {
-      cudaFree(d_out);
-      return fail(ctx, DFGPU_ENODEV, "reduce failed: %s", cudaGetErrorString(e));
-    }
-  }
-  cudaFree(d_out);
-  tb.nrows = K;
-  static const std::vector<std::string> tap(kTapSideNames, kTapSideNames + 18);
-  b->owned.reserve(4);
-  b->owned_pos.reserve(4);
-  for (uint32_t c = 0; c < ncols; c++) {
-    const MColDesc& dc = h->dev.descs[q.dbase + c];
-    dfgpu_col& col = tb.cols[c];
-    memset(&col, 0, sizeof col);
-    col.name = cs[c].name;
-    col.ch_type = cs[c].ch_type;
-    col.elem_size = cs[c].elem_size;
-    col.nrows = K;
-    col.data = hb + ooff[c];
-    if (dc.kind == MK_LCS || dc.kind == MK_STR) {
-      col.pos = (const dfgpu_pos*)(hb + ooff[ncols + c]);
-      col.data_bytes = sbytes[dc.which];
-    } else {
-      col.data_bytes = K * dc.elem;
-      if (dc.kind == MK_OBS) {
-        // keys were copied from the source table: its dictionary, trimmed to the codes that survive
-        // in first-row order, is rebuilt from the copied keys on the host (<= 17 entries)
-        const uint32_t* first = ctx->h_dyn->stats.lc_first[m_obs_space(table)];
-        std::vector<std::pair<uint32_t, uint32_t>> present;
-        for (uint32_t k = 0; k < 256; k++)
-          if (first[k] != NO_BAD) present.push_back({first[k], k});
-        std::sort(present.begin(), present.end());
-        // source rank -> canonical code
-        std::vector<uint32_t> code_of_rank;
-        for (auto& pr : present) code_of_rank.push_back(pr.second);
-        uint8_t* keys = hb + ooff[c];
-        std::vector<int> new_rank(code_of_rank.size(), -1);
-        b->owned.emplace_back();
-        b->owned_pos.emplace_back();
-        auto& buf = b->owned.back();
-        auto& pos = b->owned_pos.back();
-        for (uint64_t r = 0; r < K; r++) {
-          const uint32_t old = keys[r];
-          if (new_rank[old] < 0) {
-            new_rank[old] = (int)pos.size();
-            const std::string& str = tap[code_of_rank[old]];
-            pos.push_back(dfgpu_pos{(int64_t)buf.size(), (int64_t)(buf.size() + str.size())});
-            buf.insert(buf.end(), str.begin(), str.end());
-          }
-          keys[r] = (uint8_t)new_rank[old];
-        }
-        col.dict_data = buf.data();
-        col.dict_pos = pos.data();
-        col.dict_n = pos.size();
-      }
-    }
-  }
-  b->counters.rows[DFGPU_TABLE_METRICS_REDUCED] = K;
   return 0;
 }
 

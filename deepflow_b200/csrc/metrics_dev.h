@@ -241,6 +241,8 @@ struct MLayout {  // written by k_m_finish, read by the EMIT pass and by fetch
   uint32_t as_lc_first[2];
   uint32_t count;                // DocCount: documents that decoded
   uint32_t drop_count;           // DropDocCount
+  uint64_t raw_off[MT_TABLE_COUNT];  // raw meters [row][field] of the rollup-enabled tables (device only)
+  uint64_t raw_end;
 };
 
 struct MCand {  // per record: what the app_service tag stage needs
@@ -266,6 +268,8 @@ struct MDev {
   TagSetState* as_state;
   uint32_t as_mask, as_timeout, epoch;
   uint16_t org_id;
+  uint32_t raw_tables;            // dfgpu_cfg.rollup_tables: keep raw meters of these tables for the rollup
+  uint8_t raw_nf[MT_TABLE_COUNT];  // meter fields per row (M_*_FIELDS)
 };
 
 }  // namespace dfgpu

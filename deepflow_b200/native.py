@@ -46,6 +46,9 @@ def lib():
         L.dfgpu_batch_release.argtypes = [vp]
         L.dfgpu_batch_release.restype = None
         L.dfgpu_metrics_reduce.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(vp)]
+        L.dfgpu_rollup_add.argtypes = [vp, C.c_int, C.c_uint32]
+        L.dfgpu_rollup_flush.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.dfgpu_rollup_add_rows.argtypes = [vp, C.c_int, C.c_uint32, vp]
         L.dfgpu_batch_tag_fingerprints.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
         L.dfgpu_tags_import.argtypes = [vp, vp, vp, C.c_uint64]
         L.dfgpu_flush.argtypes = [vp]
@@ -172,6 +175,21 @@ class Engine:
         """Reduce-by-key over one table of the last metrics batch (still resident in HBM)."""
         out = C.c_void_p()
         self._check(lib().dfgpu_metrics_reduce(self._h, table, bucket_seconds, C.byref(out)), "dfgpu_metrics_reduce")
+        return Batch(out)
+
+    def rollup_add(self, table, bucket_seconds=60):
+        """Fold the rows of `table` of the last metrics submit into the table's rollup accumulator."""
+        self._check(lib().dfgpu_rollup_add(self._h, table, bucket_seconds), "dfgpu_rollup_add")
+
+    def rollup_add_rows(self, table, bucket_seconds, tag_col_ptrs, raw_ptr, nrows):
+        """Fold decoded rows already resident in HBM (device pointers): BASELINE config 3."""
+        cols = (C.c_void_p * len(tag_col_ptrs))(*tag_col_ptrs)
+        rows = abi.RollupRows(nrows, C.cast(cols, C.c_void_p), len(tag_col_ptrs), raw_ptr)
+        self._check(lib().dfgpu_rollup_add_rows(self._h, table, bucket_seconds, C.byref(rows)), "dfgpu_rollup_add_rows")
+
+    def rollup_flush(self, table):
+        out = C.c_void_p()
+        self._check(lib().dfgpu_rollup_flush(self._h, table, C.byref(out)), "dfgpu_rollup_flush")
         return Batch(out)
 
     def profile_enable(self, on=True):

@@ -245,7 +245,11 @@ typedef struct dfgpu_cfg {
                                   walks its length prefixes to Append into the LowCardinality column.
                                   The Go side wraps such a column in a proto.ColInput whose
                                   EncodeColumn appends data verbatim.        */
-  uint32_t reserved[6];
+  uint32_t rollup_tables;      /* bit t: keep the raw meters of flow_metrics table DFGPU_TABLE_METRICS_BASE + t
+                                  beside its packed columns (device only, 8 B per meter field per row) so
+                                  that dfgpu_rollup_add / dfgpu_metrics_reduce can fold them; 0 => none   */
+  uint32_t rollup_max_groups;  /* capacity of one table's rollup accumulator in groups; 0 => 1<<20       */
+  uint32_t reserved[4];
 } dfgpu_cfg;
 
 /* decoder.Counter (decoder.go:60-80) for one submit; the shim adds them up.   */
@@ -350,13 +354,36 @@ void dfgpu_batch_release(dfgpu_batch* b);
 int dfgpu_batch_tag_fingerprints(const dfgpu_batch* b, int table, const uint64_t** fps, uint64_t* n);
 int dfgpu_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n);
 
-/* flow_metrics reduce-by-key: merges the decoded Document rows of the
- * last metrics run by (time bucket, all tag columns) with the per-field rules of
- * FlowMeter.ConcurrentMerge (flow-metrics/basic_meter.go:94-113,277-315,417-424,
- * 556-577).  bucket_seconds = 60 for the 1s -> 1m rollup.  `table` is one of
- * DFGPU_TABLE_METRICS_BASE+0..8; its rows stay resident in HBM after the metrics
- * run, the reduced rows come back as table DFGPU_TABLE_METRICS_REDUCED in
- * first-appearance order of the groups.                                        */
+/* flow_metrics rollup (BASELINE config 3: 1s -> 1m).  A persistent device
+ * accumulator per flow_metrics table, keyed by (time bucket, every tag column of the
+ * table) and holding RAW meters, merged with the per-field rules of
+ * FlowMeter.ConcurrentMerge (flow-metrics/flow_meter.go:91-99, basic_meter.go:94-113,
+ * 277-315,417-424,556-577: wrapping sums, maxes, OooTx/OooRx assigned from the merged
+ * row, the derived *Fail fields kept from the first row).
+ *   dfgpu_rollup_add      folds the rows of `table` of the last dfgpu_submit (metrics) —
+ *                         they stay resident in HBM until the next submit; the table
+ *                         must be enabled in dfgpu_cfg.rollup_tables.  A 1s -> 1m
+ *                         rollup calls it after every metrics submit of the minute.
+ *   dfgpu_rollup_add_rows folds decoded rows the caller already holds in HBM.
+ *   dfgpu_rollup_flush    returns every group as table DFGPU_TABLE_METRICS_REDUCED
+ *                         (same columns as `table`), in first-appearance order of the
+ *                         groups across all adds, and resets the accumulator.
+ *   dfgpu_metrics_reduce  = dfgpu_rollup_add + dfgpu_rollup_flush.
+ * `table` is one of DFGPU_TABLE_METRICS_BASE+0..8; bucket_seconds = 60 for 1s -> 1m.   */
+typedef struct dfgpu_rollup_rows {
+  uint64_t nrows;               /* < 2^32                                                */
+  const void* const* tag_cols;  /* HOST array of ntag DEVICE pointers: the tag columns of
+                                   the table in ToInput order, ch-go container layout
+                                   (fixed-width kinds only; observation_point = the
+                                   canonical tap-side code, 1 byte)                      */
+  int32_t ntag;
+  const uint64_t* raw;          /* DEVICE [nrows][nfields]: raw meter fields in struct
+                                   order (basic_meter.go:26-44,195-219,386-393,470-496,
+                                   691-693; dfgpu_rollup_nfields)                         */
+} dfgpu_rollup_rows;
+int dfgpu_rollup_add(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds);
+int dfgpu_rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, const dfgpu_rollup_rows* rows);
+int dfgpu_rollup_flush(dfgpu_ctx* ctx, int table, dfgpu_batch** out);
 int dfgpu_metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch** out);
 
 #ifdef __cplusplus

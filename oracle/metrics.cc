@@ -514,6 +514,40 @@ static std::string group_key(const MDoc& d, uint64_t code, uint32_t bucket) {
   return k;
 }
 
+// The rollup accumulator: the same grouping and merge, with the groups kept across submits
+// (a 1s -> 1m rollup folds every submit of the minute) until rollup_flush emits them.
+int MetricsBlocks::rollup_add(int table, uint32_t bucket_seconds) {
+  if (table < 0 || table >= MT_TABLE_COUNT || bucket_seconds == 0) return DFGPU_EINVAL;
+  const uint64_t code = metrics_table_code(table);
+  auto& idx = acc_idx[table];
+  auto& out = acc_out[table];
+  for (const MDoc& d : rows[table]) {
+    uint32_t bucket = d.t.time / bucket_seconds * bucket_seconds;
+    std::string k = group_key(d, code, bucket);
+    auto it = idx.find(k);
+    if (it == idx.end()) {
+      idx.emplace(std::move(k), out.size());
+      out.push_back(d);
+      out.back().t.time = bucket;
+    } else {
+      MDoc& a = out[it->second];
+      a.flow.ConcurrentMerge(d.flow);
+      a.app.ConcurrentMerge(d.app);
+      a.usage.ConcurrentMerge(d.usage);
+    }
+  }
+  return 0;
+}
+int MetricsBlocks::rollup_flush(int table) {
+  if (table < 0 || table >= MT_TABLE_COUNT) return DFGPU_EINVAL;
+  reduced = Block();
+  add_columns(reduced, table);
+  for (const MDoc& d : acc_out[table]) append_row(reduced, table, d);
+  acc_out[table].clear();
+  acc_idx[table].clear();
+  return 0;
+}
+
 int MetricsBlocks::reduce(int table, uint32_t bucket_seconds) {
   if (table < 0 || table >= MT_TABLE_COUNT || bucket_seconds == 0) return DFGPU_EINVAL;
   reduced = Block();

@@ -15,6 +15,7 @@
  *   ConcurrentMerge              basic_meter.go:94-113,277-315,417-424,556-577,707-709; app_meter.go; usage_meter.go
  */
 #pragma once
+#include <unordered_map>
 #include <string>
 
 #include "../include/dfgpu_metrics_schema.h"
@@ -170,6 +171,11 @@ struct MetricsBlocks {
   void append_record(const Msg& doc, uint16_t orgId, uint16_t teamId, const PlatformInfoTable* pd,
                      dfgpu_counters& cnt, L7State& st);
   int reduce(int table, uint32_t bucket_seconds);
+  // rollup accumulator across submits (dfgpu_rollup_add / dfgpu_rollup_flush)
+  std::unordered_map<std::string, size_t> acc_idx[MT_TABLE_COUNT];
+  std::vector<MDoc> acc_out[MT_TABLE_COUNT];
+  int rollup_add(int table, uint32_t bucket_seconds);
+  int rollup_flush(int table);
   static void add_columns(Block& b, int table);
   static void append_row(Block& b, int table, const MDoc& d);
 };

@@ -217,6 +217,14 @@ int oracle_counters(oracle_ctx* c, dfgpu_counters* out) {
 
 // reduce the rows of the last metrics submit (table `table`) by
 // (time bucket, tag columns) with ConcurrentMerge semantics.
+int oracle_rollup_add(oracle_ctx* c, int table, uint32_t bucket_seconds) {
+  if (!c || !c->metrics) return DFGPU_ENOENT;
+  return c->metrics->rollup_add(table - DFGPU_TABLE_METRICS_BASE, bucket_seconds);
+}
+int oracle_rollup_flush(oracle_ctx* c, int table) {
+  if (!c || !c->metrics) return DFGPU_ENOENT;
+  return c->metrics->rollup_flush(table - DFGPU_TABLE_METRICS_BASE);
+}
 int oracle_metrics_reduce(oracle_ctx* c, int table, uint32_t bucket_seconds) {
   if (!c->metrics) return DFGPU_ENOENT;
   return c->metrics->reduce(table - DFGPU_TABLE_METRICS_BASE, bucket_seconds);

@@ -33,6 +33,8 @@ def lib():
                                      C.POINTER(C.c_uint64)]
         L.oracle_counters.argtypes = [C.c_void_p, C.POINTER(abi.Counters)]
         L.oracle_metrics_reduce.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        L.oracle_rollup_add.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        L.oracle_rollup_flush.argtypes = [C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -81,6 +83,12 @@ class Oracle:
         c = abi.Counters()
         lib().oracle_counters(self._h, C.byref(c))
         return c
+
+    def rollup_add(self, table, bucket_seconds=60):
+        return lib().oracle_rollup_add(self._h, table, bucket_seconds)
+
+    def rollup_flush(self, table):
+        return lib().oracle_rollup_flush(self._h, table)
 
     def metrics_reduce(self, table, bucket_seconds=60):
         return lib().oracle_metrics_reduce(self._h, table, bucket_seconds)

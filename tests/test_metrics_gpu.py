@@ -17,6 +17,9 @@ COUNTERS = ("raw_count", "count", "error_count", "drop_count")
 def fresh(synth, cfg=None):
     from deepflow_b200.native import Engine
     from oracle_binding import Oracle
+    if cfg is None:
+        cfg = abi.Cfg()
+    cfg.rollup_tables = 0x1ff  # keep raw meters of every table beside its columns: the reduce folds them
     eng = Engine(0, cfg)
     eng.load_synth(synth)
     ora = Oracle(cfg)
@@ -123,6 +126,48 @@ def test_metrics_app_service_expiry_across_batches(synth, built):
         _, on = ora.columns(abi.TABLE_METRICS_APP_SERVICE)
         b.release()
         assert n == on
+    finally:
+        eng.close()
+        ora.close()
+
+
+def test_rollup_across_submits(synth, built):
+    """The 1s -> 1m rollup proper: the accumulator persists across submits.  Three consecutive batches whose
+    groups overlap (the same documents replayed with others in between) are folded one by one; the flush
+    must equal the oracle's accumulation — groups in first-appearance order across ALL batches, sums / maxes
+    over every batch, OooTx/OooRx from the LAST batch's last row, the *_fail fields from the FIRST row."""
+    import numpy as np
+    from parity import compare_tables
+    eng, ora = fresh(synth)
+    try:
+        wls = [synth.gen(MSG, 30000, seed=300), synth.gen(MSG, 20000, seed=301), synth.gen(MSG, 30000, seed=300),
+               synth.gen(MSG, 25000, seed=302)]
+        tables = [abi.TABLE_METRICS_BASE + 6, abi.TABLE_METRICS_BASE + 1, abi.TABLE_METRICS_BASE + 3,
+                  abi.TABLE_METRICS_BASE + 8, abi.TABLE_METRICS_BASE + 4]
+        for wl in wls:
+            ora.submit(wl)
+            eng.submit(wl).release()
+            for t in tables:
+                assert ora.rollup_add(t, 60) == 0
+                eng.rollup_add(t, 60)
+        problems = []
+        for t in tables:
+            assert ora.rollup_flush(t) == 0
+            rb = eng.rollup_flush(t)
+            cols, n = rb.columns(abi.TABLE_METRICS_REDUCED)
+            assert n > 0
+            problems += [f"rollup(table {t}): {p}" for p in compare_tables(rb, ora, [abi.TABLE_METRICS_REDUCED])]
+            rb.release()
+        assert not problems, "\n".join(problems[:20])
+        # the accumulator started over: one more batch reduces like a fresh one
+        ora.submit(wls[1])
+        eng.submit(wls[1]).release()
+        t = tables[0]
+        assert ora.metrics_reduce(t, 60) == 0
+        rb = eng.metrics_reduce(t, 60)
+        problems = compare_tables(rb, ora, [abi.TABLE_METRICS_REDUCED])
+        rb.release()
+        assert not problems, "\n".join(problems[:20])
     finally:
         eng.close()
         ora.close()
