@@ -1,33 +1,37 @@
 #!/usr/bin/env python3
-"""bench.py — flow records/sec of the ingest hot path (decode -> SmartEncoding ->
-flow_tag -> ClickHouse column pack) on B200, per BASELINE.json.
+"""bench.py — flow records/sec of the ingest hot path (decode -> SmartEncoding -> flow_tag / rollup ->
+ClickHouse column pack) on B200, per BASELINE.json.
 
-Workload at N=1 (BASELINE.json configs[1]): 10 M synthetic L7 HTTP
-AppProtoLogsData records, submitted the way the ingester's decoder sees them:
-sub-batches of <= 1024 agent frames (decoder.go:56 BUFFER_SIZE x 256 KiB frames).
-One "step" = one pass over all sub-batches.  Under torchrun every rank owns the
-vtap_id % N == rank shard of the firehose (weak scaling: 10 M records per GPU);
-per-record work has no collective — the only exchange is the all-gather of newly
-emitted flow_tag keys after every e2e step (deepflow_b200/sharded.py).
+Headline (N=1: BASELINE.json configs[1], "C2"): 10 M synthetic L7 HTTP AppProtoLogsData records per GPU,
+submitted the way the ingester's decoder sees them: sub-batches of <= 1024 agent frames (decoder.go:56
+BUFFER_SIZE x 256 KiB frames).  One "step" = one pass over all sub-batches.  Under torchrun every rank owns
+the vtap_id % N == rank shard (weak scaling); per-record work has no collective — the only exchange is the
+all-gather of newly emitted flow_tag keys after every e2e step (deepflow_b200/sharded.py).
 
-  value     device-resident: inputs already in HBM, kernels only; every decoder context of
-            the GPU (default 3, like the ingester's decoder goroutines) runs its share of
-            the sub-batches on its own stream, timed by CUDA events on a timing stream that
-            waits for all of them
-  e2e       through the C ABI with HOST buffers: pinned H2D of every sub-batch, all
-            kernels, D2H of every column block, inside the timed region
-  roofline  the dominant kernel (EMIT/pack pass), timed live in a separate leg where ONE
-            decoder runs alone (CUDA events on its stream around each launch):
-            algorithmic bytes / average launch time vs the measured HBM peak; `traffic` is
-            the DRAM bytes of one launch from the committed ncu capture (profiles/);
-            `path` = the same for SIZE + EMIT + SmartEncoding over SURVEY §8(d)'s bytes
+  value     device-resident: inputs already in HBM, kernels only; every decoder context of the GPU runs its
+            share of the sub-batches on its own stream; CUDA events on a timing stream that waits for all
+  e2e       through the C ABI with HOST buffers: pinned H2D of every sub-batch, all kernels, D2H of every
+            column block inside the timed region
+  roofline  the dominant kernel stage, timed live in a leg where ONE decoder runs alone (CUDA events of the
+            library on its stream around every stage): algorithmic bytes / stage time vs the measured HBM
+            peak; `path` = all stages over SURVEY 8(d)'s bytes; `traffic` = DRAM bytes of one launch from
+            the committed ncu capture (profiles/)
   cpu_baseline   the CPU oracle (a C++ restatement of the Go path) on a bounded sample
 
---impl reference times that CPU restatement with all host threads instead (the Go
-reference cannot be built in this image: no Go toolchain).
+Further legs in the same JSON line (`legs`), each with value / e2e / roofline / cpu_baseline:
+  c4_mixed     BASELINE configs[3]: 50 % L4 / 35 % L7 / 15 % metric records, one decoder pool per message type
+  c3_rollup    BASELINE configs[2]: 100 M decoded network_map.1s rows -> 1 m groups (N=1 only)
+  c5_highcard  BASELINE configs[4]: P = 1 M dictionary, high-cardinality attributes, cold flow_tag set every
+               step: emitted keys, merge bytes and seconds
+  parity       column hashes of one full-size sub-batch per decoder context (3 contexts concurrently, the
+               bench's dictionary) against the oracle on the same sub-batch (N=1 only)
+
+--impl reference times the CPU restatement with all host threads instead (the Go reference cannot be built in
+this image: no Go toolchain).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -42,8 +46,9 @@ sys.path.insert(0, ROOT)
 
 from deepflow_b200 import abi  # noqa: E402
 
-MSG = abi.DFGPU_MSG_PROTOCOLLOG
+L4, L7, MET = abi.DFGPU_MSG_TAGGEDFLOW, abi.DFGPU_MSG_PROTOCOLLOG, abi.DFGPU_MSG_METRICS
 METRIC = "flow records/sec ingest+SmartEncode (L7 decode + tag-inject + flow_tag + column pack)"
+MAIN_TABLE = {L4: abi.TABLE_L4_FLOW_LOG, L7: abi.TABLE_L7_FLOW_LOG}
 
 
 def parse_args():
@@ -52,30 +57,27 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dfgpu", choices=["dfgpu", "reference"])
-    ap.add_argument("--records", type=int, default=10_000_000, help="records per GPU per step")
+    ap.add_argument("--records", type=int, default=10_000_000, help="records per GPU per step (C2, C4)")
     ap.add_argument("--sub-batch", type=int, default=625_000, help="records per dfgpu_submit")
-    ap.add_argument("--pods", type=int, default=100_000, help="dictionary size P (SURVEY §8d)")
-    ap.add_argument("--decoders", type=int, default=3, help="contexts per GPU in the e2e leg (DecoderQueueCount)")
+    ap.add_argument("--pods", type=int, default=100_000, help="dictionary size P (SURVEY 8d)")
+    ap.add_argument("--decoders", type=int, default=3, help="contexts per GPU (DecoderQueueCount)")
+    ap.add_argument("--legs", default="c2,c4,c3,c5,parity,native", help="comma list; c2 always runs")
+    ap.add_argument("--c3-rows", type=int, default=100_000_000)
+    ap.add_argument("--c3-groups", type=int, default=1_000_000)
+    ap.add_argument("--c5-records", type=int, default=5_000_000)
+    ap.add_argument("--c5-pods", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-native-leg", action="store_true", help="skip the second e2e leg (native_strings=1)")
     return ap.parse_args()
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def gen_sub_batches(synth, n_total, sub, seed0, world, rank, threads=16):
+def gen_sub_batches(synth, msg, n_total, sub, seed0, world, rank, flags=0, threads=16):
     """Generate ceil(n_total/sub) sub-batches in parallel threads (ctypes drops the GIL)."""
     sizes = [min(sub, n_total - i) for i in range(0, n_total, sub)]
     out = [None] * len(sizes)
-
-    def work(i):
-        out[i] = synth.gen(MSG, sizes[i], seed=seed0 + i, vtap_mod=world if world > 1 else 0, vtap_rem=rank)
-
     it = iter(range(len(sizes)))
     lock = threading.Lock()
 
@@ -85,7 +87,7 @@ def gen_sub_batches(synth, n_total, sub, seed0, world, rank, threads=16):
                 i = next(it, None)
             if i is None:
                 return
-            work(i)
+            out[i] = synth.gen(msg, sizes[i], seed=seed0 + i, flags=flags, vtap_mod=world if world > 1 else 0, vtap_rem=rank)
 
     ts = [threading.Thread(target=loop) for _ in range(min(threads, len(sizes)))]
     [t.start() for t in ts]
@@ -95,10 +97,10 @@ def gen_sub_batches(synth, n_total, sub, seed0, world, rank, threads=16):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
 
     def __init__(self, index):
-        self.index, self.p, self.lines = index, None, []
+        self.index, self.p = index, None
 
     def start(self):
         try:
@@ -117,26 +119,30 @@ class ClockSampler:
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, busy, reasons = [], [], [], set()
         for ln in out.splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
+                util = float(f[7])
             except ValueError:
                 continue
+            if util >= 50:  # "under load": the sampler also spans the host-side generation between the legs
+                busy.append(sm[-1])
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)) if busy else (float(np.median(sm)) if sm else None),
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_under_load": len(busy)}
 
 
 def bind_near_gpu(index):
-    """Run this rank's host threads (and, by first touch, place its pinned staging buffers) on the CPUs
-    local to its GPU's PCIe root, like a NUMA-aware ingester deployment would.  Returns what it did."""
+    """Run this rank's host threads (and, by first touch, place its pinned staging buffers) on the CPUs local to
+    its GPU's PCIe root, like a NUMA-aware ingester deployment would.  Returns what it did."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -153,17 +159,39 @@ def bind_near_gpu(index):
         return f"unbound ({type(ex).__name__})"
 
 
-def ncu_traffic(kernel, recs_per_launch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json names the capture), scaled to this launch's record
-    count.  None when no capture is recorded: ncu cannot run inside the bench."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def host_info():
+    """What the CPU arm ran on: affinity, cgroup quota, load — the baseline is only interpretable with these."""
+    info = {"cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))}
     try:
-        t = json.load(open(p))[kernel]
-        b = (t["dram_bytes_read"] + t["dram_bytes_write"]) * recs_per_launch / t["records_per_launch"]
-        return b, t["source"]
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        info["cgroup_cpu_max"] = "unlimited" if q[0] == "max" else round(int(q[0]) / int(q[1]), 2)
     except Exception:  # noqa: BLE001
-        return None, None
+        info["cgroup_cpu_max"] = None
+    try:
+        info["loadavg_1m"] = float(open("/proc/loadavg").read().split()[0])
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["cpu_model"] = ln.split(":", 1)[1].strip()
+                break
+    except Exception:  # noqa: BLE001
+        pass
+    return info
+
+
+def ncu_traffic(kernel, recs_per_launch):
+    """dram bytes of one launch of `kernel` from the committed ncu --set full capture (profiles/r02_traffic.json),
+    scaled to this launch's record count; None when no capture is recorded (ncu cannot run inside the bench)."""
+    for name in ("r02_traffic.json",):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            t = json.load(open(p))[kernel]
+            return (t["dram_bytes_read"] + t["dram_bytes_write"]) * recs_per_launch / t["records_per_launch"], t["source"]
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
 
 
 def measured_peak_hbm():
@@ -171,186 +199,231 @@ def measured_peak_hbm():
     if os.path.exists(p):
         try:
             return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        except Exception:
+        except Exception:  # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def output_bytes(batch):
-    """Exact size of the packed l7_flow_log column block (what the EMIT kernel writes)."""
-    cols, nrows = batch.columns(abi.TABLE_L7_FLOW_LOG)
-    total = strings = 0
+def block_bytes(batch, table):
+    """Byte census of one packed column block: total, fixed-width, Positions / offsets, variable bytes."""
+    cols, nrows = batch.columns(table)
+    fixed = aux = var = 0
     for c in cols:
         t = c.ch_type
         if t in (abi.CH_STR, abi.CH_LC_STR_ROWS):
-            total += (0 if c.native else nrows * 16) + c.buf.nbytes
-            strings += c.buf.nbytes
+            aux += 0 if c.native else nrows * 16
+            var += c.buf.nbytes
         elif t in (abi.CH_ARR_STR, abi.CH_ARR_LC_STR):
-            total += nrows * 8 + (0 if c.native else c.pos.nbytes) + c.buf.nbytes
-            strings += c.buf.nbytes
+            aux += nrows * 8 + (0 if c.native else c.pos.nbytes)
+            var += c.buf.nbytes
         elif t in (abi.CH_ARR_UINT16, abi.CH_ARR_FLOAT64):
-            total += nrows * 8 + c.values.nbytes
-            strings += c.values.nbytes
+            aux += nrows * 8
+            var += c.values.nbytes
         else:
-            total += nrows * c.elem_size + (nrows if c.nulls is not None else 0)
-    return total, nrows, strings
+            fixed += nrows * c.elem_size + (nrows if c.nulls is not None else 0)
+    return {"total": fixed + aux + var, "fixed": fixed, "aux": aux, "var": var, "rows": nrows}
 
 
-def cpu_port_run(synth, sample_records, threads, seed, warm=True):
-    """The CPU oracle (C++ restatement of decoder.Run ... AppendToColumnBlock) on `threads`
-    independent decoder instances, each with its own dictionary view and caches."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_binding import Oracle
-    oras, wls = [], []
-    ocfg = abi.Cfg()
-    ocfg.flow_tag_cache_max_size = 1 << 20
-    for t in range(threads):
-        o = Oracle(ocfg)
-        o.load_synth(synth)
-        oras.append(o)
-        wls.append(synth.gen(MSG, sample_records, seed=seed + t))
-    if warm:
-        # steady state, like a long-running ingester: column blocks and caches already sized
-        ts = [threading.Thread(target=o.submit, args=(w,)) for o, w in zip(oras, wls)]
+# ---------------------------------------------------------------------------------------------------------
+# CPU side
+# ---------------------------------------------------------------------------------------------------------
+class CpuPool:
+    """`threads` independent CPU decoder instances (the oracle: a C++ restatement of decoder.Run ...
+    AppendToColumnBlock), each with its own dictionary view and caches — the reference's goroutine-per-decoder
+    ownership.  Built once (in parallel), then fed workloads."""
+
+    def __init__(self, synth, threads):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_binding import Oracle
+        self.synth = synth
+        ocfg = abi.Cfg()
+        ocfg.flow_tag_cache_max_size = 1 << 20
+        self.oras = [None] * threads
+
+        def mk(i):
+            o = Oracle(ocfg)
+            o.load_synth(synth)
+            self.oras[i] = o
+
+        self._par(mk)
+
+    def _par(self, fn):
+        ts = [threading.Thread(target=fn, args=(i,)) for i in range(len(self.oras))]
         [t.start() for t in ts]
         [t.join() for t in ts]
-    t0 = time.perf_counter()
-    ts = [threading.Thread(target=o.submit, args=(w,)) for o, w in zip(oras, wls)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
-    dt = time.perf_counter() - t0
-    n = sum(w.nrecords for w in wls)
-    for o in oras:
-        o.close()
-    return n / dt, n, dt
+
+    def run(self, msg, records_each, seed, flags=0):
+        """Generates one workload per instance (untimed), then times all instances decoding concurrently."""
+        wls = [None] * len(self.oras)
+
+        def gen(i):
+            wls[i] = self.synth.gen(msg, records_each, seed=seed + i, flags=flags)
+
+        self._par(gen)
+        t0 = time.perf_counter()
+        self._par(lambda i: self.oras[i].submit(wls[i]))
+        dt = time.perf_counter() - t0
+        n = sum(w.nrecords for w in wls)
+        return n / dt, n, dt
+
+    def close(self):
+        for o in self.oras:
+            o.close()
 
 
-def main():
-    a = parse_args()
-    rank, world, local = dist_env()
-    if world != a.gpus and world > 1:
-        a.gpus = world
+def cpu_port_run(synth, msg, sample_records, threads, seed, warm=True, flags=0):
+    pool = CpuPool(synth, threads)
+    if warm:  # steady state, like a long-running ingester: column blocks and caches already sized
+        pool.run(msg, sample_records, seed, flags)
+    r = pool.run(msg, sample_records, seed, flags)
+    pool.close()
+    return r
+
+
+def reference_arm(a):
+    """--impl reference: the CPU restatement of the path on every host thread this process may use."""
     from deepflow_b200 import build
     from deepflow_b200.synth import Synth
-    if rank == 0:
-        build.build_synth()
-    synth = None
-    cfg_common = {"workload": "C2: L7 HTTP AppProtoLogsData, SmartEncoding on, flow_tag on (BASELINE.json configs[1])",
-                  "records_per_gpu_per_step": a.records, "sub_batch_records": a.sub_batch,
-                  "dictionary_pods": a.pods, "sharding": "vtap_id % n_gpus" if a.gpus > 1 else "none",
-                  "l2": "inputs 4+ GB per step >> 126 MB L2 (no flush needed)"}
-
-    # ------------------------------------------------------------------ reference arm --
-    if a.impl == "reference":
-        if rank != 0:
-            return 0
-        build.build_oracle()
-        synth = Synth(n_pods=a.pods)
-        cores = os.cpu_count() or 1
-        threads = min(cores, 64)
-        sample = 50000
-        for _ in range(a.warmup):
-            cpu_port_run(synth, 2000, threads, 900)
-        t_all, n_all = 0.0, 0
-        for s in range(a.steps):
-            v, n, dt = cpu_port_run(synth, sample, threads, 1000 + s * 100)
-            t_all += dt
-            n_all += n
-        value = n_all / t_all
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "records/s", "n_gpus": a.gpus,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * t_all / max(1, a.steps),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer",
-                "data": "synthetic", "config": cfg_common,
-                "cpu_baseline": {"value": value, "unit": "records/s", "cores": threads, "kind": "port",
-                                 "sample": f"{threads} decoder instances x {sample} L7 records per step "
-                                           "(C++ restatement of the Go path; the Go ingester cannot be built here)"},
-                "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
-
-    # ------------------------------------------------------------------------ GPU arm --
-    import torch
-    import torch.distributed as dist
-    if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: libdfgpu has no CPU fallback"}))
-        return 2
-    torch.cuda.set_device(local)
-    numa = bind_near_gpu(local)  # before any pinned allocation: first touch places the staging buffers
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from deepflow_b200.native import Engine
+    build.build_synth()
+    build.build_oracle()
     synth = Synth(n_pods=a.pods)
+    threads = len(os.sched_getaffinity(0))
+    sample = 50000
     t0 = time.time()
-    subs = gen_sub_batches(synth, a.records, a.sub_batch, 1000 + 7919 * rank, world, rank)
-    nrec_step = sum(w.nrecords for w in subs)
-    in_bytes = sum(w.nbytes for w in subs)
-    gen_s = time.time() - t0
+    pool = CpuPool(synth, threads)
+    setup_s = time.time() - t0
+    for w in range(a.warmup):
+        pool.run(L7, 4000, 900 + 1000 * w)
+    t_all, n_all = 0.0, 0
+    for s in range(a.steps):
+        _v, n, dt = pool.run(L7, sample, 100_000 + s * 1000)
+        t_all += dt
+        n_all += n
+    pool.close()
+    value = n_all / t_all
+    per_step = threads * sample
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "records/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000 * t_all / max(1, a.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer",
+            "data": "synthetic",
+            "config": {"workload": "C2: L7 HTTP AppProtoLogsData, SmartEncoding on, flow_tag on (BASELINE.json configs[1])",
+                       "records_per_step": per_step, "records_per_gpu_per_step_of_the_gpu_arm": a.records,
+                       "note": "a bounded sample of the GPU arm's workload per step: same generator, same dictionary, every "
+                               "host thread; the CPU arm does not grow with --gpus (one host)",
+                       "dictionary_pods": a.pods, "setup_seconds": setup_s, "host": host_info()},
+            "cpu_baseline": {"value": value, "unit": "records/s", "cores": threads, "kind": "port",
+                             "sample": f"{threads} decoder instances x {sample} L7 records per step = {per_step} records "
+                                       "(C++ restatement of the Go path; the Go ingester cannot be built here)"},
+            "e2e": {"value": value, "unit": "records/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
 
-    # pinned host copies of every sub-batch (the Go shim's staging buffers)
-    pinned = []
-    for w in subs:
-        t = torch.empty(max(1, w.nbytes), dtype=torch.uint8, pin_memory=True)
-        t[:w.nbytes].copy_(torch.from_numpy(w.data))
-        pinned.append(t)
-    # device-resident copies for the `value` leg
-    dev_data = [p.to(f"cuda:{local}", non_blocking=True) for p in pinned]
-    torch.cuda.synchronize()
 
-    cfg = abi.Cfg()
-    cfg.max_batch_bytes = max(w.nbytes for w in subs) + (1 << 20)
-    cfg.flow_tag_cache_max_size = 1 << 20  # tag set of this workload stays below it: no LRU eviction either side
-    engines = [Engine(local, cfg) for _ in range(max(1, a.decoders))]
-    for e in engines:
-        e.load_synth(synth)
-    main_eng = engines[0]
-    stream = torch.cuda.ExternalStream(main_eng.stream, device=local)
+# ---------------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------------
+class Feed:
+    """The sub-batches one decoder pool works through in a step: host (pinned) and device-resident copies."""
+
+    def __init__(self, torch, local, msg, subs):
+        self.msg, self.subs = msg, subs
+        self.pinned, self.dev = [], []
+        for w in subs:
+            t = torch.empty(max(1, w.nbytes), dtype=torch.uint8, pin_memory=True)
+            t[:w.nbytes].copy_(torch.from_numpy(w.data))
+            self.pinned.append(t)
+            self.dev.append(t.to(f"cuda:{local}", non_blocking=True))
+        self.records = sum(w.nrecords for w in subs)
+        self.in_bytes = sum(w.nbytes for w in subs)
+        self.frame_bytes = sum(w.frames.nbytes for w in subs)
+
+
+def run_pools(torch, dist, local, world, pools, steps, warmup, after_step=None, before_step=None):
+    """pools: list of (Feed, [Engine...]).  Returns timings of the device-resident and the end-to-end leg."""
+    from deepflow_b200.native import lib
+    engines = [e for _f, es in pools for e in es]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM, kernels only --------------------------------------
-    # The decoders of this GPU (DecoderQueueCount contexts, the reference default is 2) each take
-    # every len(engines)-th sub-batch on their own stream, like the e2e leg and like the ingester's
-    # decoder goroutines; the framing chase of one overlaps the passes of the other.
+    def worker_lists():
+        out = []
+        for feed, es in pools:
+            for k, e in enumerate(es):
+                out.append((e, feed, list(range(k, len(feed.subs), len(es)))))
+        return out
+
+    jobs = worker_lists()
+
     def resident_step():
         err = []
 
-        def worker(k):
+        def work(e, feed, idx):
             try:
-                eng = engines[k]
-                for i in range(k, len(subs), len(engines)):
-                    w = subs[i]
-                    eng.stage_ptr(MSG, dev_data[i].data_ptr(), w.nbytes, w.frames.ctypes.data, len(w.frames))
-                    eng.run()
+                for i in idx:
+                    w = feed.subs[i]
+                    e.stage_ptr(feed.msg, feed.dev[i].data_ptr(), w.nbytes, w.frames.ctypes.data, len(w.frames))
+                    e.run()
             except Exception as ex:  # noqa: BLE001
                 err.append(ex)
 
-        ts = [threading.Thread(target=worker, args=(k,)) for k in range(len(engines))]
+        ts = [threading.Thread(target=work, args=j) for j in jobs]
         [t.start() for t in ts]
         [t.join() for t in ts]
         if err:
             raise err[0]
 
+    collected = []
+
+    def e2e_step():
+        err = []
+
+        def work(e, feed, idx):
+            try:
+                for i in idx:
+                    w = feed.subs[i]
+                    out = C.c_void_p()
+                    rc = lib().dfgpu_submit(e._h, feed.msg, feed.pinned[i].data_ptr(), w.nbytes, w.frames.ctypes.data,
+                                            len(w.frames), None, None, C.byref(out))
+                    if rc != 0:
+                        raise RuntimeError(f"dfgpu_submit rc={rc}: {lib().dfgpu_last_error(e._h).decode()}")
+                    if after_step is not None and feed.msg == L7:
+                        collected.append(out)  # the merge reads the emitted keys, then releases
+                    else:
+                        lib().dfgpu_batch_release(out)
+            except Exception as ex:  # noqa: BLE001
+                err.append(ex)
+
+        if before_step is not None:
+            before_step()
+        ts = [threading.Thread(target=work, args=j) for j in jobs]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        if err:
+            raise err[0]
+        if after_step is not None:
+            after_step(collected)
+            collected.clear()
+
     streams = [torch.cuda.ExternalStream(e.stream, device=local) for e in engines]
-    tstream = torch.cuda.Stream(device=local)  # timing stream: start event before, end event after every decoder
-    # clocks / throttle reasons: sampled from the first warm-up step to the end of the e2e leg (the
-    # value leg alone lasts ~0.1 s, less than nvidia-smi needs to start on an 8-GPU box)
-    sampler = ClockSampler(local)
-    sampler.start()
-    for _ in range(a.warmup):
+    tstream = torch.cuda.Stream(device=local)
+    for _ in range(warmup):
+        if before_step is not None:
+            before_step()
         resident_step()
     for e in engines:
         e.sync()
-        e.profile_enable(True)
     launches0 = sum(e.launch_count for e in engines)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(tstream)
     for st in streams:
         st.wait_event(ev0)
-    for _ in range(a.steps):
+    for _ in range(steps):
+        if before_step is not None:
+            before_step()
         resident_step()
     for st in streams:
         done = torch.cuda.Event()
@@ -362,208 +435,587 @@ def main():
     tstream.synchronize()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    emit_ms, emit_n, emit_in = 0.0, 0, 0
-    stage_ms = {}
-    for e in engines:
-        st_ms, _n = e.profile_stages()
-        for k, v in st_ms.items():
-            stage_ms[k] = stage_ms.get(k, 0.0) + v
-        ms, n, nb = e.profile_read()
-        emit_ms, emit_n, emit_in = emit_ms + ms, emit_n + n, emit_in + nb
-        e.profile_enable(False)
-    launches_value = sum(e.launch_count for e in engines) - launches0
-    # validate the last resident run + get exact output sizes for the roofline
-    last_i = len(subs) - 1
-    b = engines[last_i % len(engines)].fetch()
-    cnt = b.counters()
-    assert cnt.error_count == 0 and cnt.count == subs[last_i].nrecords, (cnt.error_count, cnt.count)
-    out_b_last, rows_last, str_b_last = output_bytes(b)
-    b.release()
-
-    # ---- roofline leg: the dominant kernel timed alone -------------------------------------------------
-    # In the value leg the decoders' kernels share the SMs, so a kernel's event time there contains its
-    # neighbours.  One more pass of one decoder by itself: CUDA events of the library, on its stream,
-    # right around every EMIT launch.
-    main_eng.sync()
-    main_eng.profile_enable(True)
-    for i, w in enumerate(subs):
-        main_eng.stage_ptr(MSG, dev_data[i].data_ptr(), w.nbytes, w.frames.ctypes.data, len(w.frames))
-        main_eng.run()
-    main_eng.sync()
-    solo_stage_ms, solo_runs = main_eng.profile_stages()
-    solo_emit_ms, solo_emit_n, _ = main_eng.profile_read()
-    main_eng.profile_enable(False)
-    main_eng.fetch().release()
-
-    # ---- e2e: host buffers through the C ABI, H2D + kernels + D2H per sub-batch -------------
-    d2h_total = [0]
-    from deepflow_b200.native import Batch, lib
-    from deepflow_b200.sharded import FLOW_TAG_TABLES, TagMerge
-    merge = TagMerge(device=torch.device("cuda", local)) if world > 1 else None
-
-    def e2e_step(engines=engines):
-        err = []
-        new_fps, new_times = [], []
-
-        def worker(k):
-            eng = engines[k]
-            try:
-                for i in range(k, len(subs), len(engines)):
-                    w = subs[i]
-                    out = C.c_void_p()
-                    rc = lib().dfgpu_submit(eng._h, MSG, pinned[i].data_ptr(), w.nbytes, w.frames.ctypes.data,
-                                            len(w.frames), None, None, C.byref(out))
-                    if rc != 0:
-                        raise RuntimeError(f"dfgpu_submit rc={rc}")
-                    if merge is not None:  # keys this decoder discovered: published after the step
-                        b = Batch(out)
-                        for t in FLOW_TAG_TABLES:
-                            f = b.tag_fingerprints(t)
-                            if len(f):
-                                cols, _ = b.columns(t)
-                                new_fps.append(f)
-                                new_times.append(cols[0].values.astype(np.uint32))
-                        b.release()
-                    else:
-                        lib().dfgpu_batch_release(out)
-            except Exception as ex:  # noqa: BLE001
-                err.append(ex)
-
-        ts = [threading.Thread(target=worker, args=(k,)) for k in range(len(engines))]
-        [t.start() for t in ts]
-        [t.join() for t in ts]
-        if err:
-            raise err[0]
-        if merge is not None:
-            # the one collective of the path: all-gather of the newly emitted flow_tag keys (NCCL),
-            # then every decoder of this rank imports the union
-            fps = np.concatenate(new_fps) if new_fps else np.zeros((0, 2), np.uint64)
-            tms = np.concatenate(new_times) if new_times else np.zeros(0, np.uint32)
-            _keep, rf, rt = merge.exchange(fps, tms)
-            allf, allt = np.concatenate([rf, fps]), np.concatenate([rt, tms])
-            for e in engines:
-                e.tags_import(allf, allt)
-
-    for _ in range(a.warmup):
+    launches = sum(e.launch_count for e in engines) - launches0
+    # every resident run must have fit and decoded: fetch the last batch of every engine
+    for e, feed, idx in jobs:
+        if idx:
+            b = e.fetch()
+            cnt = b.counters()
+            assert cnt.error_count == 0, (cnt.error_count, cnt.count)
+            b.release()
+    for _ in range(warmup):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(steps):
         e2e_step()
     for e in engines:
         e.sync()
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
+    return dev_ms, e2e_s, launches
 
-    # ---- e2e again with dfgpu_cfg.native_strings (first step): String / Array(String)
-    # columns cross PCIe in ClickHouse native encoding, their Position arrays stay on the GPU ------------
-    e2e_nat_s = nat_bytes_per_row = None
-    if not a.no_native_leg and world == 1:  # N=1 only: the scaling runs keep to the two legs above
+
+def solo_stages(engine, feed):
+    """One decoder alone over its feed: the library's CUDA events around every stage (kernels of concurrent
+    decoders would overlap the events)."""
+    engine.sync()
+    engine.profile_enable(True)
+    for i, w in enumerate(feed.subs):
+        engine.stage_ptr(feed.msg, feed.dev[i].data_ptr(), w.nbytes, w.frames.ctypes.data, len(w.frames))
+        engine.run()
+    engine.sync()
+    st, runs = engine.profile_stages()
+    pack_ms, pack_n, _ = engine.profile_read()
+    engine.profile_enable(False)
+    engine.fetch().release()
+    return st, runs, pack_ms, pack_n
+
+
+def reduce_max(torch, dist, world, local, vals):
+    t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def reduce_sum(torch, dist, world, local, vals):
+    t = torch.tensor(vals, dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.tolist()
+
+
+def make_merge_hooks(torch, local, world, engines):
+    """The one collective of the path: after an e2e step all ranks all-gather the flow_tag keys they emitted
+    (NCCL), the lowest rank keeps the row, every decoder imports the union."""
+    from deepflow_b200.native import Batch
+    from deepflow_b200.sharded import FLOW_TAG_TABLES, TagMerge
+    merge = TagMerge(device=torch.device("cuda", local))
+    emitted = [0]
+
+    def after(handles):
+        fps, tms = [], []
+        for h in handles:
+            b = Batch(h)
+            for t in FLOW_TAG_TABLES:
+                f = b.tag_fingerprints(t)
+                if len(f):
+                    cols, _ = b.columns(t)
+                    fps.append(f)
+                    tms.append(cols[0].values.astype(np.uint32))
+            b.release()
+        f = np.concatenate(fps) if fps else np.zeros((0, 2), np.uint64)
+        t = np.concatenate(tms) if tms else np.zeros(0, np.uint32)
+        emitted[0] += len(t)
+        _keep, rf, rt = merge.exchange(f, t)
+        if world > 1:
+            allf, allt = np.concatenate([rf, f]), np.concatenate([rt, t])
+            for e in engines:
+                e.tags_import(allf, allt)
+
+    return merge, after, emitted
+
+
+def roofline_for(stage_ms, runs, alg_bytes_by_stage, recs_per_launch, peak, peak_src, kernels):
+    """Dominant stage = the one with the most device time in the solo leg."""
+    stage_ms = {k: v for k, v in stage_ms.items()}
+    dom = max(alg_bytes_by_stage, key=lambda k: stage_ms.get(k, 0.0))
+    per_launch_s = stage_ms[dom] / 1000.0 / max(1, runs)
+    achieved = alg_bytes_by_stage[dom] * recs_per_launch / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    traffic, tsrc = ncu_traffic(kernels.get(dom, dom), recs_per_launch)
+    tot = sum(stage_ms.values())
+    return {"bound": "hbm", "kernel": kernels.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+            "traffic_source": tsrc, "peak_source": peak_src, "algorithmic_bytes_per_record": alg_bytes_by_stage[dom],
+            "launches_timed": runs, "avg_launch_ms": stage_ms[dom] / max(1, runs),
+            "timed": "one decoder alone, CUDA events of the library on its stream around every stage",
+            "share_of_device_time": stage_ms[dom] / tot if tot else None,
+            "stage_ms_per_step_one_decoder": stage_ms,
+            "stage_frac": {k: (alg_bytes_by_stage[k] * recs_per_launch / (stage_ms[k] / 1000.0 / max(1, runs)) / 1e9 / peak
+                               if stage_ms.get(k) else None) for k in alg_bytes_by_stage}}
+
+
+def column_hashes(batch, tables):
+    """One digest per column of every table: the bytes of every array of the ch-go container."""
+    out = {}
+    for t in tables:
+        cols, n = batch.columns(t)
+        for c in cols:
+            h = hashlib.blake2b(digest_size=12)
+            h.update(str(n).encode())
+            for attr in ("values", "buf", "pos", "arr_offsets", "nulls"):
+                x = getattr(c, attr)
+                if x is not None:
+                    h.update(attr.encode())
+                    h.update(np.ascontiguousarray(x).tobytes())
+            if c.dict is not None:
+                for s in c.dict:
+                    h.update(b"|" + s)
+            out[f"{t}:{c.name}"] = h.hexdigest()
+    return out
+
+
+def leg_parity(a, synth, local, cfg, subs):
+    """Parity AT the benchmarked configuration: full-size sub-batches, the bench's dictionary, `decoders` contexts
+    concurrently on one GPU, every column of the four L7 tables hashed and compared with the oracle run on the
+    same sub-batch from the same (empty) state."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from deepflow_b200.native import Engine
+    from oracle_binding import Oracle
+    tables = [abi.TABLE_L7_FLOW_LOG, abi.TABLE_L7_CUSTOM_FIELD, abi.TABLE_L7_CUSTOM_FIELD_VALUE, abi.TABLE_L7_APP_SERVICE]
+    n = max(1, min(a.decoders, len(subs)))
+    engs = [Engine(local, cfg) for _ in range(n)]
+    oras = [Oracle(cfg) for _ in range(n)]
+    for e, o in zip(engs, oras):
+        e.load_synth(synth)
+        o.load_synth(synth)
+    g, o_h = [None] * n, [None] * n
+    err = []
+
+    def gpu(k):
+        try:
+            b = engs[k].submit(subs[k])
+            g[k] = (column_hashes(b, tables), b.counters().as_dict())
+            b.release()
+        except Exception as ex:  # noqa: BLE001
+            err.append(ex)
+
+    def cpu(k):
+        try:
+            oras[k].submit(subs[k])
+
+            class _B:
+                def columns(self, t):
+                    return oras[k].columns(t)
+            o_h[k] = (column_hashes(_B(), tables), oras[k].counters().as_dict())
+        except Exception as ex:  # noqa: BLE001
+            err.append(ex)
+
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=gpu, args=(k,)) for k in range(n)] + [threading.Thread(target=cpu, args=(k,)) for k in range(n)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if err:
+        raise err[0]
+    mism, ncols = [], 0
+    for k in range(n):
+        ncols += len(o_h[k][0])
+        for name, hv in o_h[k][0].items():
+            if g[k][0].get(name) != hv:
+                mism.append(f"ctx{k}:{name}")
+        for key in ("count", "error_count", "l7_http_count", "new_field_count", "new_field_value_count"):
+            if g[k][1].get(key) != o_h[k][1].get(key):
+                mism.append(f"ctx{k}:counter:{key}")
+    digest = hashlib.blake2b("".join(sorted(f"{k}{n_}{h}" for k in range(n) for n_, h in g[k][0].items())).encode(),
+                             digest_size=12).hexdigest()
+    for e in engs:
+        e.close()
+    for o in oras:
+        o.close()
+    return {"contexts": n, "records_per_context": [s.nrecords for s in subs[:n]], "dictionary_pods": a.pods,
+            "tables": len(tables), "columns_compared": ncols, "mismatches": mism[:20], "ok": not mism,
+            "digest": digest, "seconds": time.perf_counter() - t0}
+
+
+def leg_c3(a, torch, local, peak, peak_src):
+    """BASELINE configs[2]: flow_metrics 1s -> 1m rollup, N decoded network_map.1s rows -> K groups, on one GPU,
+    input resident in HBM (generated on the device).  Checks: every summed meter field totals the same before
+    and after the fold, every max field has the same maximum, the number of groups equals the number of distinct
+    keys (size-independent properties; bit-exact parity against the oracle is tests/test_metrics_gpu.py)."""
+    from deepflow_b200.native import Engine
+    table = abi.TABLE_METRICS_BASE + 6  # network_map.1s
+    cfg = abi.Cfg()
+    cfg.max_batch_bytes = 1 << 20
+    cfg.max_batch_records = 4096
+    cfg.rollup_max_groups = max(1 << 20, 2 * a.c3_groups)
+    eng = Engine(local, cfg)
+    elem, kind, nf = eng.rollup_describe(table)
+    n, K = a.c3_rows, a.c3_groups
+    dev = f"cuda:{local}"
+    dts = {1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    t0 = time.time()
+    raw = torch.empty((n, nf), dtype=torch.int64, device=dev)
+    group = torch.empty(n, dtype=torch.int64, device=dev)
+    CH = 4_000_000
+    for s in range(0, n, CH):
+        m = min(CH, n - s)
+        u = torch.rand(m, device=dev, generator=g, dtype=torch.float64)
+        group[s:s + m] = torch.clamp((float(K) ** u).to(torch.int64) - 1, 0, K - 1)  # Zipf(1.0): rank = K^u
+        v = torch.randint(0, 1 << 31, (m, nf), device=dev, generator=g, dtype=torch.int64)  # every field width holds it
+        small = torch.rand((m, nf), device=dev, generator=g) < 0.9
+        v = torch.where(small, v & 0xffff, v)
+        v = torch.where(torch.rand((m, nf), device=dev, generator=g) < 0.6, torch.zeros_like(v), v)  # 60 % zeros
+        raw[s:s + m] = v
+        del u, v, small
+    cols = []
+    base_time = 1_700_000_040  # a minute boundary: 60 consecutive seconds -> one 1 m bucket
+    for c, (es, kd) in enumerate(zip(elem, kind)):
+        if c == 0:
+            col = (base_time + (torch.arange(n, device=dev, dtype=torch.int64) % 60)).to(torch.int32)
+        elif kd == 1:  # IPv6: 16 bytes per row, a function of the group
+            col = torch.stack([group * 0x9E3779B1 + c, group * 0x85EBCA77 + 7 * c], dim=1).contiguous()
+        elif kd == 2:
+            col = (group % 17).to(torch.int8)  # canonical tap-side code 0..16
+        else:
+            col = ((group + 1) * (2654435761 + 40503 * c) >> 7).to(dts[es])  # any function of the group
+        cols.append(col)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    key_bytes = sum(16 if kd == 1 else es for es, kd in zip(elem, kind))
+    distinct = int(torch.unique(group).numel())
+    stream = torch.cuda.ExternalStream(eng.stream, device=local)
+    ptrs = [c.data_ptr() for c in cols]
+    ms, out_rows, checks = [], None, {}
+    for it in range(1 + a.steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.rollup_add_rows(table, 60, ptrs, raw.data_ptr(), n)
+        e1.record(stream)
+        b = eng.rollup_flush(table)  # D2H of the K groups: outside the timed fold
+        torch.cuda.synchronize()
+        if it:
+            ms.append(e0.elapsed_time(e1))
+        rcols, out_rows = b.columns(abi.TABLE_METRICS_REDUCED)
+        if it == a.steps:
+            by = {c.name: c for c in rcols}
+            names = [c.name for c in rcols]
+            # size-independent properties on fields the columns hold losslessly (integers)
+            checks["groups_equal_distinct_keys"] = bool(out_rows == distinct)
+            tot_in = raw.sum(dim=0)  # int64 wrap = uint64 wrap
+            for fname, fidx in (("packet_tx", 0), ("byte_tx", 2), ("new_flow", 8)):
+                if fname in by:
+                    got = int(by[fname].values.astype(np.uint64).sum(dtype=np.uint64))
+                    exp = int(tot_in[fidx].item()) & 0xffffffffffffffff
+                    checks[f"sum_{fname}"] = bool(got == exp)
+            if "rtt_max" in by:
+                checks["max_rtt_max"] = bool(int(by["rtt_max"].values.max()) == int(raw[:, 15].max().item() & 0xffffffff))
+            checks["columns"] = len(names)
+        b.release()
+    t = float(np.mean(ms)) / 1000.0
+    alg = n * (key_bytes + nf * 8) + out_rows * (key_bytes + nf * 8)
+    achieved = alg / t / 1e9
+    res = {"workload": "C3: flow_metrics 1s -> 1m rollup (BASELINE.json configs[2])", "rows": n, "groups": out_rows,
+           "distinct_keys_in_input": distinct, "key_bytes": key_bytes, "meter_fields": nf, "value": n / t, "unit": "rows/s",
+           "ms_per_step": t * 1000, "input": "decoded rows resident in HBM (generated on the device)", "gen_seconds": gen_s,
+           "roofline": {"bound": "hbm", "kernel": "k_ru_key + k_ru_hist/scatter + k_ru_fold + k_ru_edge (rollup.cu)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "algorithmic_bytes": alg, "multiple_of_bound": (t * peak * 1e9) / alg, "peak_source": peak_src},
+           "checks": checks,
+           "e2e": {"value": n / t, "unit": "rows/s", "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": int(out_rows * (key_bytes + nf * 8)),
+                   "note": "config 3 keeps its input in HBM by definition; the D2H of the K groups is the flush"}}
+    if not a.no_cpu_baseline:  # one thread, one hash map, on the first 2 M rows of the same input
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding
+        L = oracle_binding.lib()
+        L.oracle_rollup_rows.restype = C.c_uint64
+        L.oracle_rollup_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+        m = min(n, 2_000_000)
+        keys = np.concatenate([c[:m].cpu().numpy().reshape(m, -1).view(np.uint8) for c in cols], axis=1)
+        keys[:, 0:4] = np.frombuffer(np.uint32(base_time).tobytes(), np.uint8)  # time -> bucket start
+        keys = np.ascontiguousarray(keys)
+        rawh = np.ascontiguousarray(raw[:m].cpu().numpy())
+        ops = np.zeros(nf, np.uint8)  # sums: the cheapest rule (a lower bound of the CPU cost)
+        sums = np.zeros(nf, np.uint64)
+        t0 = time.perf_counter()
+        kk = L.oracle_rollup_rows(keys.ctypes.data, keys.shape[1], rawh.ctypes.data, nf, ops.ctypes.data, m, sums.ctypes.data)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": m / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                               "sample": f"{m} decoded rows of the same input -> {kk} groups, one thread, one hash map, {dt:.1f} s"}
+    del raw, group, cols
+    eng.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    a = parse_args()
+    rank, world, local = dist_env()
+    if world > 1:
+        a.gpus = world
+    if a.impl == "reference":
+        return reference_arm(a) if rank == 0 else 0
+    legs = set(x for x in a.legs.split(",") if x)
+
+    import torch
+    import torch.distributed as dist
+    from deepflow_b200 import build
+    from deepflow_b200.synth import F_HIGH_CARD, Synth
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: libdfgpu has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local)
+    numa = bind_near_gpu(local)  # before any pinned allocation: first touch places the staging buffers
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        build.build_synth()
+    from deepflow_b200.native import Engine
+    peak, peak_src = measured_peak_hbm()
+    sampler = ClockSampler(local)
+    sampler.start()
+    synth = Synth(n_pods=a.pods)
+
+    def mk_cfg(max_bytes, cache=1 << 20, native=0):
+        c = abi.Cfg()
+        c.max_batch_bytes = max_bytes + (1 << 20)
+        c.max_batch_records = a.sub_batch + a.sub_batch // 8 + 4096
+        c.flow_tag_cache_max_size = cache  # the tag set of the C2 workload stays below it: no eviction either side
+        c.native_strings = native
+        return c
+
+    # =================================================================================== C2 (headline)
+    t0 = time.time()
+    subs = gen_sub_batches(synth, L7, a.records, a.sub_batch, 1000 + 7919 * rank, world, rank)
+    gen_s = time.time() - t0
+    feed = Feed(torch, local, L7, subs)
+    torch.cuda.synchronize()
+    cfg = mk_cfg(max(w.nbytes for w in subs))
+    engines = [Engine(local, cfg) for _ in range(max(1, a.decoders))]
+    for e in engines:
+        e.load_synth(synth)
+    merge, after, emitted = (None, None, [0])
+    if world > 1:
+        merge, after, emitted = make_merge_hooks(torch, local, world, engines)
+    dev_ms, e2e_s, launches = run_pools(torch, dist, local, world, [(feed, engines)], a.steps, a.warmup, after_step=after)
+    st_ms, st_runs, pack_ms, pack_n = solo_stages(engines[0], feed)
+    b = engines[0].submit(subs[-1])
+    cen = block_bytes(b, abi.TABLE_L7_FLOW_LOG)
+    b.release()
+    row_b = cen["total"] / max(1, cen["rows"])
+    fixed_b, aux_b, var_b = (cen[k] / max(1, cen["rows"]) for k in ("fixed", "aux", "var"))
+    wire_b = feed.in_bytes / feed.records
+    kg_b = 116.0  # the 39 SmartEncoding columns + team_id / gprocess ids (schema_l7.h)
+    alg = {"decode": wire_b + 4 + (fixed_b - kg_b), "pack": 2 * var_b + aux_b, "smartencoding": kg_b + 32 * 12, "flow_tag": 32 * 8.0}
+    kernels = {"decode": "k_l7_decode", "pack": "k_l7_strings<0> + k_l7_strings<1>", "smartencoding": "k_l7_kg",
+               "flow_tag": "k_l7_flow_tag<0..3>"}
+    recs_per_launch = feed.records / max(1, st_runs)
+    roof = roofline_for(st_ms, st_runs, alg, recs_per_launch, peak, peak_src, kernels)
+    path_bytes = wire_b + 4 + row_b + 32 * 12 + 32 * 8
+    path_ms = sum(st_ms.values())
+    path_ach = path_bytes * feed.records / (path_ms / 1000.0) / 1e9 if path_ms else 0.0
+    roof["path"] = {"kernels": "framing + decode + scans + pack + SmartEncoding + flow_tag (every kernel of dfgpu_run)",
+                    "algorithmic_bytes_per_record": path_bytes, "ms_per_step": path_ms, "achieved": path_ach,
+                    "frac": path_ach / peak}
+    dev_ms_max, e2e_ms_max = reduce_max(torch, dist, world, local, [dev_ms, e2e_s * 1000.0])
+    (total_recs,) = reduce_sum(torch, dist, world, local, [float(feed.records)])
+    value = total_recs * a.steps / (dev_ms_max / 1000.0)
+    e2e_value = total_recs * a.steps / (e2e_ms_max / 1000.0)
+    line = {"metric": METRIC, "value": value, "unit": "records/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/u32/u64 integer (f64 casts only at pack)", "data": "synthetic",
+            "config": {"workload": "C2: L7 HTTP AppProtoLogsData, SmartEncoding on, flow_tag on (BASELINE.json configs[1])",
+                       "records_per_gpu_per_step": a.records, "sub_batch_records": a.sub_batch, "dictionary_pods": a.pods,
+                       "sharding": "vtap_id % n_gpus" if a.gpus > 1 else "none",
+                       "l2": "inputs 4+ GB per step >> 126 MB L2 (no flush needed)", "mean_wire_bytes": wire_b,
+                       "packed_bytes_per_row": row_b, "gen_seconds": gen_s, "decoders_per_gpu": len(engines),
+                       "host_affinity": numa,
+                       "tag_merge": (None if merge is None else {
+                           "collective": "all_gather of emitted flow_tag key fingerprints, once per e2e step (NCCL)",
+                           "bytes_sent_rank0": merge.bytes_sent, "seconds_rank0": merge.seconds,
+                           "keys_emitted_rank0": emitted[0]})},
+            "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": int(feed.in_bytes + feed.frame_bytes),
+                    "d2h_bytes_per_step": int(row_b * feed.records), "ms_per_step": e2e_ms_max / a.steps,
+                    "d2h_gbs_per_rank": row_b * feed.records * a.steps / e2e_s / 1e9},
+            "gpu_launches": int(launches), "roofline": roof, "legs": {}}
+
+    # one decoder alone against all of them: how much of the GPU a single context keeps busy
+    if "c2" in legs and world == 1:
+        d1, _e1, _l1 = run_pools(torch, dist, local, world, [(feed, engines[:1])], max(1, a.steps // 2), 1)
+        line["config"]["one_decoder_value"] = feed.records * max(1, a.steps // 2) / (d1 / 1000.0)
+
+    # ---- e2e with dfgpu_cfg.native_strings (SURVEY 8(f) N1): String columns cross PCIe in native encoding ----
+    if "native" in legs and world == 1:
         for e in engines:
             e.sync()
-        ncfg = abi.Cfg()
-        ncfg.max_batch_bytes = cfg.max_batch_bytes
-        ncfg.flow_tag_cache_max_size = cfg.flow_tag_cache_max_size
-        ncfg.native_strings = 1
-        nat_engines = [Engine(local, ncfg) for _ in range(len(engines))]
-        for e in nat_engines:
+        ncfg = mk_cfg(max(w.nbytes for w in subs), native=1)
+        neng = [Engine(local, ncfg) for _ in range(len(engines))]
+        for e in neng:
             e.load_synth(synth)
-        for _ in range(a.warmup):
-            e2e_step(nat_engines)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            e2e_step(nat_engines)
-        for e in nat_engines:
-            e.sync()
-        barrier()
-        e2e_nat_s = time.perf_counter() - t0
-        w = subs[-1]
-        nb = nat_engines[0].submit(w)
-        nc = nb.counters()
-        assert nc.error_count == 0 and nc.count == w.nrecords, (nc.error_count, nc.count)
-        nat_out_b, nat_rows, _ = output_bytes(nb)
-        nat_bytes_per_row = nat_out_b / max(1, nat_rows)
+        _d, nat_s, _l = run_pools(torch, dist, local, world, [(feed, neng)], a.steps, max(1, a.warmup - 1))
+        nb = neng[0].submit(subs[-1])
+        ncen = block_bytes(nb, abi.TABLE_L7_FLOW_LOG)
         nb.release()
-        for e in nat_engines:
+        for e in neng:
             e.close()
+        line["e2e_native_strings"] = {
+            "value": feed.records * a.steps / nat_s, "unit": "records/s", "h2d_bytes_per_step": int(feed.in_bytes + feed.frame_bytes),
+            "d2h_bytes_per_step": int(ncen["total"] / max(1, ncen["rows"]) * feed.records), "ms_per_step": nat_s * 1000 / a.steps,
+            "what": "same call, dfgpu_cfg.native_strings=1: String / Array(String) columns leave the GPU as ClickHouse "
+                    "native column data (uvarint length + bytes), no Position arrays over PCIe"}
 
-    # per-step byte accounting for e2e (H2D = staging buffers + frame tables; D2H = column blocks)
-    bytes_per_row = out_b_last / max(1, rows_last)
-    d2h_per_step = int(bytes_per_row * nrec_step)
-    h2d_per_step = int(in_bytes + sum(w.frames.nbytes for w in subs))
+    # =================================================================================== parity at size
+    if "parity" in legs and world == 1:
+        line["legs"]["parity"] = leg_parity(a, synth, local, cfg, subs)
 
-    # ---- max over ranks ----------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1000.0, (e2e_nat_s or 0.0) * 1000.0], dtype=torch.float64,
-                         device=f"cuda:{local}")
-    recs = torch.tensor([float(nrec_step)], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(recs, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max, e2e_nat_ms_max = times.tolist()
-    total_recs_step = recs.item()
-
-    if rank == 0:
-        value = total_recs_step * a.steps / (dev_ms_max / 1000.0)
-        e2e_value = total_recs_step * a.steps / (e2e_ms_max / 1000.0)
-        peak, peak_src = measured_peak_hbm()
-        # Dominant kernel = the EMIT/pack pass.  Its algorithmic bytes per record: every byte of the packed
-        # row it writes (all of the block except the 41 SmartEncoding columns the KG kernel writes: 116 B)
-        # + the string / array bytes it copies out of the wire record.  The slot buffer it also reads is an
-        # artefact of this design, not compulsory traffic, and is NOT counted.
-        str_per_row = str_b_last / max(1, rows_last)
-        alg_per_rec = (bytes_per_row - 116) + str_per_row
-        emit_launch_s = solo_emit_ms / 1000.0 / max(1, solo_emit_n)
-        recs_per_launch = nrec_step / max(1, solo_emit_n)
-        achieved = alg_per_rec * recs_per_launch / emit_launch_s / 1e9 if emit_launch_s > 0 else 0.0
-        # the whole per-record path (SURVEY §8d B_L7: wire + 4 + packed row + 32 B x 12 probes) over the
-        # three kernels that carry it (SIZE/decode, EMIT, SmartEncoding)
-        path_bytes = in_bytes / nrec_step + bytes_per_row + 32 * 12
-        path_ms = solo_stage_ms.get("size_pass", 0) + solo_stage_ms.get("emit_pass", 0)
-        path_achieved = path_bytes * nrec_step / (path_ms / 1000.0) / 1e9 if path_ms else 0.0
-        traffic, traffic_src = ncu_traffic("k_l7_pass<EMIT>", recs_per_launch)
-        roof = {"bound": "hbm", "kernel": "k_l7_pass<EMIT>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch",
-                "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_record": alg_per_rec, "launches_timed": solo_emit_n,
-                "avg_launch_ms": solo_emit_ms / max(1, solo_emit_n),
-                "timed": "one decoder alone (kernels of concurrent decoders would overlap the events)",
-                "share_of_device_time": solo_emit_ms / sum(solo_stage_ms.values()) if solo_stage_ms else None,
-                "stage_ms_per_step_one_decoder": solo_stage_ms,
-                "path": {"kernels": "k_l7_pass<SIZE> + k_l7_pass<EMIT> + k_l7_kg",
-                         "algorithmic_bytes_per_record": path_bytes, "ms_per_step": path_ms,
-                         "achieved": path_achieved, "frac": path_achieved / peak},
-                "stage_ms_per_step_all_decoders": {k: v / a.steps for k, v in stage_ms.items()}}
-        line = {"metric": METRIC, "value": value, "unit": "records/s", "n_gpus": a.gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer (f64 casts only at pack)",
-                "data": "synthetic", "config": dict(cfg_common, mean_wire_bytes=in_bytes / nrec_step,
-                                                    packed_bytes_per_row=bytes_per_row, gen_seconds=gen_s,
-                                                    decoders_per_gpu=len(engines), host_affinity=numa,
-                                                    tag_merge=(None if merge is None else {
-                                                        "collective": "all_gather of emitted flow_tag key fingerprints, "
-                                                                      "once per e2e step (NCCL)",
-                                                        "bytes_sent_rank0": merge.bytes_sent,
-                                                        "seconds_rank0": merge.seconds})),
-                "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": h2d_per_step,
-                        "d2h_bytes_per_step": d2h_per_step, "ms_per_step": e2e_ms_max / a.steps},
-                "gpu_launches": int(launches_value), "clocks": clocks, "roofline": roof}
-        if e2e_nat_s:
-            line["e2e_native_strings"] = {
-                "value": total_recs_step * a.steps / (e2e_nat_ms_max / 1000.0), "unit": "records/s",
-                "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": int(nat_bytes_per_row * nrec_step),
-                "ms_per_step": e2e_nat_ms_max / a.steps,
-                "what": "same call, dfgpu_cfg.native_strings=1: String / Array(String) columns leave the GPU as "
-                        "ClickHouse native column data (uvarint length + bytes), no Position arrays over PCIe"}
-        if not a.no_cpu_baseline:
-            build.build_oracle()
-            v, n, dt = cpu_port_run(synth, 400_000, 1, 4242)
-            line["cpu_baseline"] = {"value": v, "unit": "records/s", "cores": 1, "kind": "port",
-                                    "sample": f"{n} L7 records of the same generator, one decoder instance, {dt:.1f} s"}
-        print(json.dumps(line))
+    if not a.no_cpu_baseline and rank == 0 and world == 1:
+        build.build_oracle()
+        v, n, dt = cpu_port_run(synth, L7, 400_000, 1, 4242)
+        line["cpu_baseline"] = {"value": v, "unit": "records/s", "cores": 1, "kind": "port",
+                                "sample": f"{n} L7 records of the same generator, one decoder instance, {dt:.1f} s",
+                                "host": host_info()}
     for e in engines:
         e.close()
+    del feed
+    torch.cuda.empty_cache()
+
+    # =================================================================================== C4 mixed firehose
+    if "c4" in legs:
+        n4, n7, nm = int(a.records * 0.50), int(a.records * 0.35), a.records - int(a.records * 0.50) - int(a.records * 0.35)
+        t0 = time.time()
+        f4 = Feed(torch, local, L4, gen_sub_batches(synth, L4, n4, a.sub_batch, 4000 + 7919 * rank, world, rank))
+        f7 = Feed(torch, local, L7, gen_sub_batches(synth, L7, n7, a.sub_batch, 5000 + 7919 * rank, world, rank))
+        fm = Feed(torch, local, MET, gen_sub_batches(synth, MET, nm, a.sub_batch, 6000 + 7919 * rank, world, rank))
+        gen4 = time.time() - t0
+        mx = max(w.nbytes for f in (f4, f7, fm) for w in f.subs)
+        c4cfg = mk_cfg(mx)
+        pools = [(f4, [Engine(local, c4cfg) for _ in range(2)]), (f7, [Engine(local, c4cfg) for _ in range(2)]),
+                 (fm, [Engine(local, c4cfg)])]
+        all_e = [e for _f, es in pools for e in es]
+        for e in all_e:
+            e.load_synth(synth)
+        m4, after4, em4 = (None, None, [0])
+        if world > 1:
+            m4, after4, em4 = make_merge_hooks(torch, local, world, pools[1][1])
+        d_ms, e_s, l4n = run_pools(torch, dist, local, world, pools, a.steps, a.warmup, after_step=after4)
+        per_type = {}
+        tot_alg = 0.0
+        for name, (f, es) in zip(("l4", "l7", "metrics"), pools):
+            st, runs, _pm, _pn = solo_stages(es[0], f) if f.msg != MET else ({}, 0, 0, 0)
+            if f.msg == MET:
+                # the metrics pipeline has no stage marks: time one solo pass with CUDA events of the bench
+                es[0].sync()
+                s = torch.cuda.ExternalStream(es[0].stream, device=local)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s)
+                for i, w in enumerate(f.subs):
+                    es[0].stage_ptr(f.msg, f.dev[i].data_ptr(), w.nbytes, w.frames.ctypes.data, len(w.frames))
+                    es[0].run()
+                e1.record(s)
+                es[0].sync()
+                st = {"all": e0.elapsed_time(e1)}
+                es[0].fetch().release()
+            bb = es[0].submit(f.subs[-1])
+            if f.msg == MET:
+                rb = sum(block_bytes(bb, abi.TABLE_METRICS_BASE + t)["total"] for t in range(9)) / max(1, f.subs[-1].nrecords)
+            else:
+                c = block_bytes(bb, MAIN_TABLE[f.msg])
+                rb = c["total"] / max(1, c["rows"])
+            bb.release()
+            algb = f.in_bytes / f.records + 4 + rb + 32 * (12 if f.msg != MET else 8)
+            ms_solo = sum(st.values())
+            ach = algb * f.records / (ms_solo / 1000.0) / 1e9 if ms_solo else 0.0
+            per_type[name] = {"records_per_step": f.records, "mean_wire_bytes": f.in_bytes / f.records, "packed_bytes_per_record": rb,
+                              "algorithmic_bytes_per_record": algb, "solo_ms_per_step": ms_solo, "solo_records_per_s": f.records / (ms_solo / 1000.0) if ms_solo else None,
+                              "stage_ms": st, "achieved_gbs": ach, "frac": ach / peak}
+            tot_alg += algb * f.records
+        recs = f4.records + f7.records + fm.records
+        d_mx, e_mx = reduce_max(torch, dist, world, local, [d_ms, e_s * 1000.0])
+        (recs_all,) = reduce_sum(torch, dist, world, local, [float(recs)])
+        v4 = recs_all * a.steps / (d_mx / 1000.0)
+        ach4 = tot_alg * a.steps / (d_ms / 1000.0) / 1e9
+        dom = max(per_type, key=lambda k: per_type[k]["solo_ms_per_step"])
+        h2d = sum(f.in_bytes + f.frame_bytes for f in (f4, f7, fm))
+        d2h = sum(per_type[k]["packed_bytes_per_record"] * per_type[k]["records_per_step"] for k in per_type)
+        leg = {"workload": "C4: mixed firehose 50 % L4 / 35 % L7 / 15 % metric by record count (BASELINE.json configs[3]), "
+                           "one decoder pool per message type (2 + 2 + 1 contexts per GPU), sharded by vtap_id % n_gpus",
+               "records_per_gpu_per_step": recs, "value": v4, "unit": "records/s", "ms_per_step": d_mx / a.steps,
+               "e2e": {"value": recs_all * a.steps / (e_mx / 1000.0), "unit": "records/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": e_mx / a.steps},
+               "gpu_launches": int(l4n), "gen_seconds": gen4, "per_type": per_type,
+               "roofline": {"bound": "hbm", "kernel": f"the {dom} pipeline (largest share of device time)",
+                            "achieved": ach4, "peak": peak, "unit": "GB/s", "frac": ach4 / peak, "traffic": None,
+                            "what": "algorithmic bytes of all three message types per step / device time of the step with every "
+                                    "decoder pool running concurrently (rank 0)", "peak_source": peak_src},
+               "tag_merge": None if m4 is None else {"bytes_sent_rank0": m4.bytes_sent, "seconds_rank0": m4.seconds,
+                                                     "keys_emitted_rank0": em4[0]}}
+        if not a.no_cpu_baseline and rank == 0 and world == 1:
+            parts = []
+            tsec = 0.0
+            for msg, share in ((L4, 0.5), (L7, 0.35), (MET, 0.15)):
+                nn = int(200_000 * share)
+                _v, n_, dt = cpu_port_run(synth, msg, nn, 1, 777)
+                parts.append(n_)
+                tsec += dt
+            leg["cpu_baseline"] = {"value": sum(parts) / tsec, "unit": "records/s", "cores": 1, "kind": "port",
+                                   "sample": f"{parts} L4/L7/metric records of the same generator, one decoder instance each, {tsec:.1f} s"}
+        line["legs"]["c4_mixed"] = leg
+        for e in all_e:
+            e.close()
+        del f4, f7, fm, pools
+        torch.cuda.empty_cache()
+
+    # =================================================================================== C5 high cardinality
+    if "c5" in legs:
+        t0 = time.time()
+        big = Synth(n_pods=a.c5_pods)
+        synth_s = time.time() - t0
+        t0 = time.time()
+        subs5 = gen_sub_batches(big, L7, a.c5_records, a.sub_batch, 9000 + 7919 * rank, world, rank, flags=F_HIGH_CARD)
+        gen5 = time.time() - t0
+        f5 = Feed(torch, local, L7, subs5)
+        c5cfg = mk_cfg(max(w.nbytes for w in subs5), cache=1 << 22)
+        e5 = [Engine(local, c5cfg) for _ in range(max(1, a.decoders))]
+        t0 = time.time()
+        for e in e5:
+            e.load_synth(big)
+        dict_s = (time.time() - t0) / len(e5)
+        m5, after5, em5 = make_merge_hooks(torch, local, world, e5)
+
+        def cold():
+            for e in e5:
+                e.tags_reset()  # every step starts from an empty flow_tag set: all keys are new, all are merged
+
+        d_ms, e_s, l5 = run_pools(torch, dist, local, world, [(f5, e5)], a.steps, max(1, a.warmup - 1), after_step=after5,
+                                  before_step=cold)
+        cold()
+        st5, runs5, _pm, _pn = solo_stages(e5[0], f5)
+        bb = e5[0].submit(subs5[0])
+        cnt = bb.counters()
+        unrec, evi = int(cnt.flow_tag_unrecorded), int(cnt.flow_tag_evicted)
+        bb.release()
+        d_mx, e_mx = reduce_max(torch, dist, world, local, [d_ms, e_s * 1000.0])
+        recs_all, keys_all, bytes_all = reduce_sum(torch, dist, world, local, [float(f5.records), float(em5[0]), float(m5.bytes_sent)])
+        (merge_s,) = reduce_max(torch, dist, world, local, [m5.seconds])
+        steps_e2e = a.steps + max(1, a.warmup - 1)
+        line["legs"]["c5_highcard"] = {
+            "workload": "C5: high-cardinality SmartEncoding (BASELINE.json configs[4]): P = %d pod dictionary, L7 records whose "
+                        "attributes draw from ~1 M (name, value) pairs, flow_tag set emptied before every step" % a.c5_pods,
+            "records_per_gpu_per_step": f5.records, "dictionary_pods": a.c5_pods, "dict_build_seconds": synth_s,
+            "dict_load_seconds_per_context": dict_s, "gen_seconds": gen5,
+            "value": recs_all * a.steps / (d_mx / 1000.0), "unit": "records/s", "ms_per_step": d_mx / a.steps,
+            "e2e": {"value": recs_all * a.steps / (e_mx / 1000.0), "unit": "records/s",
+                    "h2d_bytes_per_step": int(f5.in_bytes + f5.frame_bytes), "d2h_bytes_per_step": None, "ms_per_step": e_mx / a.steps},
+            "flow_tag_keys_emitted_per_step_all_ranks": keys_all / steps_e2e,
+            "merge": {"collective": "all_gather of (128-bit fingerprint, time) of every emitted flow_tag row, once per step (NCCL)",
+                      "bytes_per_step_all_ranks": bytes_all / steps_e2e, "seconds_per_step_max_rank": merge_s / steps_e2e,
+                      "share_of_e2e_step": (merge_s / steps_e2e) / (e_mx / 1000.0 / a.steps) if e_mx else None},
+            "flow_tag_unrecorded": unrec, "flow_tag_evicted": evi, "gpu_launches": int(l5),
+            "roofline": {"bound": "hbm", "kernel": "k_l7_flow_tag<0..3> (cold set: every key is inserted and emitted)",
+                         "stage_ms_per_step_one_decoder": st5, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                         "traffic": None,
+                         "what": "the flow_tag stage against a cold set next to the other stages of the same run; "
+                                 "compare with the C2 line's warm-set stage times"}}
+        for e in e5:
+            e.close()
+        del f5
+        big.close()
+        torch.cuda.empty_cache()
+
+    # =================================================================================== C3 rollup
+    if "c3" in legs and world == 1:
+        try:
+            line["legs"]["c3_rollup"] = leg_c3(a, torch, local, peak, peak_src)
+        except torch.OutOfMemoryError as ex:  # noqa: BLE001
+            line["legs"]["c3_rollup"] = {"error": f"out of device memory for {a.c3_rows} rows: {ex}"}
+
+    line["clocks"] = sampler.stop()
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

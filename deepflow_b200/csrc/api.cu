@@ -24,6 +24,7 @@ void l7_grids(dfgpu_ctx* ctx, unsigned* decode, unsigned* strings, unsigned* kg)
 int l7_flow_tags(dfgpu_ctx* ctx, cudaStream_t s);
 int l7_prepare(dfgpu_ctx* ctx, cudaStream_t s);
 int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n);
+int l7_tags_reset(dfgpu_ctx* ctx);
 // metrics.cu
 int metrics_passes(dfgpu_ctx* ctx, int repair);
 int metrics_fetch(dfgpu_ctx* ctx, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t));
@@ -31,6 +32,7 @@ int rollup_add_resident(dfgpu_ctx* ctx, int table, uint32_t bucket);
 int rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket, const dfgpu_rollup_rows* rows);
 int rollup_flush(dfgpu_ctx* ctx, int table, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t));
 void rollup_free_state(dfgpu_ctx* ctx);
+int rollup_describe(dfgpu_ctx* ctx, int table, int* ntag, int* nfields, uint8_t* elem, uint8_t* kind);
 void metrics_free_state(dfgpu_ctx* ctx);
 }  // namespace dfgpu
 
@@ -919,6 +921,12 @@ int dfgpu_batch_tag_fingerprints(const dfgpu_batch* b, int table, const uint64_t
   return DFGPU_ENOENT;
 }
 
+int dfgpu_tags_reset(dfgpu_ctx* ctx) {
+  if (!ctx) return DFGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  return l7_tags_reset(ctx);
+}
+
 int dfgpu_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n) {
   if (!ctx || (n && (!fps || !times))) return DFGPU_EINVAL;
   CU(cudaSetDevice(ctx->device));
@@ -944,6 +952,13 @@ int dfgpu_rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, co
   if (int rc = metrics_table_arg(ctx, table)) return rc;
   CU(cudaSetDevice(ctx->device));
   return rollup_add_rows(ctx, table - DFGPU_TABLE_METRICS_BASE, bucket_seconds, rows);
+}
+
+int dfgpu_rollup_describe(dfgpu_ctx* ctx, int table, int* ntag, int* nfields, uint8_t* elem_sizes, uint8_t* kinds) {
+  if (!ctx) return DFGPU_EINVAL;
+  if (int rc = metrics_table_arg(ctx, table)) return rc;
+  CU(cudaSetDevice(ctx->device));
+  return rollup_describe(ctx, table - DFGPU_TABLE_METRICS_BASE, ntag, nfields, elem_sizes, kinds);
 }
 
 int dfgpu_rollup_flush(dfgpu_ctx* ctx, int table, dfgpu_batch** out) {

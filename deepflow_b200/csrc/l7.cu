@@ -814,6 +814,17 @@ int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, u
   return 0;
 }
 
+// forget every flow_tag key (what restarting the decoder does to its lru caches)
+int l7_tags_reset(dfgpu_ctx* ctx) {
+  int rc = l7_ensure_state(ctx);
+  if (rc) return rc;
+  L7Host* h = reinterpret_cast<L7Host*>(ctx->ft);
+  CU(cudaMemsetAsync(h->set.cur, 0, (size_t)h->set.slots() * sizeof(FtEntry), ctx->stream));
+  CU(cudaMemsetAsync(h->set.d_state, 0, sizeof(TagSetState), ctx->stream));
+  h->set.count_seen = 0;
+  return 0;
+}
+
 }  // namespace dfgpu
 
 extern "C" void dfgpu_l7_free_state(dfgpu_ctx* ctx) {

@@ -675,6 +675,21 @@ int rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket, const dfgpu_roll
   return ru_add(ctx, mh, h, table, src);
 }
 
+// schema of a table's rollup input: tag columns (bytes per value, kind) and raw meter fields
+int rollup_describe(dfgpu_ctx* ctx, int table, int* ntag, int* nfields, uint8_t* elem, uint8_t* kind) {
+  int rc = metrics_ensure_state(ctx);
+  if (rc) return rc;
+  MHost* mh = reinterpret_cast<MHost*>(ctx->mt);
+  if (ntag) *ntag = (int)mh->dev.ntag[table];
+  if (nfields) *nfields = mh->dev.raw_nf[table];
+  for (uint32_t c = 0; c < mh->dev.ntag[table]; c++) {
+    const MColDesc& dc = mh->dev.descs[mh->dev.desc_base[table] + c];
+    if (elem) elem[c] = dc.elem;
+    if (kind) kind[c] = dc.kind;
+  }
+  return 0;
+}
+
 // every group of the table -> REDUCED column block, first-appearance order; the accumulator starts over
 int rollup_flush(dfgpu_ctx* ctx, int table, dfgpu_batch* b, uint8_t* (*acquire)(dfgpu_ctx*, size_t)) {
   int rc = metrics_ensure_state(ctx);

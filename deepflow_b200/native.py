@@ -49,9 +49,11 @@ def lib():
         L.dfgpu_rollup_add.argtypes = [vp, C.c_int, C.c_uint32]
         L.dfgpu_rollup_flush.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.dfgpu_rollup_add_rows.argtypes = [vp, C.c_int, C.c_uint32, vp]
+        L.dfgpu_rollup_describe.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp]
         L.dfgpu_batch_tag_fingerprints.argtypes = [vp, C.c_int, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
         L.dfgpu_tags_import.argtypes = [vp, vp, vp, C.c_uint64]
         L.dfgpu_flush.argtypes = [vp]
+        L.dfgpu_tags_reset.argtypes = [vp]
         L.dfgpu_profile_enable.argtypes = [vp, C.c_int]
         L.dfgpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.dfgpu_profile_stages.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -177,6 +179,9 @@ class Engine:
         self._check(lib().dfgpu_metrics_reduce(self._h, table, bucket_seconds, C.byref(out)), "dfgpu_metrics_reduce")
         return Batch(out)
 
+    def tags_reset(self):
+        self._check(lib().dfgpu_tags_reset(self._h), "dfgpu_tags_reset")
+
     def rollup_add(self, table, bucket_seconds=60):
         """Fold the rows of `table` of the last metrics submit into the table's rollup accumulator."""
         self._check(lib().dfgpu_rollup_add(self._h, table, bucket_seconds), "dfgpu_rollup_add")
@@ -186,6 +191,13 @@ class Engine:
         cols = (C.c_void_p * len(tag_col_ptrs))(*tag_col_ptrs)
         rows = abi.RollupRows(nrows, C.cast(cols, C.c_void_p), len(tag_col_ptrs), raw_ptr)
         self._check(lib().dfgpu_rollup_add_rows(self._h, table, bucket_seconds, C.byref(rows)), "dfgpu_rollup_add_rows")
+
+    def rollup_describe(self, table):
+        """(elem sizes per tag column, kinds per tag column, raw meter fields per row)"""
+        ntag, nf = C.c_int(), C.c_int()
+        elem, kind = (C.c_uint8 * 128)(), (C.c_uint8 * 128)()
+        self._check(lib().dfgpu_rollup_describe(self._h, table, C.byref(ntag), C.byref(nf), elem, kind), "dfgpu_rollup_describe")
+        return list(elem[:ntag.value]), list(kind[:ntag.value]), nf.value
 
     def rollup_flush(self, table):
         out = C.c_void_p()

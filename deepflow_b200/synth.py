@@ -10,7 +10,7 @@ from . import abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-F_UNKNOWN_FIELDS, F_UNPACKED, F_DUP_FIELDS, F_OMIT_SUBMSG, F_CORRUPT, F_WIDE_VARINT = 1, 2, 4, 8, 16, 32
+F_UNKNOWN_FIELDS, F_UNPACKED, F_DUP_FIELDS, F_OMIT_SUBMSG, F_CORRUPT, F_WIDE_VARINT, F_HIGH_CARD = 1, 2, 4, 8, 16, 32, 64
 F_ALL_WIRE = F_UNKNOWN_FIELDS | F_UNPACKED | F_DUP_FIELDS | F_OMIT_SUBMSG | F_WIDE_VARINT
 
 

@@ -139,6 +139,8 @@ enum : uint32_t {
   F_OMIT_SUBMSG = 8,      // drop optional sub-messages entirely
   F_CORRUPT = 16,         // truncate / damage ~1 record per 50 frames
   F_WIDE_VARINT = 32,     // over-long varints, uint32 fields carrying >32-bit values
+  F_HIGH_CARD = 64,       // L7: attribute values from a 2^17 space x 8 names (~1 M (name, value) pairs): the
+                          // high-cardinality flow_tag workload of BASELINE config 5
 };
 
 struct Endpoint {
@@ -907,13 +909,15 @@ void gen_l7(synth_ctx* c, Rng& r, uint32_t vtap, uint64_t base_ns, uint32_t flag
   if ((flags & F_DUP_FIELDS) && r.chance(0.05)) nval = nattr ? nattr - 1 : 1;  // mismatched lengths
   // 60 names x 4 values each; with the bounded (vpc, pod_ns) set this keeps the tag key space small
   uint32_t name_idx[8];
+  const bool hc = (flags & F_HIGH_CARD) != 0;
   for (uint32_t i = 0; i < nattr; i++) {
-    name_idx[i] = r.skew(40);
+    name_idx[i] = hc ? r.below(8) : r.skew(40);
     snprintf(t, sizeof t, "attr_%u", name_idx[i]);
     ext.str_always(16, t);
   }
   for (uint32_t i = 0; i < nval; i++) {
-    snprintf(t, sizeof t, "val-%u", (i < nattr ? name_idx[i] : 0) * 3 + r.skew(3));
+    if (hc) snprintf(t, sizeof t, "user-%u", r.below(1u << 17));
+    else snprintf(t, sizeof t, "val-%u", (i < nattr ? name_idx[i] : 0) * 3 + r.skew(3));
     ext.str_always(17, r.chance(0.03) ? std::string() : std::string(t));
   }
   if (r.chance(0.1)) {

@@ -353,6 +353,9 @@ void dfgpu_batch_release(dfgpu_batch* b);
  *   times : the `time` column value of the emitting row (lru Add(key, time))          */
 int dfgpu_batch_tag_fingerprints(const dfgpu_batch* b, int table, const uint64_t** fps, uint64_t* n);
 int dfgpu_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, uint64_t n);
+/* Forgets every flow_tag key of this context (a restarted decoder starts with empty lru caches,
+ * flow_tag_writer.go:65-77); asynchronous on the ctx stream.                                      */
+int dfgpu_tags_reset(dfgpu_ctx* ctx);
 
 /* flow_metrics rollup (BASELINE config 3: 1s -> 1m).  A persistent device
  * accumulator per flow_metrics table, keyed by (time bucket, every tag column of the
@@ -384,6 +387,9 @@ typedef struct dfgpu_rollup_rows {
 int dfgpu_rollup_add(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds);
 int dfgpu_rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, const dfgpu_rollup_rows* rows);
 int dfgpu_rollup_flush(dfgpu_ctx* ctx, int table, dfgpu_batch** out);
+/* layout of a table's rollup input: number of tag columns / raw meter fields, bytes per value of every tag
+ * column and its kind (0 fixed, 1 IPv6, 2 observation_point code, 3/4 strings); arrays of >= 72 entries    */
+int dfgpu_rollup_describe(dfgpu_ctx* ctx, int table, int* ntag, int* nfields, uint8_t* elem_sizes, uint8_t* kinds);
 int dfgpu_metrics_reduce(dfgpu_ctx* ctx, int table, uint32_t bucket_seconds, dfgpu_batch** out);
 
 #ifdef __cplusplus

@@ -15,6 +15,8 @@
  * The entry points mirror include/dfgpu.h one-to-one so the parity tests can run
  * the same call sequence against both libraries.
  */
+#include <algorithm>
+#include <unordered_map>
 #include <map>
 #include <memory>
 
@@ -225,6 +227,48 @@ int oracle_rollup_flush(oracle_ctx* c, int table) {
   if (!c || !c->metrics) return DFGPU_ENOENT;
   return c->metrics->rollup_flush(table - DFGPU_TABLE_METRICS_BASE);
 }
+// CPU baseline of BASELINE config 3 on DECODED rows (what dfgpu_rollup_add_rows consumes): packed tag
+// bytes per row (key_stride, time already the bucket start) + row-major raw meters; ops = the
+// ConcurrentMerge rule per field (0 sum u64, 1 sum u32, 2/3 max, 4 first, 5 last).  One thread, one hash
+// map — the single-goroutine shape of the reference's merge.  Returns the number of groups; out_sums[nf]
+// = per-field fold over all groups (a checksum the caller compares with the GPU's).
+uint64_t oracle_rollup_rows(const uint8_t* keys, uint32_t key_stride, const uint64_t* raw, uint32_t nf,
+                            const uint8_t* ops, uint64_t n, uint64_t* out_sums) {
+  std::unordered_map<std::string, size_t> idx;
+  std::vector<uint64_t> acc;
+  idx.reserve((size_t)std::min<uint64_t>(n, 1u << 22));
+  for (uint64_t r = 0; r < n; r++) {
+    std::string k((const char*)keys + r * key_stride, key_stride);
+    const uint64_t* v = raw + r * nf;
+    auto it = idx.find(k);
+    if (it == idx.end()) {
+      idx.emplace(std::move(k), acc.size() / nf);
+      acc.insert(acc.end(), v, v + nf);
+      for (uint32_t f = 0; f < nf; f++)
+        if (ops[f] == 1) acc[acc.size() - nf + f] = (uint32_t)v[f];
+    } else {
+      uint64_t* a = acc.data() + it->second * nf;
+      for (uint32_t f = 0; f < nf; f++) {
+        switch (ops[f]) {
+          case 0: a[f] += v[f]; break;
+          case 1: a[f] = (uint32_t)((uint32_t)a[f] + (uint32_t)v[f]); break;
+          case 2:
+          case 3: if (a[f] < v[f]) a[f] = v[f]; break;
+          case 5: a[f] = v[f]; break;
+          default: break;  // first: kept
+        }
+      }
+    }
+  }
+  if (out_sums)
+    for (uint32_t f = 0; f < nf; f++) {
+      uint64_t t = 0;
+      for (size_t g = 0; g < acc.size() / nf; g++) t += acc[g * nf + f];
+      out_sums[f] = t;
+    }
+  return acc.size() / nf;
+}
+
 int oracle_metrics_reduce(oracle_ctx* c, int table, uint32_t bucket_seconds) {
   if (!c->metrics) return DFGPU_ENOENT;
   return c->metrics->reduce(table - DFGPU_TABLE_METRICS_BASE, bucket_seconds);
