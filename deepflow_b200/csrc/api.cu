@@ -486,13 +486,22 @@ int dfgpu_stage(dfgpu_ctx* ctx, int msg_type, const uint8_t* frames, size_t nbyt
   uint16_t org = nframes ? tbl[0].org_id : 1;
   for (int i = 1; i < nframes; i++)
     if (tbl[i].org_id != org) return fail(ctx, DFGPU_EMIXEDORG, "frames of one submit must share org_id");
+  bool sorted = true;
   for (int i = 0; i < nframes; i++) {
     // offset + len may wrap in uint64: compare without the addition
     if (tbl[i].offset > nbytes || tbl[i].len > nbytes - tbl[i].offset)
       return fail(ctx, DFGPU_EINVAL, "frame %d outside the staging buffer", i);
-    // frames share framing scratch by byte range: they must be laid out in order, without overlap
-    if (i && tbl[i].offset < tbl[i - 1].offset + tbl[i - 1].len)
-      return fail(ctx, DFGPU_EINVAL, "frame %d overlaps or precedes frame %d (frames must be sorted by offset)", i, i - 1);
+    if (i && tbl[i].offset < tbl[i - 1].offset + tbl[i - 1].len) sorted = false;
+  }
+  if (!sorted) {
+    // frames may come in any order (they are separate RecvBuffers), but they share framing scratch by byte
+    // range: two frames must not overlap
+    std::vector<std::pair<uint64_t, uint32_t>> v((size_t)nframes);
+    for (int i = 0; i < nframes; i++) v[(size_t)i] = {tbl[i].offset, tbl[i].len};
+    std::sort(v.begin(), v.end());
+    for (int i = 1; i < nframes; i++)
+      if (v[(size_t)i].second && v[(size_t)i].first < v[(size_t)i - 1].first + v[(size_t)i - 1].second)
+        return fail(ctx, DFGPU_EINVAL, "frames overlap inside the staging buffer (at offset %llu)", (unsigned long long)v[(size_t)i].first);
   }
   {
     std::lock_guard<std::mutex> g(ctx->dict_mu);

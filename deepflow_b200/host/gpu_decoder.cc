@@ -5,6 +5,8 @@
  */
 #include "gpu_decoder.h"
 
+#include "../../include/dfgpu_wire.h"
+
 #include <cstdlib>
 #include <cstring>
 
@@ -247,6 +249,18 @@ void dfhost_decoder_stats(void* h, int64_t* out /*[16 + DFGPU_TABLE_MAX]*/) {
                    (int64_t)t->sink.flushes};
   memcpy(out, v, sizeof v);
   memcpy(out + 16, t->sink.rows, sizeof t->sink.rows);
+}
+// A1 (include/dfgpu_wire.h): one received message -> frame fields; out = {rc, msg_type, payload_off, len, vtap,
+// org, team, encoder, invalid}
+void dfhost_parse_message(const uint8_t* msg, uint64_t len, int64_t* out) {
+  dfgpu_frame fr{};
+  int mt = -1;
+  size_t off = 0;
+  uint8_t enc = 0;
+  uint64_t invalid = 0;
+  const int rc = dfgpu_frame_from_message(msg, (size_t)len, &fr, &mt, &off, &enc, &invalid);
+  const int64_t v[9] = {rc, mt, (int64_t)off, fr.len, fr.vtap_id, fr.org_id, fr.team_id, enc, (int64_t)invalid};
+  memcpy(out, v, sizeof v);
 }
 // i-th block handed to the sink (owned by the harness)
 dfgpu_batch* dfhost_decoder_batch(void* h, int i) {

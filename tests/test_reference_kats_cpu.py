@@ -207,3 +207,22 @@ def test_auto_instance_service_type_codes_match_trident_enums(built):
                                                          "POD_SERVICE_IP": 3, "LB_SERVICE": 4, "CUSTOM_SERVICE": 7}
     assert g["trident.proto:enums"]["ServiceProtocol"] == {"ANY": 0, "TCP_SERVICE": 1, "UDP_SERVICE": 2}
     assert g["trident.proto:enums"]["CidrType"] == {"WAN": 1, "LAN": 2}
+
+
+def test_exception_tables_header_regenerates_from_reference():
+    """include/dfgpu_exception_tables.h is read by the product, the oracle and the second-opinion tests alike:
+    it must be exactly what tools/gen_exception_tables.py produces from the reference's exception_desc.go.
+    Runs where the reference tree is mounted (the build container); skipped on the GPU box."""
+    import os
+    import subprocess
+    import sys
+    import pytest
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "server/ingester/flow_log/log_data/exception_desc.go")):
+        pytest.skip("reference tree not present")
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_exception_tables.py"), ref],
+                         capture_output=True, text=True, check=True).stdout
+    committed = open(os.path.join(root, "include", "dfgpu_exception_tables.h"), encoding="utf-8").read()
+    assert out == committed, "include/dfgpu_exception_tables.h differs from the generator's output"

@@ -157,3 +157,53 @@ def test_reference_tagged_flow_literal(synth, built):
     assert (v["retrans_tx"], v["retrans_rx"], v["zero_win_tx"]) == (601, 601, 602)
     assert (v["capture_nic"], v["capture_nic_type"], v["capture_network_type_id"]) == (201, 0, 3)
     assert v["_id"] == (0 << 32) | ((7 & 0x3ff) << 22) | 1  # analyzer_id 7 (synth), first record
+
+
+# ---- droplet message headers + org / team normalisation (include/dfgpu_wire.h) ------------------
+def _message(msg_type, payload, version=0x8000, encoder=0, team=7, org=3, agent=1234, frame_size=None):
+    """BaseHeader.Encode + FlowHeader.Encode (droplet-message.go:177-180, 248-256): u32 BE frame size (headers
+    included), u8 type | u16 LE version, u8 encoder, u32 LE team, u16 LE org, u16 reserved, u16 LE agent id,
+    u8 reserved."""
+    import struct
+    flow = struct.pack("<HBIHHHB", version, encoder, team, org, 0, agent, 0)
+    assert len(flow) == 14
+    size = 5 + len(flow) + len(payload) if frame_size is None else frame_size
+    return struct.pack(">IB", size, msg_type) + flow + payload
+
+
+def _parse(msg):
+    import ctypes as C
+    import os
+    from deepflow_b200 import build
+    build.build_all()
+    L = C.CDLL(os.path.join(os.path.dirname(build.__file__), "host", "libdfhost.so"))
+    L.dfhost_parse_message.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_int64)]
+    out = (C.c_int64 * 9)()
+    L.dfhost_parse_message(msg, len(msg), out)
+    keys = ("rc", "msg_type", "payload_off", "len", "vtap", "org", "team", "encoder", "invalid")
+    return dict(zip(keys, list(out)))
+
+
+def test_droplet_headers_and_org_team_rules():
+    body = b"\x05\x00\x00\x00hello"
+    r = _parse(_message(5, body))
+    assert r == dict(rc=0, msg_type=5, payload_off=19, len=len(body), vtap=1234, org=3, team=7, encoder=0, invalid=0)
+    # parseOrgIdTeamId (receiver.go:688-704): org 0 -> 1, team 0 -> 1, org > 1024 -> 1 and counted
+    r = _parse(_message(4, body, team=0, org=0))
+    assert (r["org"], r["team"], r["invalid"]) == (1, 1, 0)
+    r = _parse(_message(3, body, org=1025))
+    assert (r["org"], r["invalid"]) == (1, 1)
+    assert _parse(_message(3, body, org=1024))["org"] == 1024
+    # encoder flag travels to the caller (compressed frames are inflated before staging)
+    assert _parse(_message(5, body, encoder=3))["encoder"] == 3
+    # header of agents <= v6.5.8 (FlowHeaderOld): version != 0x8000 -> default org / team, vtap at offset 12
+    import struct
+    old = struct.pack(">IB", 5 + 14 + len(body), 4) + struct.pack("<IIIH", 20210101, 9, 9, 77) + body
+    r = _parse(old)
+    assert (r["rc"], r["vtap"], r["org"], r["team"], r["len"]) == (0, 77, 1, 1, len(body))
+    # BaseHeader.Decode errors: frame size smaller than the headers, unknown message type
+    assert _parse(_message(5, b"", frame_size=18))["rc"] == abi.DFGPU_EINVAL if hasattr(abi, "DFGPU_EINVAL") else _parse(_message(5, b"", frame_size=18))["rc"] == -22
+    assert _parse(_message(200, body))["rc"] == -22
+    # message types outside this path are not ours (ENOENT), a short buffer is invalid
+    assert _parse(_message(6, body))["rc"] == -2
+    assert _parse(_message(5, body)[:10] + b"")["rc"] == -22
