@@ -561,11 +561,12 @@ static int l7_ensure_rec_buffers(dfgpu_ctx* ctx, L7Host* h, size_t cap) {
   if (cap <= h->rec_cap) return 0;
   if (h->d_rec_buf) CU(cudaFree(h->d_rec_buf));
   h->d_rec_buf = nullptr;
-  const size_t per_rec = (size_t)L7REF_COUNT * 8 + 8 + (size_t)L7ARR_COUNT * 4 + 4 + (size_t)L7KG_WORDS * 4 + 4 + 1;
+  const size_t per_rec = (size_t)L7REF_COUNT * 8 + (size_t)L7E_COUNT * 8 + 8 + (size_t)L7ARR_COUNT * 4 + 4 + (size_t)L7KG_WORDS * 4 + 4 + 1;
   CU(cudaMalloc(&h->d_rec_buf, per_rec * cap + 4096));
   uint8_t* q = h->d_rec_buf;
   L7Dev& d = h->dev;
   d.refs = reinterpret_cast<uint64_t*>(q); q += (size_t)L7REF_COUNT * 8 * cap;
+  d.elems = reinterpret_cast<uint64_t*>(q); q += (size_t)L7E_COUNT * 8 * cap;
   d.thash = reinterpret_cast<uint64_t*>(q); q += 8 * cap;
   d.arr = reinterpret_cast<uint32_t*>(q); q += (size_t)L7ARR_COUNT * 4 * cap;
   d.meta = reinterpret_cast<uint32_t*>(q); q += 4 * cap;

@@ -46,6 +46,7 @@ struct L7Dev {
   // ---- decode kernel -> strings / SmartEncoding kernels (all indexed by record, stride rec_cap) ----
   uint64_t* raw_scratch;  // [resident warps][R7_COUNT][32]: wire references while a record is being decoded
   uint64_t* refs;         // [L7REF_COUNT][rec_cap]
+  uint64_t* elems;        // [rec_cap][L7E_COUNT] elements of the repeated ext_info fields (l7_tok.h)
   uint32_t* arr;          // [L7ARR_COUNT][rec_cap]
   uint32_t* meta;         // [rec_cap]
   uint64_t* thash;        // [rec_cap] DJB hash of the row's trace id

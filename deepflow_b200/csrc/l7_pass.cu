@@ -26,6 +26,7 @@ constexpr int A_THREADS = 128;
 struct SlotSink {
   uint32_t* w;               // s_words + tid, stride A_THREADS
   unsigned long long* refs;  // scratch + lane, stride 32
+  unsigned long long* elems;  // this record's block of element references (global, L7E_COUNT entries)
   uint32_t mask;             // references present
   __device__ __forceinline__ void u32(uint32_t s, uint32_t v) { w[s * A_THREADS] = v; }
   __device__ __forceinline__ void u64(uint32_t s, uint32_t lo, uint32_t hi) {
@@ -37,6 +38,11 @@ struct SlotSink {
   __device__ __forceinline__ void ref(uint32_t r, uint32_t off, uint32_t len) {
     refs[r * 32] = (unsigned long long)len << 32 | off;
     mask |= 1u << r;
+  }
+  __device__ __forceinline__ void velem(uint32_t, uint32_t, uint32_t, uint32_t) {}
+  __device__ __forceinline__ void elem(uint32_t base, uint32_t i, uint32_t off, uint32_t len) {
+    if (i < (base < L7E_METRICS_NAMES ? L7E_CAP_ATTR : base < L7E_METRICS_VALUES ? L7E_CAP_METRICS : 1u))
+      elems[base + i] = (unsigned long long)len << 32 | off;
   }
 };
 
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(A_THREADS, L7_DECODE_MIN_BLOCKS) k_l7_decode(c
     const bool in_range = rec < nrec;
 #pragma unroll
     for (int i = 0; i < W7_COUNT; i++) my_words[i * A_THREADS] = 0;
-    SlotSink sink{my_words, my_refs, 0u};
+    SlotSink sink{my_words, my_refs, reinterpret_cast<unsigned long long*>(dv->elems) + (size_t)(in_range ? rec : 0) * L7E_COUNT, 0u};
     bool ok = false;
     uint32_t frame = 0;
     if (in_range) {

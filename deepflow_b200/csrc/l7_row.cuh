@@ -305,7 +305,10 @@ DF_HD L7RowInfo l7_build_row(const L7Tables& tb, const uint8_t* in, const S& sl,
   const uint32_t n_an = sl.w(W7_ATTR_NAMES), n_av = sl.w(W7_ATTR_VALUES), n_mn = sl.w(W7_METRICS_NAMES),
                  n_mv = sl.w(W7_METRICS_VALUES);
   const bool any_rep = (n_an | n_av | n_mn | n_mv) != 0;
-  const bool single = sl.w(W7_EXT_CNT) == 1 && sl.w(W7_BASE_CNT) <= 1;
+  // fast path of the arrays kernel: the element references the tokenizer left are complete — one ext_info
+  // occurrence, no more elements than a block holds, metrics_values as one packed run
+  const bool single = sl.w(W7_EXT_CNT) == 1 && sl.w(W7_BASE_CNT) <= 1 && n_an <= L7E_CAP_ATTR && n_av <= L7E_CAP_ATTR &&
+                      n_mn <= L7E_CAP_METRICS && sl.w(W7_METRICS_VALUES_OCC) == (n_mv ? 1u : 0u);
   e.aux(0, (any_rep && single) ? rr[R7_EXT_RANGE] : none);
   e.aux(1, ua);
   e.aux(2, rf);

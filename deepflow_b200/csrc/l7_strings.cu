@@ -250,9 +250,52 @@ __global__ void __launch_bounds__(256, ARRAYS ? L7_ARR_MIN_BLOCKS : L7_STR_MIN_B
           sink.mn_buf = p.arena + dyn->var_buf_off[L7V_METRICS_NAMES];
           sink.mn_off = mn_b;
           sink.mv = reinterpret_cast<uint64_t*>(p.arena + dyn->var_buf_off[L7V_METRICS_VALUES]) + mv_e;
-          // pseudo attributes first, in the reference's order (:418-429)
+          const unsigned long long ext = R[(size_t)L7REF_EXT_RANGE * cap];
+        if ((uint32_t)(ext >> 32) || !(meta & L7META_SLOW_ARRAYS)) {
+          // Fast path: the decode kernel left a reference to every element (l7_tok.h L7E_*): no second walk
+          // over the record.  Pseudo attributes first, in the reference's order (:418-429).
+          uint32_t np = 0;
           if (meta & L7META_HAS_EXT) {
-  #pragma unroll
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+              const unsigned long long r = R[(size_t)(L7REF_UA + k) * cap];
+              if ((uint32_t)(r >> 32)) {
+                const SRef nm = cs_ref(dv, CS_ATTR_UA + k);
+                sink.attr_name(nm.p, nm.n);
+                sink.attr_value(p.in + (uint32_t)r, (uint32_t)(r >> 32));
+                np++;
+              }
+            }
+          }
+          const unsigned long long* E = reinterpret_cast<const unsigned long long*>(dv->elems) + (size_t)rec * L7E_COUNT;
+          const uint32_t n_an = z_an_e - np, n_av = z_av_e - np;
+          for (uint32_t i = 0; i < n_an; i++) {
+            const unsigned long long r = __ldg(E + L7E_ATTR_NAMES + i);
+            sink.attr_name(p.in + (uint32_t)r, (uint32_t)(r >> 32));
+          }
+          for (uint32_t i = 0; i < n_av; i++) {
+            const unsigned long long r = __ldg(E + L7E_ATTR_VALUES + i);
+            sink.attr_value(p.in + (uint32_t)r, (uint32_t)(r >> 32));
+          }
+          for (uint32_t i = 0; i < z_mn_e; i++) {
+            const unsigned long long r = __ldg(E + L7E_METRICS_NAMES + i);
+            sink.metric_name(p.in + (uint32_t)r, (uint32_t)(r >> 32));
+          }
+          if (z_mv_e) {  // one packed run of doubles
+            const unsigned long long r = __ldg(E + L7E_METRICS_VALUES);
+            const uint8_t* q = p.in + (uint32_t)r;
+            for (uint32_t i = 0; i < z_mv_e; i++) {
+              uint64_t v = 0;
+              for (int k = 0; k < 8; k++) v |= (uint64_t)ldb(q + 8 * i + k) << (8 * k);
+              sink.metric_value(v);
+            }
+          }
+        } else {
+          // ext_info split over several occurrences / more elements than a reference block holds (merge
+          // semantics): pseudo attributes, then a full re-walk, out of line, on a copy so that the address of
+          // `sink` itself never escapes
+          if (meta & L7META_HAS_EXT) {
+#pragma unroll
             for (int k = 0; k < 3; k++) {
               const unsigned long long r = R[(size_t)(L7REF_UA + k) * cap];
               if ((uint32_t)(r >> 32)) {
@@ -262,17 +305,10 @@ __global__ void __launch_bounds__(256, ARRAYS ? L7_ARR_MIN_BLOCKS : L7_STR_MIN_B
               }
             }
           }
-          const unsigned long long ext = R[(size_t)L7REF_EXT_RANGE * cap];
-          if ((uint32_t)(ext >> 32)) {
-            // the common case: one ext_info occurrence — walk just that range
-            walk_ext_range(p.in + (uint32_t)ext, (uint32_t)(ext >> 32), sink);
-          } else if (meta & L7META_SLOW_ARRAYS) {
-            // ext_info split over several occurrences (merge semantics): full re-walk, out of line, on a
-            // copy so that the address of `sink` itself never escapes
-            L7EmitSink cold = sink;
-            l7_arrays_slow(p.in + p.rec_off[rec], p.rec_len[rec], cold);
-          }
+          L7EmitSink cold = sink;
+          l7_arrays_slow(p.in + p.rec_off[rec], p.rec_len[rec], cold);
         }
+      }
       }
     } else {
       // ---- trace_id_index (ParseTraceIdIndex :296-310): hash, or previous valid hash + 1 ------------------

@@ -24,7 +24,7 @@ enum L7Word : int {
   // ---- occurrence / element counters ----
   W7_BASE_CNT, W7_HEAD_CNT, W7_REQ_CNT, W7_RESP_CNT, W7_TRACE_CNT, W7_EXT_CNT, W7_TRACE_IDS_N,
   W7_ATTR_NAMES, W7_ATTR_NAMES_B, W7_ATTR_VALUES, W7_ATTR_VALUES_B, W7_METRICS_NAMES, W7_METRICS_NAMES_B,
-  W7_METRICS_VALUES,
+  W7_METRICS_VALUES, W7_METRICS_VALUES_OCC,
   // ---- uint64 (lo, hi) ----
   W7_START_TIME, W7_START_TIME_HI, W7_END_TIME, W7_END_TIME_HI, W7_FLOW_ID, W7_FLOW_ID_HI, W7_TAP_PORT,
   W7_TAP_PORT_HI, W7_MAC_SRC, W7_MAC_SRC_HI, W7_MAC_DST, W7_MAC_DST_HI, W7_SYS_REQ, W7_SYS_REQ_HI, W7_SYS_RESP,
@@ -41,6 +41,12 @@ enum L7Raw : int {
   R7_COUNT
 };
 static_assert(R7_COUNT <= 32, "presence mask of the raw references is one 32-bit word");
+
+// elements of the repeated ExtendedInfo fields, per record: [L7E_COUNT] references.  A record with more
+// elements than a block holds (or with its repeated fields split over several ext_info occurrences) takes the
+// slow path of the arrays kernel (a walk over the record).
+enum : uint32_t { L7E_ATTR_NAMES = 0, L7E_ATTR_VALUES = 8, L7E_METRICS_NAMES = 16, L7E_METRICS_VALUES = 20, L7E_COUNT = 21 };
+constexpr uint32_t L7E_CAP_ATTR = 8, L7E_CAP_METRICS = 4;
 
 inline std::vector<uint32_t> l7_tok_table() {
   std::vector<uint32_t> t(M7_COUNT * L7_MAXF, 0u);
@@ -87,10 +93,10 @@ inline std::vector<uint32_t> l7_tok_table() {
   str(M7_EXT, 1, R7_SERVICE_NAME); str(M7_EXT, 2, R7_CLIENT_IP); u32(M7_EXT, 3, W7_REQUEST_ID);
   str(M7_EXT, 4, R7_X_REQUEST_ID_0); str(M7_EXT, 6, R7_USER_AGENT); str(M7_EXT, 7, R7_REFERER);
   str(M7_EXT, 8, R7_RPC_SERVICE); str(M7_EXT, 9, R7_PROTOCOL_STR); str(M7_EXT, 10, R7_X_REQUEST_ID_1);
-  set(M7_EXT, 16, TK_ENT(TK_RSTR_CNT, W7_ATTR_NAMES, 0, 0));
-  set(M7_EXT, 17, TK_ENT(TK_RSTR_CNT, W7_ATTR_VALUES, 0, 0));
-  set(M7_EXT, 18, TK_ENT(TK_RSTR_CNT, W7_METRICS_NAMES, 0, 0));
-  set(M7_EXT, 19, TK_ENT(TK_RDBL_CNT, W7_METRICS_VALUES, 0, 0));
+  set(M7_EXT, 16, TK_ENT(TK_RSTR_CNT, W7_ATTR_NAMES, 0, L7E_ATTR_NAMES));
+  set(M7_EXT, 17, TK_ENT(TK_RSTR_CNT, W7_ATTR_VALUES, 0, L7E_ATTR_VALUES));
+  set(M7_EXT, 18, TK_ENT(TK_RSTR_CNT, W7_METRICS_NAMES, 0, L7E_METRICS_NAMES));
+  set(M7_EXT, 19, TK_ENT(TK_RDBL_CNT, W7_METRICS_VALUES, 0, L7E_METRICS_VALUES));
   return t;
 }
 

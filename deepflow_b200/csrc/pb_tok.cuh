@@ -37,7 +37,9 @@
 #define DF_LDG(p) __ldg(p)
 #define DF_FUNNEL_R(lo, hi, s) __funnelshift_r(lo, hi, s)
 #define DF_BYTE_PERM(a, b, k) __byte_perm(a, b, k)
+#define DF_FFS(x) __ffs((int)(x))
 #else
+#define DF_FFS(x) __builtin_ffs((int)(x))
 #define DF_LDG(p) (*(p))
 #define DF_FUNNEL_R(lo, hi, s) ((uint32_t)((((uint64_t)(hi) << 32) | (uint64_t)(lo)) >> ((s) & 31u)))
 #define DF_BYTE_PERM(a, b, k) ((uint32_t)(((((uint64_t)(b) << 32) | (uint64_t)(a)) >> (((k) & 7u) * 8u)) & 0xffu))
@@ -54,11 +56,15 @@ enum TokKind : uint32_t {
   TK_U64 = 2,        // uint64 varint -> word[slot], word[slot + 1]
   TK_STR = 3,        // string / bytes -> ref[ref]
   TK_MSG = 4,        // nested message: word[slot] += 1 (occurrences); TKF_RANGE: ref[ref] = its byte range
-  TK_RSTR_CNT = 5,   // repeated string: word[slot] += 1, word[slot + 1] += bytes (+ length prefixes)
+  TK_RSTR_CNT = 5,   // repeated string: word[slot] += 1, word[slot + 1] += bytes (+ length prefixes);
+                     // element i also goes to sink.elem(ref, i, off, len)
   TK_RSTR_FIRST2 = 6,  // repeated string: ref[ref], ref[ref + 1] = first two, word[slot] = count
-  TK_RDBL_CNT = 7,   // repeated double (packed or not): word[slot] += 1 per value
+  TK_RDBL_CNT = 7,   // repeated double (packed or not): word[slot] += 1 per value; word[slot + 1] += 1 per packed
+                     // occurrence (its range -> sink.elem(ref, 0, off, len)), += 2 per unpacked value
   TK_RVAR_CNT = 8,   // repeated varint (packed or not): word[slot] += 1 per value
   TK_RVAR_DIGITS = 9,  // repeated uint64: word[slot] += 1, word[slot + 1] += decimal chars + ',' separators
+                       // (both RVAR kinds: value i also goes to sink.velem(ref, i, lo, hi))
+  TK_STR2W = 10,     // string / bytes -> word[slot] = offset, word[slot + 1] = length
 };
 constexpr uint32_t TKF_RANGE = 1u << 4;
 // entry: kind[0:4) | flags[4:8) | slot[8:16) | sub-message[16:20) | ref[20:26)
@@ -80,19 +86,21 @@ DF_HD uint32_t tk_digits(uint64_t v) {
 }
 
 // ---- byte window over the input arena ---------------------------------------------------------------
-// `in` is the staging buffer (device), positions are absolute byte offsets into it.  The window holds the
-// aligned 8-byte block of the cursor and the block after it, so that a 4-byte peek never needs a load of
-// its own.  last_blk bounds the prefetch inside the buffer.
+// `in` is the staging buffer (device, 8-byte aligned), positions are absolute byte offsets into it.  The
+// window holds THREE aligned 8-byte blocks starting at the cursor's block, so that one seek per field makes
+// the 12 bytes behind the cursor available (a tag of <= 2 bytes + a varint of <= 10): tag and value are
+// decoded from registers, with no load of their own.  Sequential walks reload one block per 8 bytes
+// consumed (the third block doubles as the prefetch); last_blk bounds the loads inside the buffer.
 struct TokWin {
   const TokU2* in8;
-  TokU2 cur, nxt;
-  uint32_t blk;       // index of `cur`
+  TokU2 b0, b1, b2;
+  uint32_t blk;       // index of b0
   uint32_t last_blk;  // last block holding a valid byte of the buffer
   DF_HD void init(const uint8_t* in, uint64_t nbytes) {
     in8 = reinterpret_cast<const TokU2*>(in);
     blk = 0xfffffff0u;
     last_blk = nbytes ? (uint32_t)((nbytes - 1) >> 3) : 0u;
-    cur = nxt = TokU2{0, 0};
+    b0 = b1 = b2 = TokU2{0, 0};
   }
   static DF_HD TokU2 ld8(const TokU2* p) {
 #if defined(__CUDA_ARCH__)
@@ -102,27 +110,59 @@ struct TokWin {
     return *p;
 #endif
   }
+  DF_HD TokU2 ldc(uint32_t b) const { return ld8(in8 + (b < last_blk ? b : last_blk)); }
   DF_HD void seek(uint32_t pos) {
-    const uint32_t b = pos >> 3;
-    if (b != blk) {
-      const uint32_t nb = b < last_blk ? b + 1 : last_blk;
-      if (b == blk + 1) cur = nxt; else cur = ld8(in8 + b);
-      nxt = ld8(in8 + nb);
-      blk = b;
+    const uint32_t nb = pos >> 3;
+    if (nb != blk) {
+      if (nb == blk + 1) {
+        b0 = b1;
+        b1 = b2;
+      } else {
+        b0 = ldc(nb);
+        b1 = ldc(nb + 1);
+      }
+      b2 = ldc(nb + 2);
+      blk = nb;
     }
   }
-  // bytes pos .. pos + 3, little endian (caller guarantees they are inside the buffer or unused)
-  DF_HD uint32_t peek4(uint32_t pos) {
-    seek(pos);
-    const uint32_t k = pos & 7u;
-    const uint32_t a = k < 4 ? cur.x : cur.y, b = k < 4 ? cur.y : nxt.x;
-    return DF_FUNNEL_R(a, b, (k & 3u) * 8u);
+  // bytes pos .. pos + 11 as three little-endian words (after seek(pos)); bytes past the buffer are garbage
+  // the caller never uses (it bounds every field by the enclosing message)
+  DF_HD void get12(uint32_t pos, uint32_t& x0, uint32_t& x1, uint32_t& x2) const {
+    const uint32_t k = pos & 7u, s = (k & 3u) * 8u;
+    const bool up = k >= 4;
+    const uint32_t w0 = up ? b0.y : b0.x, w1 = up ? b1.x : b0.y, w2 = up ? b1.y : b1.x, w3 = up ? b2.x : b1.y;
+    x0 = DF_FUNNEL_R(w0, w1, s);
+    x1 = DF_FUNNEL_R(w1, w2, s);
+    x2 = DF_FUNNEL_R(w2, w3, s);
   }
   DF_HD uint32_t byte(uint32_t pos) {
     seek(pos);
-    return DF_BYTE_PERM(cur.x, cur.y, pos & 7u) & 0xffu;
+    return DF_BYTE_PERM(b0.x, b0.y, pos & 7u) & 0xffu;
   }
 };
+
+// Varint of 1..10 bytes held in registers (v0 = bytes 0..3, v1 = 4..7, v2 = 8..9), branch-free on its value:
+// the terminator is found with one bit scan, the 7-bit groups are compacted with masks and shifts.  (ncu,
+// round 2: the byte-at-a-time loop was 40 % of the decode kernel's instructions at 9 of 32 lanes — in a warp
+// of 32 records some lane is always inside a 9-byte timestamp or a 10-byte negative int32.)
+// Returns the length in bytes, 0 when the varint has no terminator within 10 bytes (ErrIntOverflow).
+DF_HD uint32_t tk_varint_regs(const uint32_t v0, const uint32_t v1, const uint32_t v2, uint32_t& vlo, uint32_t& vhi) {
+  const uint32_t tl = ~v0 & 0x80808080u, th = ~v1 & 0x80808080u;  // bytes without the continuation bit
+  uint32_t len;
+  if (tl) len = (uint32_t)DF_FFS(tl) >> 3;
+  else if (th) len = 4u + ((uint32_t)DF_FFS(th) >> 3);
+  else if (!(v2 & 0x80u)) len = 9u;
+  else if (!(v2 & 0x8000u)) len = 10u;
+  else return 0u;
+  const uint32_t nlo = len < 4u ? len : 4u, nhi = len > 4u ? (len > 8u ? 4u : len - 4u) : 0u;
+  const uint32_t xl = v0 & 0x7f7f7f7fu & (0xffffffffu >> ((4u - nlo) * 8u));
+  const uint32_t xh = nhi ? v1 & 0x7f7f7f7fu & (0xffffffffu >> ((4u - nhi) * 8u)) : 0u;
+  const uint32_t tl2 = (xl & 0x007f007fu) | ((xl & 0x7f007f00u) >> 1), th2 = (xh & 0x007f007fu) | ((xh & 0x7f007f00u) >> 1);
+  const uint32_t l28 = (tl2 & 0x3fffu) | ((tl2 >> 2) & 0x0fffc000u), h28 = (th2 & 0x3fffu) | ((th2 >> 2) & 0x0fffc000u);
+  vlo = l28 | (h28 << 28);
+  vhi = (h28 >> 4) | (len >= 9u ? (v2 & 0x7fu) << 24 : 0u) | (len == 10u ? (v2 & 0x100u) << 23 : 0u);
+  return len;
+}
 
 // varint at pos (< lim), slow path: any length.  false: truncated or longer than 10 bytes.
 DF_HD bool tk_varint(TokWin& w, uint32_t& pos, const uint32_t lim, uint64_t& out) {
@@ -156,7 +196,7 @@ DF_HD_NOINLINE uint32_t tk_skip_slow(const TokU2* in8, uint32_t last_blk, uint32
   w.in8 = in8;
   w.last_blk = last_blk;
   w.blk = 0xfffffff0u;
-  w.cur = w.nxt = TokU2{0, 0};
+  w.b0 = w.b1 = w.b2 = TokU2{0, 0};
   int depth = 0;
   for (;;) {
     switch (wt) {
@@ -198,6 +238,8 @@ DF_HD_NOINLINE uint32_t tk_skip_slow(const TokU2* in8, uint32_t last_blk, uint32
 //   void u32(slot, v); void u64(slot, lo, hi); void add(slot, v)           scalar words
 //   uint32_t word(slot)                                                     read a word back
 //   void ref(r, off, len)                                                   string reference (absolute offset)
+//   void elem(base, i, off, len)                                            i-th element of a repeated string field
+//   void velem(base, i, lo, hi)                                             i-th value of a repeated varint field
 // Decodes the record at [rec_off, rec_off + len) of the buffer.  tbl: [nmsg][maxf] entries in shared memory.
 template <uint32_t MAXF, class Sink>
 DF_HD bool tk_decode(TokWin& w, const uint32_t rec_off, const uint32_t len,
@@ -218,19 +260,18 @@ DF_HD bool tk_decode(TokWin& w, const uint32_t rec_off, const uint32_t len,
       msg = msgs & 15u;
       msgs >>= 4;
     }
-    // ---- tag + first varint: one 4-byte peek covers the common case ----
+    // ---- tag (1-2 bytes) and the varint behind it (value of wire type 0, length of wire type 2), both out
+    // of the 12 bytes the window holds behind the cursor ----
     uint32_t wt, f;
-    uint32_t vlo = 0, vhi = 0;  // value varint (wire type 0) or length (wire type 2)
+    uint32_t vlo = 0, vhi = 0;
     bool have_v = false;
-    if (end - pos >= 4) {
-      uint32_t x = w.peek4(pos);
-      uint32_t t = x & 0x7fu, nb = 1;
-      if (x & 0x80u) {
-        t |= (x >> 1) & 0x3f80u;
-        nb = 2;
-      }
-      if (nb == 2 && (x & 0x8000u)) {
-        // tag of 3+ bytes (field number >= 2048): generic path
+    {
+      w.seek(pos);
+      uint32_t x0, x1, x2;
+      w.get12(pos, x0, x1, x2);
+      const uint32_t two = (x0 >> 7) & 1u;
+      if ((two && (x0 & 0x8000u)) || (two && end - pos < 2)) {
+        // tag of 3+ bytes (field number >= 2048) or cut by the message end: generic path
         uint64_t tv;
         if (!tk_varint(w, pos, end, tv)) return false;
         wt = (uint32_t)(tv & 7);
@@ -238,30 +279,20 @@ DF_HD bool tk_decode(TokWin& w, const uint32_t rec_off, const uint32_t len,
         if (wt == 4 || fi <= 0) return false;
         f = (uint32_t)fi;
       } else {
+        const uint32_t t = (x0 & 0x7fu) | (two ? (x0 >> 1) & 0x3f80u : 0u);
         wt = t & 7u;
         f = t >> 3;
         if (wt == 4 || f == 0) return false;
+        const uint32_t nb = 1u + two, sh = nb * 8u;
         pos += nb;
-        x >>= 8 * nb;  // 2 or 3 value bytes left in x
-        if ((wt == 0 || wt == 2)) {
-          if (!(x & 0x80u)) {
-            vlo = x & 0x7fu;
-            pos += 1;
-            have_v = true;
-          } else if (!(x & 0x8000u)) {
-            vlo = (x & 0x7fu) | ((x >> 1) & 0x3f80u);
-            pos += 2;
-            have_v = true;
-          }
+        if (wt == 0 || wt == 2) {
+          if (pos >= end) return false;
+          const uint32_t n = tk_varint_regs(DF_FUNNEL_R(x0, x1, sh), DF_FUNNEL_R(x1, x2, sh), x2 >> sh, vlo, vhi);
+          if (n == 0 || n > end - pos) return false;  // longer than 10 bytes / truncated by the enclosing message
+          pos += n;
+          have_v = true;
         }
       }
-    } else {
-      uint64_t tv;
-      if (!tk_varint(w, pos, end, tv)) return false;
-      wt = (uint32_t)(tv & 7);
-      const int32_t fi = (int32_t)(tv >> 3);
-      if (wt == 4 || fi <= 0) return false;
-      f = (uint32_t)fi;
     }
     const uint32_t ent = f < maxf ? tbl[msg * maxf + f] : 0u;
     const uint32_t kind = ent & 15u, slot = (ent >> 8) & 0xffu;
@@ -274,11 +305,11 @@ DF_HD bool tk_decode(TokWin& w, const uint32_t rec_off, const uint32_t len,
       }
       if (kind == TK_U32) sink.u32(slot, vlo);
       else if (kind == TK_U64) sink.u64(slot, vlo, vhi);
-      else if (kind == TK_RVAR_CNT) sink.add(slot, 1);
-      else if (kind == TK_RVAR_DIGITS) {
+      else if (kind == TK_RVAR_CNT || kind == TK_RVAR_DIGITS) {
         const uint32_t c = sink.word(slot);
         sink.u32(slot, c + 1);
-        sink.add(slot + 1, tk_digits((uint64_t)vhi << 32 | vlo) + (c ? 1u : 0u));
+        if (kind == TK_RVAR_DIGITS) sink.add(slot + 1, tk_digits((uint64_t)vhi << 32 | vlo) + (c ? 1u : 0u));
+        sink.velem((ent >> 20) & 63u, c, vlo, vhi);
       } else if (kind != TK_SKIP) return false;  // known field, wrong wire type
     } else if (wt == 2) {
       if (!have_v) {
@@ -302,9 +333,15 @@ DF_HD bool tk_decode(TokWin& w, const uint32_t rec_off, const uint32_t len,
         continue;
       }
       if (kind == TK_STR) sink.ref((ent >> 20) & 63u, off, n);
+      else if (kind == TK_STR2W) {
+        sink.u32(slot, off);
+        sink.u32(slot + 1, n);
+      }
       else if (kind == TK_RSTR_CNT) {
-        sink.add(slot, 1);
+        const uint32_t c = sink.word(slot);
+        sink.u32(slot, c + 1);
         sink.add(slot + 1, n + (tk_vsize(n) & len_prefix_mask));
+        sink.elem((ent >> 20) & 63u, c, off, n);
       } else if (kind == TK_RSTR_FIRST2) {
         const uint32_t c = sink.word(slot);
         if (c < 2) sink.ref(((ent >> 20) & 63u) + c, off, n);
@@ -314,15 +351,15 @@ DF_HD bool tk_decode(TokWin& w, const uint32_t rec_off, const uint32_t len,
         while (pos < pend) {  // packed: varints bounded by the enclosing message, loop while before postIndex
           uint64_t v;
           if (!tk_varint(w, pos, end, v)) return false;
-          if (kind == TK_RVAR_CNT) sink.add(slot, 1);
-          else {
-            const uint32_t c = sink.word(slot);
-            sink.u32(slot, c + 1);
-            sink.add(slot + 1, tk_digits(v) + (c ? 1u : 0u));
-          }
+          const uint32_t c = sink.word(slot);
+          sink.u32(slot, c + 1);
+          if (kind == TK_RVAR_DIGITS) sink.add(slot + 1, tk_digits(v) + (c ? 1u : 0u));
+          sink.velem((ent >> 20) & 63u, c, (uint32_t)v, (uint32_t)(v >> 32));
         }
         continue;
       } else if (kind == TK_RDBL_CNT) {
+        sink.add(slot + 1, 1);
+        sink.elem((ent >> 20) & 63u, 0, off, n);
         const uint32_t pend = off + n;
         while (pos < pend) {
           if (end - pos < 8) return false;
@@ -336,7 +373,10 @@ DF_HD bool tk_decode(TokWin& w, const uint32_t rec_off, const uint32_t len,
       if (kind != TK_RDBL_CNT && kind != TK_SKIP) return false;
       if (end - pos < 8) return false;
       pos += 8;
-      if (kind == TK_RDBL_CNT) sink.add(slot, 1);
+      if (kind == TK_RDBL_CNT) {
+        sink.add(slot, 1);
+        sink.add(slot + 1, 2);
+      }
     } else {
       if (kind != TK_SKIP) return false;
       pos = tk_skip_slow(w.in8, w.last_blk, pos, end, wt);  // fixed32, groups, illegal wire types

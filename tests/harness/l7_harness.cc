@@ -21,6 +21,8 @@ struct HostSink {
   void add(uint32_t s, uint32_t v) { w[s] += v; }
   uint32_t word(uint32_t s) const { return w[s]; }
   void ref(uint32_t r, uint32_t off, uint32_t len) { refs[r] = (uint64_t)len << 32 | off; mask |= 1u << r; }
+  void elem(uint32_t, uint32_t, uint32_t, uint32_t) {}
+  void velem(uint32_t, uint32_t, uint32_t, uint32_t) {}
 };
 struct HostView {
   const HostSink* s;
