@@ -15,7 +15,11 @@
 using namespace dfgpu;
 
 namespace dfgpu {
-void launch_l4_pass(const BatchParams& p, int emit, cudaStream_t s);
+int l4_prepare(dfgpu_ctx* ctx, cudaStream_t s);
+void l4_free_state(dfgpu_ctx* ctx);
+void launch_l4_decode(dfgpu_ctx* ctx, cudaStream_t s);
+void launch_l4_pack(dfgpu_ctx* ctx, cudaStream_t s);
+void launch_l4_kg(dfgpu_ctx* ctx, cudaStream_t s);
 void launch_l7_repair_plan(const BatchParams& p, cudaStream_t s);
 void launch_l7_decode(const BatchParams& p, unsigned grid, cudaStream_t s);
 void launch_l7_strings(const BatchParams& p, unsigned grid, cudaStream_t s);
@@ -151,6 +155,7 @@ int dfgpu_close(dfgpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   dfgpu_l7_free_state(ctx);
+  l4_free_state(ctx);
   rollup_free_state(ctx);
   metrics_free_state(ctx);
   cudaFree(ctx->d_in);
@@ -358,7 +363,7 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
   // reset first-appearance tables
   CU(cudaMemsetAsync(&ctx->d_dyn->stats.lc_first, 0xff, sizeof(ctx->d_dyn->stats.lc_first), s));
   const bool l7 = ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG;
-  if (l7) {
+  {
     if (repair) {
       launch_l7_repair_plan(bp, s);  // rows dropped before every frame, rows the layout is planned for
       ctx->launches++;
@@ -378,7 +383,7 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
     l7_grids(ctx, &g_dec, &g_str, &g_kg);
     launch_l7_decode(bp, g_dec, s);  // decode + fixed-width columns + per-warp sizes (+ trace carry scan)
   } else {
-    launch_l4_pass(bp, 0, s);
+    launch_l4_decode(ctx, s);
   }
   ctx->mark(3);
   launch_slot_scan(bp, s);
@@ -394,7 +399,7 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
     CU(cudaEventRecord(pe0, s));
   }
   if (l7) launch_l7_strings(bp, g_str, s);
-  else launch_l4_pass(bp, 1, s);
+  else launch_l4_pack(ctx, s);
   if (pe1) CU(cudaEventRecord(pe1, s));  // the profile events bracket the pack kernel alone
   ctx->launches++;
   if (l7) {
@@ -406,6 +411,7 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
     if (rc) return rc;
   } else {
     ctx->mark(5);
+    launch_l4_kg(ctx, s);
     ctx->mark(6);
     launch_commit(bp, 0, s);
     ctx->launches++;
@@ -458,6 +464,9 @@ static int run_pipeline(dfgpu_ctx* ctx) {
   }
   if (ctx->cur_msg == DFGPU_MSG_PROTOCOLLOG) {
     int rc = l7_prepare(ctx, s);
+    if (rc) return rc;
+  } else if (ctx->cur_msg == DFGPU_MSG_TAGGEDFLOW) {
+    int rc = l4_prepare(ctx, s);
     if (rc) return rc;
   }
   ctx->mark(0);

@@ -93,6 +93,8 @@ struct dfgpu_ctx {
 
   // flow tag state (l7)
   void* ft = nullptr;
+  // L4 per-record hand-over buffers (l4.cu)
+  void* l4 = nullptr;
   // flow_metrics state (metrics.cu)
   void* mt = nullptr;
   // flow_metrics rollup accumulators (rollup.cu)

@@ -76,7 +76,7 @@ __device__ __forceinline__ Pre t64_pre(const DevDict& d, uint32_t tid, uint64_t 
   return r;
 }
 // the rest of the sequence (linear probing past a foreign key): rare, out of line
-__device__ __noinline__ uint64_t t64_more(const T64Entry* t, uint32_t mask, uint32_t tid, uint64_t key) {
+static __device__ __noinline__ uint64_t t64_more(const T64Entry* t, uint32_t mask, uint32_t tid, uint64_t key) {
   uint32_t s = t64_slot(tid, key, mask);
   for (;;) {
     s = (s + 1) & mask;
@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t t64_z(const DevDict& d, uint32_t tid, uint64
 static_assert(sizeof(T6Entry) == 32 && offsetof(T6Entry, epc) == 16 && offsetof(T6Entry, port) == 20 &&
                   offsetof(T6Entry, proto) == 22 && offsetof(T6Entry, tid) == 23 && offsetof(T6Entry, val) == 24,
               "T6Entry is read as two uint4");
-__device__ __noinline__ uint64_t t6_get(const T6Entry* t, uint32_t mask, uint32_t tid, uint64_t lo, uint64_t hi,
+static __device__ __noinline__ uint64_t t6_get(const T6Entry* t, uint32_t mask, uint32_t tid, uint64_t lo, uint64_t hi,
                                         int32_t epc, uint32_t port, uint32_t proto) {
   const uint64_t c = (uint64_t)(uint32_t)epc << 32 | (uint64_t)port << 16 | (uint64_t)proto << 8 | tid;
   uint32_t s = (uint32_t)mix64(lo ^ mix64(hi ^ mix64(c))) & mask;  // = t6_hash
@@ -132,7 +132,7 @@ __device__ __forceinline__ uint64_t epc_base(const DevDict& d, int32_t epc) {  /
   return r ? hit(H_REGION, (uint32_t)r) : 0;
 }
 // QueryIPV4Infos :292-308 after the exact (epc, ip) probe missed: first containing CIDR, then epc base
-__device__ __noinline__ uint64_t ip4_rest(const DevDict& d, int32_t epc, uint32_t ip) {
+static __device__ __noinline__ uint64_t ip4_rest(const DevDict& d, int32_t epc, uint32_t ip) {
   const uint64_t r = t64_get(d, TID_CIDR4, (uint64_t)(uint32_t)epc);
   if (r) {
     const DRange rg = d.cidr4_ranges[(uint32_t)r];
@@ -158,7 +158,7 @@ __device__ __forceinline__ uint64_t byte_mask(uint32_t bits) {  // prefix mask o
   return m;
 }
 // QueryIPV6Infos :310-326
-__device__ __noinline__ uint64_t query_ip6(const DevDict& d, int32_t epc, uint64_t lo, uint64_t hi, uint32_t len6) {
+static __device__ __noinline__ uint64_t query_ip6(const DevDict& d, int32_t epc, uint64_t lo, uint64_t hi, uint32_t len6) {
   if (epc == EPC_FROM_INTERNET) return 0;
   const uint64_t r = t6_get(d.t6, d.t6_mask, T6_IP6, lo, hi, epc, 0, 0);
   if (r) return hit(H_INFO, (uint32_t)r);
@@ -246,7 +246,7 @@ __device__ __forceinline__ void apply(const DevDict& d, uint64_t h, KGSide& o) {
 // consumed (up to 11 sectors in flight per lane, executed by the whole warp), then the answers are taken
 // in the reference's order.  Only customServicePodService (keyed by the pod-service answer) and the
 // "does the address still belong to this pod" re-check (:150-158) stay dependent.
-__device__ __noinline__ uint32_t custom_service_ip6(const DevDict& d, int32_t epc, uint64_t lo, uint64_t hi,
+static __device__ __noinline__ uint32_t custom_service_ip6(const DevDict& d, int32_t epc, uint64_t lo, uint64_t hi,
                                                     uint32_t server_port, uint32_t sp) {
   uint32_t sid = 0;
   if (d.counts6[T6_CS_IP6PORT]) {
