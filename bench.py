@@ -885,20 +885,7 @@ def main():
         per_type = {}
         tot_alg = 0.0
         for name, (f, es) in zip(("l4", "l7", "metrics"), pools):
-            st, runs, _pm, _pn = solo_stages(es[0], f) if f.msg != MET else ({}, 0, 0, 0)
-            if f.msg == MET:
-                # the metrics pipeline has no stage marks: time one solo pass with CUDA events of the bench
-                es[0].sync()
-                s = torch.cuda.ExternalStream(es[0].stream, device=local)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(s)
-                for i, w in enumerate(f.subs):
-                    es[0].stage_ptr(f.msg, f.dev[i].data_ptr(), w.nbytes, w.frames.ctypes.data, len(w.frames))
-                    es[0].run()
-                e1.record(s)
-                es[0].sync()
-                st = {"all": e0.elapsed_time(e1)}
-                es[0].fetch().release()
+            st, runs, _pm, _pn = solo_stages(es[0], f)
             bb = es[0].submit(f.subs[-1])
             if f.msg == MET:
                 rb = sum(block_bytes(bb, abi.TABLE_METRICS_BASE + t)["total"] for t in range(9)) / max(1, f.subs[-1].nrecords)

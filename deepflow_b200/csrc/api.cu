@@ -562,7 +562,7 @@ int dfgpu_run(dfgpu_ctx* ctx, uint32_t* id_counter, uint64_t* trace_id_index) {
     CU(cudaMemcpyAsync(ctx->d_persist, ctx->h_persist, sizeof(PersistState), cudaMemcpyHostToDevice, s));
   }
   CU(cudaEventRecord(ctx->ev0, s));
-  ctx->stage_open = ctx->prof_on && ctx->stage_used < dfgpu_ctx::PROF_SLOTS && ctx->cur_msg != DFGPU_MSG_METRICS;
+  ctx->stage_open = ctx->prof_on && ctx->stage_used < dfgpu_ctx::PROF_SLOTS;
   int rc = run_pipeline(ctx);
   if (rc) return rc;
   ctx->mark(7);

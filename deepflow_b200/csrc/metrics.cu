@@ -821,11 +821,16 @@ int metrics_passes(dfgpu_ctx* ctx, int repair) {
   CU(cudaMemsetAsync(&ctx->d_dyn->stats.lc_first, 0xff, sizeof(ctx->d_dyn->stats.lc_first), s));
   CU(cudaMemsetAsync(&ctx->d_dyn->stats.var_total, 0, sizeof(ctx->d_dyn->stats.var_total), s));
   dim3 grid(rec_grid(bp)), block(256);
+  ctx->mark(2);
   k_m_pass<0><<<grid, block, 0, s>>>(bp);
+  ctx->mark(3);
   launch_slot_scan(bp, s);
   launch_finish(bp, s);  // LowCardinality ranks of the 4 observation_point spaces
   k_m_layout<<<1, 1, 0, s>>>(bp);
+  ctx->mark(4);
   k_m_pass<1><<<grid, block, 0, s>>>(bp);
+  ctx->mark(5);
+  ctx->mark(6);
   k_m_as_prep<<<grid, block, 0, s>>>(bp);
   ctx->launches += 7;
   rc = m_as_rounds(ctx, s, AS_ROUNDS);
