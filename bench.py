@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--sub-batch", type=int, default=625_000, help="records per dfgpu_submit")
     ap.add_argument("--pods", type=int, default=100_000, help="dictionary size P (SURVEY 8d)")
     ap.add_argument("--decoders", type=int, default=3, help="contexts per GPU (DecoderQueueCount)")
-    ap.add_argument("--legs", default="c2,c4,c3,c5,parity,native", help="comma list; c2 always runs")
+    ap.add_argument("--legs", default="c2,c4,c3,c5,parity,native,lz4", help="comma list; c2 always runs")
     ap.add_argument("--c3-rows", type=int, default=100_000_000)
     ap.add_argument("--c3-groups", type=int, default=1_000_000)
     ap.add_argument("--c5-records", type=int, default=5_000_000)
@@ -501,18 +501,26 @@ def make_merge_hooks(torch, local, world, engines):
             for t in FLOW_TAG_TABLES:
                 f = b.tag_fingerprints(t)
                 if len(f):
-                    cols, _ = b.columns(t)
+                    col, _ = b.column(t, 0)  # the `time` column
                     fps.append(f)
-                    tms.append(cols[0].values.astype(np.uint32))
+                    tms.append(col.values.astype(np.uint32))
             b.release()
         f = np.concatenate(fps) if fps else np.zeros((0, 2), np.uint64)
         t = np.concatenate(tms) if tms else np.zeros(0, np.uint32)
         emitted[0] += len(t)
-        _keep, rf, rt = merge.exchange(f, t)
         if world > 1:
-            allf, allt = np.concatenate([rf, f]), np.concatenate([rt, t])
-            for e in engines:
-                e.tags_import(allf, allt)
+            # keys stay on the GPU: NCCL all-gather, ownership on the device, every decoder of this rank imports
+            # the union (its own keys included: the rank's other decoders have not seen them) from device memory
+            t0 = time.perf_counter()
+            _keep, others, mine = merge.exchange_device(f, t)
+            allk = torch.cat([others, mine]) if len(mine) else others
+            if len(allk):
+                kf = allk[:, 0:2].contiguous()
+                kt = allk[:, 2].to(torch.int32).contiguous()
+                torch.cuda.current_stream().synchronize()
+                for e in engines:
+                    e.tags_import_ptr(kf.data_ptr(), kt.data_ptr(), len(kt))
+            merge.seconds += time.perf_counter() - t0
 
     return merge, after, emitted
 
@@ -760,12 +768,13 @@ def main():
     sampler.start()
     synth = Synth(n_pods=a.pods)
 
-    def mk_cfg(max_bytes, cache=1 << 20, native=0):
+    def mk_cfg(max_bytes, cache=1 << 20, native=0, lz4=0):
         c = abi.Cfg()
         c.max_batch_bytes = max_bytes + (1 << 20)
         c.max_batch_records = a.sub_batch + a.sub_batch // 8 + 4096
         c.flow_tag_cache_max_size = cache  # the tag set of the C2 workload stays below it: no eviction either side
         c.native_strings = native
+        c.block_lz4 = lz4
         return c
 
     # =================================================================================== C2 (headline)
@@ -847,6 +856,31 @@ def main():
             "d2h_bytes_per_step": int(ncen["total"] / max(1, ncen["rows"]) * feed.records), "ms_per_step": nat_s * 1000 / a.steps,
             "what": "same call, dfgpu_cfg.native_strings=1: String / Array(String) columns leave the GPU as ClickHouse "
                     "native column data (uvarint length + bytes), no Position arrays over PCIe"}
+
+    # ---- e2e with native strings + dfgpu_cfg.block_lz4: every column buffer leaves the GPU as ClickHouse
+    # compressed frames (LZ4 blocks written by lz4.cu); decoding them back is checked by tests/test_lz4_gpu.py
+    if "lz4" in legs and world == 1:
+        for e in engines:
+            e.sync()
+        zcfg = mk_cfg(max(w.nbytes for w in subs), native=1, lz4=1)
+        zeng = [Engine(local, zcfg) for _ in range(len(engines))]
+        for e in zeng:
+            e.load_synth(synth)
+        _d, z_s, _l = run_pools(torch, dist, local, world, [(feed, zeng)], a.steps, max(1, a.warmup - 1))
+        zb = zeng[0].submit(subs[-1])
+        zcols, zrows = zb.columns(abi.TABLE_L7_FLOW_LOG)
+        zbytes = sum(c.compressed_bytes or 0 for c in zcols)
+        zraw = block_bytes(zb, abi.TABLE_L7_FLOW_LOG)
+        zb.release()
+        for e in zeng:
+            e.close()
+        line["e2e_lz4"] = {
+            "value": feed.records * a.steps / z_s, "unit": "records/s", "h2d_bytes_per_step": int(feed.in_bytes + feed.frame_bytes),
+            "d2h_bytes_per_step": int(zbytes / max(1, zrows) * feed.records), "ms_per_step": z_s * 1000 / a.steps,
+            "frame_bytes_per_row": zbytes / max(1, zrows), "column_bytes_per_row": zraw["total"] / max(1, zraw["rows"]),
+            "what": "same call, dfgpu_cfg.native_strings=1 + block_lz4=1: every buffer of l7_flow_log crosses PCIe as "
+                    "ClickHouse compressed frames (LZ4 per 4 KiB, compressed on the GPU inside the timed region; "
+                    "checksum slots left for the host)"}
 
     # =================================================================================== parity at size
     if "parity" in legs and world == 1:

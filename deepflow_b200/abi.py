@@ -46,6 +46,9 @@ class Col(C.Structure):
         ("pos", C.c_void_p), ("arr_offsets", C.c_void_p), ("nelems", C.c_uint64),
         ("nulls", C.c_void_p), ("dict_data", C.c_void_p), ("dict_pos", C.c_void_p),
         ("dict_n", C.c_uint64),
+        # dfgpu_cfg.block_lz4 (include/dfgpu.h): the buffers are streams of ClickHouse compressed frames
+        ("compressed", C.c_uint32), ("reserved0", C.c_uint32), ("data_raw_bytes", C.c_uint64),
+        ("pos_bytes", C.c_uint64), ("arr_offsets_bytes", C.c_uint64), ("nulls_bytes", C.c_uint64),
     ]
 
 
@@ -88,7 +91,8 @@ class Cfg(C.Structure):
     _fields_ = [("max_batch_bytes", C.c_uint64), ("max_batch_records", C.c_uint32),
                 ("flow_tag_cache_flush_timeout", C.c_uint32), ("flow_tag_cache_max_size", C.c_uint32),
                 ("trace_id_index_disabled", C.c_uint32), ("native_strings", C.c_uint32),
-                ("rollup_tables", C.c_uint32), ("rollup_max_groups", C.c_uint32), ("reserved", C.c_uint32 * 4)]
+                ("rollup_tables", C.c_uint32), ("rollup_max_groups", C.c_uint32), ("block_lz4", C.c_uint32),
+                ("reserved", C.c_uint32 * 3)]
 
 
 class RollupRows(C.Structure):
@@ -117,10 +121,127 @@ def _np_from(ptr, nbytes, dtype):
     return np.frombuffer(buf, dtype=dtype).copy()
 
 
+def lz4_block_decode(src: bytes, raw_size: int) -> bytes:
+    """Plain LZ4 block decoder (the format of lz4_Block_format.md), written for the tests: independent of the
+    compressor in lz4.cu, checks every bound."""
+    out = bytearray()
+    i, n = 0, len(src)
+    while True:
+        if i >= n:
+            raise ValueError("lz4: truncated block")
+        tok = src[i]
+        i += 1
+        lit = tok >> 4
+        if lit == 15:
+            while True:
+                b = src[i]
+                i += 1
+                lit += b
+                if b != 255:
+                    break
+        if i + lit > n:
+            raise ValueError("lz4: literals past the end")
+        out += src[i:i + lit]
+        i += lit
+        if i == n:
+            break  # the last sequence has no match
+        off = src[i] | src[i + 1] << 8
+        i += 2
+        if off == 0 or off > len(out):
+            raise ValueError(f"lz4: offset {off} outside the {len(out)} bytes produced")
+        ml = tok & 15
+        if ml == 15:
+            while True:
+                b = src[i]
+                i += 1
+                ml += b
+                if b != 255:
+                    break
+        ml += 4
+        start = len(out) - off
+        if off >= ml:
+            out += out[start:start + ml]
+        else:
+            for k in range(ml):  # overlapping copy
+                out.append(out[start + k])
+    if len(out) != raw_size:
+        raise ValueError(f"lz4: block decodes to {len(out)} bytes, header says {raw_size}")
+    return bytes(out)
+
+
+def decode_frames(ptr, nbytes):
+    """A stream of ClickHouse compressed frames (lz4.cu) -> the bytes it carries.  Every frame is decoded
+    twice, by pyarrow's LZ4 codec and by the decoder above; the checksum slot must still be zero (the
+    host fills it)."""
+    if not ptr or not nbytes:
+        return b""
+    import pyarrow as pa
+    raw = bytes((C.c_uint8 * nbytes).from_address(ptr))
+    out, i = [], 0
+    while i < nbytes:
+        if nbytes - i < 25:
+            raise ValueError("frame stream: truncated header")
+        if raw[i:i + 16] != bytes(16):
+            raise ValueError("frame stream: checksum slot not zero")
+        method = raw[i + 16]
+        csz = int.from_bytes(raw[i + 17:i + 21], "little")
+        usz = int.from_bytes(raw[i + 21:i + 25], "little")
+        payload = raw[i + 25:i + 16 + csz]
+        if len(payload) != csz - 9 or usz == 0 or usz > 4096:
+            raise ValueError(f"frame stream: bad sizes {csz} / {usz}")
+        if method == 0x82:
+            a = lz4_block_decode(payload, usz)
+            b = pa.decompress(payload, decompressed_size=usz, codec="lz4_raw", asbytes=True)
+            if a != b:
+                raise ValueError("frame stream: the two LZ4 decoders disagree")
+            if len(payload) >= usz:
+                raise ValueError("frame stream: LZ4 frame not smaller than its data (should have been stored)")
+            out.append(a)
+        elif method == 0x02:
+            if len(payload) != usz:
+                raise ValueError("frame stream: stored frame size mismatch")
+            out.append(payload)
+        else:
+            raise ValueError(f"frame stream: unknown method {method:#x}")
+        i += 16 + csz
+    return b"".join(out)
+
+
+class _Plain:
+    """dfgpu_col fields with the frame streams of a compressed column already decoded."""
+    pass
+
+
+def _decompressed(c: Col):
+    p = _Plain()
+    for k, _ in Col._fields_:
+        setattr(p, k, getattr(c, k))
+    p._keep = []
+    for field, nbytes in (("data", c.data_bytes), ("pos", c.pos_bytes), ("arr_offsets", c.arr_offsets_bytes),
+                          ("nulls", c.nulls_bytes)):
+        ptr = getattr(c, field)
+        if not ptr:
+            continue
+        raw = decode_frames(ptr, int(nbytes))
+        buf = (C.c_uint8 * max(1, len(raw))).from_buffer_copy(raw or b"\0")
+        p._keep.append(buf)
+        setattr(p, field, C.addressof(buf))
+        if field == "data":
+            if len(raw) != c.data_raw_bytes:
+                raise ValueError(f"{c.name.decode()}: {len(raw)} bytes decoded, data_raw_bytes {c.data_raw_bytes}")
+            p.data_bytes = len(raw)
+    p.compressed_bytes = int(c.data_bytes + c.pos_bytes + c.arr_offsets_bytes + c.nulls_bytes)
+    return p
+
+
 class Column:
     """Python-side copy of one dfgpu_col (numpy arrays; safe after batch release)."""
 
     def __init__(self, c: Col):
+        self.compressed_bytes = None
+        if c.compressed:
+            c = _decompressed(c)
+            self.compressed_bytes = c.compressed_bytes
         self.name = c.name.decode()
         self.ch_type = c.ch_type
         self.elem_size = c.elem_size
@@ -252,6 +373,20 @@ def columns_equal(a: Column, b: Column):
             i = idx[0] if len(idx) else None
             return f"{a.name}: {attr} differs first at {i}: {x[tuple(i)] if i is not None else '?'} vs {y[tuple(i)] if i is not None else '?'}"
     return None
+
+
+def fetch_column(fn, handle, table, index):
+    """One column of a table (a copy), without touching the others."""
+    ncols = C.c_int(0)
+    nrows = C.c_uint64(0)
+    rc = fn(handle, table, None, C.byref(ncols), C.byref(nrows))
+    if rc != 0:
+        raise RuntimeError(f"columns(table={table}) failed: {rc}")
+    arr = (Col * ncols.value)()
+    rc = fn(handle, table, arr, C.byref(ncols), C.byref(nrows))
+    if rc != 0:
+        raise RuntimeError(f"columns(table={table}) failed: {rc}")
+    return Column(arr[index]), int(nrows.value)
 
 
 def fetch_columns(fn, handle, table):

@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "ctx.h"
+#include "lz4_dev.h"
 #include "schema_l4.h"
 #include "schema_l7.h"
 
@@ -156,6 +157,7 @@ int dfgpu_close(dfgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   dfgpu_l7_free_state(ctx);
   l4_free_state(ctx);
+  lz4_free_state(ctx);
   rollup_free_state(ctx);
   metrics_free_state(ctx);
   cudaFree(ctx->d_in);
@@ -714,18 +716,25 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
   b->ctx = ctx;
   b->msg_type = ctx->cur_msg;
   b->stats = d->stats;
-  b->host = host_acquire(ctx, (size_t)total + 64);
-  if (!b->host) {
-    delete b;
-    return fail(ctx, DFGPU_ENOMEM, "pinned host allocation of %llu bytes failed", (unsigned long long)total);
+  // dfgpu_cfg.block_lz4: the arena stays on the device; the column views are first laid out against a virtual
+  // base, then every buffer is compressed into frames and the views are re-pointed at the frame streams
+  const bool lz = ctx->cfg.block_lz4 != 0 && nrows > 0;
+  uint8_t* const vbase = reinterpret_cast<uint8_t*>(uintptr_t(1) << 44);
+  uint8_t* hb = vbase;
+  if (!lz) {
+    b->host = host_acquire(ctx, (size_t)total + 64);
+    if (!b->host) {
+      delete b;
+      return fail(ctx, DFGPU_ENOMEM, "pinned host allocation of %llu bytes failed", (unsigned long long)total);
+    }
+    hb = b->host + 64;
   }
-  uint8_t* hb = b->host + 64;
   // D2H.  Common case (every record produced a row): the fixed region was planned for exactly these
   // rows, so the whole used arena is dense -> ONE copy instead of ~150 small ones.  Otherwise: per
   // column only the rows that exist; streams only their used bytes.
   const bool dense = nrows > 0 && (nrows == d->stats.nrec || (d->plan_valid && nrows == d->plan_rows));
-  if (dense) CU(cudaMemcpyAsync(hb, bp.arena, (size_t)total, cudaMemcpyDeviceToHost, s));
-  for (int c = 0; c < sch->ncols && !dense; c++) {
+  if (dense && !lz) CU(cudaMemcpyAsync(hb, bp.arena, (size_t)total, cudaMemcpyDeviceToHost, s));
+  for (int c = 0; c < sch->ncols && !dense && !lz; c++) {
     const ColSpec& cs = sch->cols[c];
     size_t es = is_array(cs.ch_type) ? 0 : (size_t)cs.elem_size;
     if (es && nrows) CU(cudaMemcpyAsync(hb + d->fix_off[c], bp.arena + d->fix_off[c], (size_t)nrows * es, cudaMemcpyDeviceToHost, s));
@@ -733,7 +742,7 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
     if (bp.native_str && (cs.ch_type == DFGPU_CH_STR || cs.ch_type == DFGPU_CH_LC_STR_ROWS)) ab = 0;  // no Positions
     if (ab && nrows) CU(cudaMemcpyAsync(hb + d->aux_off[c], bp.arena + d->aux_off[c], (size_t)nrows * ab, cudaMemcpyDeviceToHost, s));
   }
-  if (!dense && total > d->var_base)
+  if (!dense && !lz && total > d->var_base)
     CU(cudaMemcpyAsync(hb + d->var_base, bp.arena + d->var_base, (size_t)(total - d->var_base), cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(ctx->h_persist, ctx->d_persist, sizeof(PersistState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -810,6 +819,66 @@ int dfgpu_fetch(dfgpu_ctx* ctx, dfgpu_batch** out) {
         break;
       }
     }
+  }
+  if (lz) {
+    // one region per buffer of every column, in column order
+    std::vector<LzRegion> regs;
+    struct Ref { int col, which; };
+    std::vector<Ref> refs;
+    auto add = [&](int c, int which, const void* ptr, uint64_t len, uint32_t stride) {
+      if (!ptr || !len) return;
+      regs.push_back(LzRegion{(uint64_t)(reinterpret_cast<const uint8_t*>(ptr) - vbase), len, 0u, stride});
+      refs.push_back(Ref{c, which});
+    };
+    for (int c = 0; c < sch->ncols; c++) {
+      const dfgpu_col& col = t.cols[c];
+      const bool arr = is_array(col.ch_type);
+      const bool str = col.ch_type == DFGPU_CH_STR || col.ch_type == DFGPU_CH_LC_STR_ROWS || col.ch_type == DFGPU_CH_ARR_STR ||
+                       col.ch_type == DFGPU_CH_ARR_LC_STR;
+      const uint32_t es = col.ch_type == DFGPU_CH_ARR_UINT16 ? 2u : col.ch_type == DFGPU_CH_ARR_FLOAT64 ? 8u : (uint32_t)col.elem_size;
+      add(c, 0, col.data, col.data_bytes, str ? 0u : (es > 16 ? 16u : es));
+      add(c, 1, col.pos, (arr ? col.nelems : col.nrows) * 16, 16u);
+      add(c, 2, col.arr_offsets, col.nrows * 8, 8u);
+      add(c, 3, col.nulls, col.nrows, 1u);
+    }
+    const uint8_t* d_frames = nullptr;
+    std::vector<uint64_t> fpos;
+    int rc = lz4_compress_regions(ctx, bp.arena, regs, &d_frames, fpos);
+    if (rc) {
+      delete b;
+      return rc;
+    }
+    const uint64_t ftotal = fpos.empty() ? 0 : fpos.back();
+    b->host = host_acquire(ctx, (size_t)ftotal + 64);
+    if (!b->host) {
+      delete b;
+      return fail(ctx, DFGPU_ENOMEM, "pinned host allocation of %llu bytes failed", (unsigned long long)ftotal);
+    }
+    uint8_t* fb = b->host + 64;
+    if (ftotal) CU(cudaMemcpyAsync(fb, d_frames, (size_t)ftotal, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (auto& col : t.cols) {
+      col.compressed = 1;
+      col.data_raw_bytes = col.data_bytes;
+      // buffers without bytes (an empty stream) keep no frames
+      col.data = nullptr;
+      col.pos = nullptr;
+      col.arr_offsets = nullptr;
+      col.nulls = nullptr;
+      col.data_bytes = 0;
+    }
+    for (size_t r = 0; r < regs.size(); r++) {
+      dfgpu_col& col = t.cols[refs[r].col];
+      const uint8_t* p = fb + fpos[r];
+      const uint64_t n = fpos[r + 1] - fpos[r];
+      switch (refs[r].which) {
+        case 0: col.data = p; col.data_bytes = n; break;
+        case 1: col.pos = reinterpret_cast<const dfgpu_pos*>(p); col.pos_bytes = n; break;
+        case 2: col.arr_offsets = reinterpret_cast<const uint64_t*>(p); col.arr_offsets_bytes = n; break;
+        default: col.nulls = p; col.nulls_bytes = n; break;
+      }
+    }
+    b->lz_frame_bytes = ftotal;
   }
   // ---- counters (decoder.Counter, decoder.go:60-80) ------------------------------------
   dfgpu_counters& cn = b->counters;

@@ -95,6 +95,8 @@ struct dfgpu_ctx {
   void* ft = nullptr;
   // L4 per-record hand-over buffers (l4.cu)
   void* l4 = nullptr;
+  // compressed-frame stage (lz4.cu)
+  void* lz = nullptr;
   // flow_metrics state (metrics.cu)
   void* mt = nullptr;
   // flow_metrics rollup accumulators (rollup.cu)

@@ -102,7 +102,8 @@ struct BatchStats {
 struct dfgpu_batch {
   dfgpu_ctx* ctx = nullptr;
   int msg_type = 0;
-  uint8_t* host = nullptr;  // pinned copy of the arena
+  uint8_t* host = nullptr;  // pinned copy of the arena (dfgpu_cfg.block_lz4: of the frame streams)
+  uint64_t lz_frame_bytes = 0;
   dfgpu::BatchStats stats{};
   dfgpu_counters counters{};
   struct Table {

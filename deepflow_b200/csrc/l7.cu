@@ -806,8 +806,9 @@ int l7_tags_import(dfgpu_ctx* ctx, const uint64_t* fps, const uint32_t* times, u
   }
   U128* d_fps = reinterpret_cast<U128*>(h->d_import);
   uint32_t* d_times = reinterpret_cast<uint32_t*>(d_fps + h->import_cap);
-  CU(cudaMemcpyAsync(d_fps, fps, n * 16, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(d_times, times, n * 4, cudaMemcpyHostToDevice, s));
+  // host or device pointers (unified addressing): a merge that all-gathers over NCCL hands device buffers in
+  CU(cudaMemcpyAsync(d_fps, fps, n * 16, cudaMemcpyDefault, s));
+  CU(cudaMemcpyAsync(d_times, times, n * 4, cudaMemcpyDefault, s));
   k_l7_ft_import<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->set.cur, h->set.mask, d_fps, d_times, (uint32_t)n, h->set.d_state);
   ctx->launches++;
   CU(cudaStreamSynchronize(s));  // the caller's arrays may go away

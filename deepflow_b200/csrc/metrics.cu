@@ -41,7 +41,8 @@ __device__ __forceinline__ void ip_bytes(const uint8_t* base, uint64_t ref, uint
   for (uint32_t i = 0; i < n; i++) out[i] = i < len ? __ldg(base + off + i) : 0;
 }
 
-__device__ void m_read_tag(const uint64_t* sl, const uint8_t* base, MTag& t) {
+template <class SL>
+__device__ __forceinline__ void m_read_tag(const SL& sl, const uint8_t* base, MTag& t) {
   memset(&t, 0, sizeof t);
   t.code = sl[MS_CODE];
   t.time = sl_u32(sl, MS_TS);
@@ -93,13 +94,14 @@ __device__ void m_read_tag(const uint64_t* sl, const uint8_t* base, MTag& t) {
   t.tunnel_ip_id = (uint16_t)sl_u32(sl, MS_SERVER_PORT);
 }
 
-__device__ void m_read_flow(const uint64_t* sl, MFlowMeter& m) {
-  const uint64_t* t = sl + MS_TRAFFIC;
+template <class SL>
+__device__ __forceinline__ void m_read_flow(const SL& sl, MFlowMeter& m) {
+  const auto t = sl.at(MS_TRAFFIC);
   m.packet_tx = t[0]; m.packet_rx = t[1]; m.byte_tx = t[2]; m.byte_rx = t[3]; m.l3_byte_tx = t[4];
   m.l3_byte_rx = t[5]; m.l4_byte_tx = t[6]; m.l4_byte_rx = t[7]; m.new_flow = t[8]; m.closed_flow = t[9];
   m.l7_request = (uint32_t)t[10]; m.l7_response = (uint32_t)t[11]; m.syn_count = (uint32_t)t[12];
   m.synack_count = (uint32_t)t[13]; m.direction_score = (uint8_t)t[14];
-  const uint64_t* l = sl + MS_LATENCY;
+  const auto l = sl.at(MS_LATENCY);
   m.rtt_max = (uint32_t)l[0]; m.rtt_client_max = (uint32_t)l[1]; m.rtt_server_max = (uint32_t)l[2];
   m.srt_max = (uint32_t)l[3]; m.art_max = (uint32_t)l[4]; m.rrt_max = (uint32_t)l[5]; m.cit_max = (uint32_t)l[6];
   m.rtt_sum = l[7]; m.rtt_client_sum = l[8]; m.rtt_server_sum = l[9]; m.srt_sum = l[10]; m.art_sum = l[11];
@@ -107,10 +109,10 @@ __device__ void m_read_flow(const uint64_t* sl, MFlowMeter& m) {
   m.rtt_count = (uint32_t)l[14]; m.rtt_client_count = (uint32_t)l[15]; m.rtt_server_count = (uint32_t)l[16];
   m.srt_count = (uint32_t)l[17]; m.art_count = (uint32_t)l[18]; m.rrt_count = (uint32_t)l[19];
   m.cit_count = (uint32_t)l[20];
-  const uint64_t* p = sl + MS_PERF;
+  const auto p = sl.at(MS_PERF);
   m.retrans_tx = p[0]; m.retrans_rx = p[1]; m.zero_win_tx = p[2]; m.zero_win_rx = p[3];
   m.retrans_syn = (uint32_t)p[4]; m.retrans_synack = (uint32_t)p[5];
-  const uint64_t* a = sl + MS_ANOMALY;
+  const auto a = sl.at(MS_ANOMALY);
   m.client_rst_flow = a[0]; m.server_rst_flow = a[1]; m.server_syn_miss = a[2]; m.client_ack_miss = a[3];
   m.client_half_close_flow = a[4]; m.server_half_close_flow = a[5]; m.client_source_port_reuse = a[6];
   m.client_establish_reset = a[7]; m.server_reset = a[8]; m.server_queue_lack = a[9];
@@ -125,15 +127,17 @@ __device__ void m_read_flow(const uint64_t* sl, MFlowMeter& m) {
   m.ooo_tx = a[15]; m.ooo_rx = a[16];
   m.flow_load = sl[MS_FLOWLOAD];
 }
-__device__ void m_read_app(const uint64_t* sl, MAppMeter& m) {
+template <class SL>
+__device__ __forceinline__ void m_read_app(const SL& sl, MAppMeter& m) {
   m.request = (uint32_t)sl[MS_APPTRAFFIC]; m.response = (uint32_t)sl[MS_APPTRAFFIC + 1];
   m.direction_score = (uint8_t)sl[MS_APPTRAFFIC + 2];
   m.rrt_max = (uint32_t)sl[MS_APPLATENCY]; m.rrt_sum = sl[MS_APPLATENCY + 1]; m.rrt_count = (uint32_t)sl[MS_APPLATENCY + 2];
   m.client_error = (uint32_t)sl[MS_APPANOMALY]; m.server_error = (uint32_t)sl[MS_APPANOMALY + 1];
   m.timeout = (uint32_t)sl[MS_APPANOMALY + 2];
 }
-__device__ void m_read_usage(const uint64_t* sl, MUsageMeter& m) {
-  const uint64_t* u = sl + MS_USAGE;
+template <class SL>
+__device__ __forceinline__ void m_read_usage(const SL& sl, MUsageMeter& m) {
+  const auto u = sl.at(MS_USAGE);
   m.packet_tx = u[0]; m.packet_rx = u[1]; m.byte_tx = u[2]; m.byte_rx = u[3]; m.l3_byte_tx = u[4];
   m.l3_byte_rx = u[5]; m.l4_byte_tx = u[6]; m.l4_byte_rx = u[7];
 }
@@ -324,157 +328,114 @@ __device__ __forceinline__ int m_table_id(const MDev* dv, uint64_t code, bool is
 
 }  // namespace
 
-// ---- the record pass ----------------------------------------------------------------------------
-template <int EMIT>
-__global__ void __launch_bounds__(256) k_m_pass(const __grid_constant__ BatchParams p) {
+// ---- the decode kernel ------------------------------------------------------------------------------
+// One thread per record, persistent warps.  The record is decoded ONCE by the table-driven tokenizer
+// (pb_tok.cuh) into shared-memory words; the tail — tag, SmartEncoding, table routing — runs with the warp
+// converged and leaves, per record, the values of its table's tag columns and its raw meter fields in
+// plane-major buffers ([plane][record]: every store is one coalesced line per warp).  k_m_emit, after the
+// scans have fixed the row of every record, moves them into the columns.  (Round 1 decoded and expanded every
+// record twice — once to size, once to write — out of a 1 KB per-thread slot array in local memory.)
+constexpr int MD_THREADS = 64;  // MW_COUNT words per thread: 41.5 KB per CTA, 5 CTAs per SM
+
+struct MSink {
+  uint32_t* w;  // s_words + tid, stride MD_THREADS
+  __device__ __forceinline__ void u32(uint32_t s, uint32_t v) { w[s * MD_THREADS] = v; }
+  __device__ __forceinline__ void u64(uint32_t s, uint32_t lo, uint32_t hi) {
+    w[s * MD_THREADS] = lo;
+    w[(s + 1) * MD_THREADS] = hi;
+  }
+  __device__ __forceinline__ void add(uint32_t s, uint32_t v) { w[s * MD_THREADS] += v; }
+  __device__ __forceinline__ uint32_t word(uint32_t s) const { return w[s * MD_THREADS]; }
+  __device__ __forceinline__ void ref(uint32_t, uint32_t, uint32_t) {}
+  __device__ __forceinline__ void elem(uint32_t, uint32_t, uint32_t, uint32_t) {}
+  __device__ __forceinline__ void velem(uint32_t, uint32_t, uint32_t, uint32_t) {}
+};
+// the interpreter's slot array seen through the words: sl[MS_X] is the 64-bit slot value
+struct MView {
+  const uint32_t* w;
+  struct At {
+    const MView& v;
+    int base;
+    __device__ __forceinline__ uint64_t operator[](int i) const { return v[base + i]; }
+  };
+  __device__ __forceinline__ uint64_t operator[](int s) const {
+    const int k = mw(s);
+    const uint32_t lo = w[k * MD_THREADS];
+    return mw64(s) ? (uint64_t)w[(k + 1) * MD_THREADS] << 32 | lo : (uint64_t)lo;
+  }
+  __device__ __forceinline__ At at(int s) const { return At{*this, s}; }
+};
+
+// the tag words of a record as k_m_decode left them: [word][record] planes
+struct MViewG {
+  const uint32_t* w;  // tagw + rec
+  size_t cap;
+  struct At {
+    const MViewG& v;
+    int base;
+    __device__ __forceinline__ uint64_t operator[](int i) const { return v[base + i]; }
+  };
+  __device__ __forceinline__ uint64_t operator[](int s) const {
+    const int k = mw(s) - MWB_TAG;
+    const uint32_t lo = w[(size_t)k * cap];
+    return mw64(s) ? (uint64_t)w[(size_t)(k + 1) * cap] << 32 | lo : (uint64_t)lo;
+  }
+  __device__ __forceinline__ At at(int s) const { return At{*this, s}; }
+};
+constexpr int M_TAG_WORDS = MWB_TRAFFIC - MWB_TAG;  // 38
+
+__global__ void __launch_bounds__(MD_THREADS, 5) k_m_decode(const __grid_constant__ BatchParams p) {
   __shared__ uint32_t s_tbl[MM_COUNT * MM_MAXF];
+  __shared__ uint32_t s_words[MW_COUNT * MD_THREADS];
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
-  for (uint32_t i = threadIdx.x; i < MM_COUNT * MM_MAXF; i += blockDim.x) s_tbl[i] = dv->pb_tbl[i];
+  for (uint32_t i = threadIdx.x; i < MM_COUNT * MM_MAXF; i += MD_THREADS) s_tbl[i] = dv->tok_tbl[i];
   __syncthreads();
-  const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t warp = rec >> 5, lane = threadIdx.x & 31;
-  const bool in_range = rec < batch_nrec(p);
   DynState* dyn = p.dyn;
-  MLayout* lay = dv->lay;
-  if (EMIT && (dyn->stats.need_repair && !p.repair)) return;
-  if (EMIT && lay->overflow) return;
-
-  uint64_t sl[MS_COUNT];
-  bool ok = false;
-  uint32_t frame = 0;
-  const uint8_t* base = nullptr;
-  if (in_range) {
-    frame = p.rec_frame[rec];
-    base = p.in + p.rec_off[rec];
-    if (!(p.repair && rec >= p.frame_bad[frame])) {
-#pragma unroll 1
-      for (int i = 0; i < MS_COUNT; i++) sl[i] = 0;
-      ok = pb_interp(base, p.rec_len[rec], s_tbl, MM_MAXF, sl);
-      if (ok) {  // unknown meter id: DecodePB fails, the frame is abandoned (codec.go:60-63)
-        const uint8_t id = (uint8_t)sl_u32(sl, MS_METER_ID);
-        ok = id == MT_METER_FLOW || id == MT_METER_USAGE || id == MT_METER_APP;
+  if (dyn->overflow) return;
+  const uint32_t nrec = batch_nrec(p), nwarps = dyn->nwarps;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gwarp = blockIdx.x * (MD_THREADS / 32) + (threadIdx.x >> 5), total_warps = gridDim.x * (MD_THREADS / 32);
+  uint32_t* my_words = s_words + threadIdx.x;
+  const size_t cap = dv->rec_cap;
+  TokWin win;
+  win.init(p.in, p.in_bytes);
+  for (uint32_t wtile = gwarp; wtile < nwarps; wtile += total_warps) {
+    const uint32_t rec = wtile * 32 + lane;
+    const bool in_range = rec < nrec;
+#pragma unroll
+    for (int i = 0; i < MW_COUNT; i++) my_words[i * MD_THREADS] = 0;
+    MSink sink{my_words};
+    const MView sl{my_words};
+    bool ok = false;
+    uint32_t frame = 0;
+    if (in_range) {
+      frame = p.rec_frame[rec];
+      if (!(p.repair && rec >= p.frame_bad[frame])) {
+        ok = tk_decode<MM_MAXF>(win, p.rec_off[rec], p.rec_len[rec], s_tbl, sink, 0u);
+        if (ok) {  // unknown meter id: DecodePB fails, the frame is abandoned (codec.go:60-63)
+          const uint8_t id = (uint8_t)sl_u32(sl, MS_METER_ID);
+          ok = id == MT_METER_FLOW || id == MT_METER_USAGE || id == MT_METER_APP;
+        }
+        if (!ok && !p.repair) {
+          atomicMin(&p.frame_bad[frame], rec);
+          dyn->stats.need_repair = 1;
+        }
       }
-      if (!ok && !p.repair) {
-        atomicMin(&p.frame_bad[frame], rec);
-        dyn->stats.need_repair = 1;
-      }
     }
-  }
-  MTag t;
-  int table = -1;
-  uint8_t meter_id = 0;
-  if (ok) {
-    meter_id = (uint8_t)sl_u32(sl, MS_METER_ID);
-    m_read_tag(sl, base, t);
-    const dfgpu_frame fr = p.frames[frame];
-    t.team_id = (uint16_t)fr.team_id;  // unmarshaller.go:242-243
-    t.org_id = fr.org_id;
-    if (m_expand(p.dict, t, meter_id)) {
-      table = m_table_id(dv, t.code, (sl_u32(sl, MS_FLAGS) & 1) == 1);
-      // a meter the table does not store cannot be packed by the reference either: dropped
-      if (table >= 0 && dv->table_meter[table] != meter_id) table = -1;
+    // ---- hand-over (the warp is converged: every store below is one line per plane) ----
+    const uint32_t meter_id = ok ? sl_u32(sl, MS_METER_ID) & 0xffu : 0u;
+    if (in_range) {
+      uint32_t* T = dv->tagw + rec;
+#pragma unroll
+      for (int k = 0; k < M_TAG_WORDS; k++) T[(size_t)k * cap] = my_words[(MWB_TAG + k) * MD_THREADS];
+      dv->meta[rec] = (ok ? 0x100u : 0u) | meter_id;  // k_m_tag adds the table
     }
-  }
-  const bool valid = table >= 0;
-  const int app = valid ? m_app_index(table) : -1;
-  const int obs = valid ? m_obs_space(table) : -1;
-  const uint32_t tside = obs >= 0 ? tapside_code(t.tap_side) : 0;
-  const uint32_t same = __match_any_sync(0xffffffffu, valid ? table : 0xff);
-
-  if (!EMIT) {
-    if (lane == 0 && warp < p.dyn->nwarps)
-      for (int s = 0; s < M_SLOTS; s++) p.warp_tot[(size_t)s * p.warp_cap + warp] = 0;
-    __syncwarp();
-    if (valid && (int)lane == __ffs(same) - 1 && warp < p.dyn->nwarps)
-      p.warp_tot[(size_t)(M_SLOT_ROWS + table) * p.warp_cap + warp] = __popc(same);
-#pragma unroll 1
-    for (int a = 0; a < 4; a++)
-#pragma unroll 1
-      for (int w = 0; w < 3; w++) {
-        uint32_t tot = warp_sum(app == a ? t.str[w].n : 0u);
-        if (lane == 0 && warp < p.dyn->nwarps) p.warp_tot[(size_t)(M_SLOT_STR + a * 3 + w) * p.warp_cap + warp] = tot;
-      }
-    lc_note(&dyn->stats.lc_first[0][0], (uint32_t)(obs < 0 ? 0 : obs) * 256u + tside, rec, obs >= 0);
-    const uint32_t n_ok = __popc(__ballot_sync(0xffffffffu, ok)), n_drop = __popc(__ballot_sync(0xffffffffu, ok && !valid));
-    if (lane == 0) {
-      if (n_ok) atomicAdd(&lay->count, n_ok);
-      if (n_drop) atomicAdd(&lay->drop_count, n_drop);
-    }
-    return;
-  }
-
-  // ---- EMIT ------------------------------------------------------------------------------------
-  uint32_t e_str[3] = {0, 0, 0};
-#pragma unroll 1
-  for (int a = 0; a < 4; a++)
-#pragma unroll 1
-    for (int w = 0; w < 3; w++) {
-      uint32_t e = warp_excl_scan(app == a ? t.str[w].n : 0u);
-      if (app == a) e_str[w] = e;
-    }
-  MCand cand;
-  memset(&cand, 0, sizeof cand);
-  if (valid) {
-    const uint32_t wb = warp < p.dyn->nwarps ? warp : 0;
-    const uint32_t row = p.warp_base[(size_t)(M_SLOT_ROWS + table) * p.warp_cap + wb] + __popc(same & ((1u << lane) - 1));
-    const uint64_t tcode = dv->table_code[table];
-    uint32_t d = dv->desc_base[table];
-    uint8_t* A = p.arena;
-    dv->row_rec[lay->row_base[table] + row] = rec;
-#define F(bit, name, ch, ctype, expr)                                            \
-  if ((bit) == 0 || (tcode & (bit))) {                                           \
-    reinterpret_cast<ctype*>(A + lay->col_off[d])[row] = (ctype)(expr);          \
-    d++;                                                                         \
-  }
-#define V6(bit, name, side)                                                      \
-  if (tcode & (bit)) {                                                           \
-    uint4 v;                                                                     \
-    memcpy(&v, t.ip6[side], 16);                                                 \
-    reinterpret_cast<uint4*>(A + lay->col_off[d])[row] = v;                      \
-    d++;                                                                         \
-  }
-#define OBS(bit, name)                                                           \
-  if (tcode & (bit)) {                                                           \
-    (A + lay->col_off[d])[row] = dyn->lc_rank[obs < 0 ? 0 : obs][tside];         \
-    d++;                                                                         \
-  }
-#define STRCOL(bit, name, which)                                                                         \
-  if (tcode & (bit)) {                                                                                   \
-    const uint64_t off = (uint64_t)p.warp_base[(size_t)(M_SLOT_STR + app * 3 + which) * p.warp_cap + wb] + e_str[which]; \
-    const uint32_t n = t.str[which].n;                                                                   \
-    reinterpret_cast<dfgpu_pos*>(A + lay->aux_off[d])[row] = dfgpu_pos{(int64_t)off, (int64_t)(off + n)}; \
-    uint8_t* dst = A + lay->col_off[d] + off;                                                            \
-    for (uint32_t i = 0; i < n; i++) dst[i] = __ldg(t.str[which].p + i);                                 \
-    d++;                                                                                                 \
-  }
-    MT_TAG_COLUMNS(F, V6, OBS, STRCOL, STRCOL)
-#undef F
-#undef V6
-#undef OBS
-#undef STRCOL
-#define M(name, ch, ctype, expr)                                                 \
-  reinterpret_cast<ctype*>(A + lay->col_off[d])[row] = (ctype)(expr);            \
-  d++;
-    if (meter_id == MT_METER_FLOW) {
-      MFlowMeter m;
-      m_read_flow(sl, m);
-      MT_FLOW_METER_COLUMNS(M)
-    } else if (meter_id == MT_METER_APP) {
-      MAppMeter m;
-      m_read_app(sl, m);
-      MT_APP_METER_COLUMNS(M)
-    } else {
-      MUsageMeter m;
-      m_read_usage(sl, m);
-      MT_USAGE_METER_COLUMNS(M)
-    }
-#undef M
-    // the rollup accumulator (rollup.cu) folds RAW meters: the packed columns hold float64(rtt_sum) etc. and
-    // are lossy above 2^53.  Row-major [row][field] so that one warp reads a row as one contiguous segment.
-    if (dv->raw_tables & (1u << table)) {
-      uint64_t* R = reinterpret_cast<uint64_t*>(A + lay->raw_off[table]) + (size_t)row * dv->raw_nf[table];
+    if (ok) {
+      uint64_t* R = dv->rawv + rec;
       uint32_t i = 0;
-#define X(name, op) R[i++] = (uint64_t)m.name;
+#define X(name, op)                          \
+  R[(size_t)i * cap] = (uint64_t)m.name;     \
+  i++;
       if (meter_id == MT_METER_FLOW) {
         MFlowMeter m;
         m_read_flow(sl, m);
@@ -490,19 +451,223 @@ __global__ void __launch_bounds__(256) k_m_pass(const __grid_constant__ BatchPar
       }
 #undef X
     }
-    // appServiceTagWrite unmarshaller.go:309-327: only the 1m application tables
-    if ((table == MT_APPLICATION_1M || table == MT_APPLICATION_MAP_1M) && (t.str[0].n | t.str[1].n)) {
-      cand.svc_off = (uint32_t)(t.str[0].p - p.in);
-      cand.svc_len = t.str[0].n;
-      cand.inst_off = (uint32_t)(t.str[1].p - p.in);
-      cand.inst_len = t.str[1].n;
-      cand.time = t.time;
-      cand.team = t.team_id;
-      cand.table = table == MT_APPLICATION_1M ? 0 : 1;
-      cand.state = 1;
-    }
+    __syncwarp();
   }
-  if (in_range) dv->cand[rec] = cand;
+}
+
+// ---- the tag kernel: Tag.ReadFromPB, DocumentExpand, table routing, sizes ---------------------------------
+// Thread per record over the decoded tag words.  The dictionary probe chains of DocumentExpand want many warps in
+// flight, the tokenizer wants shared memory: two kernels, each at the occupancy that suits it.
+__global__ void __launch_bounds__(256) k_m_tag(const __grid_constant__ BatchParams p) {
+  const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
+  DynState* dyn = p.dyn;
+  MLayout* lay = dv->lay;
+  if (dyn->overflow) return;
+  const uint32_t nrec = batch_nrec(p), nwarps = dyn->nwarps;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), total_warps = gridDim.x * (blockDim.x >> 5);
+  const size_t cap = dv->rec_cap;
+  for (uint32_t wtile = gwarp; wtile < nwarps; wtile += total_warps) {
+    const uint32_t rec = wtile * 32 + lane;
+    const bool in_range = rec < nrec;
+    const uint32_t meta0 = in_range ? dv->meta[rec] : 0u;
+    const bool ok = (meta0 & 0x100u) != 0;
+    const uint8_t meter_id = (uint8_t)(meta0 & 0xffu);
+    const MViewG sl{dv->tagw + rec, cap};
+    MTag t;
+    int table = -1;
+    if (ok) {
+      m_read_tag(sl, p.in, t);
+      const dfgpu_frame fr = p.frames[p.rec_frame[rec]];
+      t.team_id = (uint16_t)fr.team_id;  // unmarshaller.go:242-243
+      t.org_id = fr.org_id;
+      if (m_expand(p.dict, t, meter_id)) {
+        table = m_table_id(dv, t.code, (sl_u32(sl, MS_FLAGS) & 1) == 1);
+        // a meter the table does not store cannot be packed by the reference either: dropped
+        if (table >= 0 && dv->table_meter[table] != meter_id) table = -1;
+      }
+    }
+    const bool valid = table >= 0;
+    const int app = valid ? m_app_index(table) : -1;
+    const int obs = valid ? m_obs_space(table) : -1;
+    const uint32_t tside = obs >= 0 ? tapside_code(t.tap_side) : 0;
+    const uint32_t same = __match_any_sync(0xffffffffu, valid ? table : 0xff);
+    // ---- sizes: rows per table, string bytes per (application table, column) ----
+    if (lane < M_SLOTS) p.warp_tot[(size_t)lane * p.warp_cap + wtile] = 0;
+    __syncwarp();
+    if (valid && (int)lane == __ffs(same) - 1) p.warp_tot[(size_t)(M_SLOT_ROWS + table) * p.warp_cap + wtile] = __popc(same);
+    if (__any_sync(0xffffffffu, app >= 0)) {
+#pragma unroll 1
+      for (int a = 0; a < 4; a++)
+#pragma unroll 1
+        for (int w = 0; w < 3; w++) {
+          const uint32_t tot = warp_sum(app == a ? t.str[w].n : 0u);
+          if (lane == 0) p.warp_tot[(size_t)(M_SLOT_STR + a * 3 + w) * p.warp_cap + wtile] = tot;
+        }
+    }
+    lc_note(&dyn->stats.lc_first[0][0], (uint32_t)(obs < 0 ? 0 : obs) * 256u + tside, rec, obs >= 0);
+    const uint32_t n_ok = __popc(__ballot_sync(0xffffffffu, ok)), n_drop = __popc(__ballot_sync(0xffffffffu, ok && !valid));
+    if (lane == 0) {
+      if (n_ok) atomicAdd(&lay->count, n_ok);
+      if (n_drop) atomicAdd(&lay->drop_count, n_drop);
+    }
+    // ---- hand-over to k_m_emit ----
+    MCand cand;
+    memset(&cand, 0, sizeof cand);
+    if (valid) {
+      const uint64_t tcode = dv->table_code[table];
+      uint64_t* T = dv->tagv + rec;
+      uint32_t k = 0;
+#define PUT(v)                       \
+  {                                  \
+    T[(size_t)k * cap] = (uint64_t)(v); \
+    k++;                             \
+  }
+#define F(bit, name, ch, ctype, expr) \
+  if ((bit) == 0 || (tcode & (bit))) PUT((ctype)(expr))
+      // an address column of a v4 row (or of side 1 of a single-ended tag) is all zeros: length 0
+#define V6(bit, name, side) \
+  if (tcode & (bit)) PUT((t.is_ipv4 == 0 && ((side) == 0 || (t.code & MC_IPPATH))) ? sl[(side) ? MS_IP1 : MS_IP] : 0ull)
+#define OBS(bit, name) \
+  if (tcode & (bit)) PUT(tside)
+#define STRCOL(bit, name, which) \
+  if (tcode & (bit)) PUT((uint64_t)t.str[which].n << 32 | (uint32_t)(t.str[which].p - p.in))
+      MT_TAG_COLUMNS(F, V6, OBS, STRCOL, STRCOL)
+#undef F
+#undef V6
+#undef OBS
+#undef STRCOL
+#undef PUT
+      // appServiceTagWrite unmarshaller.go:309-327: only the 1m application tables
+      if ((table == MT_APPLICATION_1M || table == MT_APPLICATION_MAP_1M) && (t.str[0].n | t.str[1].n)) {
+        cand.svc_off = (uint32_t)(t.str[0].p - p.in);
+        cand.svc_len = t.str[0].n;
+        cand.inst_off = (uint32_t)(t.str[1].p - p.in);
+        cand.inst_len = t.str[1].n;
+        cand.time = t.time;
+        cand.team = t.team_id;
+        cand.table = table == MT_APPLICATION_1M ? 0 : 1;
+        cand.state = 1;
+      }
+    }
+    if (in_range) {
+      dv->cand[rec] = cand;
+      // table (0xff: no row) | meter id << 8 | tap-side code << 16
+      dv->meta[rec] = (valid ? (uint32_t)table : 0xffu) | (uint32_t)meter_id << 8 | tside << 16;
+      dv->strv[rec] = valid && app >= 0 ? make_uint4(t.str[0].n, t.str[1].n, t.str[2].n, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- the emit kernel: planes -> columns, after the scans ------------------------------------------------
+__global__ void __launch_bounds__(256) k_m_emit(const __grid_constant__ BatchParams p) {
+  const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
+  DynState* dyn = p.dyn;
+  const MLayout* lay = dv->lay;
+  if ((dyn->stats.need_repair && !p.repair) || dyn->overflow || lay->overflow) return;
+  const uint32_t nrec = batch_nrec(p), nwarps = dyn->nwarps;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), total_warps = gridDim.x * (blockDim.x >> 5);
+  const size_t cap = dv->rec_cap;
+  uint8_t* A = p.arena;
+  for (uint32_t wtile = gwarp; wtile < nwarps; wtile += total_warps) {
+    const uint32_t rec = wtile * 32 + lane;
+    const bool in_range = rec < nrec;
+    const uint32_t meta = in_range ? dv->meta[rec] : 0xffu;
+    const int table = (meta & 0xffu) == 0xffu ? -1 : (int)(meta & 0xffu);
+    const bool valid = table >= 0;
+    const uint32_t meter_id = (meta >> 8) & 0xffu, tside = (meta >> 16) & 0xffu;
+    const int app = valid ? m_app_index(table) : -1;
+    const int obs = valid ? m_obs_space(table) : -1;
+    const uint32_t same = __match_any_sync(0xffffffffu, valid ? table : 0xff);
+    uint32_t e_str[3] = {0, 0, 0};
+    if (__any_sync(0xffffffffu, app >= 0)) {
+      const uint4 sn = in_range ? dv->strv[rec] : make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t n3[3] = {sn.x, sn.y, sn.z};
+#pragma unroll 1
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+          const uint32_t e = warp_excl_scan(app == a ? n3[w] : 0u);
+          if (app == a) e_str[w] = e;
+        }
+    }
+    uint32_t row = 0, d0 = 0, ntag = 0;
+    if (valid) {
+      row = p.warp_base[(size_t)(M_SLOT_ROWS + table) * p.warp_cap + wtile] + __popc(same & ((1u << lane) - 1));
+      d0 = dv->desc_base[table];
+      ntag = dv->ntag[table];
+      dv->row_rec[lay->row_base[table] + row] = rec;
+    }
+    // tag columns: plane k of the record -> descriptor d0 + k of its table
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, ntag);
+    for (uint32_t k = 0; k < kmax; k++) {
+      if (k >= ntag) continue;
+      const uint64_t v = dv->tagv[(size_t)k * cap + rec];
+      const uint32_t d = d0 + k;
+      const MColDesc c = dv->descs[d];
+      uint8_t* col = A + lay->col_off[d];
+      if (c.kind == MK_FIX) {
+        if (c.elem == 1) col[row] = (uint8_t)v;
+        else if (c.elem == 2) reinterpret_cast<uint16_t*>(col)[row] = (uint16_t)v;
+        else if (c.elem == 4) reinterpret_cast<uint32_t*>(col)[row] = (uint32_t)v;
+        else reinterpret_cast<uint64_t*>(col)[row] = v;
+      } else if (c.kind == MK_IP6) {  // p.Field.Ip[:16], zero extended
+        const uint32_t off = (uint32_t)v, len = (uint32_t)(v >> 32);
+        uint64_t lo = 0, hi = 0;
+        const uint32_t n = len > 16 ? 16 : len;
+        for (uint32_t i = 0; i < n; i++) {
+          const uint64_t b = (uint64_t)__ldg(p.in + off + i) << ((i & 7) * 8);
+          if (i < 8) lo |= b; else hi |= b;
+        }
+        reinterpret_cast<ulonglong2*>(col)[row] = make_ulonglong2(lo, hi);
+      } else if (c.kind == MK_OBS) {
+        col[row] = dyn->lc_rank[obs < 0 ? 0 : obs][tside];
+      } else {  // MK_LCS / MK_STR
+        const uint32_t which = c.which, n = (uint32_t)(v >> 32);
+        const uint64_t off = (uint64_t)p.warp_base[(size_t)(M_SLOT_STR + app * 3 + which) * p.warp_cap + wtile] + e_str[which];
+        reinterpret_cast<dfgpu_pos*>(A + lay->aux_off[d])[row] = dfgpu_pos{(int64_t)off, (int64_t)(off + n)};
+        uint8_t* dst = col + off;
+        const uint8_t* src = p.in + (uint32_t)v;
+        for (uint32_t i = 0; i < n; i++) dst[i] = __ldg(src + i);
+      }
+    }
+    if (valid) {
+      uint32_t d = d0 + ntag;
+      const uint64_t* R = dv->rawv + rec;
+      uint64_t* RW = (dv->raw_tables & (1u << table))
+                         ? reinterpret_cast<uint64_t*>(A + lay->raw_off[table]) + (size_t)row * dv->raw_nf[table]
+                         : nullptr;
+      uint32_t i = 0;
+#define X(name, op)                                                 \
+  {                                                                 \
+    const uint64_t r_ = R[(size_t)i * cap];                         \
+    m.name = (decltype(m.name))r_;                                  \
+    if (RW) RW[i] = r_;                                             \
+    i++;                                                            \
+  }
+#define M(name, ch, ctype, expr)                                    \
+  reinterpret_cast<ctype*>(A + lay->col_off[d])[row] = (ctype)(expr); \
+  d++;
+      if (meter_id == MT_METER_FLOW) {
+        MFlowMeter m;
+        M_FLOW_FIELDS(X)
+        MT_FLOW_METER_COLUMNS(M)
+      } else if (meter_id == MT_METER_APP) {
+        MAppMeter m;
+        M_APP_FIELDS(X)
+        MT_APP_METER_COLUMNS(M)
+      } else {
+        MUsageMeter m;
+        M_USAGE_FIELDS(X)
+        MT_USAGE_METER_COLUMNS(M)
+      }
+#undef M
+#undef X
+    }
+    __syncwarp();
+  }
 }
 
 // ---- layout: one thread walks the ~700 column descriptors ----------------------------------------
@@ -547,6 +712,7 @@ __global__ void k_m_layout(const BatchParams p) {
 
 // ---- app_service tags -----------------------------------------------------------------------------
 __global__ void k_m_as_prep(const BatchParams p) {
+  if (p.dyn->stats.need_repair && !p.repair) return;  // this pass is re-run with the frames' cut points: leave the set alone
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   if (rec >= batch_nrec(p)) return;
@@ -569,6 +735,7 @@ __global__ void k_m_as_prep(const BatchParams p) {
 // looked at again in the next round against that time — the sequential outcome, because a
 // key's stored time only grows (a record emits only if old + timeout < its time).
 __global__ void k_m_as_mark(const BatchParams p, uint32_t epoch) {
+  if (p.dyn->stats.need_repair && !p.repair) return;  // this pass is re-run with the frames' cut points: leave the set alone
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   if (rec >= batch_nrec(p)) return;
@@ -579,6 +746,7 @@ __global__ void k_m_as_mark(const BatchParams p, uint32_t epoch) {
   else c.state = 3;
 }
 __global__ void k_m_as_decide(const BatchParams p, uint32_t epoch, int last) {
+  if (p.dyn->stats.need_repair && !p.repair) return;  // this pass is re-run with the frames' cut points: leave the set alone
   const MDev* dv = reinterpret_cast<const MDev*>(p.ext);
   const uint32_t rec = blockIdx.x * blockDim.x + threadIdx.x;
   if (rec >= batch_nrec(p)) return;
@@ -680,8 +848,8 @@ static int m_ensure_state(dfgpu_ctx* ctx) {
   if (ctx->mt) return 0;
   MHost* h = new MHost();
   MDev& d = h->dev;
-  auto tbl = metrics_pb_table();
-  memcpy(d.pb_tbl, tbl.data(), sizeof d.pb_tbl);
+  auto tbl = metrics_tok_table();
+  memcpy(d.tok_tbl, tbl.data(), sizeof d.tok_tbl);
   const uint64_t codes[MT_TABLE_COUNT] = {MC_NETWORK, MC_NETWORK_MAP, MC_APPLICATION, MC_APPLICATION_MAP,
                                           MC_TRAFFIC_POLICY, MC_NETWORK, MC_NETWORK_MAP, MC_APPLICATION,
                                           MC_APPLICATION_MAP};
@@ -707,6 +875,7 @@ static int m_ensure_state(dfgpu_ctx* ctx) {
 #undef LCS
 #undef STR
     d.ntag[t] = nd - d.desc_base[t];
+    h->max_ntag = std::max(h->max_ntag, d.ntag[t]);
 #define M(name, ch, ctype, expr) add(name, ch, MK_FIX, sizeof(ctype), 0);
     if (d.table_meter[t] == MT_METER_FLOW) { MT_FLOW_METER_COLUMNS(M) }
     else if (d.table_meter[t] == MT_METER_APP) { MT_APP_METER_COLUMNS(M) }
@@ -729,6 +898,13 @@ static int m_ensure_state(dfgpu_ctx* ctx) {
   d.as_timeout = ctx->cfg.flow_tag_cache_flush_timeout;
   CU(cudaMalloc(&h->d_dev, sizeof(MDev)));
   CU(cudaMalloc(&h->d_lay, sizeof(MLayout)));
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    h->grid_decode = (unsigned)sms * 5;
+    h->grid_emit = (unsigned)sms * 6;
+    cudaFuncSetAttribute(k_m_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   CU(cudaHostAlloc(&h->h_lay, sizeof(MLayout), cudaHostAllocDefault));
   ctx->mt = h;
   return 0;
@@ -742,6 +918,7 @@ void metrics_free_state(dfgpu_ctx* ctx) {
   cudaFree(h->d_lay);
   cudaFree(h->d_cand);
   cudaFree(h->d_row_rec);
+  cudaFree(h->d_planes);
   cudaFreeHost(h->h_lay);
   delete h;
   ctx->mt = nullptr;
@@ -805,6 +982,18 @@ int metrics_passes(dfgpu_ctx* ctx, int repair) {
     if (h->d_row_rec) CU(cudaFree(h->d_row_rec));
     h->d_row_rec = nullptr;
     CU(cudaMalloc(&h->d_row_rec, cap * sizeof(uint32_t)));
+    // hand-over of the decode kernel: tag column values, raw meter fields, string lengths, meta word
+    if (h->d_planes) CU(cudaFree(h->d_planes));
+    h->d_planes = nullptr;
+    const size_t per_rec = ((size_t)h->max_ntag + M_MAX_FIELDS) * 8 + 16 + 4 + (size_t)M_TAG_WORDS * 4;
+    CU(cudaMalloc(&h->d_planes, per_rec * cap + 1024));
+    uint8_t* q = h->d_planes;
+    h->dev.strv = reinterpret_cast<uint4*>(q); q += 16 * cap;
+    h->dev.tagv = reinterpret_cast<uint64_t*>(q); q += (size_t)h->max_ntag * 8 * cap;
+    h->dev.rawv = reinterpret_cast<uint64_t*>(q); q += (size_t)M_MAX_FIELDS * 8 * cap;
+    h->dev.meta = reinterpret_cast<uint32_t*>(q); q += 4 * cap;
+    h->dev.tagw = reinterpret_cast<uint32_t*>(q);
+    h->dev.rec_cap = (uint32_t)cap;
     h->cand_cap = cap;
   }
   tagset_maybe_rebuild(h->as_set, s, &ctx->launches);
@@ -822,13 +1011,15 @@ int metrics_passes(dfgpu_ctx* ctx, int repair) {
   CU(cudaMemsetAsync(&ctx->d_dyn->stats.var_total, 0, sizeof(ctx->d_dyn->stats.var_total), s));
   dim3 grid(rec_grid(bp)), block(256);
   ctx->mark(2);
-  k_m_pass<0><<<grid, block, 0, s>>>(bp);
+  k_m_decode<<<h->grid_decode, MD_THREADS, 0, s>>>(bp);
+  k_m_tag<<<h->grid_emit, 256, 0, s>>>(bp);
+  ctx->launches++;
   ctx->mark(3);
   launch_slot_scan(bp, s);
   launch_finish(bp, s);  // LowCardinality ranks of the 4 observation_point spaces
   k_m_layout<<<1, 1, 0, s>>>(bp);
   ctx->mark(4);
-  k_m_pass<1><<<grid, block, 0, s>>>(bp);
+  k_m_emit<<<h->grid_emit, 256, 0, s>>>(bp);
   ctx->mark(5);
   ctx->mark(6);
   k_m_as_prep<<<grid, block, 0, s>>>(bp);

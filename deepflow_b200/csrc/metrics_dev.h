@@ -7,6 +7,7 @@
 #pragma once
 #include "ctx.h"
 #include "pb_interp.cuh"
+#include "pb_tok.cuh"
 #include "tagset.cuh"
 
 #include "../../include/dfgpu_metrics_schema.h"
@@ -102,6 +103,100 @@ inline std::vector<uint32_t> metrics_pb_table() {
   set(MM_APPLATENCY, 2, PK_U64, MS_APPLATENCY + 1);
   set(MM_APPLATENCY, 3, PK_U32, MS_APPLATENCY + 2);
   for (uint32_t f = 1; f <= 3; f++) set(MM_APPANOMALY, f, PK_U32, MS_APPANOMALY + (int)f - 1);
+  return t;
+}
+
+// ---- tokenizer words (pb_tok.cuh) ----------------------------------------------------------------------
+// The decode kernel keeps a record as 4-byte words in shared memory: one word for a uint32 slot, two (lo, hi)
+// for a uint64 slot, (offset, length) for a bytes / string slot; the occurrence counters and ranges of the
+// sub-messages, which nothing reads, share word 0.  mw() maps a slot to its first word with plain arithmetic so
+// that it folds to a constant wherever the slot is one.
+enum : int {
+  MWB_TAG = 1,                    // 38 words, see mw()
+  MWB_TRAFFIC = MWB_TAG + 38,     // 10 x u64, 5 x u32
+  MWB_LATENCY = MWB_TRAFFIC + 25, // 7 x u32 max, 7 x u64 sum, 7 x u32 count
+  MWB_PERF = MWB_LATENCY + 28,    // 4 x u64, 2 x u32
+  MWB_ANOMALY = MWB_PERF + 10,    // 12 x u64, 3 x u32, 2 x u64
+  MWB_FLOWLOAD = MWB_ANOMALY + 31,
+  MWB_USAGE = MWB_FLOWLOAD + 2,   // 8 x u64
+  MWB_APP = MWB_USAGE + 16,       // traffic 3, latency 1 + 2 + 1, anomaly 3
+  MW_COUNT = MWB_APP + 10
+};
+DF_HD constexpr bool mw64(int s) {
+  return s == MS_CODE || s == MS_IP || s == MS_IP1 || s == MS_MAC || s == MS_MAC1 || s == MS_TAP_PORT ||
+         s == MS_APP_SERVICE || s == MS_APP_INSTANCE || s == MS_ENDPOINT || (s >= MS_TRAFFIC && s < MS_TRAFFIC + 10) ||
+         (s >= MS_LATENCY + 7 && s < MS_LATENCY + 14) || (s >= MS_PERF && s < MS_PERF + 4) ||
+         (s >= MS_ANOMALY && s < MS_ANOMALY + 12) || s == MS_ANOMALY + 15 || s == MS_ANOMALY + 16 || s == MS_FLOWLOAD ||
+         (s >= MS_USAGE && s < MS_USAGE + 8) || s == MS_APPLATENCY + 1;
+}
+DF_HD constexpr int mw(int s) {
+  if (s >= MS_TRAFFIC && s < MS_LATENCY) return MWB_TRAFFIC + (s - MS_TRAFFIC < 10 ? 2 * (s - MS_TRAFFIC) : 20 + (s - MS_TRAFFIC - 10));
+  if (s >= MS_LATENCY && s < MS_PERF) {
+    const int i = s - MS_LATENCY;
+    return MWB_LATENCY + (i < 7 ? i : i < 14 ? 7 + 2 * (i - 7) : 21 + (i - 14));
+  }
+  if (s >= MS_PERF && s < MS_ANOMALY) return MWB_PERF + (s - MS_PERF < 4 ? 2 * (s - MS_PERF) : 8 + (s - MS_PERF - 4));
+  if (s >= MS_ANOMALY && s < MS_FLOWLOAD) {
+    const int i = s - MS_ANOMALY;
+    return MWB_ANOMALY + (i < 12 ? 2 * i : i < 15 ? 24 + (i - 12) : 27 + 2 * (i - 15));
+  }
+  if (s == MS_FLOWLOAD) return MWB_FLOWLOAD;
+  if (s >= MS_USAGE && s < MS_APP_SUB) return MWB_USAGE + 2 * (s - MS_USAGE);
+  if (s >= MS_APPTRAFFIC && s < MS_APPLATENCY) return MWB_APP + (s - MS_APPTRAFFIC);
+  if (s >= MS_APPLATENCY && s < MS_APPANOMALY) return MWB_APP + 3 + (s == MS_APPLATENCY ? 0 : s == MS_APPLATENCY + 1 ? 1 : 3);
+  if (s >= MS_APPANOMALY && s < MS_COUNT) return MWB_APP + 7 + (s - MS_APPANOMALY);
+  switch (s) {
+    case MS_TS: return MWB_TAG + 0;
+    case MS_FLAGS: return MWB_TAG + 1;
+    case MS_CODE: return MWB_TAG + 2;
+    case MS_IP: return MWB_TAG + 4;
+    case MS_IP1: return MWB_TAG + 6;
+    case MS_GTID: return MWB_TAG + 8;
+    case MS_IS_IPV6: return MWB_TAG + 9;
+    case MS_EPC: return MWB_TAG + 10;
+    case MS_EPC1: return MWB_TAG + 11;
+    case MS_MAC: return MWB_TAG + 12;
+    case MS_MAC1: return MWB_TAG + 14;
+    case MS_DIRECTION: return MWB_TAG + 16;
+    case MS_TAP_SIDE: return MWB_TAG + 17;
+    case MS_PROTOCOL: return MWB_TAG + 18;
+    case MS_ACL_GID: return MWB_TAG + 19;
+    case MS_SERVER_PORT: return MWB_TAG + 20;
+    case MS_VTAP_ID: return MWB_TAG + 21;
+    case MS_TAP_PORT: return MWB_TAG + 22;
+    case MS_TAP_TYPE: return MWB_TAG + 24;
+    case MS_L7_PROTOCOL: return MWB_TAG + 25;
+    case MS_GPID: return MWB_TAG + 26;
+    case MS_GPID1: return MWB_TAG + 27;
+    case MS_SIGNAL_SOURCE: return MWB_TAG + 28;
+    case MS_APP_SERVICE: return MWB_TAG + 29;
+    case MS_APP_INSTANCE: return MWB_TAG + 31;
+    case MS_ENDPOINT: return MWB_TAG + 33;
+    case MS_POD_ID: return MWB_TAG + 35;
+    case MS_BIZ_TYPE: return MWB_TAG + 36;
+    case MS_METER_ID: return MWB_TAG + 37;
+  }
+  return 0;  // occurrence counters / ranges of the sub-messages
+}
+
+// pb_tok table of metric.Document from the interpreter table above: same messages, fields and acceptance
+// rules, slots replaced by words (string / bytes fields keep offset + length in two words: TK_STR2W)
+inline std::vector<uint32_t> metrics_tok_table() {
+  const std::vector<uint32_t> src = metrics_pb_table();
+  std::vector<uint32_t> t(MM_COUNT * MM_MAXF, 0u);
+  for (uint32_t i = 0; i < src.size(); i++) {
+    const uint32_t e = src[i];
+    if (!e) continue;
+    const uint32_t kind = e & 15u, slot = (e >> 8) & 0xffu, sub = (e >> 16) & 0xffu;
+    const uint32_t w = (uint32_t)mw((int)slot);
+    switch (kind) {
+      case PK_U32: t[i] = TK_ENT(TK_U32, w, 0, 0); break;
+      case PK_U64: t[i] = TK_ENT(TK_U64, w, 0, 0); break;
+      case PK_STR: t[i] = TK_ENT(TK_STR2W, w, 0, 0); break;
+      case PK_MSG: t[i] = TK_ENT(TK_MSG, 0, sub, 0); break;
+      default: t[i] = 0; break;
+    }
+  }
   return t;
 }
 
@@ -255,7 +350,7 @@ struct MCand {  // per record: what the app_service tag stage needs
 };
 
 struct MDev {
-  uint32_t pb_tbl[MM_COUNT * MM_MAXF];
+  uint32_t tok_tbl[MM_COUNT * MM_MAXF];  // pb_tok table (metrics_tok_table)
   MColDesc descs[M_MAX_DESC];
   uint32_t desc_base[MT_TABLE_COUNT + 1];
   uint32_t ntag[MT_TABLE_COUNT];  // tag columns of the table (the meter columns follow)
@@ -264,6 +359,13 @@ struct MDev {
   MLayout* lay;
   MCand* cand;
   uint32_t* row_rec;  // [row_base[table] + row] -> record index (the reduce re-reads raw meters)
+  // decode kernel -> emit kernel, all indexed by record (plane-major: [plane][rec_cap])
+  uint64_t* tagv;     // values of the tag columns of the record's table, in descriptor order
+  uint64_t* rawv;     // raw meter fields (M_*_FIELDS order)
+  uint4* strv;        // lengths of app_service / app_instance / endpoint (application tables)
+  uint32_t* meta;     // table | meter id << 8 | tap-side code << 16
+  uint32_t* tagw;     // decoded tag words (MWB_TAG ...), k_m_decode -> k_m_tag
+  uint32_t rec_cap;
   FtEntry* as_set;
   TagSetState* as_state;
   uint32_t as_mask, as_timeout, epoch;

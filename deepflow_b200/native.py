@@ -68,6 +68,10 @@ class Batch:
     def columns(self, table):
         return abi.fetch_columns(lib().dfgpu_batch_columns, self._h, table)
 
+    def column(self, table, index):
+        """One column (copied), e.g. the `time` column of a flow_tag table."""
+        return abi.fetch_column(lib().dfgpu_batch_columns, self._h, table, index)
+
     def counters(self):
         c = abi.Counters()
         lib().dfgpu_batch_counters(self._h, C.byref(c))
@@ -172,6 +176,11 @@ class Engine:
         n = len(times)
         if n:
             self._check(lib().dfgpu_tags_import(self._h, fps.ctypes.data, times.ctypes.data, n), "dfgpu_tags_import")
+
+    def tags_import_ptr(self, fps_ptr, times_ptr, n):
+        """Same, from raw pointers — host or device memory ((n, 2) uint64 fingerprints, (n,) uint32 times)."""
+        if n:
+            self._check(lib().dfgpu_tags_import(self._h, fps_ptr, times_ptr, n), "dfgpu_tags_import")
 
     def metrics_reduce(self, table, bucket_seconds=60):
         """Reduce-by-key over one table of the last metrics batch (still resident in HBM)."""

@@ -54,6 +54,11 @@ class TagMerge:
         assert len(fps) == n
         if self.world == 1:
             return np.ones(n, bool), np.zeros((0, 2), np.uint64), np.zeros(0, np.uint32)
+        if self.device.type == "cuda":
+            keep, others, _mine = self.exchange_device(fps, times)
+            o = others.cpu().numpy()
+            self.seconds += _t.perf_counter() - t0
+            return keep, np.ascontiguousarray(o[:, 0:2]).view(np.uint64), o[:, 2].astype(np.uint32)
         # 1) lengths
         cnt = torch.tensor([n], dtype=torch.int64, device=self.device)
         cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
@@ -83,6 +88,43 @@ class TagMerge:
                 remote_times = o[:, 2].astype(np.uint32)
         self.seconds += _t.perf_counter() - t0
         return keep, remote_fps, remote_times
+
+
+    def exchange_device(self, fps, times):
+        """The same exchange with the keys kept on the GPU (NCCL all-gather, ownership by sort + binary search).
+        Returns keep (n,) bool numpy, others (m, 3) int64 CUDA tensor (lo, hi, time) of the other ranks' keys,
+        mine (n, 3) int64 CUDA tensor.  A 64-bit collision between two distinct fingerprints can only make a
+        duplicate row survive (idempotent in ClickHouse), never drop one: both halves are compared."""
+        fps = np.ascontiguousarray(fps, np.uint64).reshape(-1, 2)
+        times = np.ascontiguousarray(times, np.uint32).reshape(-1)
+        n = len(times)
+        cnt = torch.tensor([n], dtype=torch.int64, device=self.device)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(cnts, cnt, group=self.group)
+        counts = [int(c.item()) for c in cnts]
+        m = max(counts)
+        empty = torch.zeros((0, 3), dtype=torch.int64, device=self.device)
+        if m == 0:
+            return np.ones(n, bool), empty, empty
+        pay = np.zeros((m, 3), np.int64)
+        pay[:n, 0:2] = fps.view(np.int64)
+        pay[:n, 2] = times
+        mine_pad = torch.from_numpy(pay).to(self.device)
+        parts = [torch.empty_like(mine_pad) for _ in range(self.world)]
+        dist.all_gather(parts, mine_pad, group=self.group)
+        self.bytes_sent += n * 24
+        mine = mine_pad[:n]
+        keep = np.ones(n, bool)
+        lower = [parts[r][:counts[r]] for r in range(self.rank) if counts[r]]
+        if lower and n:
+            lw = torch.cat(lower)
+            lo_sorted, order = torch.sort(lw[:, 0])
+            hi_sorted = lw[:, 1][order]
+            idx = torch.searchsorted(lo_sorted, mine[:, 0].contiguous()).clamp_(max=len(lo_sorted) - 1)
+            dup = (lo_sorted[idx] == mine[:, 0]) & (hi_sorted[idx] == mine[:, 1])
+            keep = (~dup).cpu().numpy()
+        others = [parts[r][:counts[r]] for r in range(self.world) if r != self.rank and counts[r]]
+        return keep, (torch.cat(others) if others else empty), mine
 
 
 FLOW_TAG_TABLES = (2, 3, 4)  # DFGPU_TABLE_L7_CUSTOM_FIELD, _VALUE, L7_APP_SERVICE

@@ -117,6 +117,17 @@ typedef struct dfgpu_col {
   const void* dict_data; /* LC_STR: dictionary Buf                             */
   const dfgpu_pos* dict_pos;
   uint64_t dict_n;
+  /* dfgpu_cfg.block_lz4: data / pos / arr_offsets / nulls each point at a stream of
+     ClickHouse compressed frames (lz4.cu: 16 B checksum slot left zero + method +
+     sizes + payload, one frame per 4 KiB of the buffer) instead of the buffer itself;
+     the *_bytes fields are the lengths of those streams, data_raw_bytes the length of
+     the uncompressed data buffer.  compressed == 0: plain buffers, fields unused.   */
+  uint32_t compressed;
+  uint32_t reserved0;
+  uint64_t data_raw_bytes;
+  uint64_t pos_bytes;
+  uint64_t arr_offsets_bytes;
+  uint64_t nulls_bytes;
 } dfgpu_col;
 
 /* ---- input frame table --------------------------------------------------- */
@@ -249,7 +260,11 @@ typedef struct dfgpu_cfg {
                                   beside its packed columns (device only, 8 B per meter field per row) so
                                   that dfgpu_rollup_add / dfgpu_metrics_reduce can fold them; 0 => none   */
   uint32_t rollup_max_groups;  /* capacity of one table's rollup accumulator in groups; 0 => 1<<20       */
-  uint32_t reserved[4];
+  uint32_t block_lz4;          /* 1: the column buffers of l4_flow_log / l7_flow_log leave the GPU as ClickHouse
+                                  compressed frames (LZ4 block per 4 KiB, lz4.cu) — see dfgpu_col.compressed.
+                                  Fewer bytes over PCIe and no CPU compression in the writer; the host only
+                                  fills each frame's CityHash128 checksum slot.        */
+  uint32_t reserved[3];
 } dfgpu_cfg;
 
 /* decoder.Counter (decoder.go:60-80) for one submit; the shim adds them up.   */
