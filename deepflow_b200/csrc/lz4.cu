@@ -15,10 +15,11 @@
  *   1. match finding, position-parallel: the 4096 positions are visited 32 at a time in order; every lane hashes
  *      the 4 bytes at its position, reads the candidate the table holds (an EARLIER tile's position), publishes
  *      its own, and also tries the fixed distance `stride` (the element size of the column: equal or
- *      nearly equal neighbours are what fixed-width columns are made of).  Verified candidates are extended;
- *      the best (length, offset) per position stays in shared memory.
- *   2. parse, segment-parallel: lane j walks positions [128 j, 128 j + 128) greedily (first match wins, jump
- *      behind it), matches cut at the segment end.  Literal runs may span segments: the end of the last match
+ *      nearly equal neighbours are what fixed-width columns are made of).  A candidate that agrees in its first
+ *      4 bytes is kept (offset per position + a bit mask of the positions that have one).
+ *   2. parse, segment-parallel: lane j walks positions [128 j, 128 j + 128) greedily (first match wins; only
+ *      the matches it takes are extended, so every byte is compared at most once; jump behind the match),
+ *      matches cut at the segment end.  Literal runs may span segments: the end of the last match
  *      of the lower lanes comes from a warp max-scan.
  *   3. emit: per-lane output sizes -> exclusive scan -> every lane writes its own sequences; the final literal
  *      run is copied by the whole warp.
@@ -33,13 +34,13 @@ namespace {
 
 constexpr uint32_t HT_BITS = 11, HT_SIZE = 1u << HT_BITS;
 constexpr uint32_t SEG = LZ_CHUNK / 32;  // bytes per lane in the parse
-constexpr uint32_t CW = 4;               // warps per CTA
+constexpr uint32_t CW = 2;               // warps per CTA (16.5 KB of shared memory each: 6 CTAs per SM)
 
-struct WarpSmem {
+struct alignas(16) WarpSmem {
   uint32_t in[LZ_CHUNK / 4 + 4];  // the chunk (+ slack so that 4-byte reads at the end stay inside)
   uint16_t tab[HT_SIZE];
-  uint16_t moff[LZ_CHUNK];
-  uint8_t mlen[LZ_CHUNK];
+  uint16_t moff[LZ_CHUNK + 1];  // candidate offset per position; [p + 1] of a TAKEN match at p holds its length
+  uint16_t pad_;
   uint32_t mask[LZ_CHUNK / 32];  // bit set: a match of >= 4 bytes starts here
 };
 
@@ -127,44 +128,46 @@ __global__ void __launch_bounds__(CW * 32) k_lz4_compress(const uint8_t* __restr
       const uint32_t n16 = (n + 15) / 16;  // reads at most 15 bytes past n: inside the arena's 256-byte padding
       for (uint32_t i = lane; i < LZ_CHUNK / 16 + 1; i += 32) d4[i] = i < n16 ? __ldg(s4 + i) : make_uint4(0, 0, 0, 0);
       uint4* t4 = reinterpret_cast<uint4*>(S.tab);
-      for (uint32_t i = lane; i < HT_SIZE * 2 / 16; i += 32) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      if (stride < 8)
+        for (uint32_t i = lane; i < HT_SIZE * 2 / 16; i += 32) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
     __syncwarp();
     // matches start at <= n - 12 and end at <= n - 5 (LZ4 block format end conditions)
     const uint32_t mstart_lim = n >= 13 ? n - 12 : 0, mend = n >= 5 ? n - 5 : 0;
     // ---- 1. candidates ----
-    for (uint32_t t = 0; t < LZ_CHUNK / 32; t++) {
-      const uint32_t pos = t * 32 + lane;
-      const bool valid = n >= 13 && pos <= mstart_lim;
-      uint32_t best_len = 0, best_off = 0;
-      uint32_t v4 = 0, h = 0, cand = 0xffffu;
-      if (valid) {
-        v4 = ld4(S.in, pos);
-        h = (v4 * 2654435761u) >> (32 - HT_BITS);
-        cand = S.tab[h];
+    // A buffer of 8- or 16-byte elements only tries the distance of one element — equal high bytes of neighbouring
+    // values are its redundancy, and the test needs no table; byte streams (strings) and narrow elements (whose
+    // repeats sit at any distance: enums, ports, flags) use the hash table.  Either way a candidate only has to
+    // agree in its first 4 bytes here; the parse extends what it takes.
+    const bool by_stride = stride >= 8;
+    if (by_stride) {
+      for (uint32_t t = 0; t < LZ_CHUNK / 32; t++) {
+        const uint32_t pos = t * 32 + lane;
+        const bool hit = n >= 13 && pos <= mstart_lim && pos >= stride && ld4(S.in, pos - stride) == ld4(S.in, pos);
+        S.moff[pos] = (uint16_t)(hit ? stride : 0u);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) S.mask[t] = m;
       }
-      __syncwarp();
-      if (valid) S.tab[h] = (uint16_t)pos;
-      if (valid) {
-        const uint32_t cap = mend - pos;  // >= 7
-        if (stride && pos >= stride && ld4(S.in, pos - stride) == v4) {
-          best_len = match_len(S.in, pos + 4, pos - stride + 4, cap - 4) + 4;
-          best_off = stride;
+    } else {
+      for (uint32_t t = 0; t < LZ_CHUNK / 32; t++) {
+        const uint32_t pos = t * 32 + lane;
+        const bool valid = n >= 13 && pos <= mstart_lim;
+        uint32_t v4 = 0, h = 0, cand = 0xffffu;
+        if (valid) {
+          v4 = ld4(S.in, pos);
+          h = (v4 * 2654435761u) >> (32 - HT_BITS);
+          cand = S.tab[h];
         }
-        if (cand != 0xffffu && best_len < 32 && ld4(S.in, cand) == v4) {
-          const uint32_t l = match_len(S.in, pos + 4, cand + 4, cap - 4) + 4;
-          if (l > best_len) {
-            best_len = l;
-            best_off = pos - cand;
-          }
-        }
+        __syncwarp();
+        if (valid) S.tab[h] = (uint16_t)pos;
+        const bool hit = valid && cand != 0xffffu && ld4(S.in, cand) == v4;
+        S.moff[pos] = (uint16_t)(hit ? pos - cand : 0u);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) S.mask[t] = m;
+        __syncwarp();
       }
-      S.mlen[pos] = (uint8_t)(best_len > 255 ? 255 : best_len);
-      S.moff[pos] = (uint16_t)best_off;
-      const uint32_t m = __ballot_sync(0xffffffffu, best_len >= 4);
-      if (lane == 0) S.mask[t] = m;
-      __syncwarp();
     }
+    __syncwarp();
     // ---- 2. parse: sizes ----
     const uint32_t seg0 = lane * SEG, seg1 = seg0 + SEG;
     uint32_t my_first = 0xffffffffu, my_last_end = 0, my_bytes = 0;  // my_bytes: sequences after my first match
@@ -179,12 +182,14 @@ __global__ void __launch_bounds__(CW * 32) k_lz4_compress(const uint8_t* __restr
           continue;
         }
         p += (uint32_t)__ffs((int)w) - 1u;
-        uint32_t ml = S.mlen[p];
-        if (ml > seg1 - p) ml = seg1 - p;
-        if (ml < 4) {
+        if (p >= seg1) break;
+        const uint32_t lim = seg1 < mend ? seg1 : mend;  // matches are cut at the segment end
+        if (p + 4 > lim) {
           p++;
           continue;
         }
+        const uint32_t ml = 4 + match_len(S.in, p + 4, p + 4 - S.moff[p], lim - p - 4);
+        S.moff[p + 1] = (uint16_t)ml;  // p + 1 is inside the match: the walks never look at it as a start
         if (!have) {
           have = true;
           my_first = p;
@@ -227,25 +232,36 @@ __global__ void __launch_bounds__(CW * 32) k_lz4_compress(const uint8_t* __restr
       continue;
     }
     // ---- 3. emit ----
+    // round r = the r-th taken match of every lane: the lanes write their sequences side by side instead of each
+    // running through its own list (ncu: the per-lane loop ran at 3 of 32 lanes, a quarter of the kernel)
     {
       uint8_t* o = out + ex;
       uint32_t p = seg0, prev_end = below;
-      while (p < seg1) {
-        const uint32_t w = S.mask[p >> 5] >> (p & 31u);
-        if (!w) {
-          p = (p | 31u) + 1;
-          continue;
+      const uint32_t lim = seg1 < mend ? seg1 : mend;
+      for (;;) {
+        bool have = false;
+        while (p < seg1) {
+          const uint32_t w = S.mask[p >> 5] >> (p & 31u);
+          if (!w) {
+            p = (p | 31u) + 1;
+            continue;
+          }
+          p += (uint32_t)__ffs((int)w) - 1u;
+          if (p + 4 > lim) {
+            p++;
+            continue;
+          }
+          have = true;
+          break;
         }
-        p += (uint32_t)__ffs((int)w) - 1u;
-        uint32_t ml = S.mlen[p];
-        if (ml > seg1 - p) ml = seg1 - p;
-        if (ml < 4) {
-          p++;
-          continue;
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+          const uint32_t ml = S.moff[p + 1];
+          o = put_seq(o, S.in, prev_end, p - prev_end, S.moff[p], ml);
+          prev_end = p + ml;
+          p = prev_end;
         }
-        o = put_seq(o, S.in, prev_end, p - prev_end, S.moff[p], ml);
-        prev_end = p + ml;
-        p = prev_end;
+        __syncwarp();
       }
     }
     {

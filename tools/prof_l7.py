@@ -25,12 +25,16 @@ def main():
     ap.add_argument("--pods", type=int, default=100_000)
     ap.add_argument("--runs", type=int, default=8)
     ap.add_argument("--msg", type=int, default=abi.DFGPU_MSG_PROTOCOLLOG)
+    ap.add_argument("--lz4", action="store_true", help="native strings + compressed frames; every run is fetched")
     a = ap.parse_args()
     synth = Synth(n_pods=a.pods)
     wl = synth.gen(a.msg, a.records, seed=1000)
     cfg = abi.Cfg()
     cfg.max_batch_bytes = wl.nbytes + (1 << 20)
     cfg.flow_tag_cache_max_size = int(os.environ.get("FT_CACHE", 1 << 19))
+    if a.lz4:
+        cfg.native_strings = 1
+        cfg.block_lz4 = 1
     eng = Engine(0, cfg)
     eng.load_synth(synth)
     dev = torch.from_numpy(wl.data).cuda()
@@ -42,9 +46,20 @@ def main():
     print("warm-up: count", c.count, "errors", c.error_count)
     b.release()
     eng.profile_enable(True)
+    import time
     for _ in range(a.runs):
         eng.stage_ptr(wl.msg_type, dev.data_ptr(), wl.nbytes, wl.frames.ctypes.data, len(wl.frames))
         eng.run()
+        if a.lz4:
+            eng.sync()
+            t0 = time.perf_counter()
+            bb = eng.fetch()
+            t1 = time.perf_counter()
+            cols, rows = bb.columns(abi.TABLE_L7_FLOW_LOG if a.msg == 5 else abi.TABLE_L4_FLOW_LOG) if _ == 0 else ([], 0)
+            if cols:
+                print("frame bytes per row", sum(c.compressed_bytes or 0 for c in cols) / max(1, rows))
+            print(f"fetch (compress + D2H of frames) {1000 * (t1 - t0):.3f} ms")
+            bb.release()
     eng.sync()
     st, n = eng.profile_stages()
     if n:
