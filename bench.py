@@ -61,7 +61,10 @@ def parse_args():
     ap.add_argument("--sub-batch", type=int, default=625_000, help="records per dfgpu_submit")
     ap.add_argument("--pods", type=int, default=100_000, help="dictionary size P (SURVEY 8d)")
     ap.add_argument("--decoders", type=int, default=3, help="contexts per GPU (DecoderQueueCount)")
-    ap.add_argument("--legs", default="c2,c4,c3,c5,parity,native,lz4", help="comma list; c2 always runs")
+    ap.add_argument("--legs", default="c2,c4,c3,c5,parity,modes", help="comma list; c2 always runs; modes = e2e in the other output modes")
+    ap.add_argument("--e2e-mode", default="lz4", choices=["containers", "native", "lz4"],
+                    help="output mode of the headline e2e: ch-go containers (Buf + Positions), native string streams, "
+                         "or native strings + LZ4 frames compressed on the GPU (dfgpu_cfg.native_strings / block_lz4)")
     ap.add_argument("--c3-rows", type=int, default=100_000_000)
     ap.add_argument("--c3-groups", type=int, default=1_000_000)
     ap.add_argument("--c5-records", type=int, default=5_000_000)
@@ -783,7 +786,15 @@ def main():
     gen_s = time.time() - t0
     feed = Feed(torch, local, L7, subs)
     torch.cuda.synchronize()
-    cfg = mk_cfg(max(w.nbytes for w in subs))
+    MODES = {"containers": (0, 0), "native": (1, 0), "lz4": (1, 1)}
+    MODE_WHAT = {
+        "containers": "ch-go containers: String columns as Buf + one 16-byte Position per value",
+        "native": "dfgpu_cfg.native_strings=1: String / Array(String) columns leave the GPU as ClickHouse native column data "
+                  "(uvarint length + bytes), no Position arrays over PCIe",
+        "lz4": "dfgpu_cfg.native_strings=1 + block_lz4=1: every buffer of l7_flow_log crosses PCIe as ClickHouse compressed "
+               "frames (LZ4 per 4 KiB, compressed on the GPU inside the timed region; checksum slots left for the host)"}
+    cfg_plain = mk_cfg(max(w.nbytes for w in subs))  # container mode: byte census, parity leg
+    cfg = mk_cfg(max(w.nbytes for w in subs), native=MODES[a.e2e_mode][0], lz4=MODES[a.e2e_mode][1])
     engines = [Engine(local, cfg) for _ in range(max(1, a.decoders))]
     for e in engines:
         e.load_synth(synth)
@@ -792,10 +803,26 @@ def main():
         merge, after, emitted = make_merge_hooks(torch, local, world, engines)
     dev_ms, e2e_s, launches = run_pools(torch, dist, local, world, [(feed, engines)], a.steps, a.warmup, after_step=after)
     st_ms, st_runs, pack_ms, pack_n = solo_stages(engines[0], feed)
-    b = engines[0].submit(subs[-1])
+    def mode_bytes(engine, mode):
+        """D2H bytes per row of l7_flow_log in an output mode (one sub-batch through `engine`)."""
+        bb = engine.submit(subs[-1])
+        if mode == "lz4":
+            fb, fr = bb.frame_bytes(abi.TABLE_L7_FLOW_LOG)
+            out = fb / max(1, fr)
+        else:
+            c = block_bytes(bb, abi.TABLE_L7_FLOW_LOG)
+            out = c["total"] / max(1, c["rows"])
+        bb.release()
+        return out
+
+    ceng = Engine(local, cfg_plain)
+    ceng.load_synth(synth)
+    b = ceng.submit(subs[-1])
     cen = block_bytes(b, abi.TABLE_L7_FLOW_LOG)
     b.release()
+    ceng.close()
     row_b = cen["total"] / max(1, cen["rows"])
+    e2e_row_b = row_b if a.e2e_mode == "containers" else mode_bytes(engines[0], a.e2e_mode)
     fixed_b, aux_b, var_b = (cen[k] / max(1, cen["rows"]) for k in ("fixed", "aux", "var"))
     wire_b = feed.in_bytes / feed.records
     kg_b = 116.0  # the 39 SmartEncoding columns + team_id / gprocess ids (schema_l7.h)
@@ -828,8 +855,11 @@ def main():
                            "bytes_sent_rank0": merge.bytes_sent, "seconds_rank0": merge.seconds,
                            "keys_emitted_rank0": emitted[0]})},
             "e2e": {"value": e2e_value, "unit": "records/s", "h2d_bytes_per_step": int(feed.in_bytes + feed.frame_bytes),
-                    "d2h_bytes_per_step": int(row_b * feed.records), "ms_per_step": e2e_ms_max / a.steps,
-                    "d2h_gbs_per_rank": row_b * feed.records * a.steps / e2e_s / 1e9},
+                    "d2h_bytes_per_step": int(e2e_row_b * feed.records), "ms_per_step": e2e_ms_max / a.steps,
+                    "d2h_gbs_per_rank": e2e_row_b * feed.records * a.steps / e2e_s / 1e9,
+                    "h2d_gbs_per_rank": (feed.in_bytes + feed.frame_bytes) * a.steps / e2e_s / 1e9,
+                    "mode": a.e2e_mode, "what": MODE_WHAT[a.e2e_mode], "d2h_bytes_per_row": e2e_row_b,
+                    "container_bytes_per_row": row_b},
             "gpu_launches": int(launches), "roofline": roof, "legs": {}}
 
     # one decoder alone against all of them: how much of the GPU a single context keeps busy
@@ -837,54 +867,31 @@ def main():
         d1, _e1, _l1 = run_pools(torch, dist, local, world, [(feed, engines[:1])], max(1, a.steps // 2), 1)
         line["config"]["one_decoder_value"] = feed.records * max(1, a.steps // 2) / (d1 / 1000.0)
 
-    # ---- e2e with dfgpu_cfg.native_strings: String columns cross PCIe in native encoding ----
-    if "native" in legs and world == 1:
-        for e in engines:
-            e.sync()
-        ncfg = mk_cfg(max(w.nbytes for w in subs), native=1)
-        neng = [Engine(local, ncfg) for _ in range(len(engines))]
-        for e in neng:
-            e.load_synth(synth)
-        _d, nat_s, _l = run_pools(torch, dist, local, world, [(feed, neng)], a.steps, max(1, a.warmup - 1))
-        nb = neng[0].submit(subs[-1])
-        ncen = block_bytes(nb, abi.TABLE_L7_FLOW_LOG)
-        nb.release()
-        for e in neng:
-            e.close()
-        line["e2e_native_strings"] = {
-            "value": feed.records * a.steps / nat_s, "unit": "records/s", "h2d_bytes_per_step": int(feed.in_bytes + feed.frame_bytes),
-            "d2h_bytes_per_step": int(ncen["total"] / max(1, ncen["rows"]) * feed.records), "ms_per_step": nat_s * 1000 / a.steps,
-            "what": "same call, dfgpu_cfg.native_strings=1: String / Array(String) columns leave the GPU as ClickHouse "
-                    "native column data (uvarint length + bytes), no Position arrays over PCIe"}
-
-    # ---- e2e with native strings + dfgpu_cfg.block_lz4: every column buffer leaves the GPU as ClickHouse
-    # compressed frames (LZ4 blocks written by lz4.cu); decoding them back is checked by tests/test_lz4_gpu.py
-    if "lz4" in legs and world == 1:
-        for e in engines:
-            e.sync()
-        zcfg = mk_cfg(max(w.nbytes for w in subs), native=1, lz4=1)
-        zeng = [Engine(local, zcfg) for _ in range(len(engines))]
-        for e in zeng:
-            e.load_synth(synth)
-        _d, z_s, _l = run_pools(torch, dist, local, world, [(feed, zeng)], a.steps, max(1, a.warmup - 1))
-        zb = zeng[0].submit(subs[-1])
-        zcols, zrows = zb.columns(abi.TABLE_L7_FLOW_LOG)
-        zbytes = sum(c.compressed_bytes or 0 for c in zcols)
-        zraw = block_bytes(zb, abi.TABLE_L7_FLOW_LOG)
-        zb.release()
-        for e in zeng:
-            e.close()
-        line["e2e_lz4"] = {
-            "value": feed.records * a.steps / z_s, "unit": "records/s", "h2d_bytes_per_step": int(feed.in_bytes + feed.frame_bytes),
-            "d2h_bytes_per_step": int(zbytes / max(1, zrows) * feed.records), "ms_per_step": z_s * 1000 / a.steps,
-            "frame_bytes_per_row": zbytes / max(1, zrows), "column_bytes_per_row": zraw["total"] / max(1, zraw["rows"]),
-            "what": "same call, dfgpu_cfg.native_strings=1 + block_lz4=1: every buffer of l7_flow_log crosses PCIe as "
-                    "ClickHouse compressed frames (LZ4 per 4 KiB, compressed on the GPU inside the timed region; "
-                    "checksum slots left for the host)"}
+    # ---- the same e2e call in the other output modes (N=1 only: the scaling runs keep the measured legs short) ----
+    if "modes" in legs and world == 1:
+        for mode in MODES:
+            if mode == a.e2e_mode:
+                continue
+            for e in engines:
+                e.sync()
+            mcfg = mk_cfg(max(w.nbytes for w in subs), native=MODES[mode][0], lz4=MODES[mode][1])
+            meng = [Engine(local, mcfg) for _ in range(len(engines))]
+            for e in meng:
+                e.load_synth(synth)
+            _d, m_s, _l = run_pools(torch, dist, local, world, [(feed, meng)], a.steps, max(1, a.warmup - 1))
+            mb = mode_bytes(meng[0], mode)
+            for e in meng:
+                e.close()
+            key = {"containers": "e2e_containers", "native": "e2e_native_strings", "lz4": "e2e_lz4"}[mode]
+            line[key] = {"value": feed.records * a.steps / m_s, "unit": "records/s",
+                         "h2d_bytes_per_step": int(feed.in_bytes + feed.frame_bytes), "d2h_bytes_per_step": int(mb * feed.records),
+                         "d2h_bytes_per_row": mb, "ms_per_step": m_s * 1000 / a.steps, "what": MODE_WHAT[mode]}
 
     # =================================================================================== parity at size
     if "parity" in legs and world == 1:
-        line["legs"]["parity"] = leg_parity(a, synth, local, cfg, subs)
+        # container mode: the same kernels up to the string emission; the native / LZ4 output modes are compared
+        # with the oracle by tests/test_l7_native_gpu.py and tests/test_lz4_gpu.py
+        line["legs"]["parity"] = leg_parity(a, synth, local, cfg_plain, subs)
 
     if not a.no_cpu_baseline and rank == 0 and world == 1:
         build.build_oracle()

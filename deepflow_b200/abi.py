@@ -375,6 +375,25 @@ def columns_equal(a: Column, b: Column):
     return None
 
 
+def frame_bytes(fn, handle, table):
+    """(bytes of compressed frames over all columns, rows) of a dfgpu_cfg.block_lz4 table, without decoding."""
+    ncols = C.c_int(0)
+    nrows = C.c_uint64(0)
+    rc = fn(handle, table, None, C.byref(ncols), C.byref(nrows))
+    if rc != 0:
+        raise RuntimeError(f"columns(table={table}) failed: {rc}")
+    arr = (Col * ncols.value)()
+    rc = fn(handle, table, arr, C.byref(ncols), C.byref(nrows))
+    if rc != 0:
+        raise RuntimeError(f"columns(table={table}) failed: {rc}")
+    tot = 0
+    for i in range(ncols.value):
+        c = arr[i]
+        if c.compressed:
+            tot += int(c.data_bytes + c.pos_bytes + c.arr_offsets_bytes + c.nulls_bytes)
+    return tot, int(nrows.value)
+
+
 def fetch_column(fn, handle, table, index):
     """One column of a table (a copy), without touching the others."""
     ncols = C.c_int(0)

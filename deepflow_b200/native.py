@@ -68,6 +68,10 @@ class Batch:
     def columns(self, table):
         return abi.fetch_columns(lib().dfgpu_batch_columns, self._h, table)
 
+    def frame_bytes(self, table):
+        """(compressed frame bytes, rows) of a block_lz4 table — sizes only, nothing is decoded."""
+        return abi.frame_bytes(lib().dfgpu_batch_columns, self._h, table)
+
     def column(self, table, index):
         """One column (copied), e.g. the `time` column of a flow_tag table."""
         return abi.fetch_column(lib().dfgpu_batch_columns, self._h, table, index)
