@@ -7,6 +7,9 @@
  * pair of adjacent lanes settles with one shuffle.
  */
 #pragma once
+#ifndef KG_SIDES_IN_SEQUENCE
+#define KG_SIDES_IN_SEQUENCE 0
+#endif
 #include "kg_side.cuh"
 #include "pipeline.cuh"
 
@@ -61,12 +64,24 @@ __device__ __forceinline__ void kg_rows(const BatchParams& p, const KgSrc& q, co
   if ((dyn->stats.need_repair && !p.repair) || dyn->overflow) return;
   const uint32_t nrec = batch_nrec(p);
   const size_t cap = q.rec_cap;
+#if KG_SIDES_IN_SEQUENCE
+  // one lane per RECORD, its two sides one after the other through the same code: all 32 lanes of a warp are on
+  // the same side at the same time (a lane per (record, side) puts the client and the server path — different
+  // branches of fill — into alternating lanes), and every column store is 32 consecutive rows
+  const uint64_t total = (uint64_t)nrec;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < total; base += (uint64_t)gridDim.x * blockDim.x)
+#pragma unroll 1
+  for (int s = 0; s < 2; s++) {
+  const uint32_t rec = (uint32_t)(base + threadIdx.x);
+  const bool in_range = rec < nrec;
+#else
   const uint64_t total = (uint64_t)nrec * 2;
   for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < total; base += (uint64_t)gridDim.x * blockDim.x) {
   const uint64_t t = base + threadIdx.x;  // the loop bound is uniform across the CTA: warps stay whole
   const uint32_t rec = (uint32_t)(t >> 1);
   const int s = (int)(t & 1);
   const bool in_range = rec < nrec;
+#endif
   const uint32_t row = in_range ? q.rec_row[rec] : 0xffffffffu;
   const bool ok = row != 0xffffffffu;  // both lanes of a pair agree
   const uint32_t* K = q.kgin + rec;
@@ -101,8 +116,29 @@ __device__ __forceinline__ void kg_rows(const BatchParams& p, const KgSrc& q, co
   {  // :556-567 with the partner lane (the pair sits in adjacent lanes of one warp)
     const uint32_t my_pod = ok ? K[(KG_POD_0 + s) * cap] : 0u;
     const bool my_lb = ok && kgs::loopback(in.v6, in.ip);
+#if KG_SIDES_IN_SEQUENCE
+    const uint32_t other_pod = ok ? K[(KG_POD_0 + (1 - s)) * cap] : 0u;
+    bool other_lb = false;
+    if (ok) {
+      kgs::IpV oip;
+      oip.ip4 = K[(KG_IP_SRC + (1 - s)) * cap];
+      const unsigned long long o6 = (s ? q.ip6_src : q.ip6_dst)[rec];
+      const uint32_t on6 = (uint32_t)(o6 >> 32);
+      oip.len6 = on6;
+      uint64_t lo = 0, hi = 0;
+      const uint8_t* ob = p.in + (uint32_t)o6;
+      for (uint32_t i = 0; i < (on6 < 16 ? on6 : 16u); i++) {
+        const uint64_t v = (uint64_t)__ldg(ob + i) << ((i & 7) * 8);
+        if (i < 8) lo |= v; else hi |= v;
+      }
+      oip.lo = lo;
+      oip.hi = hi;
+      other_lb = kgs::loopback(in.v6, oip);
+    }
+#else
     const uint32_t other_pod = __shfl_xor_sync(0xffffffffu, my_pod, 1);
     const bool other_lb = __shfl_xor_sync(0xffffffffu, (int)my_lb, 1) != 0;
+#endif
     uint32_t pod0 = s ? other_pod : my_pod, pod1 = s ? my_pod : other_pod;
     uint8_t ts0 = 0, ts1 = 0;
     kg_peer_pods(s ? other_lb : my_lb, s ? my_lb : other_lb, pod0, pod1, ts0, ts1);
