@@ -762,6 +762,7 @@ def main():
     torch.cuda.set_device(local)
     numa = bind_near_gpu(local)  # before any pinned allocation: first touch places the staging buffers
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: the JSON line stands alone
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         build.build_synth()
