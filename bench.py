@@ -914,9 +914,12 @@ def main():
         fm = Feed(torch, local, MET, gen_sub_batches(synth, MET, nm, a.sub_batch, 6000 + 7919 * rank, world, rank))
         gen4 = time.time() - t0
         mx = max(w.nbytes for f in (f4, f7, fm) for w in f.subs)
-        c4cfg = mk_cfg(mx)
-        pools = [(f4, [Engine(local, c4cfg) for _ in range(2)]), (f7, [Engine(local, c4cfg) for _ in range(2)]),
+        c4cfg = mk_cfg(mx)  # flow_metrics tables: containers (block_lz4 covers the flow_log tables only)
+        c4log = mk_cfg(mx, native=MODES[a.e2e_mode][0], lz4=MODES[a.e2e_mode][1])  # l4 / l7: the headline output mode
+        pools = [(f4, [Engine(local, c4log) for _ in range(2)]), (f7, [Engine(local, c4log) for _ in range(2)]),
                  (fm, [Engine(local, c4cfg)])]
+        c4plain = Engine(local, c4cfg)  # byte census of the packed blocks
+        c4plain.load_synth(synth)
         all_e = [e for _f, es in pools for e in es]
         for e in all_e:
             e.load_synth(synth)
@@ -928,17 +931,28 @@ def main():
         tot_alg = 0.0
         for name, (f, es) in zip(("l4", "l7", "metrics"), pools):
             st, runs, _pm, _pn = solo_stages(es[0], f)
-            bb = es[0].submit(f.subs[-1])
+            bb = c4plain.submit(f.subs[-1])
             if f.msg == MET:
                 rb = sum(block_bytes(bb, abi.TABLE_METRICS_BASE + t)["total"] for t in range(9)) / max(1, f.subs[-1].nrecords)
             else:
                 c = block_bytes(bb, MAIN_TABLE[f.msg])
                 rb = c["total"] / max(1, c["rows"])
             bb.release()
+            d2h_rb = rb
+            if f.msg != MET and a.e2e_mode != "containers":
+                bb = es[0].submit(f.subs[-1])
+                if a.e2e_mode == "lz4":
+                    fb, fr = bb.frame_bytes(MAIN_TABLE[f.msg])
+                    d2h_rb = fb / max(1, fr)
+                else:
+                    c = block_bytes(bb, MAIN_TABLE[f.msg])
+                    d2h_rb = c["total"] / max(1, c["rows"])
+                bb.release()
             algb = f.in_bytes / f.records + 4 + rb + 32 * (12 if f.msg != MET else 8)
             ms_solo = sum(st.values())
             ach = algb * f.records / (ms_solo / 1000.0) / 1e9 if ms_solo else 0.0
             per_type[name] = {"records_per_step": f.records, "mean_wire_bytes": f.in_bytes / f.records, "packed_bytes_per_record": rb,
+                              "d2h_bytes_per_record": d2h_rb,
                               "algorithmic_bytes_per_record": algb, "solo_ms_per_step": ms_solo, "solo_records_per_s": f.records / (ms_solo / 1000.0) if ms_solo else None,
                               "stage_ms": st, "achieved_gbs": ach, "frac": ach / peak}
             tot_alg += algb * f.records
@@ -949,12 +963,13 @@ def main():
         ach4 = tot_alg * a.steps / (d_ms / 1000.0) / 1e9
         dom = max(per_type, key=lambda k: per_type[k]["solo_ms_per_step"])
         h2d = sum(f.in_bytes + f.frame_bytes for f in (f4, f7, fm))
-        d2h = sum(per_type[k]["packed_bytes_per_record"] * per_type[k]["records_per_step"] for k in per_type)
+        d2h = sum(per_type[k]["d2h_bytes_per_record"] * per_type[k]["records_per_step"] for k in per_type)
         leg = {"workload": "C4: mixed firehose 50 % L4 / 35 % L7 / 15 % metric by record count (BASELINE.json configs[3]), "
                            "one decoder pool per message type (2 + 2 + 1 contexts per GPU), sharded by vtap_id % n_gpus",
                "records_per_gpu_per_step": recs, "value": v4, "unit": "records/s", "ms_per_step": d_mx / a.steps,
                "e2e": {"value": recs_all * a.steps / (e_mx / 1000.0), "unit": "records/s", "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": int(d2h), "ms_per_step": e_mx / a.steps},
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": e_mx / a.steps,
+                       "mode": f"l4 / l7 blocks: {a.e2e_mode}; flow_metrics tables: containers"},
                "gpu_launches": int(l4n), "gen_seconds": gen4, "per_type": per_type,
                "roofline": {"bound": "hbm", "kernel": f"the {dom} pipeline (largest share of device time)",
                             "achieved": ach4, "peak": peak, "unit": "GB/s", "frac": ach4 / peak, "traffic": None,
@@ -973,6 +988,7 @@ def main():
             leg["cpu_baseline"] = {"value": sum(parts) / tsec, "unit": "records/s", "cores": 1, "kind": "port",
                                    "sample": f"{parts} L4/L7/metric records of the same generator, one decoder instance each, {tsec:.1f} s"}
         line["legs"]["c4_mixed"] = leg
+        c4plain.close()
         for e in all_e:
             e.close()
         del f4, f7, fm, pools

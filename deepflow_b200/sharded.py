@@ -32,6 +32,31 @@ def _void16(a):
     return a.view(np.dtype((np.void, 16))).ravel()
 
 
+def duplicates_of(mine, lower):
+    """mine (n, >=2), lower (m, >=2) int64 tensors of 128-bit fingerprints (lo, hi) on one device -> bool (n,):
+    mine[i] also occurs in lower.  Sort by (lo, hi) — two stable sorts — then a binary search on lo over the FIRST
+    entry of every lo run and a bounded scan of that run is avoided by searching the pair directly: keys are
+    compared as (lo, hi) tuples through a rank built from the sorted order."""
+    lo, hi = lower[:, 0].contiguous(), lower[:, 1].contiguous()
+    order = torch.argsort(hi, stable=True)
+    order = order[torch.argsort(lo[order], stable=True)]  # lexicographic (lo, hi)
+    lo_s, hi_s = lo[order], hi[order]
+    mlo, mhi = mine[:, 0].contiguous(), mine[:, 1].contiguous()
+    left = torch.searchsorted(lo_s, mlo, right=False)
+    right = torch.searchsorted(lo_s, mlo, right=True)
+    dup = torch.zeros(len(mlo), dtype=torch.bool, device=mine.device)
+    run = right - left
+    one = run == 1
+    idx = left.clamp(max=max(0, len(lo_s) - 1))
+    if len(lo_s):
+        dup |= one & (hi_s[idx] == mhi)
+    many = torch.nonzero(run > 1).flatten()  # several fingerprints share the low half: vanishingly rare, exact anyway
+    for i in many.tolist():
+        seg = hi_s[int(left[i]):int(right[i])]
+        dup[i] = bool((seg == mhi[i]).any())
+    return dup
+
+
 class TagMerge:
     """All-gather of (fingerprint, time) lists + the ownership rule."""
 
@@ -93,8 +118,7 @@ class TagMerge:
     def exchange_device(self, fps, times):
         """The same exchange with the keys kept on the GPU (NCCL all-gather, ownership by sort + binary search).
         Returns keep (n,) bool numpy, others (m, 3) int64 CUDA tensor (lo, hi, time) of the other ranks' keys,
-        mine (n, 3) int64 CUDA tensor.  A 64-bit collision between two distinct fingerprints can only make a
-        duplicate row survive (idempotent in ClickHouse), never drop one: both halves are compared."""
+        mine (n, 3) int64 CUDA tensor.  Ownership compares both halves of the fingerprint (duplicates_of)."""
         fps = np.ascontiguousarray(fps, np.uint64).reshape(-1, 2)
         times = np.ascontiguousarray(times, np.uint32).reshape(-1)
         n = len(times)
@@ -117,12 +141,7 @@ class TagMerge:
         keep = np.ones(n, bool)
         lower = [parts[r][:counts[r]] for r in range(self.rank) if counts[r]]
         if lower and n:
-            lw = torch.cat(lower)
-            lo_sorted, order = torch.sort(lw[:, 0])
-            hi_sorted = lw[:, 1][order]
-            idx = torch.searchsorted(lo_sorted, mine[:, 0].contiguous()).clamp_(max=len(lo_sorted) - 1)
-            dup = (lo_sorted[idx] == mine[:, 0]) & (hi_sorted[idx] == mine[:, 1])
-            keep = (~dup).cpu().numpy()
+            keep = (~duplicates_of(mine, torch.cat(lower))).cpu().numpy()
         others = [parts[r][:counts[r]] for r in range(self.world) if r != self.rank and counts[r]]
         return keep, (torch.cat(others) if others else empty), mine
 

@@ -54,3 +54,42 @@ def test_round_trip_on_oracle_columns(synth, built):
         assert seen == 26 and n == 3000
     finally:
         ora.close()
+
+
+def test_lz4_block_decoder_against_pyarrow():
+    """abi.lz4_block_decode (the plain decoder the GPU frame tests use as their second opinion) on blocks produced by
+    pyarrow's LZ4 compressor: literals only, long literal / match length extensions, overlapping copies."""
+    import os
+    import numpy as np
+    import pyarrow as pa
+    from deepflow_b200 import abi
+    rng = np.random.default_rng(7)
+    cases = [b"a", b"abcd" * 3, bytes(4096), os.urandom(300), b"0123456789abcdef" * 256,
+             (b"x" * 300 + os.urandom(20)) * 5, bytes(rng.integers(0, 4, 4096, dtype=np.uint8)),
+             np.arange(512, dtype=np.uint64).tobytes()]
+    for data in cases:
+        blk = pa.compress(data, codec="lz4_raw", asbytes=True)
+        assert abi.lz4_block_decode(blk, len(data)) == data
+    import pytest
+    with pytest.raises(ValueError):
+        abi.lz4_block_decode(pa.compress(b"hello hello hello hello", codec="lz4_raw", asbytes=True), 5)
+
+
+def test_frame_stream_reader_rejects_malformed():
+    import ctypes as C
+    import pyarrow as pa
+    import pytest
+    from deepflow_b200 import abi
+
+    def stream(method, payload, usz, checksum=bytes(16)):
+        return checksum + bytes([method]) + (len(payload) + 9).to_bytes(4, "little") + usz.to_bytes(4, "little") + payload
+
+    data = b"flow_log " * 100
+    good = stream(0x82, pa.compress(data, codec="lz4_raw", asbytes=True), len(data)) + stream(0x02, b"tail", 4)
+    buf = (C.c_uint8 * len(good)).from_buffer_copy(good)
+    assert abi.decode_frames(C.addressof(buf), len(good)) == data + b"tail"
+    for bad in (stream(0x90, b"zzzz", 4), stream(0x02, b"abc", 4), stream(0x02, b"abcd", 4, checksum=b"\x01" * 16),
+                stream(0x82, b"\x00" * 10, 4)):
+        b2 = (C.c_uint8 * len(bad)).from_buffer_copy(bad)
+        with pytest.raises(ValueError):
+            abi.decode_frames(C.addressof(b2), len(bad))

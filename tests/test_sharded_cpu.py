@@ -135,3 +135,23 @@ def test_tag_merge_world2_gloo(built):
     assert codes == [0, 0], (codes, msgs)
     oks = [m for m in msgs if m[0] == "ok"]
     assert len(oks) == WORLD and all(m[2] > 0 for m in oks)
+
+
+def test_duplicates_of_matches_set_membership():
+    """The ownership rule of the device-side merge (sharded.duplicates_of) against plain set membership, including
+    fingerprints that share their low half."""
+    import numpy as np
+    import torch
+    from deepflow_b200.sharded import duplicates_of
+    rng = np.random.default_rng(3)
+    lower = rng.integers(-2**62, 2**62, size=(5000, 3), dtype=np.int64)
+    mine = rng.integers(-2**62, 2**62, size=(3000, 3), dtype=np.int64)
+    mine[:1000, :2] = lower[rng.integers(0, 5000, 1000), :2]        # real duplicates
+    mine[1000:1100, 0] = lower[:100, 0]                              # same low half, different high half
+    lower[200:300, 0] = lower[100:200, 0]                            # runs of equal low halves inside `lower`
+    mine[1100:1150, :2] = lower[250:300, :2]
+    got = duplicates_of(torch.from_numpy(mine), torch.from_numpy(lower)).numpy()
+    keys = {(int(a), int(b)) for a, b in lower[:, :2]}
+    want = np.array([(int(a), int(b)) in keys for a, b in mine[:, :2]])
+    assert (got == want).all()
+    assert not duplicates_of(torch.from_numpy(mine), torch.zeros((0, 3), dtype=torch.int64)).any()
