@@ -49,6 +49,10 @@ struct RuSrc {  // one batch of rows: columnar tags + row-major raw meters
   const uint8_t* col[RU_MAX_TAG];  // fixed kinds: values (elem stride); strings: bytes
   const uint8_t* aux[RU_MAX_TAG];  // strings: dfgpu_pos per row
   uint8_t kind[RU_MAX_TAG], elem[RU_MAX_TAG], which[RU_MAX_TAG];
+  // plain fixed-width columns (no bucket / rank translation) grouped by element width, for the key kernel:
+  // plain[w] .. plain[w + 1] index into plain_col (w = 0..3: 1, 2, 4, 8 bytes); the others are in special
+  uint8_t plain_col[RU_MAX_TAG], special_col[RU_MAX_TAG];
+  uint8_t plain[5], nspecial;
   const uint64_t* raw;      // [n][nf]
   const uint8_t* obs_inv;   // [256] LowCardinality rank -> canonical tap-side code (nullptr: the column holds codes)
 };
@@ -93,11 +97,47 @@ __device__ __forceinline__ uint64_t ru_load(const uint8_t* src, uint32_t elem) {
   }
 }
 
+__device__ __forceinline__ void ru_round(uint64_t& lo, uint64_t& hi, uint64_t a, uint64_t b, uint32_t c) {
+  const uint64_t x = (lo ^ a) + (uint64_t)c * 0x9E3779B97F4A7C15ull;
+  lo = ((x << 27) | (x >> 37)) * 0xff51afd7ed558ccdull;
+  const uint64_t y = (hi + b) ^ ((uint64_t)c << 32);
+  hi = ((y << 31) | (y >> 33)) * 0xc4ceb9fe1a85ec53ull;
+}
+// plain columns k0..k1 of one element width: four loads in flight per thread, then their rounds
+template <class T>
+__device__ __forceinline__ void ru_hash_cols(const RuSrc& s, uint32_t k0, uint32_t k1, uint64_t row, uint64_t& lo, uint64_t& hi) {
+  uint32_t k = k0;
+  for (; k + 4 <= k1; k += 4) {
+    const uint32_t c0 = s.plain_col[k], c1 = s.plain_col[k + 1], c2 = s.plain_col[k + 2], c3 = s.plain_col[k + 3];
+    const uint64_t a0 = reinterpret_cast<const T*>(s.col[c0])[row], a1 = reinterpret_cast<const T*>(s.col[c1])[row];
+    const uint64_t a2 = reinterpret_cast<const T*>(s.col[c2])[row], a3 = reinterpret_cast<const T*>(s.col[c3])[row];
+    ru_round(lo, hi, a0, a0 * 0x9E3779B97F4A7C15ull, c0);
+    ru_round(lo, hi, a1, a1 * 0x9E3779B97F4A7C15ull, c1);
+    ru_round(lo, hi, a2, a2 * 0x9E3779B97F4A7C15ull, c2);
+    ru_round(lo, hi, a3, a3 * 0x9E3779B97F4A7C15ull, c3);
+  }
+  for (; k < k1; k++) {
+    const uint32_t c = s.plain_col[k];
+    const uint64_t a = reinterpret_cast<const T*>(s.col[c])[row];
+    ru_round(lo, hi, a, a * 0x9E3779B97F4A7C15ull, c);
+  }
+}
+
 // ---- key: fingerprint, find-or-insert, first / last sequence numbers -----------------------------------
 __global__ void __launch_bounds__(256) k_ru_key(const RuDev d, const __grid_constant__ RuSrc s, uint32_t* gslot) {
   for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < s.n; row += (uint64_t)gridDim.x * blockDim.x) {
+    // 128-bit fingerprint of (time bucket, every tag column): two accumulators, one multiply-rotate round each
+    // per column (the column index enters the round), avalanche at the end (fp_finish).  Plain fixed-width
+    // columns are walked by element width, without a switch per value.  (r2: a general loop with two full
+    // mix64 per column was 7 000 instructions per row — 52 of the 75 ms of a 100 M-row add.)
     uint64_t lo = 0x243F6A8885A308D3ull, hi = 0x13198A2E03707344ull;
-    for (uint32_t c = 0; c < s.ntag; c++) {
+#define RU_ROUND(a_, b_, c_) ru_round(lo, hi, (a_), (b_), (c_))
+    ru_hash_cols<uint8_t>(s, s.plain[0], s.plain[1], row, lo, hi);
+    ru_hash_cols<uint16_t>(s, s.plain[1], s.plain[2], row, lo, hi);
+    ru_hash_cols<uint32_t>(s, s.plain[2], s.plain[3], row, lo, hi);
+    ru_hash_cols<uint64_t>(s, s.plain[3], s.plain[4], row, lo, hi);
+    for (uint32_t k = 0; k < s.nspecial; k++) {  // time, observation_point, IPv6, strings
+      const uint32_t c = s.special_col[k];
       uint64_t a = 0, b = 0;
       const uint32_t kind = s.kind[c], elem = s.elem[c];
       if (kind == MK_LCS || kind == MK_STR) {
@@ -115,9 +155,9 @@ __global__ void __launch_bounds__(256) k_ru_key(const RuDev d, const __grid_cons
         if (c == 0) a = (uint32_t)a / s.bucket * s.bucket;  // the time column: bucket start
         b = a * 0x9E3779B97F4A7C15ull;
       }
-      lo = mix64(lo ^ (a + c));
-      hi = mix64(hi + (b ^ ((uint64_t)c << 32)));
+      RU_ROUND(a, b, c);
     }
+#undef RU_ROUND
     const U128 fp = fp_finish(lo, hi);
     uint32_t slot = (uint32_t)(fp.lo ^ (fp.hi >> 17)) & d.mask;
     RuGroup* g = nullptr;
@@ -182,9 +222,14 @@ __global__ void __launch_bounds__(256) k_ru_key(const RuDev d, const __grid_cons
         }
       }
     }
+    // first row of the group: only a row EARLIER than the one recorded has anything to say, and after the first
+    // few there is none — a plain read decides (a stale read only costs a redundant atomic).  The last row is
+    // recorded by the fold, once per run of the group's rows.  (r2: one atomicMax pair per row was 55 of the 75 ms
+    // of a 100 M-row add — the hot groups of a Zipf key distribution serialise on their two words.)
     const unsigned long long seq = s.seq_base + row;
-    atomicMax(&g->first_inv, ~seq);
-    atomicMax(&g->last_seq, seq + 1);
+    unsigned long long seen;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(seen) : "l"(&g->first_inv) : "memory");
+    if (~seq > seen) atomicMax(&g->first_inv, ~seq);
     gslot[row] = slot;
   }
 }
@@ -270,6 +315,7 @@ __global__ void __launch_bounds__(256) k_ru_fold(const RuDev d, const __grid_con
     const uint32_t lo = ch * RU_CHUNK, hi = min(n_sorted, lo + RU_CHUNK);
     uint32_t cur = 0xffffffffu;
     uint64_t a0 = 0, a1 = 0, a2 = 0;
+    unsigned long long run_max = 0;  // largest row index of the current run: the group's last row so far
     for (uint32_t base = lo; base < hi; base += 32) {
       const uint32_t i = base + lane;
       const uint32_t my_row = i < hi ? order[i] : 0u;
@@ -284,10 +330,13 @@ __global__ void __launch_bounds__(256) k_ru_fold(const RuDev d, const __grid_con
             ru_flush(d, cur, f0, op0, a0);
             ru_flush(d, cur, f1, op1, a1);
             ru_flush(d, cur, f2, op2, a2);
+            if (lane == 0) atomicMax(&d.groups[cur].last_seq, s.seq_base + run_max + 1);
           }
           cur = slot;
           a0 = a1 = a2 = 0;
+          run_max = 0;
         }
+        run_max = row > run_max ? row : run_max;
         a0 = ru_op(op0, a0, v0);
         a1 = ru_op(op1, a1, v1);
         a2 = ru_op(op2, a2, v2);
@@ -297,6 +346,7 @@ __global__ void __launch_bounds__(256) k_ru_fold(const RuDev d, const __grid_con
       ru_flush(d, cur, f0, op0, a0);
       ru_flush(d, cur, f1, op1, a1);
       ru_flush(d, cur, f2, op2, a2);
+      if (lane == 0) atomicMax(&d.groups[cur].last_seq, s.seq_base + run_max + 1);
     }
   }
 }
@@ -599,6 +649,25 @@ void rollup_free_state(dfgpu_ctx* ctx) {
 }
 
 // rows of `table` of the last metrics run (still resident in the arena, raw meters beside them)
+// groups the tag columns for the key kernel (RuSrc::plain_col / special_col)
+static void ru_classify(RuSrc& src) {
+  uint32_t np = 0;
+  src.nspecial = 0;
+  for (int w = 0; w < 4; w++) {
+    src.plain[w] = (uint8_t)np;
+    const uint32_t width = 1u << w;
+    for (uint32_t c = 0; c < src.ntag; c++) {
+      const bool plain = src.kind[c] == MK_FIX && c != 0 && (src.elem[c] == 1 || src.elem[c] == 2 || src.elem[c] == 4 || src.elem[c] == 8);
+      if (plain && src.elem[c] == width) src.plain_col[np++] = (uint8_t)c;
+    }
+  }
+  src.plain[4] = (uint8_t)np;
+  for (uint32_t c = 0; c < src.ntag; c++) {
+    const bool plain = src.kind[c] == MK_FIX && c != 0 && (src.elem[c] == 1 || src.elem[c] == 2 || src.elem[c] == 4 || src.elem[c] == 8);
+    if (!plain) src.special_col[src.nspecial++] = (uint8_t)c;
+  }
+}
+
 int rollup_add_resident(dfgpu_ctx* ctx, int table, uint32_t bucket) {
   MHost* mh = reinterpret_cast<MHost*>(ctx->mt);
   if (!mh) return fail(ctx, DFGPU_ENOENT, "no metrics batch resident on the device");
@@ -625,6 +694,7 @@ int rollup_add_resident(dfgpu_ctx* ctx, int table, uint32_t bucket) {
     has_obs |= dc.kind == MK_OBS;
   }
   src.raw = reinterpret_cast<const uint64_t*>(A + L.raw_off[table]);
+  ru_classify(src);
   int rc = ru_ensure_scratch(ctx, h, src.n);
   if (rc) return rc;
   if (has_obs) {
@@ -671,6 +741,7 @@ int rollup_add_rows(dfgpu_ctx* ctx, int table, uint32_t bucket, const dfgpu_roll
     src.col[c] = reinterpret_cast<const uint8_t*>(rows->tag_cols[c]);
   }
   src.raw = rows->raw;
+  ru_classify(src);
   src.obs_inv = nullptr;  // the observation_point column carries canonical tap-side codes
   return ru_add(ctx, mh, h, table, src);
 }
