@@ -93,6 +93,8 @@ struct BatchStats {
   uint32_t ft_count;            // entries held by the flow_tag set (TagSetState::count): the host schedules rebuilds
   uint32_t ft_unrecorded;       // cumulative: emissions of keys the saturated set could not store
   uint32_t ft_evicted;          // cumulative: live entries dropped oldest-first by rebuilds
+  uint32_t ft_any;              // phase 0 found a row with a new / expired key: phases 1-3 have work to do
+  uint32_t ft_pad;
   uint64_t last_trace_id_index;
   uint32_t lc_first[8][256];    // first record index each LowCardinality code appears at
 };

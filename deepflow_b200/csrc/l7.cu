@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
   const L7Dev* d = reinterpret_cast<const L7Dev*>(p.ext);
   if ((dyn->stats.need_repair && !p.repair) || dyn->overflow) return;
   if (PHASE == 3 && dyn->stats.ft_overflow) return;
+  // steady state: phase 0 flagged no row of the batch — the count / write walks have nothing to do (their per-warp
+  // counts are then never read: k_l7_ft_layout takes the totals as zero)
+  if (PHASE != 0 && !dyn->stats.ft_any) return;
   const uint32_t nrows = dyn->stats.nrows;
   const uint32_t nwarps = dyn->nwarps;
   const size_t wstride = p.warp_cap;
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(256, PHASE == 0 ? FT_P0_MIN_BLOCKS : 1) k_l7_f
         }
       }
       d->row_flag[row] = any ? 1 : 0;
+      if (any) dyn->stats.ft_any = 1;
     }
     {  // newest lru time of the batch: the clock the rebuild measures expiry against
       uint32_t tmax = row < nrows ? (v.time > v.time_as ? v.time : v.time_as) : 0u;
@@ -489,6 +493,8 @@ __global__ void k_l7_ft_layout(const BatchParams p) {
   const L7Dev* d = reinterpret_cast<const L7Dev*>(p.ext);
   if ((dyn->stats.need_repair && !p.repair) || dyn->overflow) return;
   uint64_t* tot = dyn->stats.ft_tot;
+  if (!dyn->stats.ft_any)  // the counting walks did not run: what the scan summed is stale
+    for (int i = 0; i < 8; i++) tot[i] = 0;
   uint64_t* fo = dyn->stats.ft_off;
   uint64_t cur = 0;
   auto take = [&](int id, uint64_t bytes) {
