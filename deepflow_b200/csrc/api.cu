@@ -124,6 +124,12 @@ int dfgpu_init(int device, const dfgpu_cfg* cfg, dfgpu_ctx** out) {
   if (!ctx->cfg.flow_tag_cache_max_size) ctx->cfg.flow_tag_cache_max_size = 1u << 18;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  if (const char* v = getenv("DFGPU_KG_OVERLAP")) ctx->kg_overlap = atoi(v);
+  if (const char* v = getenv("DFGPU_KG_CTAS")) ctx->kg_ctas = atoi(v);
+  if (const char* v = getenv("DFGPU_STR_CTAS")) ctx->str_ctas = atoi(v);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_dyn, sizeof(DynState));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_persist, sizeof(PersistState));
   if (e == cudaSuccess) e = cudaMemset(ctx->d_persist, 0, sizeof(PersistState));
@@ -176,6 +182,9 @@ int dfgpu_close(dfgpu_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
   return DFGPU_OK;
 }
@@ -381,9 +390,19 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
   }
   ctx->mark(2);
   unsigned g_dec = 0, g_str = 0, g_kg = 0;
+  const bool kg_side = l7 && ctx->kg_overlap;
   if (l7) {
     l7_grids(ctx, &g_dec, &g_str, &g_kg);
+    if (ctx->kg_ctas) g_kg = g_kg / 4 * (unsigned)ctx->kg_ctas;
+    if (ctx->str_ctas) g_str = g_str / 6 * (unsigned)ctx->str_ctas;
     launch_l7_decode(bp, g_dec, s);  // decode + fixed-width columns + per-warp sizes (+ trace carry scan)
+    if (kg_side) {  // SmartEncoding needs nothing but the decode kernel's hand-over: fork
+      CU(cudaEventRecord(ctx->ev_fork, s));
+      CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+      launch_l7_kg(bp, g_kg, ctx->stream2);
+      ctx->launches++;
+      CU(cudaEventRecord(ctx->ev_join, ctx->stream2));
+    }
   } else {
     launch_l4_decode(ctx, s);
   }
@@ -406,8 +425,12 @@ static int launch_passes(dfgpu_ctx* ctx, int repair) {
   ctx->launches++;
   if (l7) {
     ctx->mark(5);
-    launch_l7_kg(bp, g_kg, s);  // SmartEncoding columns, one lane per (record, side)
-    ctx->launches++;
+    if (kg_side) {
+      CU(cudaStreamWaitEvent(s, ctx->ev_join, 0));  // the flow_tag rows read SmartEncoding columns
+    } else {
+      launch_l7_kg(bp, g_kg, s);  // SmartEncoding columns, one lane per (record, side)
+      ctx->launches++;
+    }
     ctx->mark(6);
     int rc = l7_flow_tags(ctx, s);  // commits the counters at its end
     if (rc) return rc;

@@ -28,6 +28,11 @@ struct HostBuf {
 struct dfgpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side stream of the SmartEncoding kernel: it depends on the decode kernel only, so it runs beside the scans and the
+  // string kernels (kg_overlap) and joins before the flow_tag stage
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int kg_overlap = 0, kg_ctas = 0, str_ctas = 0;  // 0: defaults
   dfgpu_cfg cfg{};
   std::string err;
   std::mutex dict_mu;
