@@ -111,6 +111,7 @@ type Config struct {
 	FlowTagCacheMaxSize      uint32 // config.go:60
 	TraceIdIndexDisabled     bool   // flow_log/config TraceIdWithIndex.Disabled
 	NativeStrings            bool
+	BlockLZ4                 bool // column buffers arrive as ClickHouse compressed frames (dfgpu_cfg.block_lz4)
 }
 
 func NewDecoder(index int, msgType datatype.MessageType, platformData *grpc.PlatformInfoTable,
@@ -124,6 +125,9 @@ func NewDecoder(index int, msgType datatype.MessageType, platformData *grpc.Plat
 	}
 	if cfg.NativeStrings {
 		c.native_strings = 1
+	}
+	if cfg.BlockLZ4 {
+		c.block_lz4 = 1
 	}
 	d := &Decoder{index: index, msgType: msgType, platformData: platformData, inQueue: inQueue, writer: writer,
 		dictVersion: make(map[uint16]uint64), counter: &Counter{}}
@@ -287,4 +291,27 @@ func releaseShared(batch *C.dfgpu_batch, shared *int32) {
 	if atomic.AddInt32(shared, -1) == 0 {
 		C.dfgpu_batch_release(batch)
 	}
+}
+
+// Frames walks a stream of compressed frames as dfgpu_cfg.block_lz4 returns them for one column buffer
+// (dfgpu_col.data / pos / arr_offsets / nulls with compressed == 1): 16 bytes of checksum slot, 1 byte
+// method (0x82 LZ4, 0x02 stored), uint32 compressed size (9-byte header included), uint32 uncompressed
+// size, payload.  The GPU leaves the checksum slot zero; seal fills it (CityHash128 of header + payload,
+// github.com/go-faster/city — the hash ch-go's compress.Writer uses) right before the frame goes to the
+// connection, so that the bytes written are exactly what a ClickHouse server expects.
+func Frames(stream []byte, seal func(frame []byte), emit func(frame []byte)) error {
+	for len(stream) > 0 {
+		if len(stream) < 25 {
+			return fmt.Errorf("truncated frame header (%d bytes left)", len(stream))
+		}
+		size := int(uint32(stream[17]) | uint32(stream[18])<<8 | uint32(stream[19])<<16 | uint32(stream[20])<<24)
+		if size < 9 || 16+size > len(stream) {
+			return fmt.Errorf("frame of %d bytes in a stream of %d", size, len(stream))
+		}
+		frame := stream[:16+size]
+		seal(frame)
+		emit(frame)
+		stream = stream[16+size:]
+	}
+	return nil
 }
