@@ -310,10 +310,14 @@ def reference_arm(a):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32/u64 integer",
             "data": "synthetic",
             "config": {"workload": "C2: L7 HTTP AppProtoLogsData, SmartEncoding on, flow_tag on (BASELINE.json configs[1])",
-                       "records_per_step": per_step, "records_per_gpu_per_step_of_the_gpu_arm": a.records,
+                       # the GPU arm's workload definition, same keys and values ...
+                       "records_per_gpu_per_step": a.records, "sub_batch_records": a.sub_batch, "dictionary_pods": a.pods,
+                       "sharding": "vtap_id % n_gpus" if a.gpus > 1 else "none",
+                       # ... of which every step of this arm runs a bounded sample
+                       "sample_records_per_step": per_step,
                        "note": "a bounded sample of the GPU arm's workload per step: same generator, same dictionary, every "
                                "host thread; the CPU arm does not grow with --gpus (one host)",
-                       "dictionary_pods": a.pods, "setup_seconds": setup_s, "host": host_info()},
+                       "setup_seconds": setup_s, "host": host_info()},
             "cpu_baseline": {"value": value, "unit": "records/s", "cores": threads, "kind": "port",
                              "sample": f"{threads} decoder instances x {sample} L7 records per step = {per_step} records "
                                        "(C++ restatement of the Go path; the Go ingester cannot be built here)"},
