@@ -34,27 +34,31 @@ def _void16(a):
 
 def duplicates_of(mine, lower):
     """mine (n, >=2), lower (m, >=2) int64 tensors of 128-bit fingerprints (lo, hi) on one device -> bool (n,):
-    mine[i] also occurs in lower.  Sort by (lo, hi) — two stable sorts — then a binary search on lo over the FIRST
-    entry of every lo run and a bounded scan of that run is avoided by searching the pair directly: keys are
-    compared as (lo, hi) tuples through a rank built from the sorted order."""
+    mine[i] also occurs in lower.  `lower` is sorted lexicographically by (lo, hi); a binary search on lo gives the
+    run of entries sharing the low half (the same key emitted by several decoders: long runs of equal pairs), a
+    second, vectorised binary search on hi inside that run decides.  No per-element Python anywhere: a step of the
+    high-cardinality leg merges tens of millions of keys."""
+    n = len(mine)
+    dup = torch.zeros(n, dtype=torch.bool, device=mine.device)
+    if n == 0 or len(lower) == 0:
+        return dup
     lo, hi = lower[:, 0].contiguous(), lower[:, 1].contiguous()
     order = torch.argsort(hi, stable=True)
     order = order[torch.argsort(lo[order], stable=True)]  # lexicographic (lo, hi)
     lo_s, hi_s = lo[order], hi[order]
     mlo, mhi = mine[:, 0].contiguous(), mine[:, 1].contiguous()
-    left = torch.searchsorted(lo_s, mlo, right=False)
-    right = torch.searchsorted(lo_s, mlo, right=True)
-    dup = torch.zeros(len(mlo), dtype=torch.bool, device=mine.device)
-    run = right - left
-    one = run == 1
-    idx = left.clamp(max=max(0, len(lo_s) - 1))
-    if len(lo_s):
-        dup |= one & (hi_s[idx] == mhi)
-    many = torch.nonzero(run > 1).flatten()  # several fingerprints share the low half: vanishingly rare, exact anyway
-    for i in many.tolist():
-        seg = hi_s[int(left[i]):int(right[i])]
-        dup[i] = bool((seg == mhi[i]).any())
-    return dup
+    a = torch.searchsorted(lo_s, mlo, right=False)
+    b = torch.searchsorted(lo_s, mlo, right=True)
+    last = len(lo_s) - 1
+    steps = int(torch.log2((b - a).max().clamp(min=1).double()).ceil().item()) + 1
+    for _ in range(steps):  # lower bound of mhi inside [a, b)
+        active = a < b
+        mid = (a + b) // 2
+        right = active & (hi_s[mid.clamp(max=last)] < mhi)
+        a = torch.where(right, mid + 1, a)
+        b = torch.where(active & ~right, mid, b)
+    end = torch.searchsorted(lo_s, mlo, right=True)
+    return (a < end) & (lo_s[a.clamp(max=last)] == mlo) & (hi_s[a.clamp(max=last)] == mhi)
 
 
 class TagMerge:
