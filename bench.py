@@ -900,7 +900,7 @@ def main():
 
     if not a.no_cpu_baseline and rank == 0 and world == 1:
         build.build_oracle()
-        v, n, dt = cpu_port_run(synth, L7, 400_000, 1, 4242)
+        v, n, dt = cpu_port_run(synth, L7, 1_500_000, 1, 4242)
         line["cpu_baseline"] = {"value": v, "unit": "records/s", "cores": 1, "kind": "port",
                                 "sample": f"{n} L7 records of the same generator, one decoder instance, {dt:.1f} s",
                                 "host": host_info()}
