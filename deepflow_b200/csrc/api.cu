@@ -967,7 +967,7 @@ void dfgpu_batch_release(dfgpu_batch* b) {
 int dfgpu_flush(dfgpu_ctx* ctx) { return dfgpu_sync(ctx); }
 
 // Measurement hook (bench.py roofline leg): CUDA events recorded on the ctx stream
-// right around the dominant kernel (the EMIT pass) of every dfgpu_run.
+// right around the pack kernels (string / array columns) of every dfgpu_run.
 int dfgpu_profile_enable(dfgpu_ctx* ctx, int on) {
   if (!ctx) return DFGPU_EINVAL;
   CU(cudaSetDevice(ctx->device));

@@ -320,7 +320,7 @@ DF_HD int m_obs_space(int table) {
        : table == MT_APPLICATION_MAP_1S ? 3 : -1;
 }
 
-struct MLayout {  // written by k_m_finish, read by the EMIT pass and by fetch
+struct MLayout {  // written by k_m_layout, read by k_m_emit and by fetch
   uint64_t col_off[M_MAX_DESC];  // values / keys / string bytes
   uint64_t aux_off[M_MAX_DESC];  // dfgpu_pos array of string columns
   uint64_t str_bytes[12];

@@ -4,14 +4,15 @@
  * simple_codec.go:229-248), the per-warp slot scans that turn per-record sizes
  * into output offsets, and LowCardinality first-appearance ranking.
  *
- * Pipeline shape (one CUDA stream, no host round trip after framing):
- *   frame_count -> frame_scan -> [nrec to host] -> frame_fill
- *   pass<SIZE>   : 1 thread / record, decode + size every variable-length output,
- *                  warp-reduce -> warp_tot[slot][warp]
- *   slot_scan    : exclusive scan over warps, one CTA per slot
- *   finish       : stream offsets inside the arena, LC code ranks
- *   pass<EMIT>   : decode again, warp-shuffle scan for the row / byte offsets,
- *                  write every column (row-major threads => coalesced column stores)
+ * Pipeline shape (one CUDA stream; the record count and everything sized by it stay on the device):
+ *   frame_walk -> frame_scan -> prepare (plan: warps, column offsets) -> frame_fill
+ *   decode      : 1 thread / record, the record decoded once into shared-memory words, the row built with the
+ *                 warp converged (coalesced column stores), per-warp sizes of the variable-length outputs
+ *                 -> warp_tot[slot][warp]
+ *   slot_scan   : exclusive scan over warps, one CTA per slot
+ *   finish      : stream offsets inside the arena, LC code ranks
+ *   pack / SmartEncoding / flow_tag kernels of the message type (l7_strings.cu, kg_kernel.cuh, l7.cu, l4.cu,
+ *                 metrics.cu), commit
  */
 #pragma once
 #include "internal.h"

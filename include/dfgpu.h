@@ -340,12 +340,12 @@ void* dfgpu_stream(dfgpu_ctx* ctx);
 /* number of kernels this ctx has launched since init                           */
 uint64_t dfgpu_launch_count(const dfgpu_ctx* ctx);
 /* Measurement hooks: CUDA events recorded on the ctx stream right around the
- * dominant kernel (the pack/EMIT pass) of every dfgpu_run (<= 256 runs between reads).
+ * pack kernels (string / array columns) of every dfgpu_run (<= 256 runs between reads).
  * dfgpu_profile_read synchronises, sums and resets.                               */
 int dfgpu_profile_enable(dfgpu_ctx* ctx, int on);
 int dfgpu_profile_read(dfgpu_ctx* ctx, double* emit_ms, uint64_t* launches, uint64_t* in_bytes);
 /* stage breakdown of the profiled runs, ms[7]: framing, prepare, decode pass, scans, pack (string / array
- * columns), SmartEncoding, flow_tag (flow_log message types; L4 packs inside its second pass)            */
+ * columns), SmartEncoding, flow_tag / app_service tags (all three message types)                          */
 int dfgpu_profile_stages(dfgpu_ctx* ctx, double* ms7, uint64_t* runs);
 int dfgpu_flush(dfgpu_ctx* ctx);
 
